@@ -1,0 +1,485 @@
+"""aicb200 — Python binding over the C ABI of libaicb200.so.
+
+Mirrors the reference's raytracer surface (names and argument meaning):
+`GraphicsOptions` (all-is-cubes-render/src/camera/graphics_options.rs:28), `Viewport`
+(camera/viewport.rs:24), `Camera` (camera/camera_struct.rs:43), `SpaceRaytracer`
+(raytracer/sr.rs:51), `RtRenderer` / `HeadlessRenderer` (raytracer/renderer.rs:35,
+headless.rs:17), `Rendering` (headless.rs:52).  `Space`/`Block` here are only the flattened
+snapshot the raytracer reads (SpaceRaytracer::new, sr.rs:64-88) — not the reference's world model.
+
+This module contains no compute: every pixel comes from the CUDA kernels behind the C ABI.
+If the library is missing or there is no GPU the calls fail loudly (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .abi import (FOG_ABRUPT, FOG_COMPROMISE, FOG_NONE, FOG_PHYSICAL, LIGHT_COARSE, LIGHT_FLAT, LIGHT_LINEAR,
+                  LIGHT_NONE, LIGHT_SMOOTHSTEP, TONE_CLAMP, TONE_REINHARD, TRANSPARENCY_SURFACE,
+                  TRANSPARENCY_THRESHOLD, TRANSPARENCY_VOLUMETRIC)
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libaicb200.so")
+
+
+class AicbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{abi.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libaicb200.so (built in-tree by __graft_entry__.build()). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.aicb_abi_version.restype = C.c_uint32
+    lib.aicb_last_error.restype = C.c_char_p
+    lib.aicb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.aicb_ctx_destroy.argtypes = [C.c_void_p]
+    lib.aicb_scene_create.argtypes = [C.c_void_p, C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
+    lib.aicb_scene_destroy.argtypes = [C.c_void_p]
+    lib.aicb_scene_device_bytes.argtypes = [C.c_void_p]
+    lib.aicb_scene_device_bytes.restype = C.c_uint64
+    lib.aicb_scene_update_cubes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_scene_upload_light.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_shard_pixel_count.argtypes = [C.POINTER(abi.CameraData), C.POINTER(abi.Shard)]
+    lib.aicb_shard_pixel_count.restype = C.c_size_t
+    lib.aicb_render_srgb8.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
+                                      C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.POINTER(abi.RenderInfo)]
+    lib.aicb_render_colorbuf.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
+                                         C.POINTER(abi.Shard), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.POINTER(abi.RenderInfo)]
+    lib.aicb_render_srgb8_device.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
+                                             C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_render_finish.argtypes = [C.c_void_p, C.POINTER(abi.RenderInfo)]
+    lib.aicb_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(abi.Options), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.RenderInfo)]
+    lib.aicb_camera_look_at.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double,
+                                        C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_float,
+                                        C.POINTER(abi.CameraData)]
+    lib.aicb_camera_from_view.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double,
+                                          C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_float,
+                                          C.POINTER(abi.CameraData)]
+    lib.aicb_eye_for_look_at.argtypes = [C.POINTER(abi.Aab), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.aicb_eye_for_look_at.restype = None
+    lib.aicb_camera_project_ndc.argtypes = [C.POINTER(abi.CameraData), C.c_double, C.c_double,
+                                            C.POINTER(C.c_double)]
+    lib.aicb_camera_project_ndc.restype = None
+    lib.aicb_light_edit_and_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8,
+                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
+    lib.aicb_light_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    if lib.aicb_abi_version() != abi.ABI_VERSION:
+        raise RuntimeError("libaicb200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(status: int):
+    if status != abi.OK:
+        raise AicbError(status, load_library().aicb_last_error().decode("utf-8", "replace"))
+
+
+# ------------------------------------------------------------------------------------------------
+# GraphicsOptions / Viewport / Camera
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class GraphicsOptions:
+    """The pixel-affecting subset of GraphicsOptions (graphics_options.rs:28-150).
+    Defaults are GraphicsOptions::default() (graphics_options.rs:251-281)."""
+    fog: int = FOG_ABRUPT
+    fov_y: float = 90.0
+    tone_mapping: int = TONE_CLAMP
+    maximum_intensity: float = math.inf
+    exposure: float = 1.0  # ExposureOption::Fixed(1)
+    view_distance: float = 200.0
+    lighting_display: int = LIGHT_LINEAR
+    transparency: int = TRANSPARENCY_VOLUMETRIC
+    transparency_threshold: float = 0.5
+    antialiasing_always: bool = False
+    debug_pixel_cost: bool = False
+
+    @staticmethod
+    def unaltered_colors() -> "GraphicsOptions":
+        """GraphicsOptions::UNALTERED_COLORS (graphics_options.rs:168-190)."""
+        return GraphicsOptions(fog=FOG_NONE, lighting_display=LIGHT_NONE)
+
+    def repair(self) -> "GraphicsOptions":
+        """graphics_options.rs:194-198"""
+        return dataclasses.replace(self, fov_y=min(max(self.fov_y, 1.0), 189.0),
+                                   view_distance=min(max(self.view_distance, 1.0), 10000.0))
+
+    def to_abi(self, include_sky: bool = True) -> abi.Options:
+        o = abi.Options()
+        o.fog = self.fog
+        o.lighting_display = self.lighting_display
+        o.transparency = self.transparency
+        o.antialiasing_always = 1 if self.antialiasing_always else 0
+        o.tone_mapping = self.tone_mapping
+        o.debug_pixel_cost = 1 if self.debug_pixel_cost else 0
+        o.include_sky = 1 if include_sky else 0
+        o.transparency_threshold = self.transparency_threshold
+        o.maximum_intensity = self.maximum_intensity
+        o.view_distance = min(max(self.view_distance, 1.0), 10000.0)
+        return o
+
+
+@dataclasses.dataclass
+class Viewport:
+    """camera/viewport.rs:24-37"""
+    nominal_size: tuple
+    framebuffer_size: tuple
+
+    @staticmethod
+    def with_scale(scale: float, framebuffer_size) -> "Viewport":
+        w, h = framebuffer_size
+        return Viewport((w / scale if scale else math.inf, h / scale if scale else math.inf), (int(w), int(h)))
+
+
+class Camera:
+    """Camera (camera_struct.rs:43): options + viewport + view transform -> matrices.
+    Matrix construction happens in the C ABI (host code, aicb_camera_*)."""
+
+    def __init__(self, options: GraphicsOptions, viewport: Viewport):
+        self.options = options.repair()
+        self.viewport = viewport
+        self._rotation = (0.0, 0.0, 0.0, 1.0)
+        self._translation = (0.0, 0.0, 0.0)
+        self.data = abi.CameraData()
+        self._compute()
+
+    def _compute(self):
+        lib = load_library()
+        q = (C.c_double * 4)(*self._rotation)
+        t = (C.c_double * 3)(*self._translation)
+        _check(lib.aicb_camera_from_view(q, t, self.options.fov_y, self.options.view_distance,
+                                         float(self.viewport.nominal_size[0]), float(self.viewport.nominal_size[1]),
+                                         self.viewport.framebuffer_size[0], self.viewport.framebuffer_size[1],
+                                         self.options.exposure, C.byref(self.data)))
+
+    def set_view_transform(self, rotation_ijkr: Sequence[float], translation: Sequence[float]):
+        self._rotation = tuple(float(v) for v in rotation_ijkr)
+        self._translation = tuple(float(v) for v in translation)
+        self._compute()
+
+    def look_at_y_up(self, eye: Sequence[float], target: Sequence[float]):
+        """camera_struct.rs:459-471"""
+        lib = load_library()
+        e = (C.c_double * 3)(*[float(v) for v in eye])
+        t = (C.c_double * 3)(*[float(v) for v in target])
+        _check(lib.aicb_camera_look_at(e, t, self.options.fov_y, self.options.view_distance,
+                                       float(self.viewport.nominal_size[0]), float(self.viewport.nominal_size[1]),
+                                       self.viewport.framebuffer_size[0], self.viewport.framebuffer_size[1],
+                                       self.options.exposure, C.byref(self.data)))
+
+    def project_ndc_into_world(self, x: float, y: float) -> np.ndarray:
+        """camera_struct.rs:238-257 -> [ox,oy,oz,dx,dy,dz]"""
+        out = (C.c_double * 6)()
+        load_library().aicb_camera_project_ndc(C.byref(self.data), x, y, out)
+        return np.array(out[:], dtype=np.float64)
+
+    @property
+    def inverse_projection_view(self) -> np.ndarray:
+        return np.array(self.data.inverse_projection_view[:], dtype=np.float64).reshape(4, 4)
+
+
+def eye_for_look_at(bounds_lower, bounds_size, direction) -> np.ndarray:
+    """all-is-cubes/src/camera.rs:34-40"""
+    b = abi.Aab()
+    b.lower[:] = [int(v) for v in bounds_lower]
+    b.size[:] = [int(v) for v in bounds_size]
+    d = (C.c_double * 3)(*[float(v) for v in direction])
+    out = (C.c_double * 3)()
+    load_library().aicb_eye_for_look_at(C.byref(b), d, out)
+    return np.array(out[:], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# Flattened Space snapshot
+# ------------------------------------------------------------------------------------------------
+class Block:
+    """One Space palette entry as the raytracer sees it (TracingBlock, sr.rs:569-587)."""
+
+    def __init__(self, *, color=None, emission=(0.0, 0.0, 0.0), is_air=False, resolution=1, voxel_lower=None,
+                 indices: Optional[np.ndarray] = None, palette: Optional[np.ndarray] = None):
+        self.is_air = bool(is_air)
+        self.resolution = int(resolution)
+        if indices is None:
+            c = (0.0, 0.0, 0.0, 0.0) if color is None else tuple(color)
+            self.palette = np.zeros((1, 8), dtype=np.float32)
+            self.palette[0, :4] = c
+            self.palette[0, 4:7] = emission
+            self.indices = None
+            self.voxel_lower = (0, 0, 0)
+            self.voxel_size = (1, 1, 1)
+            self.resolution = 1
+        else:
+            assert indices.ndim == 3 and indices.dtype == np.uint16
+            self.indices = np.ascontiguousarray(indices)
+            self.palette = np.ascontiguousarray(palette, dtype=np.float32)
+            assert self.palette.ndim == 2 and self.palette.shape[1] == 8
+            self.voxel_lower = tuple(int(v) for v in (voxel_lower or (0, 0, 0)))
+            self.voxel_size = tuple(int(v) for v in indices.shape)
+
+    @staticmethod
+    def air() -> "Block":
+        return Block(is_air=True)
+
+
+class Space:
+    """What SpaceRaytracer::new reads from space::Read (sr.rs:64-88): bounds, per-cube block
+    index (shape [X,Y,Z], C order == Vol Z-major, vol.rs:1013-1018), optional PackedLight texels
+    (shape [X,Y,Z,4]), block table, sky."""
+
+    def __init__(self, lower, block_ids: np.ndarray, blocks: Sequence[Block], light: Optional[np.ndarray] = None,
+                 sky_colors=None, light_max_distance: int = 0):
+        assert block_ids.ndim == 3
+        self.lower = tuple(int(v) for v in lower)
+        self.block_ids = np.ascontiguousarray(block_ids, dtype=np.uint16)
+        self.size = tuple(int(v) for v in self.block_ids.shape)
+        self.blocks = list(blocks)
+        self.light = None if light is None else np.ascontiguousarray(light, dtype=np.uint8)
+        if self.light is not None:
+            assert self.light.shape == self.size + (4,)
+        if sky_colors is None:
+            # Sky::DEFAULT = Uniform(DAY_SKY_COLOR = srgb[243 243 255]) (sky.rs:24, palette.rs:63)
+            sky_colors = [srgb8_to_linear((243, 243, 255))]
+        self.sky_colors = np.asarray(sky_colors, dtype=np.float32).reshape(-1, 3)
+        assert self.sky_colors.shape[0] in (1, 8)
+        self.light_max_distance = int(light_max_distance)
+
+    def to_desc(self):
+        """Returns (abi.SceneDesc, keepalive list)."""
+        keep = []
+        d = abi.SceneDesc()
+        d.bounds.lower[:] = self.lower
+        d.bounds.size[:] = self.size
+        d.block_ids = self.block_ids.ctypes.data
+        d.light = self.light.ctypes.data if self.light is not None else None
+        arr = (abi.BlockDesc * len(self.blocks))()
+        for i, b in enumerate(self.blocks):
+            bd = arr[i]
+            bd.resolution = b.resolution
+            bd.is_air = 1 if b.is_air else 0
+            bd.voxel_bounds.lower[:] = b.voxel_lower
+            bd.voxel_bounds.size[:] = b.voxel_size
+            if b.indices is not None:
+                bd.indices = b.indices.ctypes.data
+                bd.n_indices = b.indices.size
+            else:
+                bd.indices = None
+                bd.n_indices = 0
+            bd.palette = b.palette.ctypes.data
+            bd.n_palette = b.palette.shape[0]
+            keep.append(b)
+        d.blocks = arr
+        d.n_blocks = len(self.blocks)
+        d.sky.kind = 0 if self.sky_colors.shape[0] == 1 else 1
+        for k in range(self.sky_colors.shape[0]):
+            d.sky.colors[k][:] = [float(v) for v in self.sky_colors[k]]
+        d.light_max_distance = self.light_max_distance
+        keep.append(arr)
+        keep.append(self)
+        return d, keep
+
+
+def srgb8_to_linear(rgb) -> tuple:
+    """component_from_srgb8 (color.rs): f32 sRGB decode, used only for named palette constants."""
+    out = []
+    for c in rgb:
+        f = np.float32(c) / np.float32(255.0)
+        if f <= np.float32(0.04045):
+            out.append(float(np.float32(f * np.float32(25.0 / 323.0))))
+        else:
+            x = np.float32(np.float32(200.0) * f + np.float32(11.0)) / np.float32(211.0)
+            out.append(float(np.float32(float(x) ** float(np.float32(12.0 / 5.0)))))
+    return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# SpaceRaytracer / RtRenderer
+# ------------------------------------------------------------------------------------------------
+class Context:
+    _default = None
+
+    def __init__(self, device_id: int = -1):
+        lib = load_library()
+        self.handle = C.c_void_p()
+        _check(lib.aicb_ctx_create(device_id, C.byref(self.handle)))
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context(-1)
+        return cls._default
+
+    def close(self):
+        if self.handle:
+            load_library().aicb_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+@dataclasses.dataclass
+class RenderInfo:
+    cubes_traced: int
+    rays: int
+    algorithmic_bytes: int
+    counters: tuple
+    kernel_ms: float
+    flaws: int
+
+    @staticmethod
+    def from_abi(i: abi.RenderInfo) -> "RenderInfo":
+        return RenderInfo(int(i.cubes_traced), int(i.rays), int(i.algorithmic_bytes), tuple(int(c) for c in i.counters),
+                          float(i.kernel_ms), int(i.flaws))
+
+
+@dataclasses.dataclass
+class Rendering:
+    """headless.rs:52-67"""
+    size: tuple
+    data: np.ndarray  # [H, W, 4] uint8 sRGB RGBA
+    flaws: int
+    info: RenderInfo
+
+
+class SpaceRaytracer:
+    """SpaceRaytracer<()> (sr.rs:51): device-resident snapshot of a Space + graphics options."""
+
+    def __init__(self, space: Space, graphics_options: GraphicsOptions, ctx: Optional[Context] = None):
+        self.ctx = ctx or Context.default()
+        self.graphics_options = graphics_options.repair()
+        self.space = space
+        desc, keep = space.to_desc()
+        self.handle = C.c_void_p()
+        _check(load_library().aicb_scene_create(self.ctx.handle, C.byref(desc), C.byref(self.handle)))
+        del keep
+
+    def close(self):
+        if self.handle:
+            load_library().aicb_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(load_library().aicb_scene_device_bytes(self.handle))
+
+    def trace_rays(self, origin_dir: np.ndarray, include_sky: bool = True, want_depth=False, want_hit=False,
+                   want_steps=False):
+        """SpaceRaytracer::trace_ray (sr.rs:113-120) over a batch: returns dict of arrays."""
+        od = np.ascontiguousarray(origin_dir, dtype=np.float64).reshape(-1, 6)
+        n = od.shape[0]
+        cb = np.empty((n, 4), dtype=np.float32)
+        depth = np.empty(n, dtype=np.float64) if want_depth else None
+        hit = np.empty((n, 8), dtype=np.int32) if want_hit else None
+        steps = np.empty(n, dtype=np.uint32) if want_steps else None
+        info = abi.RenderInfo()
+        opt = self.graphics_options.to_abi(include_sky)
+        _check(load_library().aicb_trace_rays(self.handle, od.ctypes.data, n, C.byref(opt), cb.ctypes.data,
+                                              depth.ctypes.data if want_depth else None,
+                                              hit.ctypes.data if want_hit else None,
+                                              steps.ctypes.data if want_steps else None, C.byref(info)))
+        return {"colorbuf": cb, "depth": depth, "hit": hit, "steps": steps, "info": RenderInfo.from_abi(info)}
+
+    def update_cubes(self, cubes: np.ndarray, block_ids: np.ndarray, light: Optional[np.ndarray] = None):
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        ids = np.ascontiguousarray(block_ids, dtype=np.uint16)
+        lt = None if light is None else np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
+        _check(load_library().aicb_scene_update_cubes(self.handle, c.ctypes.data, ids.ctypes.data,
+                                                      lt.ctypes.data if lt is not None else None, c.shape[0]))
+
+    def upload_light(self, light: np.ndarray):
+        lt = np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
+        _check(load_library().aicb_scene_upload_light(self.handle, lt.ctypes.data, lt.shape[0]))
+
+
+def _shard_abi(shard):
+    if shard is None:
+        return None
+    s = abi.Shard()
+    s.strip_rows, s.index, s.count = shard
+    return s
+
+
+class RtRenderer:
+    """RtRenderer<()> + impl HeadlessRenderer (renderer.rs:35, 338-355; headless.rs:17-44).
+
+    update(): snapshot the Space onto the GPU (== SpaceRaytracer::new / UpdatingSpaceRaytracer).
+    draw(): trace every pixel on the GPU and return a Rendering (== draw_rgba)."""
+
+    def __init__(self, camera: Camera, ctx: Optional[Context] = None):
+        self.camera = camera
+        self.ctx = ctx or Context.default()
+        self.rt: Optional[SpaceRaytracer] = None
+
+    def update(self, space: Space):
+        if self.rt is not None:
+            self.rt.close()
+        self.rt = SpaceRaytracer(space, self.camera.options, self.ctx)
+
+    def _require(self) -> SpaceRaytracer:
+        if self.rt is None:
+            raise AicbError(abi.ERR_INVALID, "draw() before update()")
+        return self.rt
+
+    def pixel_count(self, shard=None) -> int:
+        s = _shard_abi(shard)
+        return int(load_library().aicb_shard_pixel_count(C.byref(self.camera.data), C.byref(s) if s else None))
+
+    def draw(self, info_text: str = "", shard=None) -> Rendering:
+        rt = self._require()
+        n = self.pixel_count(shard)
+        w = self.camera.data.fb_width
+        out = np.empty((n, 4), dtype=np.uint8)
+        info = abi.RenderInfo()
+        opt = rt.graphics_options.to_abi(True)
+        s = _shard_abi(shard)
+        _check(load_library().aicb_render_srgb8(rt.handle, C.byref(self.camera.data), C.byref(opt),
+                                                C.byref(s) if s else None, out.ctypes.data, n, C.byref(info)))
+        h = n // w if w else 0
+        return Rendering((w, h), out.reshape(h, w, 4) if w else out.reshape(0, 0, 4), int(info.flaws),
+                         RenderInfo.from_abi(info))
+
+    draw_rgba = draw
+
+    def draw_colorbuf(self, shard=None, want_depth=True, want_hit=True, want_steps=True):
+        """RtRenderer::draw::<ColorBuf> (+DepthBuf, +Position) (renderer.rs:183-220)."""
+        rt = self._require()
+        n = self.pixel_count(shard)
+        cb = np.empty((n, 4), dtype=np.float32)
+        depth = np.empty(n, dtype=np.float64) if want_depth else None
+        hit = np.empty((n, 8), dtype=np.int32) if want_hit else None
+        steps = np.empty(n, dtype=np.uint32) if want_steps else None
+        info = abi.RenderInfo()
+        opt = rt.graphics_options.to_abi(True)
+        s = _shard_abi(shard)
+        _check(load_library().aicb_render_colorbuf(rt.handle, C.byref(self.camera.data), C.byref(opt),
+                                                   C.byref(s) if s else None, cb.ctypes.data,
+                                                   depth.ctypes.data if want_depth else None,
+                                                   hit.ctypes.data if want_hit else None,
+                                                   steps.ctypes.data if want_steps else None, n, C.byref(info)))
+        return {"colorbuf": cb, "depth": depth, "hit": hit, "steps": steps, "info": RenderInfo.from_abi(info)}
+
+
+HeadlessRenderer = RtRenderer

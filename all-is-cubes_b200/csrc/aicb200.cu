@@ -1,0 +1,698 @@
+// aicb200.cu — host side of libaicb200.so: the C ABI of include/aicb200.h, scene flattening
+// (SpaceRaytracer::new, sr.rs:64-88, 543-549) into the two-level brick index, and kernel launch.
+//
+// No CPU fallback lives here: every compute entry point needs a CUDA device and fails with
+// AICB_ERR_CUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "trace_kernel.cuh"
+
+using namespace aicb;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error = "";
+
+static aicb_status fail(aicb_status st, const std::string &msg) {
+    g_last_error = msg;
+    return st;
+}
+static aicb_status cuda_fail(cudaError_t e, const char *what) {
+    aicb_status st = (e == cudaErrorMemoryAllocation) ? AICB_ERR_OOM : AICB_ERR_CUDA;
+    return fail(st, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context / scene objects
+// ---------------------------------------------------------------------------------------------
+struct aicb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned int *d_tile_counter = nullptr;
+    unsigned long long *d_counters = nullptr;
+    float *d_lut = nullptr;
+    // staging output buffers (grown on demand)
+    void *d_out = nullptr;
+    size_t d_out_bytes = 0;
+    void *d_aux = nullptr;
+    size_t d_aux_bytes = 0;
+    std::mutex mu;
+};
+
+struct aicb_scene {
+    aicb_ctx *ctx = nullptr;
+    DeviceScene ds{};
+    std::vector<uint8_t> block_kind;   // host copy, for update_cubes
+    size_t volume = 0;
+    uint64_t device_bytes = 0;
+    void *d_cells = nullptr;
+    uint32_t *d_light = nullptr;
+    BlockRec *d_blocks = nullptr;
+    uint16_t *d_bricks = nullptr;
+    float4 *d_palette = nullptr;
+    // state of the last asynchronous render
+    bool pending = false;
+    uint64_t pending_rays = 0;
+    uint64_t pending_pixels = 0;
+    uint32_t pending_out_bytes_per_pixel = 0;
+};
+
+// PackedLight::some -> scalar_in (light/data.rs:213-217)
+static uint8_t scalar_in(float v) {
+    float x = std::round(std::log2(v) * 10.0f + 144.0f);
+    if (!(x > 0.0f)) return 0;
+    if (x >= 255.0f) return 255;
+    return (uint8_t)x;
+}
+static uint32_t texel_some(const float rgb[3]) {
+    return (uint32_t)scalar_in(rgb[0]) | ((uint32_t)scalar_in(rgb[1]) << 8) | ((uint32_t)scalar_in(rgb[2]) << 16) |
+           (255u << 24);
+}
+static float ps_mul_h(float a, float b) {
+    float v = a * b;
+    return (v != v) ? 0.0f : v;
+}
+
+// Sky::for_blocks + Sky::mean (sky.rs:45-82)
+static void build_block_sky(const aicb_sky &sky, DeviceScene *ds) {
+    ds->sky_kind = sky.kind ? 1 : 0;
+    std::memcpy(ds->sky_colors, sky.colors, sizeof ds->sky_colors);
+    if (!sky.kind) {
+        uint32_t t = texel_some(sky.colors[0]);
+        for (int f = 0; f < 6; f++) ds->sky_faces[f] = t;
+        ds->sky_mean = t;
+        return;
+    }
+    // Face::rotation_from_nz basis (face.rs:395-405): images of +X, +Y, +Z
+    static const int basis[6][3][3] = {
+        {{0, 1, 0}, {0, 0, 1}, {1, 0, 0}},    // NX RYZX
+        {{0, 0, 1}, {1, 0, 0}, {0, 1, 0}},    // NY RZXY
+        {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}},    // NZ RXYZ
+        {{0, -1, 0}, {0, 0, 1}, {-1, 0, 0}},  // PX RyZx
+        {{0, 0, 1}, {-1, 0, 0}, {0, -1, 0}},  // PY RZxy
+        {{1, 0, 0}, {0, -1, 0}, {0, 0, -1}},  // PZ RXyz
+    };
+    static const int pts[4][3] = {{-1, -1, -1}, {-1, 1, -1}, {1, -1, -1}, {1, 1, -1}};
+    for (int f = 0; f < 6; f++) {
+        float sum[3] = {0, 0, 0};
+        for (int k = 0; k < 4; k++) {
+            int d[3];
+            for (int i = 0; i < 3; i++)
+                d[i] = pts[k][0] * basis[f][0][i] + pts[k][1] * basis[f][1][i] + pts[k][2] * basis[f][2][i];
+            int idx = ((d[0] >= 0) << 2) + ((d[1] >= 0) << 1) + (d[2] >= 0);
+            for (int i = 0; i < 3; i++) sum[i] = sum[i] + sky.colors[idx][i];
+        }
+        float q[3];
+        for (int i = 0; i < 3; i++) q[i] = ps_mul_h(sum[i], 0.25f);
+        ds->sky_faces[f] = texel_some(q);
+    }
+    float sum[3] = {0, 0, 0};
+    for (int k = 0; k < 8; k++)
+        for (int i = 0; i < 3; i++) sum[i] = sum[i] + sky.colors[k][i];
+    float q[3];
+    for (int i = 0; i < 3; i++) q[i] = ps_mul_h(sum[i], 1.0f / 8.0f);
+    ds->sky_mean = texel_some(q);
+}
+
+static bool voxel_invisible(const aicb_voxel &v) {
+    return v.rgba[3] == 0.0f && v.emission[0] == 0.0f && v.emission[1] == 0.0f && v.emission[2] == 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+typedef void (*kernel_fn)(const TraceParams);
+
+template <bool V, int LC, bool AUX>
+static kernel_fn kernel_of() {
+    return trace_kernel<V, LC, AUX>;
+}
+
+static kernel_fn select_kernel(bool volumetric, int lc, bool aux) {
+#define PICK(V, L, A) if (volumetric == V && lc == L && aux == A) return kernel_of<V, L, A>();
+    PICK(false, LC_NONE, false) PICK(false, LC_NONE, true) PICK(false, LC_FLAT, false) PICK(false, LC_FLAT, true)
+    PICK(false, LC_INTERP, false) PICK(false, LC_INTERP, true) PICK(true, LC_NONE, false) PICK(true, LC_NONE, true)
+    PICK(true, LC_FLAT, false) PICK(true, LC_FLAT, true) PICK(true, LC_INTERP, false) PICK(true, LC_INTERP, true)
+#undef PICK
+    return nullptr;
+}
+
+static aicb_status validate_options(const aicb_options *o) {
+    if (!o) return fail(AICB_ERR_INVALID, "options is NULL");
+    if (o->fog > AICB_FOG_PHYSICAL) return fail(AICB_ERR_INVALID, "bad fog option");
+    if (o->lighting_display == AICB_LIGHT_BOUNCE)
+        return fail(AICB_ERR_UNSUPPORTED, "LightingOption::Bounce is not implemented (SURVEY 8(f) N4)");
+    if (o->lighting_display > AICB_LIGHT_BOUNCE) return fail(AICB_ERR_INVALID, "bad lighting option");
+    if (o->transparency > AICB_TRANSPARENCY_THRESHOLD) return fail(AICB_ERR_INVALID, "bad transparency option");
+    if (o->tone_mapping > AICB_TONE_REINHARD) return fail(AICB_ERR_INVALID, "bad tone mapping option");
+    if (!(o->view_distance >= 1.0 && o->view_distance <= 10000.0))
+        return fail(AICB_ERR_INVALID, "view_distance must be repaired to [1, 10000]");
+    return AICB_OK;
+}
+
+static uint32_t shard_rows(uint32_t fb_height, const aicb_shard *sh) {
+    if (!sh || sh->count <= 1) return fb_height;
+    uint32_t sr = sh->strip_rows ? sh->strip_rows : 1;
+    uint32_t rows = 0;
+    uint32_t n_strips = (fb_height + sr - 1) / sr;
+    for (uint32_t s = sh->index; s < n_strips; s += sh->count) {
+        uint32_t begin = s * sr;
+        uint32_t end = begin + sr < fb_height ? begin + sr : fb_height;
+        rows += end - begin;
+    }
+    return rows;
+}
+
+struct Outputs {
+    uchar4 *srgb8 = nullptr;
+    float4 *colorbuf = nullptr;
+    double *depth = nullptr;
+    aicb_hit *hit = nullptr;
+    uint32_t *steps = nullptr;
+};
+
+// Launches the trace kernel on `stream`. Camera rays when cam != NULL, explicit rays otherwise.
+static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const aicb_options *opt,
+                                const aicb_shard *shard, const double *d_rays, uint64_t n_rays, const Outputs &out,
+                                bool aux, cudaStream_t stream) {
+    aicb_ctx *ctx = sc->ctx;
+    TraceParams P;
+    std::memset(&P, 0, sizeof P);
+    P.scene = sc->ds;
+    uint64_t pixels;
+    if (cam) {
+        std::memcpy(P.m, cam->inverse_projection_view, sizeof P.m);
+        P.fb_width = cam->fb_width;
+        P.fb_height = cam->fb_height;
+        P.exposure = cam->exposure;
+        P.local_rows = shard_rows(cam->fb_height, shard);
+        if (shard && shard->count > 1) {
+            P.strip_rows = shard->strip_rows ? shard->strip_rows : 1;
+            P.shard_index = shard->index;
+            P.shard_count = shard->count;
+        } else {
+            P.strip_rows = 1;
+            P.shard_index = 0;
+            P.shard_count = 1;
+        }
+        P.tiles_x = (P.fb_width + TILE_W - 1) / TILE_W;
+        P.tiles_y = (P.local_rows + TILE_H - 1) / TILE_H;
+        pixels = (uint64_t)P.fb_width * P.local_rows;
+    } else {
+        P.exposure = 1.0f;
+        P.rays = d_rays;
+        P.n_rays = n_rays;
+        P.tiles_x = (uint32_t)((n_rays + 31) / 32);
+        P.tiles_y = 1;
+        P.shard_count = 1;
+        P.strip_rows = 1;
+        pixels = n_rays;
+    }
+    P.fog = opt->fog;
+    P.lighting = opt->lighting_display;
+    P.transparency = opt->transparency;
+    P.threshold = opt->transparency_threshold;
+    P.antialias = (cam && opt->antialiasing_always) ? 1 : 0;
+    P.tone_mapping = opt->tone_mapping;
+    P.maximum_intensity = opt->maximum_intensity;
+    P.view_distance = opt->view_distance;
+    P.debug_pixel_cost = opt->debug_pixel_cost;
+    P.include_sky = opt->include_sky;
+    P.out_srgb8 = out.srgb8;
+    P.out_colorbuf = out.colorbuf;
+    P.out_depth = out.depth;
+    P.out_hit = out.hit;
+    P.out_steps = out.steps;
+    P.counters = ctx->d_counters;
+    P.tile_counter = ctx->d_tile_counter;
+
+    sc->pending = true;
+    sc->pending_pixels = pixels;
+    sc->pending_rays = pixels * (P.antialias ? 4 : 1);
+    sc->pending_out_bytes_per_pixel = out.srgb8 ? 4 : 16;
+
+    CU(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+    CU(cudaEventRecord(ctx->ev0, stream));
+    if ((uint64_t)P.tiles_x * P.tiles_y > 0) {
+        const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
+        const int lc = opt->lighting_display == AICB_LIGHT_NONE ? LC_NONE
+                       : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT : LC_INTERP);
+        kernel_fn k = select_kernel(volumetric, lc, aux);
+        int blocks_per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        uint64_t want = ((uint64_t)P.tiles_x * P.tiles_y + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
+        if (grid > want) grid = want;
+        k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ctx->ev1, stream));
+    return AICB_OK;
+}
+
+static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
+    aicb_ctx *ctx = sc->ctx;
+    CU(cudaEventSynchronize(ctx->ev1));
+    if (info) {
+        unsigned long long c[8];
+        CU(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+        std::memset(info, 0, sizeof *info);
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        info->kernel_ms = ms;
+        info->cubes_traced = c[0];
+        info->rays = sc->pending_rays;
+        for (int i = 0; i < 5; i++) info->counters[i] = c[1 + i];
+        info->counters[5] = sc->pending_pixels;
+        // 2 B per outer/inner step, 32 B per surface hit, 4 B per light texel,
+        // 32 B per recursive block entered (our BlockRec), + output bytes per pixel
+        info->algorithmic_bytes = 2 * c[1] + 2 * c[2] + 32 * c[3] + 4 * c[4] + 32 * c[5] +
+                                  (uint64_t)sc->pending_out_bytes_per_pixel * sc->pending_pixels;
+        info->flaws = 0;
+    }
+    sc->pending = false;
+    return AICB_OK;
+}
+
+static aicb_status ensure(void **p, size_t *cur, size_t want) {
+    if (*cur >= want) return AICB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cur = 0;
+    CU(cudaMalloc(p, want));
+    *cur = want;
+    return AICB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t aicb_abi_version(void) { return AICB_ABI_VERSION; }
+const char *aicb_last_error(void) { return g_last_error.c_str(); }
+
+aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
+    if (!out) return fail(AICB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(AICB_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device_id < 0) CU(cudaGetDevice(&device_id));
+    if (device_id >= n) return fail(AICB_ERR_INVALID, "device_id out of range");
+    CU(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10)
+        return fail(AICB_ERR_CUDA, "device is not sm_100-class; this library is built for sm_100a only");
+    aicb_ctx *c = new aicb_ctx();
+    c->device = device_id;
+    c->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
+    float lut[256];
+    lut[0] = 0.0f;
+    for (int i = 1; i < 256; i++) lut[i] = (float)std::exp2((double)(((float)i - 144.0f) / 10.0f));
+    CU(cudaMalloc(&c->d_lut, sizeof lut));
+    CU(cudaMemcpy(c->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+    *out = c;
+    return AICB_OK;
+}
+
+void aicb_ctx_destroy(aicb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->d_aux) cudaFree(c->d_aux);
+    if (c->d_lut) cudaFree(c->d_lut);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_tile_counter) cudaFree(c->d_tile_counter);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scene **out) {
+    if (!ctx || !d || !out) return fail(AICB_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const int64_t LIM = 1 << 30;
+    uint64_t volume = 1;
+    for (int a = 0; a < 3; a++) {
+        int64_t lo = d->bounds.lower[a], hi = lo + (int64_t)d->bounds.size[a];
+        if (lo < -LIM || hi > LIM) return fail(AICB_ERR_INVALID, "space bounds must lie within +-2^30");
+        volume *= d->bounds.size[a];
+        if (volume > (1ull << 31)) return fail(AICB_ERR_INVALID, "space volume exceeds 2^31 cubes");
+    }
+    if (volume && !d->block_ids) return fail(AICB_ERR_INVALID, "block_ids is NULL");
+    if (d->n_blocks > 65536) return fail(AICB_ERR_INVALID, "more than 65536 blocks");
+    if (volume && d->n_blocks == 0) return fail(AICB_ERR_INVALID, "non-empty space with an empty block table");
+
+    // ---- flatten the block table --------------------------------------------------------------
+    std::vector<BlockRec> recs(d->n_blocks);
+    std::vector<uint8_t> kinds(d->n_blocks);
+    std::vector<uint16_t> bricks;
+    std::vector<float4> palette;
+    for (size_t i = 0; i < d->n_blocks; i++) {
+        const aicb_block_desc &b = d->blocks[i];
+        BlockRec &r = recs[i];
+        std::memset(&r, 0, sizeof r);
+        const uint32_t res = b.resolution;
+        if (res == 0 || (res & (res - 1)) || res > 128) return fail(AICB_ERR_INVALID, "block resolution must be 1..128, power of 2");
+        auto push_voxel = [&](const aicb_voxel &v) {
+            palette.push_back(make_float4(v.rgba[0], v.rgba[1], v.rgba[2], v.rgba[3]));
+            palette.push_back(make_float4(v.emission[0], v.emission[1], v.emission[2], 0.0f));
+        };
+        static const aicb_voxel AIR_VOXEL = {{0, 0, 0, 0}, {0, 0, 0}, 0};
+        bool single = false;
+        aicb_voxel sv = AIR_VOXEL;
+        if (b.indices == nullptr) {
+            single = true;
+            if (b.n_palette) {
+                if (!b.palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+                sv = b.palette[0];
+            }
+        } else {
+            uint64_t nvox = (uint64_t)b.voxel_bounds.size[0] * b.voxel_bounds.size[1] * b.voxel_bounds.size[2];
+            if (nvox != b.n_indices) return fail(AICB_ERR_INVALID, "n_indices does not match voxel_bounds");
+            for (int a = 0; a < 3; a++) {
+                int64_t lo = b.voxel_bounds.lower[a], hi = lo + (int64_t)b.voxel_bounds.size[a];
+                if (lo < 0 || hi > (int64_t)res) return fail(AICB_ERR_INVALID, "voxel_bounds must lie within [0, resolution)^3");
+            }
+            if (!b.palette && b.n_palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+            for (size_t k = 0; k < b.n_indices; k++)
+                if (b.indices[k] >= b.n_palette) return fail(AICB_ERR_INVALID, "voxel index out of palette range");
+            if (res == 1) {
+                // single_voxel_or_palette (voxel_storage.rs:371-383)
+                single = true;
+                sv = (nvox == 1 && b.voxel_bounds.lower[0] == 0 && b.voxel_bounds.lower[1] == 0 && b.voxel_bounds.lower[2] == 0)
+                         ? b.palette[b.indices[0]]
+                         : AIR_VOXEL;
+            }
+        }
+        if (b.is_air) {
+            kinds[i] = KIND_INVISIBLE;
+            r.kind_res = KIND_INVISIBLE | (1u << 8);
+        } else if (single) {
+            kinds[i] = voxel_invisible(sv) ? KIND_INVISIBLE : KIND_SINGLE;
+            r.kind_res = kinds[i] | (1u << 8);
+            r.pal_off = (uint32_t)(palette.size() / 2);
+            r.vsize[0] = r.vsize[1] = r.vsize[2] = 1;
+            push_voxel(sv);
+        } else {
+            if (b.n_palette > 32768) return fail(AICB_ERR_UNSUPPORTED, "block palettes above 32768 entries are not supported");
+            kinds[i] = KIND_RECURSIVE;
+            r.kind_res = KIND_RECURSIVE | (res << 8);
+            for (int a = 0; a < 3; a++) {
+                r.vlo[a] = (int16_t)b.voxel_bounds.lower[a];
+                r.vsize[a] = (uint16_t)b.voxel_bounds.size[a];
+            }
+            if (bricks.size() + b.n_indices > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
+            r.brick_off = (uint32_t)bricks.size();
+            r.pal_off = (uint32_t)(palette.size() / 2);
+            for (size_t k = 0; k < b.n_indices; k++) {
+                uint16_t v = b.indices[k];
+                bricks.push_back((uint16_t)(v | (voxel_invisible(b.palette[v]) ? 0x8000u : 0u)));
+            }
+            for (size_t k = 0; k < b.n_palette; k++) push_voxel(b.palette[k]);
+        }
+    }
+
+    aicb_scene *s = new aicb_scene();
+    s->ctx = ctx;
+    s->volume = (size_t)volume;
+    s->block_kind = kinds;
+    DeviceScene &ds = s->ds;
+    for (int a = 0; a < 3; a++) {
+        ds.lo[a] = d->bounds.lower[a];
+        ds.size[a] = (int32_t)d->bounds.size[a];
+    }
+    ds.wide_cells = d->n_blocks > 16384 ? 1 : 0;
+
+    auto cleanup = [&](aicb_status st) {
+        aicb_scene_destroy(s);
+        return st;
+    };
+#define CUS(call)                                                        \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return cleanup(cuda_fail(e__, #call));   \
+    } while (0)
+
+    // ---- cells: block id with its kind in the top bits ------------------------------------------
+    if (volume) {
+        for (size_t i = 0; i < volume; i++)
+            if (d->block_ids[i] >= d->n_blocks) return cleanup(fail(AICB_ERR_INVALID, "block id out of range"));
+        if (ds.wide_cells) {
+            std::vector<uint32_t> cells(volume);
+            for (size_t i = 0; i < volume; i++) cells[i] = d->block_ids[i] | ((uint32_t)kinds[d->block_ids[i]] << 16);
+            CUS(cudaMalloc(&s->d_cells, volume * 4));
+            CUS(cudaMemcpy(s->d_cells, cells.data(), volume * 4, cudaMemcpyHostToDevice));
+            s->device_bytes += volume * 4;
+        } else {
+            std::vector<uint16_t> cells(volume);
+            for (size_t i = 0; i < volume; i++)
+                cells[i] = (uint16_t)(d->block_ids[i] | ((uint32_t)kinds[d->block_ids[i]] << 14));
+            CUS(cudaMalloc(&s->d_cells, volume * 2));
+            CUS(cudaMemcpy(s->d_cells, cells.data(), volume * 2, cudaMemcpyHostToDevice));
+            s->device_bytes += volume * 2;
+        }
+        if (d->light) {
+            CUS(cudaMalloc(&s->d_light, volume * 4));
+            CUS(cudaMemcpy(s->d_light, d->light, volume * 4, cudaMemcpyHostToDevice));
+            s->device_bytes += volume * 4;
+        }
+    }
+    if (!recs.empty()) {
+        CUS(cudaMalloc(&s->d_blocks, recs.size() * sizeof(BlockRec)));
+        CUS(cudaMemcpy(s->d_blocks, recs.data(), recs.size() * sizeof(BlockRec), cudaMemcpyHostToDevice));
+        s->device_bytes += recs.size() * sizeof(BlockRec);
+    }
+    if (!bricks.empty()) {
+        CUS(cudaMalloc(&s->d_bricks, bricks.size() * 2));
+        CUS(cudaMemcpy(s->d_bricks, bricks.data(), bricks.size() * 2, cudaMemcpyHostToDevice));
+        s->device_bytes += bricks.size() * 2;
+    }
+    if (!palette.empty()) {
+        CUS(cudaMalloc(&s->d_palette, palette.size() * sizeof(float4)));
+        CUS(cudaMemcpy(s->d_palette, palette.data(), palette.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        s->device_bytes += palette.size() * sizeof(float4);
+    }
+#undef CUS
+    ds.cells = s->d_cells;
+    ds.light = s->d_light;
+    ds.blocks = s->d_blocks;
+    ds.bricks = s->d_bricks;
+    ds.palette = s->d_palette;
+    ds.lut = ctx->d_lut;
+    build_block_sky(d->sky, &ds);
+    *out = s;
+    return AICB_OK;
+}
+
+void aicb_scene_destroy(aicb_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->d_cells) cudaFree(s->d_cells);
+    if (s->d_light) cudaFree(s->d_light);
+    if (s->d_blocks) cudaFree(s->d_blocks);
+    if (s->d_bricks) cudaFree(s->d_bricks);
+    if (s->d_palette) cudaFree(s->d_palette);
+    delete s;
+}
+
+uint64_t aicb_scene_device_bytes(const aicb_scene *s) { return s ? s->device_bytes : 0; }
+
+aicb_status aicb_scene_update_cubes(aicb_scene *s, const int32_t (*cubes)[3], const uint16_t *ids,
+                                    const uint8_t (*light)[4], size_t n) {
+    if (!s || (n && (!cubes || !ids))) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    const DeviceScene &ds = s->ds;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t dx = (uint32_t)(cubes[i][0] - ds.lo[0]), dy = (uint32_t)(cubes[i][1] - ds.lo[1]),
+                 dz = (uint32_t)(cubes[i][2] - ds.lo[2]);
+        if (dx >= (uint32_t)ds.size[0] || dy >= (uint32_t)ds.size[1] || dz >= (uint32_t)ds.size[2])
+            return fail(AICB_ERR_INVALID, "cube out of bounds");
+        if (ids[i] >= s->block_kind.size()) return fail(AICB_ERR_INVALID, "block id out of range");
+        size_t idx = ((size_t)dx * ds.size[1] + dy) * ds.size[2] + dz;
+        if (ds.wide_cells) {
+            uint32_t cell = ids[i] | ((uint32_t)s->block_kind[ids[i]] << 16);
+            CU(cudaMemcpyAsync((uint32_t *)s->d_cells + idx, &cell, 4, cudaMemcpyHostToDevice, s->ctx->stream));
+        } else {
+            uint16_t cell = (uint16_t)(ids[i] | ((uint32_t)s->block_kind[ids[i]] << 14));
+            CU(cudaMemcpyAsync((uint16_t *)s->d_cells + idx, &cell, 2, cudaMemcpyHostToDevice, s->ctx->stream));
+        }
+        if (light && s->d_light)
+            CU(cudaMemcpyAsync(s->d_light + idx, light[i], 4, cudaMemcpyHostToDevice, s->ctx->stream));
+        CU(cudaStreamSynchronize(s->ctx->stream));  // source is a stack temporary
+    }
+    return AICB_OK;
+}
+
+aicb_status aicb_scene_upload_light(aicb_scene *s, const uint8_t (*light)[4], size_t n_texels) {
+    if (!s || !light) return fail(AICB_ERR_INVALID, "NULL argument");
+    if (n_texels != s->volume) return fail(AICB_ERR_INVALID, "light volume size mismatch");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    if (!s->d_light && s->volume) {
+        CU(cudaMalloc(&s->d_light, s->volume * 4));
+        s->device_bytes += s->volume * 4;
+        s->ds.light = s->d_light;
+    }
+    if (s->volume) CU(cudaMemcpy(s->d_light, light, s->volume * 4, cudaMemcpyHostToDevice));
+    return AICB_OK;
+}
+
+size_t aicb_shard_pixel_count(const aicb_camera *cam, const aicb_shard *shard) {
+    if (!cam) return 0;
+    return (size_t)cam->fb_width * shard_rows(cam->fb_height, shard);
+}
+
+static aicb_status check_render_args(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt,
+                                     const aicb_shard *shard, size_t out_len) {
+    if (!s || !cam) return fail(AICB_ERR_INVALID, "NULL argument");
+    aicb_status st = validate_options(opt);
+    if (st != AICB_OK) return st;
+    if (shard && shard->count > 1 && shard->index >= shard->count) return fail(AICB_ERR_INVALID, "shard index >= count");
+    if (out_len != aicb_shard_pixel_count(cam, shard))
+        return fail(AICB_ERR_INVALID, "Viewport size does not match output buffer length");
+    return AICB_OK;
+}
+
+aicb_status aicb_render_srgb8(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, const aicb_shard *shard,
+                              uint8_t (*out)[4], size_t out_len, aicb_render_info *info) {
+    aicb_status st = check_render_args(s, cam, opt, shard, out_len);
+    if (st != AICB_OK) return st;
+    if (out_len && !out) return fail(AICB_ERR_INVALID, "out is NULL");
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    st = ensure(&ctx->d_out, &ctx->d_out_bytes, out_len * 4 + 16);
+    if (st != AICB_OK) return st;
+    Outputs o;
+    o.srgb8 = (uchar4 *)ctx->d_out;
+    st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
+    if (st != AICB_OK) return st;
+    if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return finish(s, info);
+}
+
+static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, const aicb_shard *shard,
+                              const double *d_rays, uint64_t n_rays, float (*out_cb)[4], double *depth, aicb_hit *hit,
+                              uint32_t *steps, size_t n, aicb_render_info *info) {
+    aicb_ctx *ctx = s->ctx;
+    // layout of the aux staging buffer: colorbuf | depth | hit | steps
+    size_t off_cb = 0, off_depth = off_cb + n * 16, off_hit = off_depth + n * 8, off_steps = off_hit + n * sizeof(aicb_hit);
+    size_t total = off_steps + n * 4 + 16;
+    aicb_status st = ensure(&ctx->d_aux, &ctx->d_aux_bytes, total);
+    if (st != AICB_OK) return st;
+    char *base = (char *)ctx->d_aux;
+    Outputs o;
+    o.colorbuf = (float4 *)(base + off_cb);
+    o.depth = (double *)(base + off_depth);
+    o.hit = (aicb_hit *)(base + off_hit);
+    o.steps = (uint32_t *)(base + off_steps);
+    st = launch_trace(s, cam, opt, shard, d_rays, n_rays, o, true, ctx->stream);
+    if (st != AICB_OK) return st;
+    if (n) {
+        if (out_cb) CU(cudaMemcpyAsync(out_cb, o.colorbuf, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (depth) CU(cudaMemcpyAsync(depth, o.depth, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hit) CU(cudaMemcpyAsync(hit, o.hit, n * sizeof(aicb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        if (steps) CU(cudaMemcpyAsync(steps, o.steps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return finish(s, info);
+}
+
+aicb_status aicb_render_colorbuf(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt,
+                                 const aicb_shard *shard, float (*out_cb)[4], double *depth, aicb_hit *hit,
+                                 uint32_t *steps, size_t out_len, aicb_render_info *info) {
+    aicb_status st = check_render_args(s, cam, opt, shard, out_len);
+    if (st != AICB_OK) return st;
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    return render_aux(s, cam, opt, shard, nullptr, 0, out_cb, depth, hit, steps, out_len, info);
+}
+
+aicb_status aicb_render_srgb8_device(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt,
+                                     const aicb_shard *shard, void *d_out, size_t out_len, void *stream) {
+    aicb_status st = check_render_args(s, cam, opt, shard, out_len);
+    if (st != AICB_OK) return st;
+    if (out_len && !d_out) return fail(AICB_ERR_INVALID, "d_out is NULL");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    Outputs o;
+    o.srgb8 = (uchar4 *)d_out;
+    return launch_trace(s, cam, opt, shard, nullptr, 0, o, false, stream ? (cudaStream_t)stream : s->ctx->stream);
+}
+
+aicb_status aicb_render_finish(aicb_scene *s, aicb_render_info *info) {
+    if (!s) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    return finish(s, info);
+}
+
+aicb_status aicb_trace_rays(aicb_scene *s, const double (*origin_dir)[6], size_t n, const aicb_options *opt,
+                            float (*out_cb)[4], double *depth, aicb_hit *hit, uint32_t *steps,
+                            aicb_render_info *info) {
+    if (!s || (n && !origin_dir)) return fail(AICB_ERR_INVALID, "NULL argument");
+    aicb_status st = validate_options(opt);
+    if (st != AICB_OK) return st;
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    double *d_rays = nullptr;
+    CU(cudaMalloc(&d_rays, n * 48 + 16));
+    cudaError_t e = cudaMemcpy(d_rays, origin_dir, n * 48, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_rays);
+        return cuda_fail(e, "cudaMemcpy rays");
+    }
+    st = render_aux(s, nullptr, opt, nullptr, d_rays, n, out_cb, depth, hit, steps, n, info);
+    cudaFree(d_rays);
+    return st;
+}
+
+aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*)[3], const uint16_t *, size_t, uint8_t,
+                                          uint64_t *, uint8_t *) {
+    return fail(AICB_ERR_UNSUPPORTED, "light propagation kernel is not built yet (SURVEY 8(a) L1-L4)");
+}
+
+aicb_status aicb_light_download(aicb_scene *s, uint8_t (*out)[4], size_t n_texels) {
+    if (!s || !out) return fail(AICB_ERR_INVALID, "NULL argument");
+    if (n_texels != s->volume) return fail(AICB_ERR_INVALID, "light volume size mismatch");
+    if (!s->d_light) return fail(AICB_ERR_INVALID, "scene has no light volume (LightPhysics::None)");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    CU(cudaMemcpy(out, s->d_light, s->volume * 4, cudaMemcpyDeviceToHost));
+    return AICB_OK;
+}
+}

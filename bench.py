@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the B200-native voxel raytracer on BASELINE.json's workload.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3]
+
+A "step" is one full frame (1920x1080 primary rays) of the 256^3 mixed-transparent Space
+(BASELINE.json configs[2]) traced through the C ABI of libaicb200.so.
+N > 1: one process per GPU (torchrun), the frame is sharded by interleaved 16-row strips
+(strong scaling, total work fixed) and gathered on rank 0 with NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = rays / device time with inputs resident in HBM;
+`e2e` = the same through the host-buffer call (cube-delta H2D + frame D2H inside the timed
+region); `roofline` = algorithmic bytes / kernel time vs the measured HBM peak;
+`cpu_baseline` = the oracle (CPU restatement of the reference, all host threads) on a bounded
+sample of the same frame.  `--impl reference` times only that CPU path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "all-is-cubes_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STRIP_ROWS = 16
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c2", choices=["c0", "c1", "c2", "c3"])
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return p.parse_args()
+
+
+def make_workload(name):
+    """Returns (space, options, width, height, description)."""
+    import aicb200
+    from aicb200 import scenes
+    if name == "c0":
+        space = scenes.config_c0()
+        opts = aicb200.GraphicsOptions.unaltered_colors()
+        w, h = 256, 256
+        desc = "C0: 32^3 solid/empty res-1, 256x256, UNALTERED_COLORS"
+    elif name == "c1":
+        space = scenes.config_c1(n=128)
+        opts = aicb200.GraphicsOptions.unaltered_colors()
+        opts.view_distance = 512.0
+        w, h = 1920, 1080
+        desc = "C1: 128^3, 256 res-16 recursive blocks, opaque, 1920x1080, UNALTERED_COLORS"
+    elif name == "c3":
+        space = scenes.config_c1(n=256)
+        opts = aicb200.GraphicsOptions.unaltered_colors()
+        opts.view_distance = 1024.0
+        w, h = 3840, 2160
+        desc = "C3: 256^3, res-16 recursive blocks, 3840x2160, UNALTERED_COLORS"
+    else:
+        space = scenes.config_c2(n=256, with_light=True)
+        opts = aicb200.GraphicsOptions(view_distance=1024.0)  # GraphicsOptions::default(): fog Abrupt, Linear light, Volumetric
+        w, h = 1920, 1080
+        desc = ("C2: 256^3 mixed transparent (alpha .125/.25/.5, res-1 + res-16), light volume, 1920x1080, "
+                "GraphicsOptions::default() with view_distance 1024")
+    return space, opts, w, h, desc
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the oracle; the Rust reference cannot be built in this image)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(space, cam, opts, height, target_seconds):
+    """Times the oracle on bands of rows spread over the frame; returns (Mrays/s, cores, description, rows)."""
+    import orc
+    oscene = orc.OracleScene(space)
+    threads = orc.hardware_threads()
+    width = cam.data.fb_width
+    band = 4
+    # calibrate on 3 bands
+    probe_rows = [height // 6, height // 2, (5 * height) // 6]
+    t0 = time.perf_counter()
+    for y in probe_rows:
+        oscene.render_rows(cam, opts, y, min(y + band, height), n_threads=threads)
+    dt = time.perf_counter() - t0
+    per_band = max(dt / len(probe_rows), 1e-4)
+    n_bands = int(max(4, min(height // band, target_seconds / per_band)))
+    ys = [int(i * (height - band) / max(1, n_bands - 1)) for i in range(n_bands)]
+    t0 = time.perf_counter()
+    rays = 0
+    for y in ys:
+        oscene.render_rows(cam, opts, y, min(y + band, height), n_threads=threads)
+        rays += width * (min(y + band, height) - y)
+    dt = time.perf_counter() - t0
+    return rays / dt / 1e6, threads, f"{n_bands} bands x {band} rows spread over the frame ({rays} rays, {dt:.1f} s)", ys
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; kind 'port') on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build_oracle()
+    g.build_library()  # host-only camera code lives in the product library
+    space, opts, w, h, desc = make_workload(args.workload)
+    from aicb200 import scenes
+    import orc
+    cam = scenes.standard_camera(space, opts, w, h)
+    threads = orc.hardware_threads()
+    # each step = one bounded sample of the frame, sized so the whole run stays within minutes
+    per_step = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    mr, _, sample, ys = cpu_sample(space, cam, opts, h, per_step)
+    oscene = orc.OracleScene(space)
+    band = 4
+
+    def one_step():
+        t0 = time.perf_counter()
+        rays = 0
+        for y in ys:
+            oscene.render_rows(cam, opts, y, min(y + band, h), n_threads=threads)
+            rays += w * (min(y + band, h) - y)
+        return rays, time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    tot_rays, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        r, t = one_step()
+        tot_rays += r
+        tot_t += t
+    value = tot_rays / tot_t / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour",
+        "data": "synthetic",
+        "config": {"workload": desc, "sample": sample, "note": "CPU port of the Rust reference (no rustc in this image)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.samples = []
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libaicb200 has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build_library()
+        g.build_oracle()
+    if world > 1:
+        dist.barrier()
+    import aicb200
+    from aicb200 import abi, scenes
+    lib = aicb200.load_library()
+
+    space, opts, w, h, desc = make_workload(args.workload)
+    cam = scenes.standard_camera(space, opts, w, h)
+    ctx = aicb200.Context(local_rank)
+    rt = aicb200.SpaceRaytracer(space, opts, ctx)
+    o_abi = opts.to_abi(True)
+    shard = abi.Shard(STRIP_ROWS, rank, world)
+    n_local = lib.aicb_shard_pixel_count(C.byref(cam.data), C.byref(shard))
+    n_max = max(lib.aicb_shard_pixel_count(C.byref(cam.data), C.byref(abi.Shard(STRIP_ROWS, r, world))) for r in range(world))
+    d_out = torch.empty((n_max, 4), dtype=torch.uint8, device="cuda")
+    gather_list = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    frame = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if rank == 0 else None
+    # row index of every packed local row of every rank, to reassemble the frame on rank 0
+    row_maps = None
+    if rank == 0 and world > 1:
+        row_maps = [torch.tensor([y for y in range(h) if (y // STRIP_ROWS) % world == r], device="cuda") for r in range(world)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    info = abi.RenderInfo()
+
+    def check(st):
+        if st != 0:
+            raise RuntimeError(lib.aicb_last_error().decode())
+
+    def device_step():
+        """One frame with everything resident in HBM: trace kernel (+ NCCL gather and reassembly for N>1)."""
+        check(lib.aicb_render_srgb8_device(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                           d_out.data_ptr(), n_local, C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.gather(d_out, gather_list, dst=0)
+            if rank == 0:
+                fr = frame.view(h, w * 4)
+                for r in range(world):
+                    rows = row_maps[r]
+                    fr[rows] = gather_list[r][: rows.numel() * w].view(rows.numel(), w * 4)
+
+    def timed(fn, steps):
+        """K steps; per-step CUDA events on the launch stream, L2 flushed between steps (outside the
+        events); returns total ms = sum over steps, MAX over ranks."""
+        evs = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the timed region ------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        device_step()
+    torch.cuda.synchronize()
+    check(lib.aicb_render_finish(rt.handle, C.byref(info)))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(device_step, args.steps)
+    # kernel-only duration of the last frame from the library's own events (same stream)
+    check(lib.aicb_render_finish(rt.handle, C.byref(info)))
+    kernel_ms_last = float(info.kernel_ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    rays_per_frame = w * h
+    value = rays_per_frame * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- dominant-kernel time, averaged over the timed region's launches ---------------------------
+    kernel_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        check(lib.aicb_render_srgb8_device(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                           d_out.data_ptr(), n_local, C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize()
+        check(lib.aicb_render_finish(rt.handle, C.byref(info)))
+        kernel_ms.append(float(info.kernel_ms))
+    kernel_avg_ms = float(np.mean(kernel_ms))
+
+    # ---- algorithmic bytes of this launch from device counters (one untimed AUX pass) ---------------
+    r = aicb200.RtRenderer(cam, ctx)
+    r.rt = rt
+    aux = r.draw_colorbuf(shard=(STRIP_ROWS, rank, world), want_depth=False, want_hit=False, want_steps=False)
+    ai = aux["info"]
+    alg_bytes = ai.algorithmic_bytes - 16 * ai.counters[5] + 4 * ai.counters[5]  # sRGB8 output instead of ColorBuf
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kernel_avg_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the public API ------------------------------------------------------
+    n_delta = 1024
+    rng = np.random.default_rng(0)
+    cubes = np.stack([rng.integers(0, space.size[a], n_delta) + space.lower[a] for a in range(3)], axis=1).astype(np.int32)
+    delta_ids = space.block_ids[cubes[:, 0] - space.lower[0], cubes[:, 1] - space.lower[1], cubes[:, 2] - space.lower[2]].copy()
+    delta_light = space.light[cubes[:, 0] - space.lower[0], cubes[:, 1] - space.lower[1], cubes[:, 2] - space.lower[2]].copy() \
+        if space.light is not None else None
+    host_out = torch.empty((n_local, 4), dtype=torch.uint8).pin_memory()
+    host_frame = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    h2d_bytes = cubes.nbytes + delta_ids.nbytes + (delta_light.nbytes if delta_light is not None else 0)
+
+    def e2e_step():
+        """update(): a batch of cube deltas H2D (same values: the image is unchanged); draw(): frame D2H."""
+        rt.update_cubes(cubes[:64], delta_ids[:64], None if delta_light is None else delta_light[:64])
+        if world == 1:
+            check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                        host_out.data_ptr(), n_local, None))
+        else:
+            device_step()
+            if rank == 0:
+                host_frame.copy_(frame, non_blocking=False)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = rays_per_frame * k_e2e / float(t.item()) / 1e6
+    h2d_step = 64 * (12 + 2 + (4 if delta_light is not None else 0))
+    d2h_step = w * h * 4
+
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            import orc  # the checker, used here only as the reported CPU baseline
+            mr, cores, sample, _ = cpu_sample(space, cam, opts, h, args.cpu_seconds)
+            cpu = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
+            "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips",
+                       "l2": "256 MiB buffer rewritten between timed steps", "scene_device_bytes": rt.device_bytes,
+                       "cubes_traced_per_frame_this_rank": int(ai.cubes_traced)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "kernel": "trace_kernel<volumetric,interp>", "kernel_ms": kernel_avg_ms,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "counters": {"outer_steps": ai.counters[0], "inner_steps": ai.counters[1], "surface_hits": ai.counters[2],
+                                      "light_texels": ai.counters[3], "blocks_entered": ai.counters[4], "pixels": ai.counters[5]}},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

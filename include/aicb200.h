@@ -1,0 +1,259 @@
+/*
+ * aicb200.h — C ABI of libaicb200.so: the B200-native (sm_100a) replacement for the
+ * per-pixel voxel raytracer of kpreid/all-is-cubes, behind the reference's own
+ * HeadlessRenderer / Camera / SpaceRaytracer surface.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout, commit 7ab02ee1).  All structs are plain data; all pointers in are
+ * borrowed for the duration of the call only; all pointers out are caller-allocated with
+ * explicit lengths.  Nothing throws or aborts across this boundary: errors are status codes
+ * plus aicb_last_error().
+ *
+ * There is NO CPU fallback.  Every compute entry point fails with AICB_ERR_CUDA when no
+ * sm_100-class device is available.
+ */
+#ifndef AICB200_H
+#define AICB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AICB_ABI_VERSION 1
+
+typedef enum aicb_status {
+    AICB_OK = 0,
+    AICB_ERR_INVALID = 1,     /* bad argument / length mismatch (the reference panics: renderer.rs:193-197) */
+    AICB_ERR_OOM = 2,         /* cudaMalloc failed  -> Flaws::OUT_OF_MEMORY (flaws.rs) */
+    AICB_ERR_CUDA = 3,        /* no device, launch failure, lost GPU (lib.rs:53 "TODO: lost GPU") */
+    AICB_ERR_UNSUPPORTED = 4, /* LightingOption::Bounce etc. */
+    AICB_ERR_BUSY = 5
+} aicb_status;
+
+/* ---------------------------------------------------------------------------------------------
+ * Plain-data mirrors of reference types
+ * ------------------------------------------------------------------------------------------- */
+
+/* GridAab (all-is-cubes-base/src/math/grid_aab.rs): lower corner + size. */
+typedef struct aicb_aab {
+    int32_t lower[3];
+    uint32_t size[3];
+} aicb_aab;
+
+/* Colour part of Evoxel (all-is-cubes/src/block/eval/voxel_storage.rs:41-53):
+ * non-premultiplied linear RGBA reflectance + RGB emission. 32 bytes. */
+typedef struct aicb_voxel {
+    float rgba[4];
+    float emission[3];
+    float _pad;
+} aicb_voxel;
+
+/* Face7 (all-is-cubes-base/src/math/face.rs:105). */
+enum { AICB_FACE_WITHIN = 0, AICB_FACE_NX = 1, AICB_FACE_NY = 2, AICB_FACE_NZ = 3,
+       AICB_FACE_PX = 4, AICB_FACE_PY = 5, AICB_FACE_PZ = 6 };
+
+/* One entry of Space::block_data() as the raytracer sees it: TracingBlock (sr.rs:569-587)
+ * = Evoxels (voxel_storage.rs:190-209).  `indices == NULL` means Evoxels::One(palette[0]).
+ * Otherwise `indices` holds one u16 palette index per voxel of `voxel_bounds`, Z-major
+ * (vol.rs:1013-1018: ((x-lx)*size_y + (y-ly))*size_z + (z-lz)); voxel_bounds may be smaller
+ * than resolution^3 (voxel_storage.rs:176-178) but must lie inside [0,resolution)^3.
+ * `is_air` is TracingCubeData::always_invisible (sr.rs:547).
+ * The `light_*` members are EvaluatedBlock derived data (block/eval/derived.rs:33-80) read
+ * only by the light-propagation path (space/light/updater.rs:760-884). */
+typedef struct aicb_block_desc {
+    uint8_t resolution;            /* 1,2,4,...,128 (resolution.rs:18-27) */
+    uint8_t is_air;
+    uint8_t light_opaque_faces;    /* bit (face-1) set if EvaluatedBlock::opaque()[face], NX..PZ */
+    uint8_t light_visible;         /* EvaluatedBlock::visible_or_animated() */
+    aicb_aab voxel_bounds;
+    const uint16_t *indices;       /* NULL => single voxel */
+    size_t n_indices;
+    const aicb_voxel *palette;
+    size_t n_palette;
+    float light_face_colors[6][4]; /* EvaluatedBlock::face7_color(face), NX..PZ */
+    float light_color[4];          /* EvaluatedBlock::color() */
+    float light_emission[3];       /* EvaluatedBlock::light_emission() */
+    float _pad;
+} aicb_block_desc;
+
+/* Sky (all-is-cubes/src/space/sky.rs:16-21). kind 0 = Uniform(colors[0]), 1 = Octants.
+ * Octant index = (x>=0)<<2 | (y>=0)<<1 | (z>=0)  (sky.rs:36-39). */
+typedef struct aicb_sky {
+    uint32_t kind;
+    float colors[8][3];
+} aicb_sky;
+
+/* What SpaceRaytracer::new (sr.rs:64-88) snapshots from space::Read:
+ * bounds, per-cube block index (Space::contents, Z-major), per-cube PackedLight texels
+ * (light/data.rs:162 as_texel: r,g,b,status; NULL => LightPhysics::None => PackedLight::ONE,
+ * space.rs:1241-1246), the block table and the sky. */
+typedef struct aicb_scene_desc {
+    aicb_aab bounds;
+    const uint16_t *block_ids;     /* volume entries */
+    const uint8_t (*light)[4];     /* volume texels or NULL */
+    const aicb_block_desc *blocks;
+    size_t n_blocks;
+    aicb_sky sky;
+    uint8_t light_max_distance;    /* LightPhysics::Rays{maximum_distance} (space/physics.rs:94-104); 0 = None */
+    uint8_t _pad[7];
+} aicb_scene_desc;
+
+/* Camera as the raytracer consumes it: Camera::project_ndc_into_world (camera_struct.rs:238-257)
+ * needs only inverse_projection_view (euclid Transform3D, row-vector convention, m11..m44 in
+ * row-major order), the framebuffer size (viewport.rs:104-113) and exposure
+ * (camera_struct.rs:376-382).  aicb_camera_look_at()/aicb_camera_from_view() below build it
+ * exactly as Camera::compute_matrices (camera_struct.rs:387-416) does. */
+typedef struct aicb_camera {
+    double inverse_projection_view[16];
+    uint32_t fb_width, fb_height;
+    float exposure;
+    uint32_t _pad;
+} aicb_camera;
+
+enum { AICB_FOG_NONE = 0, AICB_FOG_ABRUPT = 1, AICB_FOG_COMPROMISE = 2, AICB_FOG_PHYSICAL = 3 };
+enum { AICB_LIGHT_NONE = 0, AICB_LIGHT_FLAT = 1, AICB_LIGHT_COARSE = 2, AICB_LIGHT_LINEAR = 3,
+       AICB_LIGHT_SMOOTHSTEP = 4, AICB_LIGHT_BOUNCE = 5 /* unsupported */ };
+enum { AICB_TRANSPARENCY_SURFACE = 0, AICB_TRANSPARENCY_VOLUMETRIC = 1, AICB_TRANSPARENCY_THRESHOLD = 2 };
+enum { AICB_TONE_CLAMP = 0, AICB_TONE_REINHARD = 1 };
+
+/* The GraphicsOptions fields that affect pixels (graphics_options.rs:28-150). */
+typedef struct aicb_options {
+    uint8_t fog;
+    uint8_t lighting_display;
+    uint8_t transparency;
+    uint8_t antialiasing_always;   /* AntialiasingOption::Always => 4 fixed sub-samples (renderer.rs:426-444) */
+    uint8_t tone_mapping;
+    uint8_t debug_pixel_cost;
+    uint8_t include_sky;           /* trace_ray's include_sky argument (sr.rs:113-120); renders use 1 */
+    uint8_t _pad0;
+    float transparency_threshold;  /* TransparencyOption::Threshold(t) */
+    float maximum_intensity;       /* +inf disables tone mapping (graphics_options.rs:352-357) */
+    double view_distance;          /* repaired to [1, 10000] by the caller (graphics_options.rs:194-198) */
+} aicb_options;
+
+/* Row-strip sharding of one frame across ranks: rows are cut into strips of
+ * `strip_rows`; strip s belongs to shard (s % count).  count = 1 renders everything. */
+typedef struct aicb_shard {
+    uint32_t strip_rows;
+    uint32_t index;
+    uint32_t count;
+} aicb_shard;
+
+/* ImageInfo / RaytraceInfo (renderer.rs:609-646, sr.rs:520-522) plus device timing. */
+typedef struct aicb_render_info {
+    uint64_t cubes_traced;         /* RaytraceInfo::cubes_traced, summed over all rays */
+    uint64_t rays;                 /* primary rays traced (pixels * samples) */
+    uint64_t algorithmic_bytes;    /* SURVEY §8(d) formula, from device counters */
+    uint64_t counters[6];          /* outer steps, inner steps, surface hits, light texels, blocks entered, pixels */
+    float kernel_ms;               /* CUDA-event duration of the trace kernel on its stream */
+    uint16_t flaws;                /* Flaws bits (flaws.rs:20-91) */
+    uint16_t _pad;
+} aicb_render_info;
+
+/* Per-pixel hit record: Position of the first non-exception Hit (hit.rs:92-101):
+ * cube xyz, voxel xyz, resolution, face; all -1 when the ray hit nothing. */
+typedef struct aicb_hit {
+    int32_t cube[3];
+    int32_t voxel[3];
+    int32_t resolution;
+    int32_t face;
+} aicb_hit;
+
+typedef struct aicb_ctx aicb_ctx;     /* one CUDA device + stream */
+typedef struct aicb_scene aicb_scene; /* device-resident flattened Space */
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------- */
+uint32_t aicb_abi_version(void);
+/* device_id < 0 selects the current device. Fails with AICB_ERR_CUDA if there is no GPU. */
+aicb_status aicb_ctx_create(int device_id, aicb_ctx **out);
+void aicb_ctx_destroy(aicb_ctx *);
+/* Thread-local message for the last failing call on this thread. Never NULL. */
+const char *aicb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * update(): replaces SpaceRaytracer::new / UpdatingSpaceRaytracer::update
+ * (sr.rs:64-88, updating.rs:107-172). The library copies everything before returning.
+ * ------------------------------------------------------------------------------------------- */
+aicb_status aicb_scene_create(aicb_ctx *, const aicb_scene_desc *, aicb_scene **out);
+/* SpaceChange::CubeBlock / CubeLight (space.rs:1062-1100): light may be NULL to leave light alone. */
+aicb_status aicb_scene_update_cubes(aicb_scene *, const int32_t (*cubes)[3], const uint16_t *block_ids,
+                                    const uint8_t (*light)[4], size_t n);
+/* Whole light volume replaced (after light propagation on the host or on another rank). */
+aicb_status aicb_scene_upload_light(aicb_scene *, const uint8_t (*light)[4], size_t n_texels);
+void aicb_scene_destroy(aicb_scene *);
+uint64_t aicb_scene_device_bytes(const aicb_scene *);
+
+/* ---------------------------------------------------------------------------------------------
+ * draw(): replaces RtRenderer::draw_rgba / RtRenderer::draw::<ColorBuf> and the Rayon pixel
+ * dispatch trace_scene_to_image_impl (renderer.rs:183-220, 282-308, 516-556).
+ * Host-buffer variants copy device->host inside the call (blocking, like draw_rgba).
+ * `out_len` must equal aicb_shard_pixel_count(camera, shard) or AICB_ERR_INVALID is returned.
+ * Pixels of the shard's rows are packed in increasing row order, row-major, top-left origin.
+ * ------------------------------------------------------------------------------------------- */
+size_t aicb_shard_pixel_count(const aicb_camera *, const aicb_shard *shard_or_null);
+
+/* == draw_rgba: sRGB8 RGBA, post_process_color + to_srgb8 applied (renderer.rs:287-291). */
+aicb_status aicb_render_srgb8(aicb_scene *, const aicb_camera *, const aicb_options *,
+                              const aicb_shard *shard_or_null,
+                              uint8_t (*out)[4], size_t out_len, aicb_render_info *info_or_null);
+
+/* == draw::<ColorBuf> (+ DepthBuf, + Position): raw accumulators for parity and other callers.
+ * out_colorbuf: light.xyz, transmittance (raytracer_components.rs:20-39).
+ * depth_or_null: DepthBuf::depth (accum.rs:254-311) of the first Hit carrying a t_distance.
+ * hit_or_null: Position of the first surface hit. */
+aicb_status aicb_render_colorbuf(aicb_scene *, const aicb_camera *, const aicb_options *,
+                                 const aicb_shard *shard_or_null,
+                                 float (*out_colorbuf)[4], double *depth_or_null, aicb_hit *hit_or_null,
+                                 uint32_t *steps_or_null, size_t out_len, aicb_render_info *info_or_null);
+
+/* Device-resident output (for multi-GPU gather and kernel-only timing): `d_out` is a device
+ * pointer on the ctx's device with room for out_len pixels; `stream` is a cudaStream_t (0 =
+ * the ctx stream). Does not synchronise; info (if given) is filled by
+ * aicb_render_finish(). */
+aicb_status aicb_render_srgb8_device(aicb_scene *, const aicb_camera *, const aicb_options *,
+                                     const aicb_shard *shard_or_null,
+                                     void *d_out, size_t out_len, void *stream);
+aicb_status aicb_render_finish(aicb_scene *, aicb_render_info *info_or_null);
+
+/* == SpaceRaytracer::trace_ray (sr.rs:113-120) for a batch of explicit rays:
+ * origin_dir[i] = {ox,oy,oz,dx,dy,dz}. Output as aicb_render_colorbuf. */
+aicb_status aicb_trace_rays(aicb_scene *, const double (*origin_dir)[6], size_t n, const aicb_options *,
+                            float (*out_colorbuf)[4], double *depth_or_null, aicb_hit *hit_or_null,
+                            uint32_t *steps_or_null, aicb_render_info *info_or_null);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera construction (host only, no GPU): Camera::new + look_at_y_up + compute_matrices
+ * (camera_struct.rs:86-110, 387-416, 459-471); eye_for_look_at (all-is-cubes/src/camera.rs:34-40).
+ * ------------------------------------------------------------------------------------------- */
+/* fov_y_degrees and view_distance are repaired like GraphicsOptions::repair. nominal_* is the
+ * Viewport nominal size (aspect ratio); fb_* the framebuffer size. */
+aicb_status aicb_camera_look_at(const double eye[3], const double target[3], double fov_y_degrees,
+                                double view_distance, double nominal_width, double nominal_height,
+                                uint32_t fb_width, uint32_t fb_height, float exposure, aicb_camera *out);
+/* General form: rotation quaternion (i,j,k,r) + translation of the eye-to-world ViewTransform. */
+aicb_status aicb_camera_from_view(const double rotation_ijkr[4], const double translation[3],
+                                  double fov_y_degrees, double view_distance, double nominal_width,
+                                  double nominal_height, uint32_t fb_width, uint32_t fb_height,
+                                  float exposure, aicb_camera *out);
+void aicb_eye_for_look_at(const aicb_aab *bounds, const double direction[3], double out_eye[3]);
+/* Camera::project_ndc_into_world for one NDC point (host, for tests): out = origin xyz, dir xyz. */
+void aicb_camera_project_ndc(const aicb_camera *, double ndc_x, double ndc_y, double out_origin_dir[6]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Light propagation (secondary path): replaces Mutation::set x n + evaluate_light(epsilon)
+ * (space.rs:1346-1352, 1496-1527; space/light/updater.rs:181-363).
+ * ------------------------------------------------------------------------------------------- */
+aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*cubes)[3], const uint16_t *new_ids,
+                                          size_t n_edits, uint8_t epsilon, uint64_t *updates_done,
+                                          uint8_t *max_diff);
+aicb_status aicb_light_download(aicb_scene *, uint8_t (*out)[4], size_t n_texels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AICB200_H */

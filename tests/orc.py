@@ -1,0 +1,203 @@
+"""ctypes wrapper over oracle/liborc.so — TEST INFRASTRUCTURE (the checker, never the product)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "liborc.so")
+
+from aicb200 import abi  # noqa: E402  (conftest puts the package on sys.path)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src = [os.path.join(ROOT, "oracle", f) for f in ("aic_oracle.cpp", "aic_oracle.hpp")]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-B"], check=True, capture_output=True)
+    L = C.CDLL(LIB_PATH)
+    L.orc_scale_to_integer_step.restype = C.c_double
+    L.orc_scale_to_integer_step.argtypes = [C.c_double, C.c_double]
+    L.orc_raycast.restype = C.c_int
+    L.orc_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_recursive_raycast.restype = C.c_int
+    L.orc_recursive_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    L.orc_apply_transmittance.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    L.orc_apply_transmittance.restype = None
+    L.orc_packed_light_lut.restype = C.c_float
+    L.orc_packed_light_lut.argtypes = [C.c_int]
+    L.orc_packed_light_scalar_in.restype = C.c_int
+    L.orc_packed_light_scalar_in.argtypes = [C.c_float]
+    L.orc_to_srgb8.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    L.orc_to_srgb8.restype = None
+    L.orc_scene_create.restype = C.c_void_p
+    L.orc_scene_create.argtypes = [C.POINTER(abi.SceneDesc)]
+    L.orc_scene_destroy.argtypes = [C.c_void_p]
+    L.orc_scene_destroy.restype = None
+    L.orc_surface_steps.restype = C.c_int
+    L.orc_surface_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.orc_trace_rays.restype = C.c_int
+    L.orc_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(abi.Options), C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_render.restype = C.c_uint64
+    L.orc_render.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.POINTER(abi.Shard),
+                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_render_rows.restype = C.c_uint64
+    L.orc_render_rows.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_uint32,
+                                  C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_pixel_ray.argtypes = [C.POINTER(abi.CameraData), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.orc_pixel_ray.restype = None
+    L.orc_hardware_threads.restype = C.c_int
+    _lib = L
+    return L
+
+
+FACES = ["Within", "NX", "NY", "NZ", "PX", "PY", "PZ"]
+
+
+def scale_to_integer_step(s, ds):
+    return lib().orc_scale_to_integer_step(s, ds)
+
+
+def raycast(origin, direction, bounds=None, include_exit=True, max_steps=64):
+    """Returns list of (cube(x,y,z), face_name, t, point(x,y,z)). bounds = (lo3, hi3) exclusive."""
+    o = np.array(origin, dtype=np.float64)
+    d = np.array(direction, dtype=np.float64)
+    cf = np.zeros((max_steps, 4), dtype=np.int32)
+    t = np.zeros(max_steps, dtype=np.float64)
+    p = np.zeros((max_steps, 3), dtype=np.float64)
+    b = None
+    if bounds is not None:
+        b = np.array(list(bounds[0]) + list(bounds[1]), dtype=np.int32)
+    n = lib().orc_raycast(o.ctypes.data, d.ctypes.data, b.ctypes.data if b is not None else None,
+                          1 if include_exit else 0, max_steps, cf.ctypes.data, t.ctypes.data, p.ctypes.data)
+    return [(tuple(int(v) for v in cf[i, :3]), FACES[cf[i, 3]], float(t[i]), tuple(float(v) for v in p[i]))
+            for i in range(n)]
+
+
+def recursive_raycast(origin, direction, nth, resolution, bounds, max_steps=64):
+    o = np.array(origin, dtype=np.float64)
+    d = np.array(direction, dtype=np.float64)
+    b = np.array(list(bounds[0]) + list(bounds[1]), dtype=np.int32)
+    sub = np.zeros(6, dtype=np.float64)
+    cf = np.zeros((max_steps, 4), dtype=np.int32)
+    t = np.zeros(max_steps, dtype=np.float64)
+    n = lib().orc_recursive_raycast(o.ctypes.data, d.ctypes.data, nth, resolution, b.ctypes.data, max_steps,
+                                    sub.ctypes.data, cf.ctypes.data, t.ctypes.data)
+    steps = [(tuple(int(v) for v in cf[i, :3]), FACES[cf[i, 3]], float(t[i])) for i in range(max(n, 0))]
+    return sub, steps
+
+
+def apply_transmittance(rgba, thickness):
+    c = np.array(rgba, dtype=np.float32)
+    out = np.zeros(5, dtype=np.float32)
+    lib().orc_apply_transmittance(c.ctypes.data, thickness, out.ctypes.data)
+    return tuple(float(v) for v in out[:4]), float(out[4])
+
+
+def to_srgb8(colorbuf, exposure=1.0, tone_mapping=0, maximum_intensity=float("inf")):
+    c = np.array(colorbuf, dtype=np.float32)
+    out = np.zeros(4, dtype=np.uint8)
+    lib().orc_to_srgb8(c.ctypes.data, exposure, tone_mapping, maximum_intensity, out.ctypes.data)
+    return tuple(int(v) for v in out)
+
+
+class OracleScene:
+    def __init__(self, space):
+        self.space = space
+        desc, keep = space.to_desc()
+        self.handle = lib().orc_scene_create(C.byref(desc))
+        del keep
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().orc_scene_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def surface_steps(self, origin_dir, depth_iter=False, max_steps=64):
+        od = np.array(origin_dir, dtype=np.float64)
+        rec = np.zeros((max_steps, 18), dtype=np.float64)
+        n = lib().orc_surface_steps(self.handle, od.ctypes.data, 1 if depth_iter else 0, max_steps, rec.ctypes.data)
+        return rec[:n]
+
+    def trace_rays(self, origin_dir, options, include_sky=True, accum_mode=0):
+        od = np.ascontiguousarray(origin_dir, dtype=np.float64).reshape(-1, 6)
+        n = od.shape[0]
+        cb = np.empty((n, 4), dtype=np.float32)
+        depth = np.empty(n, dtype=np.float64)
+        hit = np.empty((n, 8), dtype=np.int32)
+        steps = np.empty(n, dtype=np.uint32)
+        text = np.empty(n, dtype=np.int32)
+        opt = options.to_abi(include_sky)
+        lib().orc_trace_rays(self.handle, od.ctypes.data, n, C.byref(opt), accum_mode, cb.ctypes.data,
+                             depth.ctypes.data, hit.ctypes.data, steps.ctypes.data, text.ctypes.data)
+        return {"colorbuf": cb, "depth": depth, "hit": hit, "steps": steps, "text": text}
+
+    def render(self, camera, options, shard=None, accum_mode=0, n_threads=0):
+        cam = camera.data
+        s = None
+        rows = cam.fb_height
+        if shard is not None:
+            s = abi.Shard()
+            s.strip_rows, s.index, s.count = shard
+            sr = max(1, shard[0])
+            rows = sum(1 for y in range(cam.fb_height) if (y // sr) % shard[2] == shard[1]) if shard[2] > 1 else rows
+        n = cam.fb_width * rows
+        srgb = np.empty((n, 4), dtype=np.uint8)
+        cb = np.empty((n, 4), dtype=np.float32)
+        depth = np.empty(n, dtype=np.float64)
+        hit = np.empty((n, 8), dtype=np.int32)
+        steps = np.empty(n, dtype=np.uint32)
+        text = np.empty(n, dtype=np.int32)
+        opt = options.to_abi(True)
+        total = lib().orc_render(self.handle, C.byref(cam), C.byref(opt), C.byref(s) if s else None, accum_mode,
+                                 n_threads, srgb.ctypes.data, cb.ctypes.data, depth.ctypes.data, hit.ctypes.data,
+                                 steps.ctypes.data, text.ctypes.data)
+        return {"srgb8": srgb, "colorbuf": cb, "depth": depth, "hit": hit, "steps": steps, "text": text,
+                "cubes_traced": int(total)}
+
+    def render_rows(self, camera, options, row_begin, row_end, n_threads=0, want_colorbuf=False):
+        cam = camera.data
+        n = cam.fb_width * (row_end - row_begin)
+        srgb = np.empty((n, 4), dtype=np.uint8)
+        cb = np.empty((n, 4), dtype=np.float32) if want_colorbuf else None
+        opt = options.to_abi(True)
+        total = lib().orc_render_rows(self.handle, C.byref(cam), C.byref(opt), row_begin, row_end, n_threads,
+                                      srgb.ctypes.data, cb.ctypes.data if want_colorbuf else None)
+        return {"srgb8": srgb, "colorbuf": cb, "cubes_traced": int(total)}
+
+
+def pixel_ray(camera, x, y, sample=-1):
+    out = np.zeros(6, dtype=np.float64)
+    lib().orc_pixel_ray(C.byref(camera.data), x, y, sample, out.ctypes.data)
+    return out
+
+
+def hardware_threads():
+    return lib().orc_hardware_threads()
+
+
+def ulp_diff(a, b):
+    """Elementwise distance in units-in-the-last-place between two float32 arrays."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7fffffff), ia)
+    ib = np.where(ib < 0, -(ib & 0x7fffffff), ib)
+    d = np.abs(ia - ib)
+    both_nan = np.isnan(a) & np.isnan(b)
+    return np.where(both_nan, 0, d)
+
+
+def max_ulp_diff(a, b):
+    return int(ulp_diff(a, b).max()) if np.size(a) else 0

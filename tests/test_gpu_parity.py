@@ -1,0 +1,373 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI,
+against the oracle on identical Space / Camera / options.
+
+Bars (BASELINE.json north_star): hit indices, step counts and depths bit-exact; ColorBuf within
+1 ULP per f32 channel where only +,-,*,/ are involved (bit-exact in practice) and within a few ULP
+where powf/expf enter (device evaluates them in f64 and rounds once; glibc's powf/expf are within
+1 ULP of that) — the tolerance is stated per test; sRGB8 bytes within 1."""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+import aicb200
+import orc
+from aicb200 import (FOG_ABRUPT, FOG_COMPROMISE, FOG_NONE, FOG_PHYSICAL, LIGHT_COARSE, LIGHT_FLAT, LIGHT_LINEAR,
+                     LIGHT_NONE, LIGHT_SMOOTHSTEP, TRANSPARENCY_SURFACE, TRANSPARENCY_THRESHOLD,
+                     TRANSPARENCY_VOLUMETRIC, Block, Camera, GraphicsOptions, RtRenderer, Space, SpaceRaytracer,
+                     Viewport, scenes)
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# ULP tolerance on ColorBuf channels when transcendental functions are on the path.
+ULP_TRANSCENDENTAL = 4
+
+
+def compare(gpu, ref, exact_color, label=""):
+    assert np.array_equal(gpu["hit"], ref["hit"]), f"{label}: hit records differ"
+    assert np.array_equal(gpu["steps"], ref["steps"]), f"{label}: step counts differ"
+    assert np.array_equal(gpu["depth"], ref["depth"]), f"{label}: depths differ"
+    ulp = orc.ulp_diff(gpu["colorbuf"], ref["colorbuf"])
+    # compare small magnitudes on an absolute scale too: 1 ULP of a channel near 0 is meaningless
+    absd = np.abs(gpu["colorbuf"].astype(np.float64) - ref["colorbuf"].astype(np.float64))
+    bad = (ulp > (0 if exact_color else ULP_TRANSCENDENTAL)) & (absd > (0.0 if exact_color else 1e-7))
+    assert not bad.any(), f"{label}: ColorBuf max ulp {ulp.max()} at {np.argwhere(bad)[:4]}"
+    return int(ulp.max())
+
+
+def render_both(space, cam, opts, shard=None):
+    r = RtRenderer(cam)
+    r.update(space)
+    gpu = r.draw_colorbuf(shard=shard)
+    img = r.draw(shard=shard)
+    ref = orc.OracleScene(space).render(cam, opts, shard=shard)
+    return gpu, img, ref
+
+
+@pytest.fixture(scope="module")
+def mixed():
+    return scenes.small_mixed_scene(n=12, seed=7)
+
+
+@pytest.mark.parametrize("transparency", [TRANSPARENCY_SURFACE, TRANSPARENCY_VOLUMETRIC, TRANSPARENCY_THRESHOLD])
+@pytest.mark.parametrize("lighting", [LIGHT_NONE, LIGHT_FLAT, LIGHT_COARSE, LIGHT_LINEAR, LIGHT_SMOOTHSTEP])
+@pytest.mark.parametrize("fog", [FOG_NONE, FOG_ABRUPT, FOG_COMPROMISE, FOG_PHYSICAL])
+def test_option_matrix(mixed, transparency, lighting, fog):
+    opts = GraphicsOptions(fog=fog, lighting_display=lighting, transparency=transparency, view_distance=40.0,
+                           transparency_threshold=0.3)
+    cam = scenes.standard_camera(mixed, opts, 96, 64)
+    gpu, img, ref = render_both(mixed, cam, opts)
+    exact = transparency != TRANSPARENCY_VOLUMETRIC and fog == FOG_NONE
+    compare(gpu, ref, exact, f"t{transparency} l{lighting} f{fog}")
+    assert gpu["info"].cubes_traced == ref["cubes_traced"] == int(ref["steps"].sum())
+    d8 = np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int))
+    assert d8.max() <= 1
+    assert (d8 > 0).mean() < 0.01
+    assert img.info.cubes_traced == ref["cubes_traced"]
+
+
+@pytest.mark.parametrize("direction", [(1, 0.6, 1), (-1, -0.3, 0.2), (0, 1, 0), (0, 0, -1), (1, 0, 0), (0.3, -1, -0.7)])
+def test_camera_directions_and_inside(mixed, direction):
+    """Axis-aligned views (zero direction components, ties) and a camera inside the Space (Face7::Within)."""
+    opts = GraphicsOptions(view_distance=60.0)
+    for scale in (1.0, 0.2):
+        cam = scenes.standard_camera(mixed, opts, 64, 48, direction=direction, distance_scale=scale)
+        gpu, img, ref = render_both(mixed, cam, opts)
+        compare(gpu, ref, False, f"dir {direction} scale {scale}")
+
+
+def test_antialiasing_and_debug_pixel_cost(mixed):
+    for kw in (dict(antialiasing_always=True), dict(debug_pixel_cost=True),
+               dict(antialiasing_always=True, transparency=TRANSPARENCY_SURFACE, fog=FOG_NONE, lighting_display=LIGHT_FLAT)):
+        opts = GraphicsOptions(view_distance=40.0, **kw)
+        cam = scenes.standard_camera(mixed, opts, 48, 32)
+        gpu, img, ref = render_both(mixed, cam, opts)
+        compare(gpu, ref, False, str(kw))
+        assert np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+
+
+def test_tone_mapping_and_exposure(mixed):
+    for kw in (dict(tone_mapping=aicb200.TONE_REINHARD, maximum_intensity=1.0, exposure=2.0),
+               dict(tone_mapping=aicb200.TONE_CLAMP, maximum_intensity=0.5, exposure=0.5)):
+        opts = GraphicsOptions(view_distance=40.0, **kw)
+        cam = scenes.standard_camera(mixed, opts, 48, 32)
+        gpu, img, ref = render_both(mixed, cam, opts)
+        assert np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+
+
+def test_no_light_volume_and_uniform_sky():
+    space = scenes.small_mixed_scene(n=10, seed=3, with_light=False, octant_sky=False)
+    for lighting in (LIGHT_FLAT, LIGHT_LINEAR):
+        opts = GraphicsOptions(lighting_display=lighting, view_distance=50.0)
+        cam = scenes.standard_camera(space, opts, 64, 48)
+        gpu, img, ref = render_both(space, cam, opts)
+        compare(gpu, ref, False, f"nolight l{lighting}")
+
+
+def test_row_strip_shards_reassemble_the_frame(mixed):
+    opts = GraphicsOptions(view_distance=40.0)
+    cam = scenes.standard_camera(mixed, opts, 64, 50)
+    r = RtRenderer(cam)
+    r.update(mixed)
+    full = r.draw().data
+    for count in (2, 3):
+        out = np.zeros_like(full)
+        for index in range(count):
+            part = r.draw(shard=(16, index, count)).data
+            rows = [y for y in range(50) if (y // 16) % count == index]
+            assert part.shape[0] == len(rows)
+            out[rows] = part
+            ref = orc.OracleScene(mixed).render(cam, opts, shard=(16, index, count))
+            assert np.abs(part.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+        assert np.array_equal(out, full), "N-shard frame differs from the 1-shard frame"
+
+
+def test_explicit_rays_including_degenerate(mixed):
+    """SpaceRaytracer::trace_ray on hand-made rays: zero / NaN / huge directions, axis-aligned, grazing."""
+    rng = np.random.default_rng(5)
+    rays = []
+    lo = np.array(mixed.lower, dtype=np.float64)
+    size = np.array(mixed.size, dtype=np.float64)
+    for _ in range(2000):
+        o = lo + rng.uniform(-0.5, 1.5, 3) * size
+        d = rng.normal(size=3) * 10.0 ** rng.uniform(-2, 2)
+        rays.append(np.concatenate([o, d]))
+    c = lo + size / 2
+    rays += [np.concatenate([c, [0, 0, 0]]), np.concatenate([c, [np.nan, 1, 0]]), np.concatenate([c, [1e200, 0, 0]]),
+             np.concatenate([c, [1, 0, 0]]), np.concatenate([c, [0, -1, 0]]), np.concatenate([c, [0, 0, 1e-30]]),
+             np.concatenate([lo - 1.0, [1, 1, 1]]), np.concatenate([lo + [0.0, 0.0, -3.0], [0, 0, 2.0]]),
+             np.concatenate([lo + size + 5.0, [-1, -1, -1]]), np.concatenate([[1e12, 0, 0], [-1, 0, 0]])]
+    rays = np.array(rays)
+    for opts in (GraphicsOptions(view_distance=50.0),
+                 GraphicsOptions(transparency=TRANSPARENCY_SURFACE, fog=FOG_NONE, lighting_display=LIGHT_NONE)):
+        for include_sky in (True, False):
+            rt = SpaceRaytracer(mixed, opts)
+            gpu = rt.trace_rays(rays, include_sky=include_sky, want_depth=True, want_hit=True, want_steps=True)
+            ref = orc.OracleScene(mixed).trace_rays(rays, opts, include_sky=include_sky)
+            compare(gpu, ref, False, f"explicit rays sky={include_sky}")
+
+
+def test_reference_kat_scenes_on_gpu():
+    """The surface.rs known-answer scenes (surface.rs:541-835) through the CUDA path: hit, depth, steps."""
+    idx = np.ones((4, 4, 4), dtype=np.uint16)
+    idx[1:, 2:, :] = 0
+    pal = np.zeros((2, 8), dtype=np.float32)
+    pal[1, :4] = (1, 1, 0, 1)
+    slab = Block(resolution=4, indices=idx, palette=pal)
+    ids = np.array([0, 1, 2], dtype=np.uint16).reshape(1, 3, 1)
+    space = Space((0, 0, 0), ids, [Block.air(), Block(color=(1, 0, 0, 1)), slab])
+    opts = GraphicsOptions.unaltered_colors()
+    opts.transparency = TRANSPARENCY_SURFACE
+    rt = SpaceRaytracer(space, opts)
+    got = rt.trace_rays([[0.25, -0.5, 0.25, 0.0, 1.0, 0.0]], include_sky=False, want_depth=True, want_hit=True, want_steps=True)
+    assert got["depth"][0] == 1.5
+    assert list(got["hit"][0]) == [0, 1, 0, 0, 0, 0, 1, aicb200.abi.FACE_NY]
+    assert list(got["colorbuf"][0]) == [1.0, 0.0, 0.0, 0.0]
+    # Invisible{0.5}, EnterSurface (opaque) -> the next count sees opacity and stops: 3 steps
+    assert got["steps"][0] == 3
+    ref = orc.OracleScene(space).trace_rays([[0.25, -0.5, 0.25, 0.0, 1.0, 0.0]], opts, include_sky=False)
+    assert ref["steps"][0] == 3
+
+
+def _ascii_from_gpu(space, direction, chars):
+    opts = GraphicsOptions()
+    cam = Camera(opts, Viewport((40.0, 40.0), (80, 40)))
+    center = [space.lower[a] + space.size[a] / 2.0 for a in range(3)]
+    cam.look_at_y_up(aicb200.eye_for_look_at(space.lower, space.size, direction), center)
+    rays = []
+    for ych in range(40):
+        y = -((ych + 0.5) / 40.0 * 2.0 - 1.0)
+        for xch in range(80):
+            rays.append(cam.project_ndc_into_world((xch + 0.5) / 80.0 * 2.0 - 1.0, y))
+    got = SpaceRaytracer(space, opts).trace_rays(np.array(rays), want_hit=True, want_steps=True)
+    rows = []
+    for ych in range(40):
+        row = ""
+        for xch in range(80):
+            i = ych * 80 + xch
+            h = got["hit"][i]
+            if h[7] >= 0:
+                bid = int(space.block_ids[h[0] - space.lower[0], h[1] - space.lower[1], h[2] - space.lower[2]])
+                row += chars[bid]
+            else:
+                row += " " if got["steps"][i] > 0 else "."
+        rows.append(row)
+    return rows
+
+
+def test_text_golden_images_on_gpu():
+    """raytracer/text.rs:196-258, 265-341: the reference's 80x40 ASCII hit-identity images from the GPU hit buffer."""
+    golden = json.load(open(os.path.join(GOLDEN, "text_images.json")))
+    ids = np.array([1, 2, 3], dtype=np.uint16).reshape(3, 1, 1)
+    grey = lambda i, n: (i / (n - 1),) * 3 + (1.0,) if n > 1 else (0.5, 0.5, 0.5, 1.0)
+    space = Space((0, 0, 0), ids, [Block.air()] + [Block(color=grey(i, 3)) for i in range(3)])
+    assert _ascii_from_gpu(space, (1.0, 1.0, 1.0), {1: "0", 2: "1", 3: "2"}) == golden["print_space_test"]
+    idx = np.zeros((4, 2, 4), dtype=np.uint16)
+    pal = np.zeros((1, 8), dtype=np.float32)
+    pal[0, :4] = (1, 1, 1, 1)
+    partial = Block(resolution=4, indices=idx, palette=pal)
+    space = Space((0, 0, 0), np.array([1, 2], dtype=np.uint16).reshape(2, 1, 1),
+                  [Block.air(), Block(color=grey(0, 1)), partial])
+    assert _ascii_from_gpu(space, (1.0, 1.0, 1.0), {1: "0", 2: "P"}) == golden["partial_voxels"]
+
+
+def test_golden_png_emission_on_gpu():
+    """test-renderers `emission` case (cases/src/lib.rs:297-348, threshold 1) rendered by the CUDA path."""
+    from test_golden_images import check_threshold, common_camera, golden
+    from aicb200 import srgb8_to_linear
+    c200 = srgb8_to_linear((200, 0, 0))[0]
+    pal = np.zeros((3, 8), dtype=np.float32)
+    pal[0, :4] = (1, 1, 1, 1)
+    pal[1, :4] = (c200, 0, 0, 1); pal[1, 4:7] = (0, c200, 0)
+    pal[2, :4] = (0, 0, 0, 1); pal[2, 4:7] = (0, c200, 0)
+    idx = np.zeros((4, 4, 4), dtype=np.uint16)
+    idx[1, 2, :] = 1
+    idx[2, 1, :] = 2
+    space = Space((0, 0, 0), np.ones((1, 1, 1), dtype=np.uint16), [Block.air(), Block(resolution=4, indices=idx, palette=pal)],
+                  sky_colors=[(0.5, 0.5, 0.5)])
+    opts = GraphicsOptions.unaltered_colors()
+    r = RtRenderer(common_camera(opts))
+    r.update(space)
+    check_threshold(r.draw().data, golden("emission-all"), [(1, 128 * 96)])
+
+
+def test_config_c0_cpu_reference_case():
+    """BASELINE configs[0]: 32^3 solid/empty res-1, 256x256 — full size."""
+    space = scenes.config_c0()
+    opts = GraphicsOptions.unaltered_colors()
+    cam = scenes.standard_camera(space, opts, 256, 256)
+    gpu, img, ref = render_both(space, cam, opts)
+    compare(gpu, ref, False, "C0")
+    assert np.array_equal(img.data.reshape(-1, 4), ref["srgb8"])
+
+
+def test_config_c1_reduced_recursive_blocks():
+    """BASELINE configs[1] shape at a size the oracle finishes in seconds: 32^3, res-16 blocks, 320x180."""
+    space = scenes.config_c1(n=32, n_voxel_blocks=24, with_light=True)
+    for opts in (GraphicsOptions.unaltered_colors(),
+                 GraphicsOptions(lighting_display=LIGHT_FLAT, fog=FOG_NONE, view_distance=128.0),
+                 GraphicsOptions(view_distance=128.0)):
+        cam = scenes.standard_camera(space, opts, 320, 180)
+        gpu, img, ref = render_both(space, cam, opts)
+        compare(gpu, ref, False, "C1 reduced")
+        assert np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+
+
+def test_config_c2_reduced_deep_transparency():
+    """BASELINE configs[2] shape reduced: 48^3 mixed transparent, both Volumetric and Surface; many rays
+    run into the 1000-step cap / the opacity cut-off."""
+    space = scenes.config_c2(n=48, n_voxel_blocks=8, with_light=True)
+    for transparency in (TRANSPARENCY_VOLUMETRIC, TRANSPARENCY_SURFACE):
+        opts = GraphicsOptions.unaltered_colors()
+        opts.transparency = transparency
+        opts.view_distance = 192.0
+        cam = scenes.standard_camera(space, opts, 240, 135)
+        gpu, img, ref = render_both(space, cam, opts)
+        compare(gpu, ref, transparency == TRANSPARENCY_SURFACE, f"C2 reduced t{transparency}")
+    opts = GraphicsOptions(view_distance=192.0)
+    cam = scenes.standard_camera(space, opts, 240, 135)
+    gpu, img, ref = render_both(space, cam, opts)
+    compare(gpu, ref, False, "C2 reduced default options")
+
+
+def test_step_cap_is_reached_and_counted():
+    """sr.rs:639-652: a long empty Space makes rays stop at exactly 1001 counted steps."""
+    n = 400
+    ids = np.zeros((n, 4, 4), dtype=np.uint16)
+    space = Space((0, 0, 0), ids, [Block.air(), Block(color=(1, 1, 1, 1))])
+    opts = GraphicsOptions.unaltered_colors()
+    rays = np.array([[-0.5, 1.3, 2.2, 1.0, 0.004, 0.003], [0.5, 0.5, 0.5, 1.0, 0.9, 0.0]])
+    gpu = SpaceRaytracer(space, opts).trace_rays(rays, want_steps=True, want_hit=True, want_depth=True)
+    ref = orc.OracleScene(space).trace_rays(rays, opts)
+    compare(gpu, ref, True, "step cap")
+    # a res-16 filled space hits the cap: 16 voxel steps + events per cube
+    blk = scenes.make_voxel_block(3, resolution=16, alpha=0.02, fill_mask=1, partial_bounds=False)
+    ids = np.ones((80, 2, 2), dtype=np.uint16)
+    space = Space((0, 0, 0), ids, [Block.air(), blk])
+    for transparency in (TRANSPARENCY_SURFACE, TRANSPARENCY_VOLUMETRIC):
+        opts = GraphicsOptions.unaltered_colors()
+        opts.transparency = transparency
+        rays = np.array([[-0.5, 1.01, 0.99, 1.0, 0.001, 0.002]])
+        gpu = SpaceRaytracer(space, opts).trace_rays(rays, want_steps=True, want_hit=True, want_depth=True)
+        ref = orc.OracleScene(space).trace_rays(rays, opts)
+        assert ref["steps"][0] == 1001
+        compare(gpu, ref, False, "step cap res16")
+
+
+def test_zero_and_prime_viewports(mixed):
+    """cases viewport_zero / viewport_prime (cases/src/lib.rs:1167-1237): empty and odd-sized frames."""
+    opts = GraphicsOptions(view_distance=40.0)
+    for size in ((0, 0), (0, 5), (7, 0), (127, 61), (1, 1), (9, 5)):
+        cam = scenes.standard_camera(mixed, opts, *size) if size[0] and size[1] else Camera(opts, Viewport((1.0, 1.0), size))
+        r = RtRenderer(cam)
+        r.update(mixed)
+        img = r.draw()
+        assert img.data.size == size[0] * size[1] * 4
+        if size[0] and size[1]:
+            ref = orc.OracleScene(mixed).render(cam, opts)
+            assert np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+
+
+def test_buffer_length_mismatch_is_an_error(mixed):
+    """renderer.rs:193-197 panics on a wrong output length; the C ABI returns AICB_ERR_INVALID."""
+    import ctypes as C
+    opts = GraphicsOptions()
+    cam = scenes.standard_camera(mixed, opts, 16, 16)
+    rt = SpaceRaytracer(mixed, opts)
+    out = np.zeros((10, 4), dtype=np.uint8)
+    o = opts.to_abi()
+    st = aicb200.load_library().aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o), None, out.ctypes.data, 10, None)
+    assert st == aicb200.abi.ERR_INVALID
+    assert b"does not match" in aicb200.load_library().aicb_last_error()
+
+
+def test_incremental_cube_update_equals_fresh_snapshot(mixed):
+    """updating.rs:295-337: applying SpaceChange deltas == rebuilding the SpaceRaytracer."""
+    opts = GraphicsOptions(view_distance=40.0)
+    cam = scenes.standard_camera(mixed, opts, 64, 48)
+    r = RtRenderer(cam)
+    r.update(mixed)
+    rng = np.random.default_rng(2)
+    cubes = np.stack([rng.integers(0, mixed.size[a], 50) + mixed.lower[a] for a in range(3)], axis=1)
+    new_ids = rng.integers(0, len(mixed.blocks), 50).astype(np.uint16)
+    new_light = rng.integers(0, 255, (50, 4)).astype(np.uint8)
+    new_light[:, 3] = 255
+    r.rt.update_cubes(cubes, new_ids, new_light)
+    ids2 = mixed.block_ids.copy()
+    light2 = mixed.light.copy()
+    for c, i, l in zip(cubes, new_ids, new_light):
+        p = tuple(c - np.array(mixed.lower))
+        ids2[p] = i
+        light2[p] = l
+    fresh = Space(mixed.lower, ids2, mixed.blocks, light=light2, sky_colors=mixed.sky_colors)
+    r2 = RtRenderer(cam)
+    r2.update(fresh)
+    assert np.array_equal(r.draw().data, r2.draw().data)
+
+
+def test_full_size_1080p_properties():
+    """BASELINE configs[1] at full size (128^3 res-16, 1920x1080): size-independent properties —
+    determinism, cubes_traced == sum of per-pixel steps, shard union == frame — plus bit-level
+    parity with the oracle on a band of rows."""
+    space = scenes.config_c1(n=128)
+    opts = GraphicsOptions.unaltered_colors()
+    opts.view_distance = 512.0
+    cam = scenes.standard_camera(space, opts, 1920, 1080)
+    r = RtRenderer(cam)
+    r.update(space)
+    a = r.draw()
+    b = r.draw()
+    assert np.array_equal(a.data, b.data), "render is not deterministic"
+    aux = r.draw_colorbuf(want_depth=False, want_hit=False)
+    assert aux["info"].cubes_traced == int(aux["steps"].astype(np.int64).sum()) == a.info.cubes_traced
+    out = np.zeros_like(a.data)
+    for index in range(4):
+        rows = [y for y in range(1080) if (y // 16) % 4 == index]
+        out[rows] = r.draw(shard=(16, index, 4)).data
+    assert np.array_equal(out, a.data)
+    band = orc.OracleScene(space).render_rows(cam, opts, 536, 544, want_colorbuf=True)
+    assert np.array_equal(a.data[536:544].reshape(-1, 4), band["srgb8"])
+    assert orc.max_ulp_diff(aux["colorbuf"].reshape(1080, 1920, 4)[536:544].reshape(-1, 4), band["colorbuf"]) <= ULP_TRANSCENDENTAL
