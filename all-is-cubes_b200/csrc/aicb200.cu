@@ -5,6 +5,7 @@
 // AICB_ERR_CUDA otherwise.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -129,6 +130,31 @@ static void build_block_sky(const aicb_sky &sky, DeviceScene *ds) {
     ds->sky_mean = texel_some(q);
 }
 
+// component_to_srgb8 (math/color.rs:1038-1054) evaluated with the platform powf — exactly what the
+// reference computes on this host — and inverted into thresholds: thr[k] = the smallest non-negative
+// f32 whose encoding is >= k.  The device encodes by searching this table.
+static uint8_t srgb8_host(float c) {
+    float s = (c <= 0.0031308f) ? c * (323.0f / 25.0f) : (211.0f * std::pow(c, 5.0f / 12.0f) - 11.0f) / 200.0f;
+    float v = std::round(s * 255.0f);
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+static void build_srgb_thresholds(float *thr) {
+    thr[0] = 0.0f;
+    for (int k = 1; k < 256; k++) {
+        // bisection over the bit patterns of non-negative floats (monotone in value)
+        uint32_t lo = 0, hi = 0x7f800000u;  // +0 .. +inf
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            float f;
+            std::memcpy(&f, &mid, 4);
+            if (srgb8_host(f) >= k) hi = mid; else lo = mid + 1;
+        }
+        std::memcpy(&thr[k], &lo, 4);
+    }
+}
+
 static bool voxel_invisible(const aicb_voxel &v) {
     return v.rgba[3] == 0.0f && v.emission[0] == 0.0f && v.emission[1] == 0.0f && v.emission[2] == 0.0f;
 }
@@ -212,13 +238,17 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         }
         P.tiles_x = (P.fb_width + TILE_W - 1) / TILE_W;
         P.tiles_y = (P.local_rows + TILE_H - 1) / TILE_H;
+        if ((uint64_t)P.tiles_x * P.tiles_y * 32 > 0xffffffffull) return fail(AICB_ERR_INVALID, "frame too large");
+        P.n_tasks = P.tiles_x * P.tiles_y * 32;
         pixels = (uint64_t)P.fb_width * P.local_rows;
     } else {
         P.exposure = 1.0f;
         P.rays = d_rays;
         P.n_rays = n_rays;
+        if (n_rays > 0xffffffffull) return fail(AICB_ERR_INVALID, "too many rays");
         P.tiles_x = (uint32_t)((n_rays + 31) / 32);
         P.tiles_y = 1;
+        P.n_tasks = (uint32_t)n_rays;
         P.shard_count = 1;
         P.strip_rows = 1;
         pixels = n_rays;
@@ -239,7 +269,12 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.out_hit = out.hit;
     P.out_steps = out.steps;
     P.counters = ctx->d_counters;
-    P.tile_counter = ctx->d_tile_counter;
+    P.task_counter = ctx->d_tile_counter;
+    {
+        const char *e = getenv("AICB_REFILL_THRESHOLD");
+        int v = e ? atoi(e) : 16;
+        P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
+    }
 
     sc->pending = true;
     sc->pending_pixels = pixels;
@@ -333,9 +368,10 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
-    float lut[256];
+    float lut[512];
     lut[0] = 0.0f;
     for (int i = 1; i < 256; i++) lut[i] = (float)std::exp2((double)(((float)i - 144.0f) / 10.0f));
+    build_srgb_thresholds(lut + 256);
     CU(cudaMalloc(&c->d_lut, sizeof lut));
     CU(cudaMemcpy(c->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
     *out = c;
@@ -509,7 +545,7 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
     ds.blocks = s->d_blocks;
     ds.bricks = s->d_bricks;
     ds.palette = s->d_palette;
-    ds.lut = ctx->d_lut;
+    ds.tables = ctx->d_lut;
     build_block_sky(d->sky, &ds);
     *out = s;
     return AICB_OK;

@@ -3,16 +3,22 @@
 // dispatch (renderer.rs:424-451, 516-556).
 //
 // Design (B200-first, not a translation):
-//  * one warp = one 8x4 pixel tile, persistent warps pull tiles from a global atomic counter;
-//  * the two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is
-//    walked by ONE unified Amanatides–Woo DDA whose state lives in registers; entering a
-//    recursive block pushes the outer state and re-initialises the same DDA on the brick, so
-//    all lanes execute the same step code whatever level they are on;
-//  * cell words carry the classification (invisible / single / recursive, voxel invisible) in
-//    their top bits, so an empty step costs exactly one dependent 2-byte load;
+//  * persistent warps; every lane owns one pixel task at a time and pulls the next one from a
+//    global counter when it finishes (tile-ordered: 32 consecutive tasks = one 8x4 pixel tile), so
+//    a warp never idles behind its slowest ray;
+//  * the warp runs a synchronous phase machine — REFILL (ray setup) | MARCH (cheap DDA steps
+//    until the lane reaches an event) | HEAVY (span shading, surface lighting, block entry) |
+//    FINALIZE (sky, encode, store) — so that lanes executing expensive code execute the SAME
+//    expensive code; the heavy math is out of line with one call site each (i-cache);
+//  * the two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is walked
+//    by ONE unified Amanatides–Woo DDA whose state lives in registers; entering a recursive block
+//    pushes the outer state and re-initialises the same DDA on the brick;
+//  * cell words carry their classification in the top bits (invisible / single / recursive;
+//    voxel invisible), so an empty step costs exactly one dependent 2-byte load;
 //  * all ray geometry is f64 and all colour is f32, operation for operation as the reference
-//    (compiled with -fmad=false: Rust never contracts to FMA); transcendentals are evaluated in
-//    f64 and rounded once.
+//    (compiled with -fmad=false: Rust never contracts to FMA); powf/expf are evaluated in f64 and
+//    rounded once; the sRGB8 encode is a search in a 255-entry threshold table built on the host
+//    with the platform powf (bit-identical to what the reference computes on that host).
 //
 // Every function cites the reference lines it reproduces.
 #pragma once
@@ -47,7 +53,7 @@ struct DeviceScene {
     const BlockRec *blocks;
     const uint16_t *bricks;     // palette index | invisible<<15
     const float4 *palette;      // 2 x float4 per entry: rgba, emission
-    const float *lut;           // 256-entry PackedLight decode table (data.rs:301-354)
+    const float *tables;        // [0,256): PackedLight decode LUT (data.rs:301-354); [256,512): sRGB8 thresholds
     uint32_t sky_faces[6];      // BlockSky faces NX..PZ as texels (sky.rs:54-82)
     uint32_t sky_mean;
     uint32_t sky_kind;
@@ -78,6 +84,8 @@ struct TraceParams {
     const double *rays;         // explicit rays (trace_rays) or nullptr (camera rays)
     uint64_t n_rays;            // number of explicit rays
     uint32_t tiles_x, tiles_y;
+    uint32_t n_tasks;           // tiles_x * tiles_y * 32 (camera) or n_rays
+    uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
     uchar4 *out_srgb8;
     float4 *out_colorbuf;
@@ -85,37 +93,51 @@ struct TraceParams {
     aicb_hit *out_hit;
     uint32_t *out_steps;
     unsigned long long *counters;  // [0] cubes_traced, [1] outer steps, [2] inner steps, [3] hits, [4] light texels, [5] blocks entered
-    unsigned int *tile_counter;
+    unsigned int *task_counter;
 };
 
 #ifdef __CUDACC__
 
 #define AICB_DEV __device__ __forceinline__
+#define AICB_NOINLINE __device__ __noinline__
 
 constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (template)
+constexpr int TILE_W = 8, TILE_H = 4;
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int MIN_BLOCKS_PER_SM = 4;
+
+
+constexpr double D_INF = __builtin_huge_val();
 
 struct Ray {
-    double ox, oy, oz, dx, dy, dz;   // original ray (camera space == world space)
+    double ox, oy, oz, dx, dy, dz;   // original ray
     double tdx, tdy, tdz;            // t_delta = 1/|d| (raycast.rs:769)
-    int sx, sy, sz;                  // signum_101(d) (raycast.rs:768)
     double half_over_len;            // 0.5 / |d| (raycast.rs:669)
-    bool steppable;                  // step != 0 (first clause of valid_for_stepping, raycast.rs:565)
+    int sx, sy, sz;                  // signum_101(d) (raycast.rs:768)
 };
 
-// State::* of the active raycaster (raycast.rs:99-121), bounds kept as the per-axis exit limit.
+// State::* of the active raycaster (raycast.rs:99-121); the cube is kept relative to the lower
+// corner of its level so that the bounds test is one unsigned compare.
 struct Caster {
     double tmx, tmy, tmz;
     double last_t;
-    int cx, cy, cz;
+    int rx, ry, rz;
     int face;        // Face7 through which the current cube was entered
     uint32_t idx;    // linear index of the current cube in its volume (+ brick offset on the inner level)
+};
+
+// Geometry of one level as the DDA needs it.
+struct Level {
+    int lox, loy, loz;
+    int nx, ny, nz;    // sizes
+    uint32_t base;
 };
 
 AICB_DEV int signum_101(double x) { return (x == 0.0 || x != x) ? 0 : (x < 0.0 ? -1 : 1); }
 
 // scale_to_integer_step (raycast.rs:797-819). fmod(s, 1) == s - trunc(s) exactly.
 AICB_DEV double scale_to_integer_step(double s, double ds) {
-    if (ds == 0.0 && !(s != s)) return __longlong_as_double(0x7ff0000000000000LL);
+    if (ds == 0.0 && !(s != s)) return D_INF;
     if (ds < 0.0) {
         s = -s;
         ds = -ds;
@@ -125,8 +147,10 @@ AICB_DEV double scale_to_integer_step(double s, double ds) {
     return (1.0 - r) / ds;
 }
 
-AICB_DEV bool in_i32_range(double x) { return (-2147483648.0 <= x) & (x < 2147483648.0); }
+// 1 / res for res = 2^k (Resolution::recip_f64): exact, no division
+AICB_DEV double recip_pow2(int res) { return __hiloint2double((1023 - (31 - __clz(res))) << 20, 0); }
 
+AICB_DEV bool in_i32_range(double x) { return (-2147483648.0 <= x) & (x < 2147483648.0); }
 AICB_DEV double rclamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }  // NaN passes through
 
 AICB_DEV float ps_mul(float a, float b) {
@@ -140,37 +164,36 @@ AICB_DEV float zo_clamped(float v) {
     return 1.0f;
 }
 
-// f32 transcendentals: evaluate in f64, round once (<= 1 ULP from glibc's powf/expf).
-AICB_DEV float powf_exact(float x, float y) { return (float)pow((double)x, (double)y); }
-AICB_DEV float expf_exact(float x) { return (float)exp((double)x); }
+// f32 transcendentals: evaluate in f64, round once (<= 1 ULP from glibc's powf/expf). Out of line:
+// one copy of the f64 pow/exp code in the kernel.
+AICB_NOINLINE float powf_exact(float x, float y) { return (float)pow((double)x, (double)y); }
+AICB_NOINLINE float expf_exact(float x) { return (float)exp((double)x); }
 
-// Bounds of one level, in the form the stepping loop needs.
-struct Level {
-    int lo[3];
-    int hi[3];     // exclusive
-    int sy_sz;     // size_y * size_z
-    int sz;        // size_z
-    uint32_t base; // index offset (brick_off on the inner level)
-};
+AICB_DEV bool tmax_valid(const Caster &c, const Ray &r) {  // valid_for_stepping (raycast.rs:563-570)
+    const bool any_nan = (c.tmx != c.tmx) | (c.tmy != c.tmy) | (c.tmz != c.tmz);
+    const bool any_fin = isfinite(c.tmx) | isfinite(c.tmy) | isfinite(c.tmz);
+    return ((r.sx | r.sy | r.sz) != 0) & !any_nan & any_fin;
+}
 
 // Raycaster::new(...).within(bounds, true) (raycast.rs:196-230, 513-545, 632-704) followed by the
 // FirstLast::Beginning part of next() (raycast.rs:255-263): advance until the first in-bounds
-// cube.  Returns false when the iterator produces nothing.
-AICB_DEV bool caster_begin(Caster &c, const Ray &r, double ox, double oy, double oz, const Level &lv) {
+// cube.  Returns false when the iterator produces nothing.  *valid = valid_for_stepping().
+AICB_NOINLINE bool caster_begin(Caster &c, const Ray &r, double ox, double oy, double oz, const Level lv, bool *valid) {
+    *valid = false;
     if (!(in_i32_range(ox) & in_i32_range(oy) & in_i32_range(oz))) return false;  // Cube::containing -> EMPTY
     {
         int fx = __double2int_rd(ox), fy = __double2int_rd(oy), fz = __double2int_rd(oz);
         const int lo = INT32_MIN + 1, hi = INT32_MAX - 1;
-        if (fx < lo | fx >= hi | fy < lo | fy >= hi | fz < lo | fz >= hi) return false;  // MAXIMUM_BOUNDS filter
+        if ((fx < lo) | (fx >= hi) | (fy < lo) | (fy >= hi) | (fz < lo) | (fz >= hi)) return false;  // MAXIMUM_BOUNDS filter
     }
-    if (lv.hi[0] <= lv.lo[0] || lv.hi[1] <= lv.lo[1] || lv.hi[2] <= lv.lo[2]) return false;  // ORIGIN_EMPTY
+    if (lv.nx <= 0 || lv.ny <= 0 || lv.nz <= 0) return false;  // ORIGIN_EMPTY
 
     // fast_forward: (plane - origin) / direction per moving axis; the dot products with an axis
     // normal reduce exactly to this quotient.
     double max_t = 0.0;
-    if (r.sx != 0) max_t = fmax(max_t, ((double)(r.sx < 0 ? lv.hi[0] : lv.lo[0]) - ox) / r.dx);
-    if (r.sy != 0) max_t = fmax(max_t, ((double)(r.sy < 0 ? lv.hi[1] : lv.lo[1]) - oy) / r.dy);
-    if (r.sz != 0) max_t = fmax(max_t, ((double)(r.sz < 0 ? lv.hi[2] : lv.lo[2]) - oz) / r.dz);
+    if (r.sx != 0) max_t = fmax(max_t, ((double)(r.sx < 0 ? lv.lox + lv.nx : lv.lox) - ox) / r.dx);
+    if (r.sy != 0) max_t = fmax(max_t, ((double)(r.sy < 0 ? lv.loy + lv.ny : lv.loy) - oy) / r.dy);
+    if (r.sz != 0) max_t = fmax(max_t, ((double)(r.sz < 0 ? lv.loz + lv.nz : lv.loz) - oz) / r.dz);
 
     double px = ox, py = oy, pz = oz, t0 = 0.0;
     if (max_t > 0.0) {
@@ -182,89 +205,80 @@ AICB_DEV bool caster_begin(Caster &c, const Ray &r, double ox, double oy, double
         if (!(in_i32_range(px) & in_i32_range(py) & in_i32_range(pz))) return false;
         t0 = t_start;
     }
-    c.cx = __double2int_rd(px);
-    c.cy = __double2int_rd(py);
-    c.cz = __double2int_rd(pz);
+    int cx = __double2int_rd(px), cy = __double2int_rd(py), cz = __double2int_rd(pz);
     c.tmx = scale_to_integer_step(px, r.dx) + t0;
     c.tmy = scale_to_integer_step(py, r.dy) + t0;
     c.tmz = scale_to_integer_step(pz, r.dz) + t0;
     c.last_t = t0;
     c.face = AICB_FACE_WITHIN;
+    const bool ok = tmax_valid(c, r);
+    *valid = ok;
 
-    // valid_for_stepping (raycast.rs:563-570)
-    const bool any_nan = (c.tmx != c.tmx) | (c.tmy != c.tmy) | (c.tmz != c.tmz);
-    const bool any_fin = isfinite(c.tmx) | isfinite(c.tmy) | isfinite(c.tmz);
-    const bool valid = r.steppable & !any_nan & any_fin;
-
+    const int hx = lv.lox + lv.nx, hy = lv.loy + lv.ny, hz = lv.loz + lv.nz;
     for (;;) {
         // is_out_of_bounds_ahead (raycast.rs:711-728)
-        bool xl = c.cx < lv.lo[0], xh = c.cx >= lv.hi[0];
-        bool yl = c.cy < lv.lo[1], yh = c.cy >= lv.hi[1];
-        bool zl = c.cz < lv.lo[2], zh = c.cz >= lv.hi[2];
+        bool xl = cx < lv.lox, xh = cx >= hx;
+        bool yl = cy < lv.loy, yh = cy >= hy;
+        bool zl = cz < lv.loz, zh = cz >= hz;
         bool enter = (r.sx == 0 ? (xl | xh) : (r.sx < 0 ? xh : xl)) | (r.sy == 0 ? (yl | yh) : (r.sy < 0 ? yh : yl)) |
                      (r.sz == 0 ? (zl | zh) : (r.sz < 0 ? zh : zl));
         bool exit_ = (r.sx == 0 ? (xl | xh) : (r.sx < 0 ? xl : xh)) | (r.sy == 0 ? (yl | yh) : (r.sy < 0 ? yl : yh)) |
                      (r.sz == 0 ? (zl | zh) : (r.sz < 0 ? zl : zh));
         if (exit_) return false;
         if (!enter) break;
-        if (!valid) return false;
+        if (!ok) return false;
         // State::step (raycast.rs:577-626)
         if (c.tmx < c.tmy) {
-            if (c.tmx < c.tmz) { c.last_t = c.tmx; c.cx += r.sx; c.tmx += r.tdx; c.face = r.sx > 0 ? AICB_FACE_NX : AICB_FACE_PX; }
-            else               { c.last_t = c.tmz; c.cz += r.sz; c.tmz += r.tdz; c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ; }
+            if (c.tmx < c.tmz) { c.last_t = c.tmx; cx += r.sx; c.tmx += r.tdx; c.face = r.sx > 0 ? AICB_FACE_NX : AICB_FACE_PX; }
+            else               { c.last_t = c.tmz; cz += r.sz; c.tmz += r.tdz; c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ; }
         } else {
-            if (c.tmy < c.tmz) { c.last_t = c.tmy; c.cy += r.sy; c.tmy += r.tdy; c.face = r.sy > 0 ? AICB_FACE_NY : AICB_FACE_PY; }
-            else               { c.last_t = c.tmz; c.cz += r.sz; c.tmz += r.tdz; c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ; }
+            if (c.tmy < c.tmz) { c.last_t = c.tmy; cy += r.sy; c.tmy += r.tdy; c.face = r.sy > 0 ? AICB_FACE_NY : AICB_FACE_PY; }
+            else               { c.last_t = c.tmz; cz += r.sz; c.tmz += r.tdz; c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ; }
         }
     }
-    c.idx = lv.base + (uint32_t)((c.cx - lv.lo[0]) * lv.sy_sz + (c.cy - lv.lo[1]) * lv.sz + (c.cz - lv.lo[2]));
-    // If stepping is impossible the iterator yields this one cube only when face == Within
-    // (raycast.rs:245-249); with !valid no Beginning step can have happened, so it is.  The
-    // caller learns about `valid` through Ray::steppable and the t_max test below.
+    c.rx = cx - lv.lox;
+    c.ry = cy - lv.loy;
+    c.rz = cz - lv.loz;
+    c.idx = lv.base + (uint32_t)((c.rx * lv.ny + c.ry) * lv.nz + c.rz);
     return true;
-}
-
-AICB_DEV bool caster_valid(const Caster &c, const Ray &r) {
-    const bool any_nan = (c.tmx != c.tmx) | (c.tmy != c.tmy) | (c.tmz != c.tmz);
-    const bool any_fin = isfinite(c.tmx) | isfinite(c.tmy) | isfinite(c.tmz);
-    return r.steppable & !any_nan & any_fin;
 }
 
 // One State::step (raycast.rs:577-626) on the active caster, with incremental index update.
 // Returns true if the new cube is outside the level (the "exit" step of raycast.rs:265-274).
-AICB_DEV bool caster_step(Caster &c, const Ray &r, const Level &lv) {
+AICB_DEV bool caster_step(Caster &c, const Ray &r, int nx, int ny, int nz) {
     bool exited;
     if (c.tmx < c.tmy) {
         if (c.tmx < c.tmz) {
-            c.last_t = c.tmx; c.cx += r.sx; c.tmx += r.tdx;
+            c.last_t = c.tmx; c.rx += r.sx; c.tmx += r.tdx;
             c.face = r.sx > 0 ? AICB_FACE_NX : AICB_FACE_PX;
-            c.idx += (uint32_t)(r.sx * lv.sy_sz);
-            exited = r.sx > 0 ? (c.cx >= lv.hi[0]) : (c.cx < lv.lo[0]);
+            c.idx += (uint32_t)(r.sx * ny * nz);
+            exited = (uint32_t)c.rx >= (uint32_t)nx;
         } else {
-            c.last_t = c.tmz; c.cz += r.sz; c.tmz += r.tdz;
+            c.last_t = c.tmz; c.rz += r.sz; c.tmz += r.tdz;
             c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ;
             c.idx += (uint32_t)r.sz;
-            exited = r.sz > 0 ? (c.cz >= lv.hi[2]) : (c.cz < lv.lo[2]);
+            exited = (uint32_t)c.rz >= (uint32_t)nz;
         }
     } else {
         if (c.tmy < c.tmz) {
-            c.last_t = c.tmy; c.cy += r.sy; c.tmy += r.tdy;
+            c.last_t = c.tmy; c.ry += r.sy; c.tmy += r.tdy;
             c.face = r.sy > 0 ? AICB_FACE_NY : AICB_FACE_PY;
-            c.idx += (uint32_t)(r.sy * lv.sz);
-            exited = r.sy > 0 ? (c.cy >= lv.hi[1]) : (c.cy < lv.lo[1]);
+            c.idx += (uint32_t)(r.sy * nz);
+            exited = (uint32_t)c.ry >= (uint32_t)ny;
         } else {
-            c.last_t = c.tmz; c.cz += r.sz; c.tmz += r.tdz;
+            c.last_t = c.tmz; c.rz += r.sz; c.tmz += r.tdz;
             c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ;
             c.idx += (uint32_t)r.sz;
-            exited = r.sz > 0 ? (c.cz >= lv.hi[2]) : (c.cz < lv.lo[2]);
+            exited = (uint32_t)c.rz >= (uint32_t)nz;
         }
     }
     return exited;
 }
 
 // RaycastStep::intersection_point (raycast.rs:409-439) for the caster's current (un-stepped)
-// state, against the ray origin (ox,oy,oz) of that level.
-AICB_DEV void intersection_point(const Caster &c, const Ray &r, double ox, double oy, double oz, double ip[3]) {
+// state (cube given in absolute coordinates of its level), against that level's ray origin.
+AICB_DEV void intersection_point(const Caster &c, const Ray &r, int cx, int cy, int cz, double ox, double oy, double oz,
+                                 double ip[3]) {
     if (c.face == AICB_FACE_WITHIN) {
         ip[0] = ox; ip[1] = oy; ip[2] = oz;
         return;
@@ -274,7 +288,7 @@ AICB_DEV void intersection_point(const Caster &c, const Ray &r, double ox, doubl
     const double d[3] = {r.dx, r.dy, r.dz};
     const double o[3] = {ox, oy, oz};
     const int s[3] = {r.sx, r.sy, r.sz};
-    const int cu[3] = {c.cx, c.cy, c.cz};
+    const int cu[3] = {cx, cy, cz};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         double p = (double)cu[a];
@@ -312,7 +326,7 @@ AICB_DEV uint32_t light_outside(const DeviceScene &s, int x, int y, int z) {
 }
 
 // SpaceRaytracer::get_packed_light (sr.rs:241-246)
-AICB_DEV uint32_t get_packed_light(const DeviceScene &s, int x, int y, int z, uint32_t &texels) {
+AICB_NOINLINE uint32_t get_packed_light(const DeviceScene &s, int x, int y, int z, uint32_t &texels) {
     uint32_t dx = (uint32_t)(x - s.lo[0]), dy = (uint32_t)(y - s.lo[1]), dz = (uint32_t)(z - s.lo[2]);
     if ((dx >= (uint32_t)s.size[0]) | (dy >= (uint32_t)s.size[1]) | (dz >= (uint32_t)s.size[2]))
         return light_outside(s, x, y, z);
@@ -321,10 +335,10 @@ AICB_DEV uint32_t get_packed_light(const DeviceScene &s, int x, int y, int z, ui
     return __ldg(s.light + ((size_t)dx * s.size[1] + dy) * s.size[2] + dz);
 }
 
-AICB_DEV void texel_value_ao(const DeviceScene &s, uint32_t t, float out[4]) {  // data.rs:145-158
-    out[0] = __ldg(s.lut + (t & 255));
-    out[1] = __ldg(s.lut + ((t >> 8) & 255));
-    out[2] = __ldg(s.lut + ((t >> 16) & 255));
+AICB_DEV void texel_value_ao(const float *lut, uint32_t t, float out[4]) {  // data.rs:145-158
+    out[0] = lut[t & 255];
+    out[1] = lut[(t >> 8) & 255];
+    out[2] = lut[(t >> 16) & 255];
     uint32_t st = t >> 24;
     out[3] = (st == 255) ? 1.0f : (st == 128 ? 0.25f : 0.0f);
 }
@@ -334,10 +348,13 @@ AICB_DEV double rem_euclid1(double x) {
     return r < 0.0 ? r + 1.0 : r;
 }
 
-// get_interpolated_light (sr.rs:248-359)
-AICB_DEV void interpolated_light(const DeviceScene &s, uint32_t mode, int cube_x, int cube_y, int cube_z, int face,
-                                 const double sp[3], float out[3], uint32_t &texels) {
+// get_interpolated_light (sr.rs:248-359). `lut` is the shared-memory copy of the decode table.
+AICB_NOINLINE void interpolated_light(const DeviceScene &s, const float *lut, uint32_t mode, int cube_x, int cube_y,
+                                      int cube_z, int face, double spx, double spy, double spz, float out[3],
+                                      uint32_t *texels_out) {
     const double eps = 0.5 / 256.0;
+    const double sp[3] = {spx, spy, spz};
+    uint32_t texels = 0;
     // Face::rotation_from_nz (face.rs:395-405): axis + sign of the images of +X and +Y
     int a1, s1, a2, s2, an, sn;
     switch (face) {
@@ -383,7 +400,7 @@ AICB_DEV void interpolated_light(const DeviceScene &s, uint32_t mode, int cube_x
         if (sn != 0) p[an] = sp[an] + (double)sn * along;
         const double b1 = p[a1], b2 = p[a2];
         uint32_t tex[4];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 4; k++) {
             // k: 0 near12, 1 near1far2, 2 near2far1, 3 far12
             p[a1] = b1 + ((k & 2) ? hi1 : lo1);
@@ -395,10 +412,10 @@ AICB_DEV void interpolated_light(const DeviceScene &s, uint32_t mode, int cube_x
         }
         if ((tex[1] >> 24) != 255 && (tex[2] >> 24) != 255) tex[3] = tex[0];  // sr.rs:317-321
         float v0[4], v1[4], v2[4], v3[4], cur[4];
-        texel_value_ao(s, tex[0], v0);
-        texel_value_ao(s, tex[1], v1);
-        texel_value_ao(s, tex[2], v2);
-        texel_value_ao(s, tex[3], v3);
+        texel_value_ao(lut, tex[0], v0);
+        texel_value_ao(lut, tex[1], v1);
+        texel_value_ao(lut, tex[2], v2);
+        texel_value_ao(lut, tex[3], v3);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float ab = v0[i] + (v1[i] - v0[i]) * m2;
@@ -421,413 +438,46 @@ AICB_DEV void interpolated_light(const DeviceScene &s, uint32_t mode, int cube_x
         float v = result[i] / w;
         out[i] = (v == 0.0f) ? 0.0f : v;
     }
+    *texels_out = texels;
 }
 
-// ---- per-ray tracing state -------------------------------------------------------------------------
-template <bool AUX>
-struct AuxState {};
-template <>
-struct AuxState<true> {
-    double depth;
-    int hit_cube[3];
-    int hit_voxel[3];
-    int hit_res;
-    int hit_face;
-    bool have_hit;
-    uint32_t n_outer, n_inner, n_hits, n_texels, n_blocks;
-};
-
-// A surface remembered between discovery and shading (Volumetric mode pairs it with the next
-// event's t, surface.rs:460-490).  Illumination depends only on geometry, so it is evaluated at
-// discovery and carried as three floats instead of carrying the intersection point.
-template <int LC, bool AUX>
-struct PendingSurface {
-    uint32_t pal;      // global palette entry index
-    double t;
-    float illum[3];
-    int cube[3];
-    uint32_t packed;   // voxel x | y<<8 | z<<16 | face<<24 ; resolution in hit_res
-    int res;
-};
-
-template <bool VOLUMETRIC, int LC, bool AUX>
-struct Tracer {
-    const TraceParams &P;
-    float lr, lg, lb, T;          // ColorBuf (raytracer_components.rs:20-39)
-    uint32_t steps;               // primary_cubes_traced (sr.rs:612)
-    double t_to_abs;              // sr.rs:146
-    float t_to_view;              // sr.rs:149-151
-    bool have_fog;
-    float fog_r, fog_g, fog_b, fog_blend;
-    AuxState<AUX> aux;
-    bool have_last;
-    PendingSurface<LC, AUX> last;
-
-    __device__ explicit Tracer(const TraceParams &p) : P(p) {}
-
-    // count_step_should_stop (sr.rs:625-656); the EnterSpace / Incomplete hits are no-ops for ColorBuf
-    AICB_DEV bool count_stop() {
-        steps += 1;
-        if (steps > 1000) return true;
-        return T < (1.0f / 256.0f);
-    }
-
-    // distance_fog (sr.rs:745-768)
-    AICB_DEV float fog_amount(double t) const {
-        float rel = (float)t * t_to_view;
-        rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
-        float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
-        float fudged = fog_exponential / 0.79810348f;
-        float p4 = (rel * rel) * (rel * rel);
-        return zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
-    }
-
-    // Surface::to_light + trace_through_surface (surface.rs:73-106, sr.rs:697-717)
-    AICB_DEV void shade(float cr, float cg, float cb, float ca, float er, float eg, float eb,
-                        const PendingSurface<LC, AUX> &sf) {
-        if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
-            if (ca > P.threshold) { ca = 1.0f; } else { cr = cg = cb = ca = 0.0f; }
-        }
-        if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) return;
-        float ir = 1.0f, ig = 1.0f, ib = 1.0f;
-        if (LC != LC_NONE) { ir = sf.illum[0]; ig = sf.illum[1]; ib = sf.illum[2]; }
-        float orr = ps_mul(ps_mul(cr, ir), ca) + er;   // reflect + emission (color.rs:708-710)
-        float og = ps_mul(ps_mul(cg, ig), ca) + eg;
-        float ob = ps_mul(ps_mul(cb, ib), ca) + eb;
-        float tr = 1.0f - ca;
-        if (have_fog) {
-            float fa = fog_amount(sf.t);
-            float comp = 1.0f - fa;
-            orr = ps_mul(orr, comp) + ps_mul(fog_r, fa);
-            og = ps_mul(og, comp) + ps_mul(fog_g, fa);
-            ob = ps_mul(ob, comp) + ps_mul(fog_b, fa);
-            tr = tr * comp;
-        }
-        // add_color_internal (raytracer_components.rs:87-92)
-        lr = lr + orr * T;
-        lg = lg + og * T;
-        lb = lb + ob * T;
-        T = T * tr;
-        if (AUX) {
-            aux_hit(sf);
-        }
-    }
-
-    AICB_DEV void aux_hit(const PendingSurface<LC, AUX> &sf) {
-        if constexpr (AUX) {
-            aux.depth = fmin(aux.depth, sf.t);
-            aux.n_hits++;
-            if (!aux.have_hit) {
-                aux.have_hit = true;
-                aux.hit_cube[0] = sf.cube[0]; aux.hit_cube[1] = sf.cube[1]; aux.hit_cube[2] = sf.cube[2];
-                aux.hit_voxel[0] = sf.packed & 255; aux.hit_voxel[1] = (sf.packed >> 8) & 255;
-                aux.hit_voxel[2] = (sf.packed >> 16) & 255;
-                aux.hit_face = sf.packed >> 24;
-                aux.hit_res = sf.res;
-            }
-        }
-    }
-
-    AICB_DEV void shade_pending(const PendingSurface<LC, AUX> &sf) {
-        float4 c = __ldg(P.scene.palette + 2 * (size_t)sf.pal);
-        float4 e = __ldg(P.scene.palette + 2 * (size_t)sf.pal + 1);
-        shade(c.x, c.y, c.z, c.w, e.x, e.y, e.z, sf);
-    }
-
-    // trace_through_span (sr.rs:720-740) with apply_transmittance (raytracer_components.rs:215-258)
-    AICB_DEV void shade_span(const PendingSurface<LC, AUX> &sf, double exit_t) {
-        float4 c = __ldg(P.scene.palette + 2 * (size_t)sf.pal);
-        float4 e = __ldg(P.scene.palette + 2 * (size_t)sf.pal + 1);
-        float thickness = fmaxf((float)((exit_t - sf.t) * t_to_abs), 0.0f);
-        float alpha, coeff;
-        float cr = c.x, cg = c.y, cb = c.z;
-        if (thickness == 0.0f) {
-            if (c.w == 1.0f) { alpha = c.w; coeff = 1.0f; }
-            else { cr = cg = cb = 0.0f; alpha = 0.0f; coeff = 0.0f; }
-        } else {
-            float unit_t = 1.0f - c.w;
-            float depth_t = powf_exact(unit_t, thickness);
-            alpha = zo_clamped(1.0f - depth_t);
-            float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
-            coeff = fmaxf(k, 0.0f);
-        }
-        float k = ps_clamped(coeff);
-        shade(cr, cg, cb, alpha, ps_mul(e.x, k), ps_mul(e.y, k), ps_mul(e.z, k), sf);
-    }
-
-    // compute_illumination (surface.rs:113-206) at discovery time
-    AICB_DEV void illuminate(PendingSurface<LC, AUX> &sf, const double ip[3]) {
-        if constexpr (LC == LC_FLAT) {
-            int x = sf.cube[0], y = sf.cube[1], z = sf.cube[2];
-            int face = sf.packed >> 24;
-            if (face != AICB_FACE_WITHIN) {
-                int d = face >= AICB_FACE_PX ? 1 : -1;
-                int ax = (face - 1) % 3;
-                if (ax == 0) x += d; else if (ax == 1) y += d; else z += d;
-            }
-            uint32_t tx = 0;
-            uint32_t t = get_packed_light(P.scene, x, y, z, tx);
-            if constexpr (AUX) aux.n_texels += tx;
-            sf.illum[0] = __ldg(P.scene.lut + (t & 255));
-            sf.illum[1] = __ldg(P.scene.lut + ((t >> 8) & 255));
-            sf.illum[2] = __ldg(P.scene.lut + ((t >> 16) & 255));
-        } else if constexpr (LC == LC_INTERP) {
-            uint32_t tx = 0;
-            interpolated_light(P.scene, P.lighting, sf.cube[0], sf.cube[1], sf.cube[2], sf.packed >> 24, ip, sf.illum, tx);
-            if constexpr (AUX) aux.n_texels += tx;
-        }
-    }
-
-    // One TraceStep through the Surface-mode loop (sr.rs:206-225) or DepthIter + the Volumetric
-    // loop (surface.rs:460-490, sr.rs:185-203).  kind: 0 EnterSurface, 1 Invisible, 2 EnterBlock.
-    // Returns true when tracing must stop.
-    AICB_DEV bool process(int kind, double t, const PendingSurface<LC, AUX> &sf) {
-        if constexpr (!VOLUMETRIC) {
-            if (count_stop()) return true;
-            if (kind == 0) shade_pending(sf);
-            return false;
-        } else {
-            const bool emit_span = have_last;
-            PendingSurface<LC, AUX> span = last;
-            double exit_t = t;
-            if (kind == 0) {
-                exit_t = sf.t;
-                last = sf;
-                have_last = true;
-            } else {
-                have_last = false;
-            }
-            if (count_stop()) return true;
-            if (emit_span) shade_span(span, exit_t);
-            if (kind == 2) {
-                if (count_stop()) return true;  // the buffered DepthStep::EnterBlock
-            }
-            return false;
-        }
-    }
-
-    // trace_ray_impl (sr.rs:135-238)
-    __device__ void trace(double ox, double oy, double oz, double dx, double dy, double dz) {
-        const DeviceScene &S = P.scene;
-        lr = lg = lb = 0.0f;
-        T = 1.0f;
-        steps = 0;
-        have_last = false;
-        if constexpr (AUX) {
-            aux.depth = __longlong_as_double(0x7ff0000000000000LL);
-            aux.have_hit = false;
-            aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
-        }
-
-        // Sky::sample (sky.rs:32-41)
-        float sky_r = 0.0f, sky_g = 0.0f, sky_b = 0.0f;
-        if (P.include_sky) {
-            int k = 0;
-            if (S.sky_kind) k = ((dx >= 0.0) << 2) + ((dy >= 0.0) << 1) + (dz >= 0.0);
-            sky_r = S.sky_colors[k][0]; sky_g = S.sky_colors[k][1]; sky_b = S.sky_colors[k][2];
-        }
-        t_to_abs = sqrt(dx * dx + dy * dy + dz * dz);
-        t_to_view = (float)(t_to_abs / P.view_distance);
-        have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
-        fog_r = sky_r; fog_g = sky_g; fog_b = sky_b;
-        fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
-
-        // Parameters::new (raycast.rs:749-771)
-        Ray r;
-        r.ox = ox; r.oy = oy; r.oz = oz;
-        if (!((fabs(dx) < 1e100) & (fabs(dy) < 1e100) & (fabs(dz) < 1e100))) { dx = dy = dz = 0.0; }
-        r.dx = dx; r.dy = dy; r.dz = dz;
-        r.sx = signum_101(dx); r.sy = signum_101(dy); r.sz = signum_101(dz);
-        r.tdx = 1.0 / fabs(dx); r.tdy = 1.0 / fabs(dy); r.tdz = 1.0 / fabs(dz);
-        r.half_over_len = 0.5 / sqrt(dx * dx + dy * dy + dz * dz);
-        r.steppable = (r.sx | r.sy | r.sz) != 0;
-
-        Level outer;
-        outer.lo[0] = S.lo[0]; outer.lo[1] = S.lo[1]; outer.lo[2] = S.lo[2];
-        outer.hi[0] = S.lo[0] + S.size[0]; outer.hi[1] = S.lo[1] + S.size[1]; outer.hi[2] = S.lo[2] + S.size[2];
-        outer.sy_sz = S.size[1] * S.size[2];
-        outer.sz = S.size[2];
-        outer.base = 0;
-
-        Caster c;
-        bool running = caster_begin(c, r, ox, oy, oz, outer);
-        bool valid = running && caster_valid(c, r);
-
-        // level state
-        bool inner = false;
-        Level lv = outer;
-        Caster saved;            // outer caster while inside a block
-        bool saved_valid = false;
-        double sub_ox = 0, sub_oy = 0, sub_oz = 0, antiscale = 1.0;
-        uint32_t pal_off = 0;
-        int res = 1;
-        bool need_advance = false;
-
-        while (running) {
-            if (need_advance) {
-                bool exited;
-                if (!valid) {
-                    // cannot step: the iterator ends without an exit step (raycast.rs:245-249)
-                    exited = true;
-                    if (inner) { inner = false; c = saved; lv = outer; valid = saved_valid; need_advance = true; continue; }
-                    break;
-                }
-                exited = caster_step(c, r, lv);
-                if (exited) {
-                    // exit step: Invisible at this t (surface.rs:296-301, 388-393)
-                    PendingSurface<LC, AUX> none;
-                    if (process(1, inner ? c.last_t * antiscale : c.last_t, none)) break;
-                    if (inner) { inner = false; c = saved; lv = outer; valid = saved_valid; need_advance = true; continue; }
-                    break;
-                }
-            }
-            need_advance = true;
-
-            // ---- look up the current cube / voxel --------------------------------------------
-            PendingSurface<LC, AUX> sf;
-            int kind;  // TraceStep kind
-            double t;
-            if (!inner) {
-                if constexpr (AUX) aux.n_outer++;
-                uint32_t cell = S.wide_cells ? __ldg((const uint32_t *)S.cells + c.idx)
-                                             : (uint32_t)__ldg((const uint16_t *)S.cells + c.idx);
-                uint32_t ck = S.wide_cells ? (cell >> 16) : (cell >> 14);
-                uint32_t id = S.wide_cells ? (cell & 0xffffu) : (cell & 0x3fffu);
-                t = c.last_t;
-                if (ck == KIND_INVISIBLE) {
-                    kind = 1;
-                } else {
-                    const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + id);
-                    uint4 b0 = __ldg(bp);
-                    uint4 b1 = __ldg(bp + 1);
-                    if (ck == KIND_SINGLE) {
-                        kind = 0;
-                        sf.pal = b1.y;
-                        sf.t = t;
-                        sf.cube[0] = c.cx; sf.cube[1] = c.cy; sf.cube[2] = c.cz;
-                        sf.packed = (uint32_t)c.face << 24;
-                        sf.res = 1;
-                        if constexpr (LC == LC_INTERP) {
-                            double ip[3];
-                            intersection_point(c, r, r.ox, r.oy, r.oz, ip);
-                            illuminate(sf, ip);
-                        } else if constexpr (LC == LC_FLAT) {
-                            double ip[3] = {0, 0, 0};
-                            illuminate(sf, ip);
-                        }
-                    } else {
-                        // recursive_raycast (raycast.rs:458-476) + TraceStep::EnterBlock (surface.rs:334-352)
-                        if constexpr (AUX) aux.n_blocks++;
-                        PendingSurface<LC, AUX> none;
-                        if (process(2, t, none)) break;
-                        res = (int)(b0.x >> 8);
-                        Level in;
-                        in.lo[0] = (int16_t)(b0.y & 0xffff); in.lo[1] = (int16_t)(b0.y >> 16); in.lo[2] = (int16_t)(b0.z & 0xffff);
-                        int vsx = (int)(b0.z >> 16), vsy = (int)(b0.w & 0xffff), vsz = (int)(b0.w >> 16);
-                        in.hi[0] = in.lo[0] + vsx; in.hi[1] = in.lo[1] + vsy; in.hi[2] = in.lo[2] + vsz;
-                        in.sy_sz = vsy * vsz;
-                        in.sz = vsz;
-                        in.base = b1.x;
-                        double fres = (double)res;
-                        double so_x = (r.ox - (double)c.cx) * fres;
-                        double so_y = (r.oy - (double)c.cy) * fres;
-                        double so_z = (r.oz - (double)c.cz) * fres;
-                        Caster ic;
-                        if (caster_begin(ic, r, so_x, so_y, so_z, in)) {
-                            saved = c;
-                            saved_valid = valid;
-                            c = ic;
-                            lv = in;
-                            valid = caster_valid(c, r);
-                            inner = true;
-                            sub_ox = so_x; sub_oy = so_y; sub_oz = so_z;
-                            antiscale = 1.0 / fres;
-                            pal_off = b1.y;
-                            need_advance = false;
-                        }
-                        continue;
-                    }
-                }
-            } else {
-                if constexpr (AUX) aux.n_inner++;
-                uint32_t v = __ldg(S.bricks + c.idx);
-                t = c.last_t * antiscale;  // surface.rs:385-386
-                if (v & 0x8000u) {
-                    kind = 1;
-                } else {
-                    kind = 0;
-                    sf.pal = pal_off + v;
-                    sf.t = t;
-                    sf.cube[0] = saved.cx; sf.cube[1] = saved.cy; sf.cube[2] = saved.cz;
-                    sf.packed = (uint32_t)c.cx | ((uint32_t)c.cy << 8) | ((uint32_t)c.cz << 16) | ((uint32_t)c.face << 24);
-                    sf.res = res;
-                    if constexpr (LC == LC_INTERP) {
-                        double ip[3];
-                        intersection_point(c, r, sub_ox, sub_oy, sub_oz, ip);
-                        ip[0] = ip[0] * antiscale + (double)saved.cx;  // surface.rs:406-407
-                        ip[1] = ip[1] * antiscale + (double)saved.cy;
-                        ip[2] = ip[2] * antiscale + (double)saved.cz;
-                        illuminate(sf, ip);
-                    } else if constexpr (LC == LC_FLAT) {
-                        double ip[3] = {0, 0, 0};
-                        illuminate(sf, ip);
-                    }
-                }
-            }
-            if (process(kind, t, sf)) break;
-        }
-
-        // finish (sr.rs:658-693): the sky is an opaque hit at t = inf
-        if (P.include_sky) {
-            lr = lr + (sky_r * 1.0f) * T;
-            lg = lg + (sky_g * 1.0f) * T;
-            lb = lb + (sky_b * 1.0f) * T;
-            T = T * (1.0f - 1.0f);
-        }
-        if (P.debug_pixel_cost) {
-            // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
-            float k = ps_clamped((float)steps);
-            float red = ps_clamped(ps_mul(0.02f, k) * 1.0f);
-            float green = ps_clamped(ps_mul(0.002f, k) * 1.0f);
-            float rgba[4];
-            colorbuf_to_rgba(lr, lg, lb, T, rgba);
-            float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
-            lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
-            T = 0.0f;
-        }
-    }
-
-    // Rgba::from(ColorBuf) (raytracer_components.rs:122-146)
-    static AICB_DEV void colorbuf_to_rgba(float l0, float l1, float l2, float tr, float out[4]) {
-        if (tr >= 1.0f) { out[0] = out[1] = out[2] = out[3] = 0.0f; return; }
-        float alpha = 1.0f - tr;
-        float c[3] = {l0 / alpha, l1 / alpha, l2 / alpha};
-        bool ok = true;
+// Rgba::from(ColorBuf) (raytracer_components.rs:122-146)
+AICB_DEV void colorbuf_to_rgba(float l0, float l1, float l2, float tr, float out[4]) {
+    if (tr >= 1.0f) { out[0] = out[1] = out[2] = out[3] = 0.0f; return; }
+    float alpha = 1.0f - tr;
+    float c[3] = {l0 / alpha, l1 / alpha, l2 / alpha};
+    bool ok = true;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            if (c[i] > 0.0f) {} else if (c[i] == 0.0f) c[i] = 0.0f; else ok = false;
-        }
-        if (!ok) { c[0] = 1.0f; c[1] = 0.0f; c[2] = 0.0f; }
-        out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
-        out[3] = (alpha > 0.0f && alpha <= 1.0f) ? alpha : (alpha == 0.0f ? 0.0f : 1.0f);
+    for (int i = 0; i < 3; i++) {
+        if (c[i] > 0.0f) {} else if (c[i] == 0.0f) c[i] = 0.0f; else ok = false;
     }
-};
+    if (!ok) { c[0] = 1.0f; c[1] = 0.0f; c[2] = 0.0f; }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+    out[3] = (alpha > 0.0f && alpha <= 1.0f) ? alpha : (alpha == 0.0f ? 0.0f : 1.0f);
+}
 
-// component_to_srgb8 (color.rs:1038-1054): `as u8` saturates, round() is half-away-from-zero
-AICB_DEV unsigned char sat_u8(float v) {
+AICB_DEV unsigned char sat_u8(float v) {  // `as u8`: saturating, NaN -> 0
     if (!(v > 0.0f)) return 0;
     if (v >= 255.0f) return 255;
     return (unsigned char)v;
 }
-AICB_DEV unsigned char component_to_srgb8(float c) {
-    float s = (c <= 0.0031308f) ? c * (323.0f / 25.0f) : (211.0f * powf_exact(c, 5.0f / 12.0f) - 11.0f) / 200.0f;
-    return sat_u8(roundf(s * 255.0f));
+
+// component_to_srgb8 (color.rs:1038-1054) as a search: thr[k] (k = 1..255) is the smallest f32 whose
+// encoding is >= k, computed on the host with the platform powf; the encoding is monotone in c.
+AICB_DEV unsigned char component_to_srgb8(const float *thr, float c) {
+    int lo = 0, hi = 255;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int mid = (lo + hi + 1) >> 1;
+        if (c >= thr[mid]) lo = mid; else hi = mid - 1;
+    }
+    return (unsigned char)lo;
 }
 
 // Camera::post_process_color + to_srgb8 (camera_struct.rs:376-382, graphics_options.rs:352-368, color.rs:669-676)
-AICB_DEV uchar4 encode_srgb8(const TraceParams &P, float l0, float l1, float l2, float tr) {
+AICB_DEV uchar4 encode_srgb8(const TraceParams &P, const float *thr, float l0, float l1, float l2, float tr) {
     float rgba[4];
-    Tracer<false, LC_NONE, false>::colorbuf_to_rgba(l0, l1, l2, tr, rgba);
+    colorbuf_to_rgba(l0, l1, l2, tr, rgba);
     float c[3] = {ps_mul(rgba[0], P.exposure), ps_mul(rgba[1], P.exposure), ps_mul(rgba[2], P.exposure)};
     if (isfinite(P.maximum_intensity)) {
         if (P.tone_mapping == AICB_TONE_CLAMP) {
@@ -840,7 +490,7 @@ AICB_DEV uchar4 encode_srgb8(const TraceParams &P, float l0, float l1, float l2,
             for (int i = 0; i < 3; i++) c[i] = ps_mul(c[i], s);
         }
     }
-    return make_uchar4(component_to_srgb8(c[0]), component_to_srgb8(c[1]), component_to_srgb8(c[2]),
+    return make_uchar4(component_to_srgb8(thr, c[0]), component_to_srgb8(thr, c[1]), component_to_srgb8(thr, c[2]),
                        sat_u8(roundf(rgba[3] * 255.0f)));
 }
 
@@ -882,118 +532,529 @@ AICB_DEV void pixel_ray(const TraceParams &P, uint32_t xch, uint32_t ych, int sa
     d[0] = farp[0] - nearp[0]; d[1] = farp[1] - nearp[1]; d[2] = farp[2] - nearp[2];
 }
 
-constexpr int TILE_W = 8, TILE_H = 4;
-constexpr int WARPS_PER_BLOCK = 4;
+// ---- per-lane state ----------------------------------------------------------------------------------
+template <bool AUX>
+struct AuxState {};
+template <>
+struct AuxState<true> {
+    double depth;
+    int hit_cube[3];
+    int hit_voxel[3];
+    int hit_res;
+    int hit_face;
+    bool have_hit;
+    uint32_t n_outer, n_inner, n_hits, n_texels, n_blocks;
+};
 
-// The frame kernel: persistent warps, one 8x4 pixel tile per warp at a time
-// (replaces the Rayon dispatch trace_scene_to_image_impl, renderer.rs:516-556).
+// A surface remembered between discovery and shading (Volumetric mode pairs it with the next
+// event's t, surface.rs:460-490).  Illumination depends only on geometry, so it is evaluated at
+// discovery and carried as three floats instead of carrying the intersection point.
+struct PendingSurface {
+    double t;
+    uint32_t pal;      // global palette entry index
+    float illum[3];
+    int cube[3];
+    uint32_t packed;   // voxel x | y<<8 | z<<16 | face<<24
+    int res;
+};
+
+enum LaneState : int { ST_IDLE = 0, ST_MARCH = 1, ST_EVENT = 2, ST_DONE = 3, ST_EXHAUSTED = 4 };
+enum EventKind : int { EV_SURFACE = 0, EV_INVISIBLE = 1, EV_ENTER_BLOCK = 2 };
+enum EventPost : int { POST_CONTINUE = 0, POST_POP = 1, POST_FINISH = 2 };
+
+// The frame kernel (replaces the Rayon dispatch trace_scene_to_image_impl, renderer.rs:516-556, and
+// everything below it).
 template <bool VOLUMETRIC, int LC, bool AUX>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
 trace_kernel(const __grid_constant__ TraceParams P) {
+    __shared__ float s_tables[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tables[i] = P.scene.tables[i];
+    __syncthreads();
+    const float *lut = s_tables;
+    const float *thr = s_tables + 256;
+
+    const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
+    const bool explicit_rays = P.rays != nullptr;
+    const int n_samples = (!explicit_rays && P.antialias) ? 4 : 1;
+
     unsigned long long cubes_traced = 0;
     unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_texels = 0, n_blocks = 0;
-    const uint32_t n_tiles = P.tiles_x * P.tiles_y;
-    const bool explicit_rays = P.rays != nullptr;
+
+    // ---- per-lane task state ---------------------------------------------------------------------
+    int st = ST_IDLE;
+    uint32_t task = 0;             // index into the tile-ordered task sequence
+    uint32_t px = 0, py = 0;       // framebuffer pixel of the task
+    size_t out_index = 0;
+    int sample = 0;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accT = 0.f;  // AA sums
+    uint32_t steps_total = 0;
+    AuxState<AUX> aa_aux;
+    bool aa_got = false;
+
+    // ---- per-ray state -----------------------------------------------------------------------------
+    Ray r;
+    Caster c, saved;
+    bool valid = false, saved_valid = false, inner = false, need_advance = false;
+    int nx = 0, ny = 0, nz = 0;          // sizes of the active level
+    uint32_t blk0y = 0, blk0z = 0;       // packed voxel bounds of the entered block (lo16|lo16, lo16|size16)
+    uint32_t pal_off = 0;
+    int res = 1;
+    float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.f;
+    uint32_t steps = 0;
+    double t_to_abs = 0.0;
+    float t_to_view = 0.f;
+    bool have_fog = false;
+    float sky_r = 0.f, sky_g = 0.f, sky_b = 0.f, fog_blend = 0.f;
+    bool have_last = false;
+    PendingSurface last;
+    AuxState<AUX> aux;
+    // event
+    int ev_kind = 0, ev_post = 0;
+    double ev_t = 0.0;
+    uint32_t ev_cell = 0;
+
+    auto count_stop = [&]() -> bool {  // count_step_should_stop (sr.rs:625-656)
+        steps += 1;
+        if (steps > 1000) return true;
+        return T < (1.0f / 256.0f);
+    };
+    auto pop_level = [&]() {
+        inner = false;
+        c = saved;
+        valid = saved_valid;
+        nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
+        need_advance = true;
+    };
 
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-
-        uint32_t lx, ly_local;  // pixel within the (local) image
-        bool active;
-        size_t out_index;
-        uint32_t gy = 0;
-        if (explicit_rays) {
-            size_t i = (size_t)tile * 32 + lane;
-            active = i < P.n_rays;
-            out_index = i;
-            lx = ly_local = 0;
-        } else {
-            const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-            lx = tx * TILE_W + (lane & (TILE_W - 1));
-            ly_local = ty * TILE_H + (lane / TILE_W);
-            active = lx < P.fb_width && ly_local < P.local_rows;
-            out_index = (size_t)ly_local * P.fb_width + lx;
-            // local row -> framebuffer row (row-strip sharding)
-            if (P.shard_count > 1) {
-                uint32_t strip_local = ly_local / P.strip_rows;
-                gy = (strip_local * P.shard_count + P.shard_index) * P.strip_rows + ly_local % P.strip_rows;
-            } else {
-                gy = ly_local;
+        // =========================== REFILL: hand new tasks to idle lanes =============================
+        {
+            const unsigned idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
+            const unsigned running = __ballot_sync(0xffffffffu, st == ST_MARCH || st == ST_EVENT || st == ST_DONE);
+            if (idle && (running == 0 || __popc(idle) >= (int)P.refill_threshold)) {
+                const int n = __popc(idle);
+                uint32_t base = 0;
+                const int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(P.task_counter, (unsigned)n);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (st == ST_IDLE) {
+                    task = base + __popc(idle & ((1u << lane) - 1u));
+                    if (task >= P.n_tasks) {
+                        st = ST_EXHAUSTED;
+                    } else {
+                        bool active;
+                        if (explicit_rays) {
+                            active = task < P.n_rays;
+                            out_index = task;
+                        } else {
+                            const uint32_t tile = task >> 5, in_tile = task & 31;
+                            const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+                            px = tx * TILE_W + (in_tile & (TILE_W - 1));
+                            const uint32_t ly = ty * TILE_H + (in_tile / TILE_W);
+                            active = px < P.fb_width && ly < P.local_rows;
+                            out_index = (size_t)ly * P.fb_width + px;
+                            py = ly;
+                            if (P.shard_count > 1) {  // local row -> framebuffer row (row-strip sharding)
+                                uint32_t strip_local = ly / P.strip_rows;
+                                py = (strip_local * P.shard_count + P.shard_index) * P.strip_rows + ly % P.strip_rows;
+                            }
+                        }
+                        if (active) {
+                            st = ST_DONE;  // "previous sample finished" -> the finalize phase starts sample 0
+                            sample = -1;
+                            acc0 = acc1 = acc2 = accT = 0.f;
+                            steps_total = 0;
+                            aa_got = false;
+                        }  // else: stays IDLE and simply takes another task next round
+                    }
+                }
             }
+            if (__all_sync(0xffffffffu, st == ST_EXHAUSTED)) break;
         }
-        if (!active) continue;
 
-        Tracer<VOLUMETRIC, LC, AUX> tr(P);
-        float l0, l1, l2, tT;
-        uint32_t steps_total = 0;
-        double depth = 0;
-        if (explicit_rays) {
-            const double *rp = P.rays + 6 * out_index;
-            tr.trace(rp[0], rp[1], rp[2], rp[3], rp[4], rp[5]);
-            l0 = tr.lr; l1 = tr.lg; l2 = tr.lb; tT = tr.T;
-            steps_total = tr.steps;
-        } else if (!P.antialias) {
-            double o[3], d[3];
-            pixel_ray(P, lx, gy, -1, o, d);
-            tr.trace(o[0], o[1], o[2], d[0], d[1], d[2]);
-            l0 = tr.lr; l1 = tr.lg; l2 = tr.lb; tT = tr.T;
-            steps_total = tr.steps;
-        } else {
-            // 4 fixed sub-samples, ColorBuf::mean (renderer.rs:426-444, raytracer_components.rs:97-102)
-            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, sT = 0.0f;
-            AuxState<AUX> first_aux;
-            bool got = false;
-            double dmin = __longlong_as_double(0x7ff0000000000000LL);
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                double o[3], d[3];
-                pixel_ray(P, lx, gy, k, o, d);
-                tr.trace(o[0], o[1], o[2], d[0], d[1], d[2]);
-                s0 = s0 + tr.lr; s1 = s1 + tr.lg; s2 = s2 + tr.lb; sT = sT + tr.T;
-                steps_total += tr.steps;
+        // =========================== FINALIZE / START: ray boundaries ================================
+        if (st == ST_DONE) {
+            if (sample >= 0) {
+                // ---- finish (sr.rs:658-693): the sky is an opaque hit at t = inf ----
+                if (P.include_sky) {
+                    lr = lr + (sky_r * 1.0f) * T;
+                    lg = lg + (sky_g * 1.0f) * T;
+                    lb = lb + (sky_b * 1.0f) * T;
+                    T = T * (1.0f - 1.0f);
+                }
+                if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
+                    float k = ps_clamped((float)steps);
+                    float red = ps_clamped(ps_mul(0.02f, k) * 1.0f);
+                    float green = ps_clamped(ps_mul(0.002f, k) * 1.0f);
+                    float rgba[4];
+                    colorbuf_to_rgba(lr, lg, lb, T, rgba);
+                    float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
+                    lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
+                    T = 0.0f;
+                }
+                steps_total += steps;
+                acc0 = acc0 + lr; acc1 = acc1 + lg; acc2 = acc2 + lb; accT = accT + T;
                 if constexpr (AUX) {
-                    dmin = fmin(dmin, tr.aux.depth);
-                    n_outer += tr.aux.n_outer; n_inner += tr.aux.n_inner; n_hits += tr.aux.n_hits;
-                    n_texels += tr.aux.n_texels; n_blocks += tr.aux.n_blocks;
-                    if (!got && (tr.aux.have_hit || k == 0)) { first_aux = tr.aux; got = tr.aux.have_hit; }
+                    n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
+                    n_texels += aux.n_texels; n_blocks += aux.n_blocks;
+                    if (sample == 0) {
+                        aa_aux = aux;
+                        aa_got = aux.have_hit;
+                    } else {
+                        double dmin = fmin(aa_aux.depth, aux.depth);  // DepthBuf::mean = min (accum.rs:284-297)
+                        if (!aa_got && aux.have_hit) { aa_aux = aux; aa_got = true; }
+                        aa_aux.depth = dmin;
+                    }
                 }
             }
-            l0 = s0 / 4.0f; l1 = s1 / 4.0f; l2 = s2 / 4.0f; tT = sT / 4.0f;
-            if constexpr (AUX) {
-                tr.aux = first_aux;
-                tr.aux.depth = dmin;
-                tr.aux.n_outer = tr.aux.n_inner = tr.aux.n_hits = tr.aux.n_texels = tr.aux.n_blocks = 0;
+            sample += 1;
+            if (sample >= n_samples) {
+                // ---- store the pixel ----
+                float l0 = acc0, l1 = acc1, l2 = acc2, tT = accT;
+                if (n_samples == 4) {  // ColorBuf::mean (raytracer_components.rs:97-102)
+                    l0 = acc0 / 4.0f; l1 = acc1 / 4.0f; l2 = acc2 / 4.0f; tT = accT / 4.0f;
+                }
+                cubes_traced += steps_total;
+                if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, thr, l0, l1, l2, tT);
+                if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
+                if constexpr (AUX) {
+                    if (P.out_depth) P.out_depth[out_index] = aa_aux.depth;
+                    if (P.out_steps) P.out_steps[out_index] = steps_total;
+                    if (P.out_hit) {
+                        aicb_hit h;
+                        if (aa_aux.have_hit) {
+                            h.cube[0] = aa_aux.hit_cube[0]; h.cube[1] = aa_aux.hit_cube[1]; h.cube[2] = aa_aux.hit_cube[2];
+                            h.voxel[0] = aa_aux.hit_voxel[0]; h.voxel[1] = aa_aux.hit_voxel[1]; h.voxel[2] = aa_aux.hit_voxel[2];
+                            h.resolution = aa_aux.hit_res;
+                            h.face = aa_aux.hit_face;
+                        } else {
+                            h.cube[0] = h.cube[1] = h.cube[2] = -1;
+                            h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
+                            h.resolution = -1;
+                            h.face = -1;
+                        }
+                        P.out_hit[out_index] = h;
+                    }
+                }
+                st = ST_IDLE;
+            } else {
+                // ---- start the next ray of this task: trace_ray_impl prologue (sr.rs:135-180) ----
+                double o[3], d[3];
+                if (explicit_rays) {
+                    const double *rp = P.rays + 6 * out_index;
+                    o[0] = rp[0]; o[1] = rp[1]; o[2] = rp[2]; d[0] = rp[3]; d[1] = rp[4]; d[2] = rp[5];
+                } else {
+                    pixel_ray(P, px, py, n_samples == 4 ? sample : -1, o, d);
+                }
+                lr = lg = lb = 0.0f;
+                T = 1.0f;
+                steps = 0;
+                have_last = false;
+                inner = false;
+                if constexpr (AUX) {
+                    aux.depth = D_INF;
+                    aux.have_hit = false;
+                    aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
+                }
+                // Sky::sample (sky.rs:32-41)
+                sky_r = sky_g = sky_b = 0.0f;
+                if (P.include_sky) {
+                    int k = 0;
+                    if (S.sky_kind) k = ((d[0] >= 0.0) << 2) + ((d[1] >= 0.0) << 1) + (d[2] >= 0.0);
+                    sky_r = S.sky_colors[k][0]; sky_g = S.sky_colors[k][1]; sky_b = S.sky_colors[k][2];
+                }
+                t_to_abs = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                t_to_view = (float)(t_to_abs / P.view_distance);
+                have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
+                fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
+                // Parameters::new (raycast.rs:749-771)
+                r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+                if (!((fabs(d[0]) < 1e100) & (fabs(d[1]) < 1e100) & (fabs(d[2]) < 1e100))) { d[0] = d[1] = d[2] = 0.0; }
+                r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+                r.sx = signum_101(d[0]); r.sy = signum_101(d[1]); r.sz = signum_101(d[2]);
+                r.tdx = 1.0 / fabs(d[0]); r.tdy = 1.0 / fabs(d[1]); r.tdz = 1.0 / fabs(d[2]);
+                r.half_over_len = 0.5 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                Level lv;
+                lv.lox = S.lo[0]; lv.loy = S.lo[1]; lv.loz = S.lo[2];
+                lv.nx = S.size[0]; lv.ny = S.size[1]; lv.nz = S.size[2];
+                lv.base = 0;
+                nx = lv.nx; ny = lv.ny; nz = lv.nz;
+                Caster oc;
+                bool ovalid;
+                const bool running = caster_begin(oc, r, o[0], o[1], o[2], lv, &ovalid);
+                c = oc;
+                valid = ovalid;
+                need_advance = false;
+                st = running ? ST_MARCH : ST_DONE;
             }
         }
-        cubes_traced += steps_total;
-        (void)depth;
 
-        if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, l0, l1, l2, tT);
-        if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
-        if constexpr (AUX) {
-            n_outer += tr.aux.n_outer; n_inner += tr.aux.n_inner; n_hits += tr.aux.n_hits;
-            n_texels += tr.aux.n_texels; n_blocks += tr.aux.n_blocks;
-            if (P.out_depth) P.out_depth[out_index] = tr.aux.depth;
-            if (P.out_steps) P.out_steps[out_index] = steps_total;
-            if (P.out_hit) {
-                aicb_hit h;
-                if (tr.aux.have_hit) {
-                    h.cube[0] = tr.aux.hit_cube[0]; h.cube[1] = tr.aux.hit_cube[1]; h.cube[2] = tr.aux.hit_cube[2];
-                    h.voxel[0] = tr.aux.hit_voxel[0]; h.voxel[1] = tr.aux.hit_voxel[1]; h.voxel[2] = tr.aux.hit_voxel[2];
-                    h.resolution = tr.aux.hit_res;
-                    h.face = tr.aux.hit_face;
-                } else {
-                    h.cube[0] = h.cube[1] = h.cube[2] = -1;
-                    h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
-                    h.resolution = -1;
-                    h.face = -1;
+        // =========================== MARCH: cheap DDA steps until an event ===========================
+        while (st == ST_MARCH) {
+            if (need_advance) {
+                if (!valid) {  // cannot step: the iterator ends without an exit step (raycast.rs:245-249)
+                    if (inner) { pop_level(); continue; }
+                    st = ST_DONE;
+                    break;
                 }
-                P.out_hit[out_index] = h;
+                if (caster_step(c, r, nx, ny, nz)) {
+                    // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
+                    const double t = inner ? c.last_t * recip_pow2(res) : c.last_t;
+                    if (VOLUMETRIC && have_last) {
+                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = inner ? POST_POP : POST_FINISH;
+                        st = ST_EVENT;
+                        break;
+                    }
+                    if (count_stop()) { st = ST_DONE; break; }
+                    if (inner) { pop_level(); continue; }
+                    st = ST_DONE;
+                    break;
+                }
             }
+            need_advance = true;
+            if (!inner) {
+                if constexpr (AUX) aux.n_outer++;
+                const uint32_t cell = S.wide_cells ? __ldg((const uint32_t *)S.cells + c.idx)
+                                                   : (uint32_t)__ldg((const uint16_t *)S.cells + c.idx);
+                const uint32_t ck = S.wide_cells ? (cell >> 16) : (cell >> 14);
+                if (ck == KIND_INVISIBLE) {
+                    if (VOLUMETRIC && have_last) {
+                        ev_kind = EV_INVISIBLE; ev_t = c.last_t; ev_post = POST_CONTINUE;
+                        st = ST_EVENT;
+                        break;
+                    }
+                    if (count_stop()) { st = ST_DONE; break; }
+                    continue;
+                }
+                ev_kind = (ck == KIND_SINGLE) ? EV_SURFACE : EV_ENTER_BLOCK;
+                ev_t = c.last_t;
+                ev_cell = S.wide_cells ? (cell & 0xffffu) : (cell & 0x3fffu);
+                ev_post = POST_CONTINUE;
+                st = ST_EVENT;
+                break;
+            } else {
+                if constexpr (AUX) aux.n_inner++;
+                const uint32_t v = __ldg(S.bricks + c.idx);
+                const double t = c.last_t * recip_pow2(res);  // surface.rs:385-386
+                if (v & 0x8000u) {
+                    if (VOLUMETRIC && have_last) {
+                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = POST_CONTINUE;
+                        st = ST_EVENT;
+                        break;
+                    }
+                    if (count_stop()) { st = ST_DONE; break; }
+                    continue;
+                }
+                ev_kind = EV_SURFACE; ev_t = t; ev_cell = v; ev_post = POST_CONTINUE;
+                st = ST_EVENT;
+                break;
+            }
+        }
+        __syncwarp();
+
+        // =========================== HEAVY: events =====================================================
+        // (1) DepthIter + the Volumetric loop (surface.rs:460-490, sr.rs:185-203) / the Surface loop (sr.rs:206-225)
+        bool do_span = false;
+        PendingSurface span;
+        double span_exit = 0.0;
+        if (st == ST_EVENT) {
+            bool stop;
+            if constexpr (VOLUMETRIC) {
+                do_span = have_last;
+                span = last;
+                span_exit = ev_t;
+                have_last = false;
+                stop = count_stop();
+                if (stop) do_span = false;
+            } else {
+                stop = count_stop();
+            }
+            if (stop) st = ST_DONE;
+        }
+        // (2) trace_through_span (sr.rs:720-740) with apply_transmittance (raytracer_components.rs:215-258)
+        float sh_r = 0.f, sh_g = 0.f, sh_b = 0.f, sh_a = 0.f, sh_er = 0.f, sh_eg = 0.f, sh_eb = 0.f;
+        bool do_shade = false;
+        PendingSurface shade_sf;
+        if constexpr (VOLUMETRIC) {
+            if (do_span) {
+                const float4 col = __ldg(S.palette + 2 * (size_t)span.pal);
+                const float4 emi = __ldg(S.palette + 2 * (size_t)span.pal + 1);
+                const float thickness = fmaxf((float)((span_exit - span.t) * t_to_abs), 0.0f);
+                float alpha, coeff;
+                sh_r = col.x; sh_g = col.y; sh_b = col.z;
+                if (thickness == 0.0f) {
+                    if (col.w == 1.0f) { alpha = col.w; coeff = 1.0f; }
+                    else { sh_r = sh_g = sh_b = 0.0f; alpha = 0.0f; coeff = 0.0f; }
+                } else if (col.w == 1.0f) {
+                    alpha = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
+                } else if (col.w == 0.0f) {
+                    alpha = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
+                } else {
+                    const float unit_t = 1.0f - col.w;
+                    const float depth_t = powf_exact(unit_t, thickness);
+                    alpha = zo_clamped(1.0f - depth_t);
+                    const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
+                    coeff = fmaxf(k, 0.0f);
+                }
+                const float k = ps_clamped(coeff);
+                sh_a = alpha;
+                sh_er = ps_mul(emi.x, k); sh_eg = ps_mul(emi.y, k); sh_eb = ps_mul(emi.z, k);
+                shade_sf = span;
+                do_shade = true;
+            }
+        }
+        // (3) surface discovery: build the Surface, evaluate compute_illumination (surface.rs:113-206)
+        PendingSurface sf;
+        const bool discover = st == ST_EVENT && ev_kind == EV_SURFACE;
+        if (discover) {
+            int cx, cy, cz;
+            if (!inner) {
+                const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + ev_cell);
+                const uint4 b1 = __ldg(bp + 1);
+                sf.pal = b1.y;
+                cx = c.rx + S.lo[0]; cy = c.ry + S.lo[1]; cz = c.rz + S.lo[2];
+                sf.packed = (uint32_t)c.face << 24;
+                sf.res = 1;
+            } else {
+                sf.pal = pal_off + ev_cell;
+                cx = saved.rx + S.lo[0]; cy = saved.ry + S.lo[1]; cz = saved.rz + S.lo[2];
+                const int vx = c.rx + (int)(int16_t)(blk0y & 0xffff), vy = c.ry + (int)(int16_t)(blk0y >> 16),
+                          vz = c.rz + (int)(int16_t)(blk0z & 0xffff);
+                sf.packed = (uint32_t)vx | ((uint32_t)vy << 8) | ((uint32_t)vz << 16) | ((uint32_t)c.face << 24);
+                sf.res = res;
+            }
+            sf.t = ev_t;
+            sf.cube[0] = cx; sf.cube[1] = cy; sf.cube[2] = cz;
+            if constexpr (LC == LC_FLAT) {
+                int x = cx, y = cy, z = cz;
+                if (c.face != AICB_FACE_WITHIN) {
+                    const int dd = c.face >= AICB_FACE_PX ? 1 : -1;
+                    const int ax = (c.face - 1) % 3;
+                    if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
+                }
+                uint32_t tx = 0;
+                const uint32_t t = get_packed_light(S, x, y, z, tx);
+                if constexpr (AUX) aux.n_texels += tx;
+                sf.illum[0] = lut[t & 255];
+                sf.illum[1] = lut[(t >> 8) & 255];
+                sf.illum[2] = lut[(t >> 16) & 255];
+            } else if constexpr (LC == LC_INTERP) {
+                double ip[3];
+                if (!inner) {
+                    intersection_point(c, r, cx, cy, cz, r.ox, r.oy, r.oz, ip);
+                } else {
+                    const double fres = (double)res, anti = recip_pow2(res);
+                    const int vx = (int)(sf.packed & 255), vy = (int)((sf.packed >> 8) & 255), vz = (int)((sf.packed >> 16) & 255);
+                    intersection_point(c, r, vx, vy, vz, (r.ox - (double)cx) * fres, (r.oy - (double)cy) * fres,
+                                       (r.oz - (double)cz) * fres, ip);
+                    ip[0] = ip[0] * anti + (double)cx;  // surface.rs:406-407
+                    ip[1] = ip[1] * anti + (double)cy;
+                    ip[2] = ip[2] * anti + (double)cz;
+                }
+                uint32_t tx = 0;
+                float il[3];
+                interpolated_light(S, lut, P.lighting, cx, cy, cz, c.face, ip[0], ip[1], ip[2], il, &tx);
+                sf.illum[0] = il[0]; sf.illum[1] = il[1]; sf.illum[2] = il[2];
+                if constexpr (AUX) aux.n_texels += tx;
+            } else {
+                sf.illum[0] = sf.illum[1] = sf.illum[2] = 1.0f;
+            }
+            if constexpr (VOLUMETRIC) {
+                last = sf;
+                have_last = true;
+            } else {
+                const float4 col = __ldg(S.palette + 2 * (size_t)sf.pal);
+                const float4 emi = __ldg(S.palette + 2 * (size_t)sf.pal + 1);
+                sh_r = col.x; sh_g = col.y; sh_b = col.z; sh_a = col.w;
+                sh_er = emi.x; sh_eg = emi.y; sh_eb = emi.z;
+                shade_sf = sf;
+                do_shade = true;
+            }
+        }
+        // (4) Surface::to_light + trace_through_surface (surface.rs:73-106, sr.rs:697-717)
+        if (do_shade) {
+            float cr = sh_r, cg = sh_g, cb = sh_b, ca = sh_a;
+            if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
+                if (ca > P.threshold) { ca = 1.0f; } else { cr = cg = cb = ca = 0.0f; }
+            }
+            if (!(ca == 0.0f && sh_er == 0.0f && sh_eg == 0.0f && sh_eb == 0.0f)) {
+                float orr = ps_mul(ps_mul(cr, shade_sf.illum[0]), ca) + sh_er;   // reflect + emission (color.rs:708-710)
+                float og = ps_mul(ps_mul(cg, shade_sf.illum[1]), ca) + sh_eg;
+                float ob = ps_mul(ps_mul(cb, shade_sf.illum[2]), ca) + sh_eb;
+                float tr = 1.0f - ca;
+                if (have_fog) {  // distance_fog (sr.rs:745-768) + blend (surface.rs:97-100)
+                    float rel = (float)shade_sf.t * t_to_view;
+                    rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
+                    const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
+                    const float fudged = fog_exponential / 0.79810348f;
+                    const float p4 = (rel * rel) * (rel * rel);
+                    const float fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
+                    const float comp = 1.0f - fa;
+                    orr = ps_mul(orr, comp) + ps_mul(sky_r, fa);
+                    og = ps_mul(og, comp) + ps_mul(sky_g, fa);
+                    ob = ps_mul(ob, comp) + ps_mul(sky_b, fa);
+                    tr = tr * comp;
+                }
+                // add_color_internal (raytracer_components.rs:87-92)
+                lr = lr + orr * T;
+                lg = lg + og * T;
+                lb = lb + ob * T;
+                T = T * tr;
+                if constexpr (AUX) {
+                    aux.depth = fmin(aux.depth, shade_sf.t);
+                    aux.n_hits++;
+                    if (!aux.have_hit) {
+                        aux.have_hit = true;
+                        aux.hit_cube[0] = shade_sf.cube[0]; aux.hit_cube[1] = shade_sf.cube[1]; aux.hit_cube[2] = shade_sf.cube[2];
+                        aux.hit_voxel[0] = shade_sf.packed & 255; aux.hit_voxel[1] = (shade_sf.packed >> 8) & 255;
+                        aux.hit_voxel[2] = (shade_sf.packed >> 16) & 255;
+                        aux.hit_face = shade_sf.packed >> 24;
+                        aux.hit_res = shade_sf.res;
+                    }
+                }
+            }
+        }
+        // (4b) the buffered DepthStep::EnterBlock is counted after the flushed span was traced
+        //      (surface.rs:478-488, sr.rs:185-203): its opacity test sees that span.
+        if constexpr (VOLUMETRIC) {
+            if (st == ST_EVENT && ev_kind == EV_ENTER_BLOCK) {
+                if (count_stop()) st = ST_DONE;
+            }
+        }
+        // (5) recursive_raycast (raycast.rs:458-476) + TraceStep::EnterBlock (surface.rs:334-352)
+        if (st == ST_EVENT && ev_kind == EV_ENTER_BLOCK) {
+            if constexpr (AUX) aux.n_blocks++;
+            const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + ev_cell);
+            const uint4 b0 = __ldg(bp);
+            const uint4 b1 = __ldg(bp + 1);
+            const int bres = (int)(b0.x >> 8);
+            Level in;
+            in.lox = (int16_t)(b0.y & 0xffff); in.loy = (int16_t)(b0.y >> 16); in.loz = (int16_t)(b0.z & 0xffff);
+            in.nx = (int)(b0.z >> 16); in.ny = (int)(b0.w & 0xffff); in.nz = (int)(b0.w >> 16);
+            in.base = b1.x;
+            const double fres = (double)bres;
+            const int cx = c.rx + S.lo[0], cy = c.ry + S.lo[1], cz = c.rz + S.lo[2];
+            Caster ic;
+            bool ivalid;
+            if (caster_begin(ic, r, (r.ox - (double)cx) * fres, (r.oy - (double)cy) * fres, (r.oz - (double)cz) * fres, in,
+                             &ivalid)) {
+                saved = c;
+                saved_valid = valid;
+                c = ic;
+                valid = ivalid;
+                inner = true;
+                nx = in.nx; ny = in.ny; nz = in.nz;
+                blk0y = b0.y; blk0z = b0.z;
+                pal_off = b1.y;
+                res = bres;
+                need_advance = false;
+            }
+        }
+        // (6) what the event's producer wanted next
+        if (st == ST_EVENT) {
+            if (ev_post == POST_POP) pop_level();
+            st = (ev_post == POST_FINISH) ? ST_DONE : ST_MARCH;
         }
     }
 

@@ -76,29 +76,43 @@ def make_workload(name):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (the oracle; the Rust reference cannot be built in this image)
 # ------------------------------------------------------------------------------------------------
+def effective_cpus():
+    """Host threads this process can actually run concurrently: the affinity mask capped by the cgroup
+    CPU quota (the GPU boxes expose 128 logical CPUs behind a 16-CPU quota; oversubscribing a quota
+    only adds throttling)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_sample(space, cam, opts, height, target_seconds):
-    """Times the oracle on bands of rows spread over the frame; returns (Mrays/s, cores, description, rows)."""
+    """Times the oracle (all usable host threads, dynamic 64-pixel work items) on rows spread evenly over
+    the frame, repeated until ~target_seconds; returns (Mrays/s, cores, description, rows)."""
     import orc
     oscene = orc.OracleScene(space)
-    threads = orc.hardware_threads()
+    threads = effective_cpus()
     width = cam.data.fb_width
-    band = 4
-    # calibrate on 3 bands
-    probe_rows = [height // 6, height // 2, (5 * height) // 6]
+    # calibrate on 16 rows spread over the frame
+    probe = [int((i + 0.5) * height / 16) for i in range(16)]
     t0 = time.perf_counter()
-    for y in probe_rows:
-        oscene.render_rows(cam, opts, y, min(y + band, height), n_threads=threads)
-    dt = time.perf_counter() - t0
-    per_band = max(dt / len(probe_rows), 1e-4)
-    n_bands = int(max(4, min(height // band, target_seconds / per_band)))
-    ys = [int(i * (height - band) / max(1, n_bands - 1)) for i in range(n_bands)]
+    orc.render_rowlist(oscene, cam, opts, probe, n_threads=threads)
+    per_row = max((time.perf_counter() - t0) / len(probe), 1e-5)
+    n_rows = int(max(16, min(height, target_seconds / per_row)))
+    rows = sorted(set(int((i + 0.5) * height / n_rows) for i in range(n_rows)))
+    passes = int(max(1, min(50, target_seconds / max(per_row * len(rows), 1e-3))))
     t0 = time.perf_counter()
-    rays = 0
-    for y in ys:
-        oscene.render_rows(cam, opts, y, min(y + band, height), n_threads=threads)
-        rays += width * (min(y + band, height) - y)
+    for _ in range(passes):
+        orc.render_rowlist(oscene, cam, opts, rows, n_threads=threads)
     dt = time.perf_counter() - t0
-    return rays / dt / 1e6, threads, f"{n_bands} bands x {band} rows spread over the frame ({rays} rays, {dt:.1f} s)", ys
+    rays = width * len(rows) * passes
+    return (rays / dt / 1e6, threads,
+            f"{len(rows)} rows spread evenly over the frame x {passes} passes ({rays} rays, {dt:.1f} s, {threads} threads; "
+            f"{os.cpu_count()} logical CPUs visible)", rows)
 
 
 def run_reference(args):
@@ -113,20 +127,16 @@ def run_reference(args):
     from aicb200 import scenes
     import orc
     cam = scenes.standard_camera(space, opts, w, h)
-    threads = orc.hardware_threads()
+    threads = effective_cpus()
     # each step = one bounded sample of the frame, sized so the whole run stays within minutes
     per_step = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
-    mr, _, sample, ys = cpu_sample(space, cam, opts, h, per_step)
+    mr, _, sample, rows = cpu_sample(space, cam, opts, h, per_step)
     oscene = orc.OracleScene(space)
-    band = 4
 
     def one_step():
         t0 = time.perf_counter()
-        rays = 0
-        for y in ys:
-            oscene.render_rows(cam, opts, y, min(y + band, h), n_threads=threads)
-            rays += w * (min(y + band, h) - y)
-        return rays, time.perf_counter() - t0
+        orc.render_rowlist(oscene, cam, opts, rows, n_threads=threads)
+        return w * len(rows), time.perf_counter() - t0
 
     for _ in range(args.warmup):
         one_step()
@@ -243,7 +253,10 @@ def run_ours(args):
     if rank == 0 and world > 1:
         row_maps = [torch.tensor([y for y in range(h) if (y // STRIP_ROWS) % world == r], device="cuda") for r in range(world)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: its handle is what the library launches on, and what the
+    # CUDA events below are recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     info = abi.RenderInfo()
 
     def check(st):

@@ -1524,16 +1524,24 @@ static uint64_t render_rows_impl(const orc_scene *sc, const aicb_camera *cam, co
                                  uint8_t (*out_srgb8)[4], float (*out_cb)[4], double *depth, aicb_hit *hit,
                                  uint32_t *steps, int32_t *text) {
     if (n_threads <= 0) n_threads = orc_hardware_threads();
-    std::atomic<size_t> next_row{0};
-    std::atomic<uint64_t> total{0};
+    // Work items are 64-pixel chunks of a row, handed out dynamically (the reference nests a
+    // per-pixel parallel iterator inside a per-row one, renderer.rs:537-555).
     const uint32_t W = cam->fb_width;
+    const uint32_t CH = 64;
+    const size_t chunks_per_row = (W + CH - 1) / CH;
+    const size_t n_items = rows.size() * chunks_per_row;
+    std::atomic<size_t> next_item{0};
+    std::atomic<uint64_t> total{0};
     auto worker = [&]() {
         uint64_t local = 0;
         for (;;) {
-            size_t ri = next_row.fetch_add(1);
-            if (ri >= rows.size()) break;
+            size_t item = next_item.fetch_add(1);
+            if (item >= n_items) break;
+            size_t ri = item / chunks_per_row;
+            uint32_t xb = (uint32_t)(item % chunks_per_row) * CH;
+            uint32_t xe = xb + CH < W ? xb + CH : W;
             uint32_t y = rows[ri];
-            for (uint32_t x = 0; x < W; x++) {
+            for (uint32_t x = xb; x < xe; x++) {
                 PixelOut po;
                 local += trace_pixel(sc, *cam, *opt, accum_mode, x, y, &po);
                 size_t o = ri * (size_t)W + x;
@@ -1577,6 +1585,12 @@ uint64_t orc_render_rows(const orc_scene *sc, const aicb_camera *cam, const aicb
                          uint32_t row_end, int n_threads, uint8_t (*out_srgb8)[4], float (*out_cb)[4]) {
     std::vector<uint32_t> rows;
     for (uint32_t y = row_begin; y < row_end && y < cam->fb_height; y++) rows.push_back(y);
+    return render_rows_impl(sc, cam, opt, rows, 0, n_threads, out_srgb8, out_cb, nullptr, nullptr, nullptr, nullptr);
+}
+
+uint64_t orc_render_rowlist(const orc_scene *sc, const aicb_camera *cam, const aicb_options *opt, const uint32_t *row_list,
+                            size_t n_rows, int n_threads, uint8_t (*out_srgb8)[4], float (*out_cb)[4]) {
+    std::vector<uint32_t> rows(row_list, row_list + n_rows);
     return render_rows_impl(sc, cam, opt, rows, 0, n_threads, out_srgb8, out_cb, nullptr, nullptr, nullptr, nullptr);
 }
 

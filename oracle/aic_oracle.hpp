@@ -134,6 +134,9 @@ uint64_t orc_render(const orc_scene *, const aicb_camera *, const aicb_options *
 uint64_t orc_render_rows(const orc_scene *, const aicb_camera *, const aicb_options *, uint32_t row_begin,
                          uint32_t row_end, int n_threads, uint8_t (*out_srgb8)[4],
                          float (*out_colorbuf)[4]);
+// Arbitrary rows (bounded CPU-baseline samples spread over the frame); outputs packed in list order.
+uint64_t orc_render_rowlist(const orc_scene *, const aicb_camera *, const aicb_options *, const uint32_t *rows,
+                            size_t n_rows, int n_threads, uint8_t (*out_srgb8)[4], float (*out_colorbuf)[4]);
 void orc_pixel_ray(const aicb_camera *, uint32_t x, uint32_t y, int sample /* -1 centre, 0..3 AA */,
                    double out_origin_dir[6]);
 int orc_hardware_threads(void);

@@ -51,6 +51,9 @@ def lib():
     L.orc_render_rows.restype = C.c_uint64
     L.orc_render_rows.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_uint32,
                                   C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_render_rowlist.restype = C.c_uint64
+    L.orc_render_rowlist.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p,
+                                     C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     L.orc_pixel_ray.argtypes = [C.POINTER(abi.CameraData), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.orc_pixel_ray.restype = None
     L.orc_hardware_threads.restype = C.c_int
@@ -174,6 +177,19 @@ class OracleScene:
         total = lib().orc_render_rows(self.handle, C.byref(cam), C.byref(opt), row_begin, row_end, n_threads,
                                       srgb.ctypes.data, cb.ctypes.data if want_colorbuf else None)
         return {"srgb8": srgb, "colorbuf": cb, "cubes_traced": int(total)}
+
+
+def render_rowlist(scene, camera, options, rows, n_threads=0, want_colorbuf=False):
+    """Renders the given framebuffer rows (any order) with all host threads; outputs packed in list order."""
+    cam = camera.data
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    n = cam.fb_width * len(rows)
+    srgb = np.empty((n, 4), dtype=np.uint8)
+    cb = np.empty((n, 4), dtype=np.float32) if want_colorbuf else None
+    opt = options.to_abi(True)
+    total = lib().orc_render_rowlist(scene.handle, C.byref(cam), C.byref(opt), rows.ctypes.data, len(rows), n_threads,
+                                     srgb.ctypes.data, cb.ctypes.data if want_colorbuf else None)
+    return {"srgb8": srgb, "colorbuf": cb, "cubes_traced": int(total)}
 
 
 def pixel_ray(camera, x, y, sample=-1):

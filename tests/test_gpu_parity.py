@@ -284,7 +284,7 @@ def test_step_cap_is_reached_and_counted():
     ref = orc.OracleScene(space).trace_rays(rays, opts)
     compare(gpu, ref, True, "step cap")
     # a res-16 filled space hits the cap: 16 voxel steps + events per cube
-    blk = scenes.make_voxel_block(3, resolution=16, alpha=0.02, fill_mask=1, partial_bounds=False)
+    blk = scenes.make_voxel_block(3, resolution=16, alpha=0.0005, fill_mask=1, partial_bounds=False)
     ids = np.ones((80, 2, 2), dtype=np.uint16)
     space = Space((0, 0, 0), ids, [Block.air(), blk])
     for transparency in (TRANSPARENCY_SURFACE, TRANSPARENCY_VOLUMETRIC):
