@@ -67,6 +67,12 @@ def load_library() -> C.CDLL:
                                          C.c_size_t, C.POINTER(abi.RenderInfo)]
     lib.aicb_render_srgb8_device.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
                                              C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_render_srgb8_device_frame.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
+                                                   C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_frame_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.aicb_frame_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.aicb_frame_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.aicb_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.aicb_render_finish.argtypes = [C.c_void_p, C.POINTER(abi.RenderInfo)]
     lib.aicb_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(abi.Options), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.RenderInfo)]

@@ -117,7 +117,12 @@ EXPORTED_SYMBOLS = [
     "aicb_render_srgb8",
     "aicb_render_colorbuf",
     "aicb_render_srgb8_device",
+    "aicb_render_srgb8_device_frame",
     "aicb_render_finish",
+    "aicb_frame_create",
+    "aicb_frame_open",
+    "aicb_frame_close",
+    "aicb_frame_read",
     "aicb_trace_rays",
     "aicb_camera_look_at",
     "aicb_camera_from_view",

@@ -205,6 +205,7 @@ static uint32_t shard_rows(uint32_t fb_height, const aicb_shard *sh) {
 }
 
 struct Outputs {
+    bool full_frame = false;
     uchar4 *srgb8 = nullptr;
     float4 *colorbuf = nullptr;
     double *depth = nullptr;
@@ -263,6 +264,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.view_distance = opt->view_distance;
     P.debug_pixel_cost = opt->debug_pixel_cost;
     P.include_sky = opt->include_sky;
+    P.out_full_frame = out.full_frame ? 1 : 0;
     P.out_srgb8 = out.srgb8;
     P.out_colorbuf = out.colorbuf;
     P.out_depth = out.depth;
@@ -687,6 +689,69 @@ aicb_status aicb_render_srgb8_device(aicb_scene *s, const aicb_camera *cam, cons
     Outputs o;
     o.srgb8 = (uchar4 *)d_out;
     return launch_trace(s, cam, opt, shard, nullptr, 0, o, false, stream ? (cudaStream_t)stream : s->ctx->stream);
+}
+
+aicb_status aicb_render_srgb8_device_frame(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt,
+                                           const aicb_shard *shard, void *d_frame, size_t frame_len, void *stream) {
+    if (!s || !cam) return fail(AICB_ERR_INVALID, "NULL argument");
+    aicb_status st = check_render_args(s, cam, opt, shard, aicb_shard_pixel_count(cam, shard));
+    if (st != AICB_OK) return st;
+    if (frame_len != (size_t)cam->fb_width * cam->fb_height)
+        return fail(AICB_ERR_INVALID, "Viewport size does not match frame buffer length");
+    if (frame_len && !d_frame) return fail(AICB_ERR_INVALID, "d_frame is NULL");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    Outputs o;
+    o.full_frame = true;
+    o.srgb8 = (uchar4 *)d_frame;
+    return launch_trace(s, cam, opt, shard, nullptr, 0, o, false, stream ? (cudaStream_t)stream : s->ctx->stream);
+}
+
+// ---- full-frame buffers shared between ranks (CUDA IPC) ------------------------------------------
+aicb_status aicb_frame_create(aicb_ctx *ctx, size_t n_pixels, void **d_frame, uint8_t handle_out[64]) {
+    if (!ctx || !d_frame || !handle_out) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *p = nullptr;
+    CU(cudaMalloc(&p, n_pixels * 4 + 16));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle_out, &h, 64);
+    *d_frame = p;
+    return AICB_OK;
+}
+
+aicb_status aicb_frame_open(aicb_ctx *ctx, const uint8_t handle[64], void **d_frame) {
+    if (!ctx || !handle || !d_frame) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    // opened on THIS rank's device: lazily enables peer access to the exporting GPU (NVLink P2P)
+    CU(cudaIpcOpenMemHandle(d_frame, h, cudaIpcMemLazyEnablePeerAccess));
+    return AICB_OK;
+}
+
+aicb_status aicb_frame_close(aicb_ctx *ctx, void *d_frame, int opened) {
+    if (!ctx || !d_frame) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (opened) CU(cudaIpcCloseMemHandle(d_frame)); else CU(cudaFree(d_frame));
+    return AICB_OK;
+}
+
+aicb_status aicb_frame_read(aicb_ctx *ctx, const void *d_frame, uint8_t (*out)[4], size_t n_pixels, void *stream) {
+    if (!ctx || !d_frame || !out) return fail(AICB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(cudaMemcpyAsync(out, d_frame, n_pixels * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AICB_OK;
 }
 
 aicb_status aicb_render_finish(aicb_scene *s, aicb_render_info *info) {

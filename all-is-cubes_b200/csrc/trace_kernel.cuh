@@ -85,6 +85,7 @@ struct TraceParams {
     uint64_t n_rays;            // number of explicit rays
     uint32_t tiles_x, tiles_y;
     uint32_t n_tasks;           // tiles_x * tiles_y * 32 (camera) or n_rays
+    uint32_t out_full_frame;    // 1: outputs are indexed by framebuffer position (full-frame buffer, possibly peer memory)
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
     uchar4 *out_srgb8;
@@ -659,6 +660,7 @@ trace_kernel(const __grid_constant__ TraceParams P) {
                                 uint32_t strip_local = ly / P.strip_rows;
                                 py = (strip_local * P.shard_count + P.shard_index) * P.strip_rows + ly % P.strip_rows;
                             }
+                            if (P.out_full_frame) out_index = (size_t)py * P.fb_width + px;
                         }
                         if (active) {
                             st = ST_DONE;  // "previous sample finished" -> the finalize phase starts sample 0

@@ -40,6 +40,9 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="c2", choices=["c0", "c1", "c2", "c3"])
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    p.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                   help="N>1: 'p2p' = trace kernel stores its strips straight into rank 0's frame over NVLink "
+                        "(CUDA IPC mapped peer memory); 'nccl' = packed strips + NCCL gather + reassembly")
     return p.parse_args()
 
 
@@ -175,7 +178,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -245,13 +248,10 @@ def run_ours(args):
     shard = abi.Shard(STRIP_ROWS, rank, world)
     n_local = lib.aicb_shard_pixel_count(C.byref(cam.data), C.byref(shard))
     n_max = max(lib.aicb_shard_pixel_count(C.byref(cam.data), C.byref(abi.Shard(STRIP_ROWS, r, world))) for r in range(world))
+    from aicb200 import multi
     d_out = torch.empty((n_max, 4), dtype=torch.uint8, device="cuda")
-    gather_list = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gather_scratch = [torch.empty_like(d_out) for _ in range(world)] if (world > 1 and rank == 0) else None
     frame = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if rank == 0 else None
-    # row index of every packed local row of every rank, to reassemble the frame on rank 0
-    row_maps = None
-    if rank == 0 and world > 1:
-        row_maps = [torch.tensor([y for y in range(h) if (y // STRIP_ROWS) % world == r], device="cuda") for r in range(world)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     # a dedicated (non-default) stream: its handle is what the library launches on, and what the
     # CUDA events below are recorded on
@@ -263,17 +263,34 @@ def run_ours(args):
         if st != 0:
             raise RuntimeError(lib.aicb_last_error().decode())
 
+    gather_mode = args.gather if world > 1 else "none"
+    peer = None
+    if gather_mode == "p2p":
+        try:
+            peer = multi.PeerFrame(ctx, h, w, rank, world)
+            # touch the mapping once from every rank
+            check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                                     peer.ptr, w * h, C.c_void_p(stream.cuda_stream)))
+            torch.cuda.synchronize()
+            ok = torch.tensor([1], device="cuda")
+        except Exception as e:  # noqa: BLE001 — any failure falls back to the NCCL gather
+            sys.stderr.write(f"[rank {rank}] p2p frame unavailable ({e}); falling back to NCCL gather\n")
+            ok = torch.tensor([0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            gather_mode, peer = "nccl", None
+
     def device_step():
-        """One frame with everything resident in HBM: trace kernel (+ NCCL gather and reassembly for N>1)."""
-        check(lib.aicb_render_srgb8_device(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
-                                           d_out.data_ptr(), n_local, C.c_void_p(stream.cuda_stream)))
-        if world > 1:
-            dist.gather(d_out, gather_list, dst=0)
-            if rank == 0:
-                fr = frame.view(h, w * 4)
-                for r in range(world):
-                    rows = row_maps[r]
-                    fr[rows] = gather_list[r][: rows.numel() * w].view(rows.numel(), w * 4)
+        """One frame with everything resident in HBM: trace kernel + delivery of the strips to rank 0."""
+        if gather_mode == "p2p":
+            check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                                     peer.ptr, w * h, C.c_void_p(stream.cuda_stream)))
+            dist.barrier()  # NCCL barrier on the current stream: rank 0's frame is complete after it
+        else:
+            check(lib.aicb_render_srgb8_device(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                               d_out.data_ptr(), n_local, C.c_void_p(stream.cuda_stream)))
+            if world > 1:
+                multi.gather_frame(d_out, h, w, rank, world, frame=frame, scratch=gather_scratch)
 
     def timed(fn, steps):
         """K steps; per-step CUDA events on the launch stream, L2 flushed between steps (outside the
@@ -311,8 +328,6 @@ def run_ours(args):
     # kernel-only duration of the last frame from the library's own events (same stream)
     check(lib.aicb_render_finish(rt.handle, C.byref(info)))
     kernel_ms_last = float(info.kernel_ms)
-    clocks = sampler.stop() if rank == 0 else None
-
     rays_per_frame = w * h
     value = rays_per_frame * args.steps / (total_ms * 1e-3) / 1e6
 
@@ -326,6 +341,26 @@ def run_ours(args):
         check(lib.aicb_render_finish(rt.handle, C.byref(info)))
         kernel_ms.append(float(info.kernel_ms))
     kernel_avg_ms = float(np.mean(kernel_ms))
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the kernel-time launches
+
+    # ---- N > 1: the delivered frame must equal the frame one GPU renders alone -----------------------
+    frame_check = None
+    if world > 1:
+        device_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            got = torch.empty((h * w, 4), dtype=torch.uint8).pin_memory()
+            if gather_mode == "p2p":
+                peer.read(got, stream.cuda_stream)
+            else:
+                got.copy_(frame.view(h * w, 4))
+            alone = torch.empty((h * w, 4), dtype=torch.uint8).pin_memory()
+            check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), None, alone.data_ptr(), h * w, None))
+            frame_check = bool(torch.equal(got, alone))
+            if not frame_check:
+                raise SystemExit("bench.py: N-rank frame differs from the 1-rank frame")
+        dist.barrier()
 
     # ---- algorithmic bytes of this launch from device counters (one untimed AUX pass) ---------------
     r = aicb200.RtRenderer(cam, ctx)
@@ -361,7 +396,10 @@ def run_ours(args):
         else:
             device_step()
             if rank == 0:
-                host_frame.copy_(frame, non_blocking=False)
+                if gather_mode == "p2p":
+                    peer.read(host_frame, stream.cuda_stream)
+                else:
+                    host_frame.copy_(frame, non_blocking=False)
 
     for _ in range(2):
         e2e_step()
@@ -393,7 +431,8 @@ def run_ours(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
-            "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips",
+            "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips", "gather": gather_mode,
+                       "n_rank_frame_equals_1_rank_frame": frame_check,
                        "l2": "256 MiB buffer rewritten between timed steps", "scene_device_bytes": rt.device_bytes,
                        "cubes_traced_per_frame_this_rank": int(ai.cubes_traced)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

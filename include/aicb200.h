@@ -218,7 +218,23 @@ aicb_status aicb_render_colorbuf(aicb_scene *, const aicb_camera *, const aicb_o
 aicb_status aicb_render_srgb8_device(aicb_scene *, const aicb_camera *, const aicb_options *,
                                      const aicb_shard *shard_or_null,
                                      void *d_out, size_t out_len, void *stream);
+/* As above, but `d_frame` is a FULL framebuffer (fb_width*fb_height pixels) and the shard's pixels
+ * are stored at their framebuffer positions.  `d_frame` may be peer memory of another GPU mapped
+ * into this process (cudaIpcOpenMemHandle / P2P): the trace kernel's epilogue then delivers its
+ * row strips straight into the root GPU's frame over NVLink, replacing the gather collective. */
+aicb_status aicb_render_srgb8_device_frame(aicb_scene *, const aicb_camera *, const aicb_options *,
+                                           const aicb_shard *shard_or_null,
+                                           void *d_frame, size_t frame_len, void *stream);
 aicb_status aicb_render_finish(aicb_scene *, aicb_render_info *info_or_null);
+
+/* Full-frame buffers shared between the ranks of one node (one process per GPU): the root creates
+ * the frame on its GPU and publishes a 64-byte CUDA IPC handle; the other ranks open it on THEIR
+ * device (peer access over NVLink is enabled lazily) and pass the mapped pointer to
+ * aicb_render_srgb8_device_frame().  aicb_frame_read() is the root's device->host copy. */
+aicb_status aicb_frame_create(aicb_ctx *, size_t n_pixels, void **d_frame, uint8_t handle_out[64]);
+aicb_status aicb_frame_open(aicb_ctx *, const uint8_t handle[64], void **d_frame);
+aicb_status aicb_frame_close(aicb_ctx *, void *d_frame, int opened);
+aicb_status aicb_frame_read(aicb_ctx *, const void *d_frame, uint8_t (*out)[4], size_t n_pixels, void *stream);
 
 /* == SpaceRaytracer::trace_ray (sr.rs:113-120) for a batch of explicit rays:
  * origin_dir[i] = {ox,oy,oz,dx,dy,dz}. Output as aicb_render_colorbuf. */
