@@ -90,6 +90,12 @@ def load_library() -> C.CDLL:
     lib.aicb_light_edit_and_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8,
                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
     lib.aicb_light_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_light_chart.argtypes = [C.c_void_p, C.c_void_p]
+    lib.aicb_light_chart.restype = C.c_uint32
+    lib.aicb_light_fast_evaluate.argtypes = [C.c_void_p]
+    lib.aicb_light_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_light_evaluate.argtypes = [C.c_void_p, C.c_uint8, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8),
+                                        C.POINTER(C.c_uint64)]
     if lib.aicb_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("libaicb200.so ABI version mismatch")
     _lib = lib
@@ -241,6 +247,53 @@ class Block:
             assert self.palette.ndim == 2 and self.palette.shape[1] == 8
             self.voxel_lower = tuple(int(v) for v in (voxel_lower or (0, 0, 0)))
             self.voxel_size = tuple(int(v) for v in indices.shape)
+        self._derive_for_light()
+
+    def _derive_for_light(self):
+        """EvaluatedBlock derived data read by light propagation (block/eval/derived.rs:80-104 for single
+        voxels).  For recursive blocks only the face-opacity rule (derived.rs:196-209) is exact; the
+        face colours are a plain mean of the surface voxels (block evaluation is out of scope) —
+        both the oracle and the GPU consume whatever is supplied here."""
+        if self.is_air:
+            self.light_opaque_faces = 0
+            self.light_visible = False
+            self.light_color = (0.0, 0.0, 0.0, 0.0)
+            self.light_face_colors = [(0.0, 0.0, 0.0, 0.0)] * 6
+            self.light_emission = (0.0, 0.0, 0.0)
+            return
+        if self.indices is None:
+            c = tuple(float(v) for v in self.palette[0, :4])
+            e = tuple(float(v) for v in self.palette[0, 4:7])
+            self.light_color = c
+            self.light_face_colors = [c] * 6
+            self.light_emission = e
+            self.light_opaque_faces = 0x3F if c[3] == 1.0 else 0
+            self.light_visible = (c[3] != 0.0) or any(v != 0.0 for v in e)
+            return
+        r = self.resolution
+        full = np.zeros((r, r, r, 8), dtype=np.float32)
+        lo = self.voxel_lower
+        sz = self.voxel_size
+        full[lo[0]:lo[0] + sz[0], lo[1]:lo[1] + sz[1], lo[2]:lo[2] + sz[2]] = self.palette[self.indices]
+        faces = [full[0], full[:, 0], full[:, :, 0], full[-1], full[:, -1], full[:, :, -1]]  # NX NY NZ PX PY PZ layers
+        self.light_opaque_faces = 0
+        cols = []
+        for f, layer in enumerate(faces):
+            a = layer[..., 3]
+            if np.all(a == 1.0):
+                self.light_opaque_faces |= 1 << f
+            w = float(a.sum())
+            if w > 0:
+                rgb = (layer[..., :3] * a[..., None]).sum(axis=(0, 1)) / w
+                cols.append((float(rgb[0]), float(rgb[1]), float(rgb[2]), min(1.0, w / (r * r))))
+            else:
+                cols.append((0.0, 0.0, 0.0, 0.0))
+        self.light_face_colors = cols
+        m = np.mean(np.array(cols), axis=0)
+        self.light_color = tuple(float(v) for v in m)
+        em = full[..., 4:7].sum(axis=(0, 1, 2)) / (6.0 * r * r)
+        self.light_emission = tuple(float(v) for v in em)
+        self.light_visible = bool((full[..., 3] != 0).any() or (full[..., 4:7] != 0).any())
 
     @staticmethod
     def air() -> "Block":
@@ -292,6 +345,12 @@ class Space:
                 bd.n_indices = 0
             bd.palette = b.palette.ctypes.data
             bd.n_palette = b.palette.shape[0]
+            bd.light_opaque_faces = b.light_opaque_faces
+            bd.light_visible = 1 if b.light_visible else 0
+            for f in range(6):
+                bd.light_face_colors[f][:] = b.light_face_colors[f]
+            bd.light_color[:] = b.light_color
+            bd.light_emission[:] = b.light_emission
             keep.append(b)
         d.blocks = arr
         d.n_blocks = len(self.blocks)
@@ -302,6 +361,16 @@ class Space:
         keep.append(arr)
         keep.append(self)
         return d, keep
+
+
+def light_chart():
+    """The static light-ray chart (space/light/chart/generator.rs) as (weights [n,6] f32, children [n,6] u32)."""
+    lib = load_library()
+    n = lib.aicb_light_chart(None, None)
+    w = np.zeros((n, 6), dtype=np.float32)
+    ch = np.zeros((n, 6), dtype=np.uint32)
+    lib.aicb_light_chart(w.ctypes.data, ch.ctypes.data)
+    return w, ch
 
 
 def srgb8_to_linear(rgb) -> tuple:
@@ -414,6 +483,38 @@ class SpaceRaytracer:
         lt = None if light is None else np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
         _check(load_library().aicb_scene_update_cubes(self.handle, c.ctypes.data, ids.ctypes.data,
                                                       lt.ctypes.data if lt is not None else None, c.shape[0]))
+
+    # ---- light propagation (space::light) ----
+    def light_fast_evaluate(self):
+        """LightStorage::fast_evaluate_light (updater.rs:537-582)"""
+        _check(load_library().aicb_light_fast_evaluate(self.handle))
+
+    def light_compute(self, cubes: np.ndarray) -> np.ndarray:
+        """LightStorage::compute_light (updater.rs:368-418) for explicit cubes; returns texels [n,4]."""
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros((c.shape[0], 4), dtype=np.uint8)
+        _check(load_library().aicb_light_compute(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data))
+        return out
+
+    def light_evaluate(self, epsilon: int = 0):
+        """Mutation::evaluate_light (space.rs:1496-1527) -> (updates, max_difference, chart_node_visits)"""
+        n, md, nv = C.c_uint64(0), C.c_uint8(0), C.c_uint64(0)
+        _check(load_library().aicb_light_evaluate(self.handle, epsilon, C.byref(n), C.byref(md), C.byref(nv)))
+        return int(n.value), int(md.value), int(nv.value)
+
+    def light_edit_and_propagate(self, cubes: np.ndarray, block_ids: np.ndarray, epsilon: int = 0):
+        """Mutation::set x n + evaluate_light(epsilon) -> (updates, max_difference)"""
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        ids = np.ascontiguousarray(block_ids, dtype=np.uint16)
+        n, md = C.c_uint64(0), C.c_uint8(0)
+        _check(load_library().aicb_light_edit_and_propagate(self.handle, c.ctypes.data, ids.ctypes.data, c.shape[0], epsilon,
+                                                            C.byref(n), C.byref(md)))
+        return int(n.value), int(md.value)
+
+    def light_download(self) -> np.ndarray:
+        out = np.zeros(self.space.size + (4,), dtype=np.uint8)
+        _check(load_library().aicb_light_download(self.handle, out.ctypes.data, out.size // 4))
+        return out
 
     def upload_light(self, light: np.ndarray):
         lt = np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)

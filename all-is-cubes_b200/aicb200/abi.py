@@ -128,6 +128,10 @@ EXPORTED_SYMBOLS = [
     "aicb_camera_from_view",
     "aicb_eye_for_look_at",
     "aicb_camera_project_ndc",
+    "aicb_light_chart",
+    "aicb_light_fast_evaluate",
+    "aicb_light_compute",
+    "aicb_light_evaluate",
     "aicb_light_edit_and_propagate",
     "aicb_light_download",
 ]

@@ -13,7 +13,7 @@
 
 #include <cuda_runtime.h>
 
-#include "trace_kernel.cuh"
+#include "internal.h"
 
 using namespace aicb;
 
@@ -22,56 +22,21 @@ using namespace aicb;
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error = "";
 
-static aicb_status fail(aicb_status st, const std::string &msg) {
+aicb_status aicb_fail(aicb_status st, const std::string &msg) {
     g_last_error = msg;
     return st;
 }
-static aicb_status cuda_fail(cudaError_t e, const char *what) {
+aicb_status aicb_cuda_fail(cudaError_t e, const char *what) {
     aicb_status st = (e == cudaErrorMemoryAllocation) ? AICB_ERR_OOM : AICB_ERR_CUDA;
-    return fail(st, std::string(what) + ": " + cudaGetErrorString(e));
+    return aicb_fail(st, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CU(call)                                        \
-    do {                                                \
-        cudaError_t e__ = (call);                       \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-    } while (0)
+static aicb_status fail(aicb_status st, const std::string &msg) { return aicb_fail(st, msg); }
+static aicb_status cuda_fail(cudaError_t e, const char *what) { return aicb_cuda_fail(e, what); }
 
-// ---------------------------------------------------------------------------------------------
-// context / scene objects
-// ---------------------------------------------------------------------------------------------
-struct aicb_ctx {
-    int device = 0;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    unsigned int *d_tile_counter = nullptr;
-    unsigned long long *d_counters = nullptr;
-    float *d_lut = nullptr;
-    // staging output buffers (grown on demand)
-    void *d_out = nullptr;
-    size_t d_out_bytes = 0;
-    void *d_aux = nullptr;
-    size_t d_aux_bytes = 0;
-    std::mutex mu;
-};
-
-struct aicb_scene {
-    aicb_ctx *ctx = nullptr;
-    DeviceScene ds{};
-    std::vector<uint8_t> block_kind;   // host copy, for update_cubes
-    size_t volume = 0;
-    uint64_t device_bytes = 0;
-    void *d_cells = nullptr;
-    uint32_t *d_light = nullptr;
-    BlockRec *d_blocks = nullptr;
-    uint16_t *d_bricks = nullptr;
-    float4 *d_palette = nullptr;
-    // state of the last asynchronous render
-    bool pending = false;
-    uint64_t pending_rays = 0;
-    uint64_t pending_pixels = 0;
-    uint32_t pending_out_bytes_per_pixel = 0;
-};
+void aicb_light_scene_init(aicb_scene *s, const aicb_scene_desc *d);   // light.cu
+aicb_status aicb_light_scene_upload(aicb_scene *s, const aicb_scene_desc *d);
+void aicb_light_scene_free(aicb_scene *s);
+void aicb_light_ctx_free(aicb_ctx *c);
 
 // PackedLight::some -> scalar_in (light/data.rs:213-217)
 static uint8_t scalar_in(float v) {
@@ -150,6 +115,22 @@ static void build_srgb_thresholds(float *thr) {
             float f;
             std::memcpy(&f, &mid, 4);
             if (srgb8_host(f) >= k) hi = mid; else lo = mid + 1;
+        }
+        std::memcpy(&thr[k], &lo, 4);
+    }
+}
+
+// PackedLight::scalar_in (light/data.rs:213-217) inverted into thresholds with the platform log2f
+// (see light_kernel.cuh scalar_in_t): thr[k] = the smallest non-negative f32 whose quantised value is >= k.
+static void build_light_thresholds(float *thr) {
+    thr[0] = 0.0f;
+    for (int k = 1; k < 256; k++) {
+        uint32_t lo = 0, hi = 0x7f800000u;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            float f;
+            std::memcpy(&f, &mid, 4);
+            if (scalar_in(f) >= k) hi = mid; else lo = mid + 1;
         }
         std::memcpy(&thr[k], &lo, 4);
     }
@@ -370,10 +351,11 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
-    float lut[512];
+    float lut[768];
     lut[0] = 0.0f;
     for (int i = 1; i < 256; i++) lut[i] = (float)std::exp2((double)(((float)i - 144.0f) / 10.0f));
     build_srgb_thresholds(lut + 256);
+    build_light_thresholds(lut + 512);
     CU(cudaMalloc(&c->d_lut, sizeof lut));
     CU(cudaMemcpy(c->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
     *out = c;
@@ -385,6 +367,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_aux) cudaFree(c->d_aux);
+    aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
@@ -549,6 +532,10 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
     ds.palette = s->d_palette;
     ds.tables = ctx->d_lut;
     build_block_sky(d->sky, &ds);
+    {
+        aicb_status lst = aicb_light_scene_upload(s, d);
+        if (lst != AICB_OK) return cleanup(lst);
+    }
     *out = s;
     return AICB_OK;
 }
@@ -561,6 +548,7 @@ void aicb_scene_destroy(aicb_scene *s) {
     if (s->d_blocks) cudaFree(s->d_blocks);
     if (s->d_bricks) cudaFree(s->d_bricks);
     if (s->d_palette) cudaFree(s->d_palette);
+    aicb_light_scene_free(s);
     delete s;
 }
 
@@ -579,6 +567,7 @@ aicb_status aicb_scene_update_cubes(aicb_scene *s, const int32_t (*cubes)[3], co
             return fail(AICB_ERR_INVALID, "cube out of bounds");
         if (ids[i] >= s->block_kind.size()) return fail(AICB_ERR_INVALID, "block id out of range");
         size_t idx = ((size_t)dx * ds.size[1] + dy) * ds.size[2] + dz;
+        if (!s->h_ids.empty()) s->h_ids[idx] = ids[i];
         if (ds.wide_cells) {
             uint32_t cell = ids[i] | ((uint32_t)s->block_kind[ids[i]] << 16);
             CU(cudaMemcpyAsync((uint32_t *)s->d_cells + idx, &cell, 4, cudaMemcpyHostToDevice, s->ctx->stream));
@@ -782,18 +771,4 @@ aicb_status aicb_trace_rays(aicb_scene *s, const double (*origin_dir)[6], size_t
     return st;
 }
 
-aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*)[3], const uint16_t *, size_t, uint8_t,
-                                          uint64_t *, uint8_t *) {
-    return fail(AICB_ERR_UNSUPPORTED, "light propagation kernel is not built yet (SURVEY 8(a) L1-L4)");
-}
-
-aicb_status aicb_light_download(aicb_scene *s, uint8_t (*out)[4], size_t n_texels) {
-    if (!s || !out) return fail(AICB_ERR_INVALID, "NULL argument");
-    if (n_texels != s->volume) return fail(AICB_ERR_INVALID, "light volume size mismatch");
-    if (!s->d_light) return fail(AICB_ERR_INVALID, "scene has no light volume (LightPhysics::None)");
-    std::lock_guard<std::mutex> lock(s->ctx->mu);
-    CU(cudaSetDevice(s->ctx->device));
-    CU(cudaMemcpy(out, s->d_light, s->volume * 4, cudaMemcpyDeviceToHost));
-    return AICB_OK;
-}
 }

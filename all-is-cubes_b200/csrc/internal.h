@@ -1,0 +1,67 @@
+// internal.h — objects behind the opaque handles of include/aicb200.h (shared by aicb200.cu and light.cu).
+#pragma once
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "trace_kernel.cuh"
+
+aicb_status aicb_fail(aicb_status st, const std::string &msg);
+aicb_status aicb_cuda_fail(cudaError_t e, const char *what);
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return aicb_cuda_fail(e__, #call); \
+    } while (0)
+
+struct LightChartNode;  // light_kernel.cuh
+struct LightBlockDev;   // light_kernel.cuh
+
+struct aicb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned int *d_tile_counter = nullptr;
+    unsigned long long *d_counters = nullptr;
+    float *d_lut = nullptr;
+    // staging output buffers (grown on demand)
+    void *d_out = nullptr;
+    size_t d_out_bytes = 0;
+    void *d_aux = nullptr;
+    size_t d_aux_bytes = 0;
+    // light propagation: the static ray chart (space/light/chart), built and uploaded on first use
+    LightChartNode *d_chart = nullptr;
+    uint32_t chart_nodes = 0;
+    std::mutex mu;
+};
+
+struct aicb_scene {
+    aicb_ctx *ctx = nullptr;
+    aicb::DeviceScene ds{};
+    std::vector<uint8_t> block_kind;   // host copy, for update_cubes
+    size_t volume = 0;
+    uint64_t device_bytes = 0;
+    void *d_cells = nullptr;
+    uint32_t *d_light = nullptr;
+    aicb::BlockRec *d_blocks = nullptr;
+    uint16_t *d_bricks = nullptr;
+    float4 *d_palette = nullptr;
+    // state of the last asynchronous render
+    bool pending = false;
+    uint64_t pending_rays = 0;
+    uint64_t pending_pixels = 0;
+    uint32_t pending_out_bytes_per_pixel = 0;
+    // ---- light propagation state (light.cu) ----
+    std::vector<uint16_t> h_ids;            // host mirror of Space::contents (edits are applied in order on the host)
+    std::vector<uint32_t> h_block_light;    // per block: bits 0-5 opaque faces, 6 all-opaque, 7 visible, 8 has emission
+    LightBlockDev *d_light_blocks = nullptr;
+    uint8_t *d_pending = nullptr;           // per cube: queued priority (0 = not queued) — LightUpdateQueue
+    uint32_t *d_list = nullptr;             // work list of one round (cube indices)
+    uint32_t *d_new_light = nullptr;        // computed texels of one round
+    uint8_t *d_diff = nullptr;              // difference_priority of one round
+    uint32_t *d_scalars = nullptr;          // [0] list length, [1] max priority, [2] max diff, [3] updates
+    uint32_t light_max_distance = 0;
+};

@@ -1,0 +1,499 @@
+// light.cu — host side of the secondary path: the static light-ray chart
+// (space/light/chart/generator.rs), the per-block derived table, and the batched relaxation driver
+// replacing LightStorage::update_light_from_queue / apply_light_update / fast_evaluate_light /
+// modified_cube_needs_update (space/light/updater.rs) and Mutation::evaluate_light (space.rs:1496-1527).
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "internal.h"
+#include "light_kernel.cuh"
+
+using namespace aicb;
+using namespace aicb_light;
+
+// ---------------------------------------------------------------------------------------------
+// chart generation (generator.rs:49-215) — host, once per context
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct TreeNode {
+    int8_t cube[3];
+    int children[6];
+    float weight[6];
+};
+
+// scale_to_integer_step (raycast.rs:797-819) for s = 0.5
+double stis_half(double ds) {
+    if (ds == 0.0) return INFINITY;
+    return (1.0 - 0.5) / std::fabs(ds);  // rem_euclid(+-0.5, 1) == 0.5 either way
+}
+
+std::vector<LightChartNode> build_chart() {
+    std::vector<TreeNode> pool;
+    pool.push_back(TreeNode{{0, 0, 0}, {-1, -1, -1, -1, -1, -1}, {0, 0, 0, 0, 0, 0}});
+    const int R = 5;  // RAY_DIRECTION_STEP
+    for (int x = -R; x <= R; x++)
+        for (int y = -R; y <= R; y++)
+            for (int z = -R; z <= R; z++) {
+                if (!(std::abs(x) == R || std::abs(y) == R || std::abs(z) == R)) continue;
+                const float fx = (float)x, fy = (float)y, fz = (float)z;
+                const float len = std::sqrt(fx * fx + fy * fy + fz * fz);
+                const float d[3] = {fx / len, fy / len, fz / len};  // Vector3D::normalize
+                float cos6[6];
+                for (int f = 0; f < 6; f++) {
+                    float u[3] = {0, 0, 0};
+                    u[f % 3] = (f < 3) ? -1.0f : 1.0f;
+                    const float dot = u[0] * d[0] + u[1] * d[1] + u[2] * d[2];
+                    cos6[f] = std::fmax(dot, 0.0f);
+                }
+                // ray_to_steps (generator.rs:100-113): Ray::new([0.5;3], direction).cast(), t <= 127.
+                // Unbounded Raycaster (raycast.rs:577-626) from the cube (0,0,0).
+                const double dd[3] = {(double)d[0], (double)d[1], (double)d[2]};
+                int step[3];
+                double t_delta[3], t_max[3];
+                for (int a = 0; a < 3; a++) {
+                    step[a] = dd[a] == 0.0 ? 0 : (dd[a] < 0.0 ? -1 : 1);
+                    t_delta[a] = 1.0 / std::fabs(dd[a]);
+                    t_max[a] = stis_half(dd[a]);
+                }
+                int cube[3] = {0, 0, 0};
+                for (int f = 0; f < 6; f++) pool[0].weight[f] += cos6[f];  // the root is on every path
+                int cur = 0;
+                for (;;) {
+                    int axis;
+                    if (t_max[0] < t_max[1]) axis = (t_max[0] < t_max[2]) ? 0 : 2;
+                    else axis = (t_max[1] < t_max[2]) ? 1 : 2;
+                    const double t = t_max[axis];
+                    cube[axis] += step[axis];
+                    t_max[axis] += t_delta[axis];
+                    if (!(t <= 127.0)) break;
+                    const int dir = step[axis] > 0 ? 3 + axis : axis;  // Face::from_adjacency(previous, this)
+                    int child = pool[cur].children[dir];
+                    if (child < 0) {
+                        child = (int)pool.size();
+                        pool[cur].children[dir] = child;
+                        pool.push_back(TreeNode{{(int8_t)cube[0], (int8_t)cube[1], (int8_t)cube[2]}, {-1, -1, -1, -1, -1, -1}, {0, 0, 0, 0, 0, 0}});
+                    }
+                    cur = child;
+                    for (int f = 0; f < 6; f++) pool[cur].weight[f] += cos6[f];
+                }
+            }
+    std::vector<LightChartNode> flat(pool.size());
+    for (size_t i = 0; i < pool.size(); i++)
+        for (int f = 0; f < 6; f++) {
+            flat[i].w[f] = pool[i].weight[f];
+            flat[i].child[f] = pool[i].children[f] < 0 ? 0u : (uint32_t)pool[i].children[f];
+        }
+    return flat;
+}
+
+aicb_status ensure_chart(aicb_ctx *ctx) {
+    if (ctx->d_chart) return AICB_OK;
+    std::vector<LightChartNode> chart = build_chart();
+    CU(cudaMalloc(&ctx->d_chart, chart.size() * sizeof(LightChartNode)));
+    CU(cudaMemcpy(ctx->d_chart, chart.data(), chart.size() * sizeof(LightChartNode), cudaMemcpyHostToDevice));
+    ctx->chart_nodes = (uint32_t)chart.size();
+    return AICB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_find_max(const LightParams P) {
+    uint32_t m = 0;
+    const uint32_t n_words = (P.volume + 3) / 4;
+    const uint32_t *w = (const uint32_t *)P.pending;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+        uint32_t v = w[i];
+        m = max(m, max(max(v & 255u, (v >> 8) & 255u), max((v >> 16) & 255u, v >> 24)));
+    }
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(P.scalars + 1, m);
+}
+
+__global__ void k_gather(const LightParams P) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.volume; i += gridDim.x * blockDim.x) {
+        if (P.pending[i] == P.priority) {
+            P.pending[i] = 0;
+            P.list[atomicAdd(P.scalars + 0, 1u)] = i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
+    __shared__ float s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z;
+    if (explicit_cubes) {
+        x = explicit_cubes[3 * i]; y = explicit_cubes[3 * i + 1]; z = explicit_cubes[3 * i + 2];
+    } else {
+        cube_of(P.scene, P.list[i], x, y, z);
+    }
+    uint32_t visits = 0;
+    P.new_light[i] = compute_light<false>(P, s_lut, x, y, z, 0, &visits);
+    atomicAdd(P.scalars + 4, visits);
+}
+
+// apply_light_update (updater.rs:295-363) minus the dependency re-queue (k_mark)
+__global__ void k_apply(const LightParams P, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t idx = P.list[i];
+    uint32_t *light = const_cast<uint32_t *>(P.scene.light);
+    const uint32_t old = light[idx], nv = P.new_light[i];
+    const int d = difference_priority(nv, old);
+    P.diff[i] = (uint8_t)d;
+    atomicAdd(P.scalars + 3, 1u);
+    if (d > 0) {
+        light[idx] = nv;
+        atomicMax(P.scalars + 2, (uint32_t)d);
+        int x, y, z;
+        cube_of(P.scene, idx, x, y, z);
+        const float *lut = P.scene.tables;
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            const int s = (f < 3) ? -1 : 1, a = f % 3;
+            uint32_t nidx;
+            if (!cube_index(P.scene, x + (a == 0 ? s : 0), y + (a == 1 ? s : 0), z + (a == 2 ? s : 0), &nidx)) continue;
+            const uint32_t nl = light[nidx];
+            if ((nl >> 24) != 0) continue;            // only LightStatus::Uninitialized neighbours
+            if (nl == nv) continue;
+            if (__ldg(&P.blocks[block_id_at(P.scene, nidx)].flags) & LB_ALL_OPAQUE) continue;
+            // PackedLight::guess(new.value()): re-quantise the decoded value, status Uninitialized
+            const uint32_t g = scalar_in_t(lut, lut[nv & 255]) | (scalar_in_t(lut, lut[(nv >> 8) & 255]) << 8) | (scalar_in_t(lut, lut[(nv >> 16) & 255]) << 16);
+            atomicCAS(&light[nidx], nl, g);
+        }
+    }
+}
+
+// the dependency re-queue of apply_light_update (updater.rs:355-360): re-walk the chart, raising the
+// queue priority of every cube whose light was read
+__global__ void __launch_bounds__(64) k_mark(const LightParams P, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = P.diff[i];
+    if (d <= 1) return;
+    int x, y, z;
+    cube_of(P.scene, P.list[i], x, y, z);
+    compute_light<true>(P, P.scene.tables, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
+}
+
+// fast_evaluate_light (updater.rs:537-582): one thread per (x, z) column, top down
+__global__ void k_fast_evaluate(const LightParams P) {
+    const DeviceScene &S = P.scene;
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= (uint32_t)S.size[0] * (uint32_t)S.size[2]) return;
+    const int x = (int)(col / (uint32_t)S.size[2]) + S.lo[0], z = (int)(col % (uint32_t)S.size[2]) + S.lo[2];
+    uint32_t *light = const_cast<uint32_t *>(S.light);
+    bool covered = false;
+    for (int y = S.lo[1] + S.size[1] - 1; y >= S.lo[1]; y--) {
+        uint32_t idx;
+        cube_index(S, x, y, z, &idx);
+        const uint32_t fl = __ldg(&P.blocks[block_id_at(S, idx)].flags);
+        uint32_t value;
+        uint8_t pend = 0;
+        if ((fl & LB_ALL_OPAQUE) && !(fl & LB_EMISSIVE)) {
+            covered = true;
+            value = TX_OPAQUE;
+        } else {
+            bool any = (fl & LB_VISIBLE) != 0;
+            if (!any) {
+                any = (flags_at(P, x - 1, y, z) | flags_at(P, x + 1, y, z) | flags_at(P, x, y - 1, z) | flags_at(P, x, y + 1, z) |
+                       flags_at(P, x, y, z - 1) | flags_at(P, x, y, z + 1)) & LB_VISIBLE;
+            }
+            if (any) {
+                pend = PRIO_ESTIMATED;
+                value = covered ? TX_UNINIT : S.sky_faces[4];  // block_sky.in_direction(PY)
+            } else {
+                value = TX_NO_RAYS;
+            }
+        }
+        light[idx] = value;
+        P.pending[idx] = pend;
+    }
+}
+
+struct EditOp {
+    uint32_t idx;
+    uint32_t cell;        // new cell word, or 0xffffffff = leave
+    uint8_t set_opaque;   // light := OPAQUE
+    uint8_t pending_op;   // 0 none, 1 remove, 2 raise to NEWLY_VISIBLE
+    uint8_t _pad[2];
+};
+
+__global__ void k_edits(const LightParams P, const EditOp *ops, uint32_t n, uint32_t wide) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EditOp op = ops[i];
+    if (op.cell != 0xffffffffu) {
+        if (wide) ((uint32_t *)P.scene.cells)[op.idx] = op.cell;
+        else ((uint16_t *)P.scene.cells)[op.idx] = (uint16_t)op.cell;
+    }
+    if (op.set_opaque) const_cast<uint32_t *>(P.scene.light)[op.idx] = TX_OPAQUE;
+    if (op.pending_op == 1) P.pending[op.idx] = 0;
+    else if (op.pending_op == 2) P.pending[op.idx] = PRIO_NEWLY_VISIBLE;
+}
+
+LightParams make_params(aicb_scene *s) {
+    LightParams P;
+    std::memset(&P, 0, sizeof P);
+    P.scene = s->ds;
+    P.blocks = s->d_light_blocks;
+    P.chart = s->ctx->d_chart;
+    P.pending = s->d_pending;
+    P.list = s->d_list;
+    P.new_light = s->d_new_light;
+    P.diff = s->d_diff;
+    P.scalars = s->d_scalars;
+    P.volume = (uint32_t)s->volume;
+    P.max_distance = s->light_max_distance;
+    return P;
+}
+
+aicb_status ensure_light_state(aicb_scene *s) {
+    if (s->light_max_distance == 0) return aicb_fail(AICB_ERR_INVALID, "scene has LightPhysics::None (light_max_distance == 0)");
+    aicb_status st = ensure_chart(s->ctx);
+    if (st != AICB_OK) return st;
+    if (!s->d_light) {  // a scene created without a light volume starts all NO_RAYS (initialize_light, updater.rs:628-656)
+        std::vector<uint32_t> init(s->volume, TX_NO_RAYS);
+        CU(cudaMalloc(&s->d_light, s->volume * 4 + 16));
+        CU(cudaMemcpy(s->d_light, init.data(), s->volume * 4, cudaMemcpyHostToDevice));
+        s->ds.light = s->d_light;
+        s->device_bytes += s->volume * 4;
+    }
+    if (!s->d_pending) {
+        CU(cudaMalloc(&s->d_pending, s->volume + 16));
+        CU(cudaMemset(s->d_pending, 0, s->volume + 16));
+        CU(cudaMalloc(&s->d_list, s->volume * 4 + 16));
+        CU(cudaMalloc(&s->d_new_light, s->volume * 4 + 16));
+        CU(cudaMalloc(&s->d_diff, s->volume + 16));
+        CU(cudaMalloc(&s->d_scalars, 8 * 4));
+        s->device_bytes += s->volume * 10;
+    }
+    return AICB_OK;
+}
+
+// evaluate_light (space.rs:1496-1527): rounds until the highest queued priority is <= from_difference(epsilon)
+aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, uint8_t *max_diff, uint64_t *node_visits) {
+    aicb_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    LightParams P = make_params(s);
+    P.epsilon_priority = (uint32_t)epsilon / 2 + 1;
+    const int blocks = ctx->num_sms * 8;
+    uint64_t total = 0, visits = 0;
+    uint32_t maxd = 0;
+    for (int round = 0; round < 100000; round++) {
+        uint32_t h[8];
+        CU(cudaMemsetAsync(s->d_scalars, 0, 8 * 4, st));
+        k_find_max<<<blocks, 256, 0, st>>>(P);
+        CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t prio = h[1];
+        if (prio <= P.epsilon_priority) break;
+        P.priority = prio;
+        k_gather<<<blocks, 256, 0, st>>>(P);
+        CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t n = h[0];
+        if (n == 0) continue;
+        k_compute<<<(n + 63) / 64, 64, 0, st>>>(P, n, nullptr);
+        k_apply<<<(n + 127) / 128, 128, 0, st>>>(P, n);
+        k_mark<<<(n + 63) / 64, 64, 0, st>>>(P, n);
+        CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        total += h[3];
+        visits += h[4];
+        if (h[2] > maxd) maxd = h[2];
+    }
+    if (updates_done) *updates_done = total;
+    if (max_diff) *max_diff = (uint8_t)maxd;
+    if (node_visits) *node_visits = visits;
+    return AICB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// called from aicb200.cu
+// ---------------------------------------------------------------------------------------------
+aicb_status aicb_light_scene_upload(aicb_scene *s, const aicb_scene_desc *d) {
+    s->light_max_distance = d->light_max_distance;
+    if (s->volume) s->h_ids.assign(d->block_ids, d->block_ids + s->volume);
+    std::vector<LightBlockDev> lb(d->n_blocks);
+    s->h_block_light.resize(d->n_blocks);
+    for (size_t i = 0; i < d->n_blocks; i++) {
+        const aicb_block_desc &b = d->blocks[i];
+        LightBlockDev &o = lb[i];
+        std::memcpy(o.face_color[0], b.light_color, 16);
+        for (int f = 0; f < 6; f++) std::memcpy(o.face_color[f + 1], b.light_face_colors[f], 16);
+        std::memcpy(o.emission, b.light_emission, 12);
+        uint32_t fl = b.light_opaque_faces & 0x3f;
+        if (fl == 0x3f) fl |= LB_ALL_OPAQUE;
+        if (b.light_visible) fl |= LB_VISIBLE;
+        if (!(b.light_emission[0] == 0.0f && b.light_emission[1] == 0.0f && b.light_emission[2] == 0.0f)) fl |= LB_EMISSIVE;
+        o.flags = fl;
+        s->h_block_light[i] = fl;
+    }
+    if (!lb.empty()) {
+        CU(cudaMalloc(&s->d_light_blocks, lb.size() * sizeof(LightBlockDev)));
+        CU(cudaMemcpy(s->d_light_blocks, lb.data(), lb.size() * sizeof(LightBlockDev), cudaMemcpyHostToDevice));
+        s->device_bytes += lb.size() * sizeof(LightBlockDev);
+    }
+    return AICB_OK;
+}
+
+void aicb_light_scene_free(aicb_scene *s) {
+    if (s->d_light_blocks) cudaFree(s->d_light_blocks);
+    if (s->d_pending) cudaFree(s->d_pending);
+    if (s->d_list) cudaFree(s->d_list);
+    if (s->d_new_light) cudaFree(s->d_new_light);
+    if (s->d_diff) cudaFree(s->d_diff);
+    if (s->d_scalars) cudaFree(s->d_scalars);
+}
+
+void aicb_light_ctx_free(aicb_ctx *c) {
+    if (c->d_chart) cudaFree(c->d_chart);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t aicb_light_chart(float *weights, uint32_t *children) {
+    static const std::vector<LightChartNode> chart = build_chart();
+    for (size_t i = 0; i < chart.size(); i++) {
+        if (weights) std::memcpy(weights + 6 * i, chart[i].w, 24);
+        if (children) std::memcpy(children + 6 * i, chart[i].child, 24);
+    }
+    return (uint32_t)chart.size();
+}
+
+aicb_status aicb_light_fast_evaluate(aicb_scene *s) {
+    if (!s) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    aicb_status st = ensure_light_state(s);
+    if (st != AICB_OK) return st;
+    LightParams P = make_params(s);
+    const uint32_t cols = (uint32_t)s->ds.size[0] * (uint32_t)s->ds.size[2];
+    if (cols) k_fast_evaluate<<<(cols + 127) / 128, 128, 0, s->ctx->stream>>>(P);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    return AICB_OK;
+}
+
+aicb_status aicb_light_compute(aicb_scene *s, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4]) {
+    if (!s || (n && (!cubes || !out))) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    if (n > s->volume) return aicb_fail(AICB_ERR_INVALID, "more cubes than the Space holds");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    aicb_status st = ensure_light_state(s);
+    if (st != AICB_OK) return st;
+    if (!n) return AICB_OK;
+    LightParams P = make_params(s);
+    int32_t *d_cubes = nullptr;
+    CU(cudaMalloc(&d_cubes, n * 12));
+    CU(cudaMemcpy(d_cubes, cubes, n * 12, cudaMemcpyHostToDevice));
+    k_compute<<<(unsigned)((n + 63) / 64), 64, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
+    cudaError_t e = cudaMemcpyAsync(out, s->d_new_light, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(d_cubes);
+    if (e != cudaSuccess) return aicb_cuda_fail(e, "light compute");
+    return AICB_OK;
+}
+
+aicb_status aicb_light_evaluate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, uint8_t *max_diff,
+                                uint64_t *node_visits) {
+    if (!s) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    aicb_status st = ensure_light_state(s);
+    if (st != AICB_OK) return st;
+    return propagate(s, epsilon, updates_done, max_diff, node_visits);
+}
+
+// Mutation::set x n (space.rs:1346-1352 -> side_effects_of_set -> modified_cube_needs_update,
+// updater.rs:135-173) applied in order on the host mirror, then evaluate_light(epsilon).
+aicb_status aicb_light_edit_and_propagate(aicb_scene *s, const int32_t (*cubes)[3], const uint16_t *new_ids, size_t n_edits,
+                                          uint8_t epsilon, uint64_t *updates_done, uint8_t *max_diff) {
+    if (!s || (n_edits && (!cubes || !new_ids))) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    aicb_status st = ensure_light_state(s);
+    if (st != AICB_OK) return st;
+    const DeviceScene &ds = s->ds;
+    auto index_of = [&](int x, int y, int z, uint32_t *idx) {
+        uint32_t dx = (uint32_t)(x - ds.lo[0]), dy = (uint32_t)(y - ds.lo[1]), dz = (uint32_t)(z - ds.lo[2]);
+        if (dx >= (uint32_t)ds.size[0] || dy >= (uint32_t)ds.size[1] || dz >= (uint32_t)ds.size[2]) return false;
+        *idx = (dx * (uint32_t)ds.size[1] + dy) * (uint32_t)ds.size[2] + dz;
+        return true;
+    };
+    std::unordered_map<uint32_t, EditOp> ops;
+    auto op_of = [&](uint32_t idx) -> EditOp & {
+        auto it = ops.find(idx);
+        if (it == ops.end()) {
+            EditOp o;
+            std::memset(&o, 0, sizeof o);
+            o.idx = idx;
+            o.cell = 0xffffffffu;
+            it = ops.emplace(idx, o).first;
+        }
+        return it->second;
+    };
+    for (size_t i = 0; i < n_edits; i++) {
+        uint32_t idx;
+        if (!index_of(cubes[i][0], cubes[i][1], cubes[i][2], &idx)) return aicb_fail(AICB_ERR_INVALID, "cube out of bounds");
+        if (new_ids[i] >= s->h_block_light.size()) return aicb_fail(AICB_ERR_INVALID, "block id out of range");
+        if (s->h_ids[idx] == new_ids[i]) continue;  // Mutation::set of the same block changes nothing
+        s->h_ids[idx] = new_ids[i];
+        EditOp &o = op_of(idx);
+        o.cell = ds.wide_cells ? (new_ids[i] | ((uint32_t)s->block_kind[new_ids[i]] << 16))
+                               : (new_ids[i] | ((uint32_t)s->block_kind[new_ids[i]] << 14));
+        const uint32_t fl = s->h_block_light[new_ids[i]];
+        if ((fl & LB_ALL_OPAQUE) && !(fl & LB_EMISSIVE)) {  // opaque_for_light_computation
+            o.set_opaque = 1;
+            o.pending_op = 1;
+        } else {
+            o.pending_op = 2;
+        }
+        for (int f = 0; f < 6; f++) {
+            const int sgn = (f < 3) ? -1 : 1, a = f % 3;
+            uint32_t nidx;
+            if (!index_of(cubes[i][0] + (a == 0 ? sgn : 0), cubes[i][1] + (a == 1 ? sgn : 0), cubes[i][2] + (a == 2 ? sgn : 0), &nidx))
+                continue;
+            const int opp = (f < 3) ? f + 3 : f - 3;
+            if (!((s->h_block_light[s->h_ids[nidx]] >> opp) & 1u)) op_of(nidx).pending_op = 2;
+        }
+    }
+    if (!ops.empty()) {
+        std::vector<EditOp> flat;
+        flat.reserve(ops.size());
+        for (auto &kv : ops) flat.push_back(kv.second);
+        EditOp *d_ops = nullptr;
+        CU(cudaMalloc(&d_ops, flat.size() * sizeof(EditOp)));
+        CU(cudaMemcpyAsync(d_ops, flat.data(), flat.size() * sizeof(EditOp), cudaMemcpyHostToDevice, s->ctx->stream));
+        LightParams P = make_params(s);
+        k_edits<<<(unsigned)((flat.size() + 127) / 128), 128, 0, s->ctx->stream>>>(P, d_ops, (uint32_t)flat.size(), ds.wide_cells);
+        cudaError_t e = cudaStreamSynchronize(s->ctx->stream);
+        cudaFree(d_ops);
+        if (e != cudaSuccess) return aicb_cuda_fail(e, "light edits");
+    }
+    return propagate(s, epsilon, updates_done, max_diff, nullptr);
+}
+
+aicb_status aicb_light_download(aicb_scene *s, uint8_t (*out)[4], size_t n_texels) {
+    if (!s || !out) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    if (n_texels != s->volume) return aicb_fail(AICB_ERR_INVALID, "light volume size mismatch");
+    if (!s->d_light) return aicb_fail(AICB_ERR_INVALID, "scene has no light volume (LightPhysics::None)");
+    std::lock_guard<std::mutex> lock(s->ctx->mu);
+    CU(cudaSetDevice(s->ctx->device));
+    CU(cudaMemcpy(out, s->d_light, s->volume * 4, cudaMemcpyDeviceToHost));
+    return AICB_OK;
+}
+}

@@ -1,0 +1,373 @@
+// light_kernel.cuh — device code of the secondary path: all-is-cubes' light propagation
+// (all-is-cubes/src/space/light/updater.rs) as batched relaxation kernels.
+//
+// Design: the reference pops one cube at a time from a priority queue (32 at a time with threads,
+// updater.rs:211-252) and recomputes its light by a depth-first walk over a static ray chart
+// (walk_ray_tree, updater.rs:427-529).  Here the queue is a per-cube priority byte in HBM; one round
+// = all cubes of the highest queued priority: gather -> compute (one thread per cube, explicit-stack
+// DFS reproducing the recursion's f32 summation order exactly) -> apply (store, fill uninitialised
+// neighbours, re-queue dependencies by re-walking the chart).  compute_light on a given field is
+// bit-identical to the reference; the relaxation order differs (batch = one priority level), which
+// the reference leaves unspecified (queue.rs:226-246) — parity contract SURVEY §8(a) L4.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "trace_kernel.cuh"
+
+// FlatNode (chart/shared.rs:13-25): 6 weights + 6 child indices (0 = none); root = 0.
+struct LightChartNode {
+    float w[6];
+    uint32_t child[6];
+};
+
+// The EvaluatedBlock members light reads (evaluated.rs:189-272), 128 bytes.
+struct LightBlockDev {
+    float face_color[7][4];  // Within, NX..PZ (face7_color)
+    float emission[3];
+    uint32_t flags;          // bits 0-5 opaque[NX..PZ], 6 all opaque, 7 visible_or_animated, 8 emission != 0
+};
+static_assert(sizeof(LightBlockDev) == 128, "LightBlockDev must be 128 bytes");
+
+constexpr uint32_t LB_ALL_OPAQUE = 1u << 6, LB_VISIBLE = 1u << 7, LB_EMISSIVE = 1u << 8;
+constexpr int LIGHT_MAX_DEPTH = 224;  // longest chart path is 219 (rays end at t = 127, generator.rs:101)
+
+constexpr uint32_t TX_OPAQUE = 128u << 24, TX_NO_RAYS = 1u << 24, TX_UNINIT = 0u;
+constexpr int PRIO_NEWLY_VISIBLE = 250, PRIO_ESTIMATED = 200;
+
+struct LightParams {
+    aicb::DeviceScene scene;        // cells, light, sky faces, tables (LUT)
+    const LightBlockDev *blocks;
+    const LightChartNode *chart;
+    uint8_t *pending;
+    uint32_t *list;
+    uint32_t *new_light;
+    uint8_t *diff;
+    uint32_t *scalars;              // [0] list length, [1] max priority, [2] max diff, [3] updates, [4] node visits (lo)
+    uint32_t volume;
+    uint32_t max_distance;
+    uint32_t priority;              // the round's priority level
+    uint32_t epsilon_priority;
+};
+
+#ifdef __CUDACC__
+
+namespace aicb_light {
+
+using aicb::DeviceScene;
+
+__device__ __forceinline__ float ps_clamped(float v) { return (v > 0.0f) ? v : 0.0f; }
+__device__ __forceinline__ float ps_mul(float a, float b) {
+    float v = a * b;
+    return (v != v) ? 0.0f : v;
+}
+__device__ __forceinline__ float fm_sum(const float w[6]) { return (w[0] + w[3]) + (w[1] + w[4]) + (w[2] + w[5]); }
+
+__device__ __forceinline__ uint32_t block_id_at(const DeviceScene &S, uint32_t idx) {
+    return S.wide_cells ? (__ldg((const uint32_t *)S.cells + idx) & 0xffffu)
+                        : ((uint32_t)__ldg((const uint16_t *)S.cells + idx) & 0x3fffu);
+}
+__device__ __forceinline__ bool cube_index(const DeviceScene &S, int x, int y, int z, uint32_t *idx) {
+    uint32_t dx = (uint32_t)(x - S.lo[0]), dy = (uint32_t)(y - S.lo[1]), dz = (uint32_t)(z - S.lo[2]);
+    if ((dx >= (uint32_t)S.size[0]) | (dy >= (uint32_t)S.size[1]) | (dz >= (uint32_t)S.size[2])) return false;
+    *idx = (dx * (uint32_t)S.size[1] + dy) * (uint32_t)S.size[2] + dz;
+    return true;
+}
+__device__ __forceinline__ void cube_of(const DeviceScene &S, uint32_t idx, int &x, int &y, int &z) {
+    z = (int)(idx % (uint32_t)S.size[2]) + S.lo[2];
+    y = (int)((idx / (uint32_t)S.size[2]) % (uint32_t)S.size[1]) + S.lo[1];
+    x = (int)(idx / ((uint32_t)S.size[2] * (uint32_t)S.size[1])) + S.lo[0];
+}
+// UpdateCtx::get_evaluated flags (updater.rs:615-621): out of bounds = AIR (flags 0)
+__device__ __forceinline__ uint32_t flags_at(const LightParams &P, int x, int y, int z) {
+    uint32_t idx;
+    if (!cube_index(P.scene, x, y, z, &idx)) return 0u;
+    return __ldg(&P.blocks[block_id_at(P.scene, idx)].flags);
+}
+// LightStorage::get (updater.rs:585-595)
+__device__ __forceinline__ uint32_t light_get(const LightParams &P, int x, int y, int z) {
+    uint32_t idx;
+    if (cube_index(P.scene, x, y, z, &idx)) return P.scene.light[idx];
+    return aicb::light_outside(P.scene, x, y, z);
+}
+// PackedLight::scalar_in (data.rs:213-217) as a search: qthr[k] (k = 1..255) is the smallest f32 whose
+// quantised value is >= k, computed on the host with the platform log2f (monotone) — bit-identical to
+// the reference on that host.  `tables` = DeviceScene::tables; the thresholds live at [512, 768).
+__device__ __forceinline__ uint32_t scalar_in_t(const float *tables, float v) {
+    const float *thr = tables + 512;
+    int lo = 0, hi = 255;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (v >= __ldg(thr + mid)) lo = mid; else hi = mid - 1;
+    }
+    return (uint32_t)lo;
+}
+__device__ __forceinline__ int difference_priority(uint32_t a, uint32_t b) {  // data.rs:193-211
+    int d = 0;
+#pragma unroll
+    for (int s = 0; s < 24; s += 8) {
+        int x = (a >> s) & 255, y = (b >> s) & 255;
+        int e = x > y ? x - y : y - x;
+        d = e > d ? e : d;
+    }
+    if ((a >> 24) != (b >> 24)) d = min(255, d + 63);
+    return d;
+}
+
+// LightUpdateQueue::insert (queue.rs:107-133): raise the queued priority of a cube (never lowers it).
+// The queue is one byte per cube; the byte is updated with a CAS on its containing word.
+__device__ __forceinline__ void raise_pending(uint8_t *pending, uint32_t idx, uint32_t prio) {
+    uint32_t *wp = (uint32_t *)(pending + (idx & ~3u));
+    const uint32_t shift = (idx & 3u) * 8u;
+    uint32_t old = *wp;
+    while (((old >> shift) & 255u) < prio) {
+        const uint32_t nv = (old & ~(255u << shift)) | (prio << shift);
+        const uint32_t prev = atomicCAS(wp, old, nv);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+// light_needs_update (updater.rs:107-111)
+__device__ __forceinline__ void mark_dependency(const LightParams &P, int x, int y, int z, uint32_t prio) {
+    uint32_t idx;
+    if (cube_index(P.scene, x, y, z, &idx)) raise_pending(P.pending, idx, prio);
+}
+
+struct Frame {
+    uint32_t node;
+    int x, y, z;          // cube entered
+    float alpha;          // ray_state.alpha after traverse()
+    float bundle;         // ray_bundle_weight
+    float child_sum;
+    uint32_t ahead;       // light_ahead_cache
+    uint8_t have_ahead;
+    uint8_t next_child;
+};
+
+struct Accum {
+    float in0, in1, in2, total;
+};
+
+// end_of_ray (updater.rs:889-924) + add_weighted_light (:926-929)
+__device__ __forceinline__ void end_of_ray(const LightParams &P, const float *lut, Accum &a, float alpha, float bundle,
+                                           const float cw[6]) {
+    if (bundle > 0.0f) {
+        float t[6][3];
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            uint32_t tx = P.scene.sky_faces[f];
+            float k = ps_clamped(cw[f]);
+            t[f][0] = ps_mul(lut[tx & 255], k);
+            t[f][1] = ps_mul(lut[(tx >> 8) & 255], k);
+            t[f][2] = ps_mul(lut[(tx >> 16) & 255], k);
+        }
+        const float kr = ps_clamped(1.0f / fm_sum(cw));
+        const float ka = ps_clamped(alpha), kb = ps_clamped(bundle);
+        float c[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float s = (t[0][i] + t[3][i]) + (t[1][i] + t[4][i]) + (t[2][i] + t[5][i]);
+            c[i] = ps_mul(ps_mul(s, kr), ka);
+        }
+        a.in0 = a.in0 + ps_mul(c[0], kb);
+        a.in1 = a.in1 + ps_mul(c[1], kb);
+        a.in2 = a.in2 + ps_mul(c[2], kb);
+        a.total += bundle;
+    }
+}
+
+// compute_light (updater.rs:368-418) with walk_ray_tree (:427-529) and LightBuffer::traverse (:760-884).
+// MARK = false: returns the new texel.  MARK = true: instead of accumulating light, raises the queue
+// priority of every dependency cube to `mark_priority` (apply_light_update's re-queue, updater.rs:355-360).
+template <bool MARK>
+__device__ uint32_t compute_light(const LightParams &P, const float *lut, int ox, int oy, int oz, uint32_t mark_priority,
+                                  uint32_t *visits_out) {
+    const DeviceScene &S = P.scene;
+    Accum acc = {0.f, 0.f, 0.f, 0.f};
+    uint32_t oidx;
+    uint32_t oflags = 0;
+    const LightBlockDev *ob = nullptr;
+    if (cube_index(S, ox, oy, oz, &oidx)) {
+        ob = &P.blocks[block_id_at(S, oidx)];
+        oflags = __ldg(&ob->flags);
+    }
+    const bool origin_opaque = (oflags & LB_ALL_OPAQUE) != 0;
+    uint32_t visits = 0;
+    if (origin_opaque) {
+        if (oflags & LB_EMISSIVE) {  // !opaque_for_light_computation: add_weighted_light(emission, 1.0)
+            acc.in0 = acc.in0 + ps_mul(__ldg(&ob->emission[0]), 1.0f);
+            acc.in1 = acc.in1 + ps_mul(__ldg(&ob->emission[1]), 1.0f);
+            acc.in2 = acc.in2 + ps_mul(__ldg(&ob->emission[2]), 1.0f);
+            acc.total += 1.0f;
+        }
+    } else {
+        float dw[6];
+        if (oflags & LB_VISIBLE) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) dw[f] = 1.0f;
+        } else {  // directions_to_seek_light (updater.rs:669-690)
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                const int s = (f < 3) ? -1 : 1, a = f % 3;
+                const uint32_t toward = flags_at(P, ox + (a == 0 ? s : 0), oy + (a == 1 ? s : 0), oz + (a == 2 ? s : 0));
+                const uint32_t away = flags_at(P, ox - (a == 0 ? s : 0), oy - (a == 1 ? s : 0), oz - (a == 2 ? s : 0));
+                dw[f] = ((away & LB_VISIBLE) || (toward & LB_EMISSIVE)) ? 1.0f : 0.0f;
+            }
+        }
+        const double max_d2 = (double)P.max_distance * (double)P.max_distance;
+
+        Frame stack[LIGHT_MAX_DEPTH];
+        int sp = 0;
+        // "call" the root
+        bool entering = true;
+        uint32_t e_node = 0;
+        int e_x = ox, e_y = oy, e_z = oz, e_face = 0;
+        float e_alpha = 1.0f;
+        bool e_have_prev = false;
+        uint32_t e_prev = 0;
+        float ret = 0.0f;
+        for (;;) {
+            if (entering) {
+                entering = false;
+                visits++;
+                const LightChartNode *node = P.chart + e_node;
+                float cw[6];
+#pragma unroll
+                for (int f = 0; f < 6; f++) cw[f] = __ldg(&node->w[f]);
+                float prod[6];
+#pragma unroll
+                for (int f = 0; f < 6; f++) prod[f] = cw[f] * dw[f];
+                const float bundle = fm_sum(prod);
+                bool done = false;
+                if (bundle <= 0.0f) {
+                    done = true;
+                } else {
+                    const double ddx = ((double)e_x + 0.5) - ((double)ox + 0.5), ddy = ((double)e_y + 0.5) - ((double)oy + 0.5),
+                                 ddz = ((double)e_z + 0.5) - ((double)oz + 0.5);
+                    uint32_t cidx;
+                    if ((ddx * ddx + ddy * ddy + ddz * ddz) > max_d2 || !cube_index(S, e_x, e_y, e_z, &cidx)) {
+                        if (!MARK) end_of_ray(P, lut, acc, e_alpha, bundle, cw);
+                        done = true;
+                    } else {
+                        // ---- LightBuffer::traverse ----
+                        const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
+                        const uint32_t fl = __ldg(&ev->flags);
+                        float alpha = e_alpha;
+                        bool have_ahead = false;
+                        uint32_t ahead = 0;
+                        if (fl & LB_VISIBLE) {
+                            const bool hit_opaque_face = (e_face == 0) ? ((fl & LB_ALL_OPAQUE) != 0) : (((fl >> (e_face - 1)) & 1u) != 0);
+                            if (hit_opaque_face && e_face == 0) {
+                                alpha = 0.0f;  // (direction weights are zeroed too; nothing reads them afterwards)
+                            } else {
+                                float col[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) col[i] = __ldg(&ev->face_color[e_face][i]);
+#pragma unroll
+                                for (int i = 0; i < 3; i++) col[i] = col[i] > 1.0f ? 1.0f : col[i];  // Rgba::clamp
+                                const float hit_alpha = col[3];
+                                const float kw = ps_clamped(fm_sum(prod));
+                                if (hit_alpha > 0.0f && e_face != 0) {
+                                    int lx = e_x, ly = e_y, lz = e_z;  // hit.adjacent(): the cube the ray came from
+                                    const int ax = (e_face - 1) % 3, sgn = (e_face >= 4) ? 1 : -1;
+                                    if (ax == 0) lx += sgn; else if (ax == 1) ly += sgn; else lz += sgn;
+                                    if (MARK) mark_dependency(P, lx, ly, lz, mark_priority);
+                                    if (!MARK) {
+                                        const uint32_t stored = e_have_prev ? e_prev : light_get(P, lx, ly, lz);
+                                        const float ka = ps_clamped(alpha);
+                                        float lf[3];
+                                        lf[0] = __ldg(&ev->emission[0]) + ps_mul(ps_mul(col[0], lut[stored & 255]), hit_alpha);
+                                        lf[1] = __ldg(&ev->emission[1]) + ps_mul(ps_mul(col[1], lut[(stored >> 8) & 255]), hit_alpha);
+                                        lf[2] = __ldg(&ev->emission[2]) + ps_mul(ps_mul(col[2], lut[(stored >> 16) & 255]), hit_alpha);
+                                        acc.in0 = acc.in0 + ps_mul(ps_mul(lf[0], ka), kw);
+                                        acc.in1 = acc.in1 + ps_mul(ps_mul(lf[1], ka), kw);
+                                        acc.in2 = acc.in2 + ps_mul(ps_mul(lf[2], ka), kw);
+                                    }
+                                    if (hit_opaque_face) alpha = 0.0f; else alpha *= 1.0f - hit_alpha;
+                                }
+                                if (hit_alpha < 1.0f) {
+                                    if (MARK) mark_dependency(P, e_x, e_y, e_z, mark_priority);
+                                    if (!MARK) {
+                                        float sv0 = 0.f, sv1 = 0.f, sv2 = 0.f;
+                                        if (e_face != 0) {
+                                            ahead = S.light[cidx];
+                                            have_ahead = true;
+                                            sv0 = lut[ahead & 255]; sv1 = lut[(ahead >> 8) & 255]; sv2 = lut[(ahead >> 16) & 255];
+                                        }
+                                        const float kh = ps_clamped(hit_alpha), ka = ps_clamped(alpha);
+                                        const float l0 = __ldg(&ev->emission[0]) + ps_mul(sv0, kh);
+                                        const float l1 = __ldg(&ev->emission[1]) + ps_mul(sv1, kh);
+                                        const float l2 = __ldg(&ev->emission[2]) + ps_mul(sv2, kh);
+                                        acc.in0 = acc.in0 + ps_mul(ps_mul(l0, ka), kw);
+                                        acc.in1 = acc.in1 + ps_mul(ps_mul(l1, ka), kw);
+                                        acc.in2 = acc.in2 + ps_mul(ps_mul(l2, ka), kw);
+                                    }
+                                    alpha *= 1.0f - hit_alpha;
+                                }
+                            }
+                        }
+                        if (!(alpha > 0.0f)) {
+                            if (!MARK) end_of_ray(P, lut, acc, alpha, bundle, cw);
+                            done = true;
+                        } else {
+                            Frame &fr = stack[sp++];
+                            fr.node = e_node; fr.x = e_x; fr.y = e_y; fr.z = e_z;
+                            fr.alpha = alpha; fr.bundle = bundle; fr.child_sum = 0.0f;
+                            fr.ahead = ahead; fr.have_ahead = have_ahead ? 1 : 0; fr.next_child = 0;
+                        }
+                    }
+                }
+                if (done) {
+                    ret = bundle;
+                    if (sp == 0) break;
+                    stack[sp - 1].child_sum += ret;
+                }
+                continue;
+            }
+            // resume the frame on top of the stack: next child, or finish
+            Frame &fr = stack[sp - 1];
+            const LightChartNode *node = P.chart + fr.node;
+            int f = fr.next_child;
+            uint32_t child = 0;
+            while (f < 6) {
+                child = __ldg(&node->child[f]);
+                if (child) break;
+                f++;
+            }
+            if (f < 6) {
+                fr.next_child = (uint8_t)(f + 1);
+                const int s = (f < 3) ? -1 : 1, a = f % 3;
+                e_node = child;
+                e_x = fr.x + (a == 0 ? s : 0); e_y = fr.y + (a == 1 ? s : 0); e_z = fr.z + (a == 2 ? s : 0);
+                e_face = ((f < 3) ? f + 3 : f - 3) + 1;
+                e_alpha = fr.alpha;
+                e_have_prev = fr.have_ahead != 0;
+                e_prev = fr.ahead;
+                entering = true;
+                continue;
+            }
+            // all children done
+            if (!MARK) {
+                float cw[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) cw[k] = __ldg(&node->w[k]);
+                end_of_ray(P, lut, acc, fr.alpha, fmaxf(fr.bundle - fr.child_sum, 0.0f), cw);
+            }
+            ret = fr.bundle;
+            sp--;
+            if (sp == 0) break;
+            stack[sp - 1].child_sum += ret;
+        }
+    }
+    if (visits_out) *visits_out = visits;
+    // LightBuffer::finish (updater.rs:932-944)
+    const float scale = ps_clamped(1.0f / fmaxf(acc.total, 1.0f));
+    if (acc.total > 0.0f)
+        return scalar_in_t(S.tables, ps_mul(acc.in0, scale)) | (scalar_in_t(S.tables, ps_mul(acc.in1, scale)) << 8) |
+               (scalar_in_t(S.tables, ps_mul(acc.in2, scale)) << 16) | (255u << 24);
+    return origin_opaque ? TX_OPAQUE : TX_NO_RAYS;
+}
+
+}  // namespace aicb_light
+#endif

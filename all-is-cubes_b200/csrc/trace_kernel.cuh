@@ -53,7 +53,8 @@ struct DeviceScene {
     const BlockRec *blocks;
     const uint16_t *bricks;     // palette index | invisible<<15
     const float4 *palette;      // 2 x float4 per entry: rgba, emission
-    const float *tables;        // [0,256): PackedLight decode LUT (data.rs:301-354); [256,512): sRGB8 thresholds
+    const float *tables;        // [0,256): PackedLight decode LUT (data.rs:301-354); [256,512): sRGB8 thresholds;
+                                // [512,768): PackedLight quantiser thresholds (light kernels)
     uint32_t sky_faces[6];      // BlockSky faces NX..PZ as texels (sky.rs:54-82)
     uint32_t sky_mean;
     uint32_t sky_kind;
@@ -100,7 +101,7 @@ struct TraceParams {
 #ifdef __CUDACC__
 
 #define AICB_DEV __device__ __forceinline__
-#define AICB_NOINLINE __device__ __noinline__
+#define AICB_NOINLINE static __device__ __noinline__
 
 constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (template)
 constexpr int TILE_W = 8, TILE_H = 4;

@@ -264,6 +264,19 @@ void aicb_camera_project_ndc(const aicb_camera *, double ndc_x, double ndc_y, do
  * Light propagation (secondary path): replaces Mutation::set x n + evaluate_light(epsilon)
  * (space.rs:1346-1352, 1496-1527; space/light/updater.rs:181-363).
  * ------------------------------------------------------------------------------------------- */
+/* The static light-ray chart (space/light/chart/generator.rs:49-215) as the flat prefix tree the kernels
+ * walk: 6 f32 weights + 6 child indices (0 = none) per node, root = 0.  Returns the node count
+ * (114 779); either pointer may be NULL.  Host only. */
+uint32_t aicb_light_chart(float *weights_or_null, uint32_t *children_or_null);
+/* LightStorage::fast_evaluate_light (updater.rs:537-582): column-sweep initial guess + queue seeding. */
+aicb_status aicb_light_fast_evaluate(aicb_scene *);
+/* LightStorage::compute_light (updater.rs:368-418) for explicit cubes against the current field; does not
+ * store anything (parity tests). out[i] = PackedLight::as_texel. */
+aicb_status aicb_light_compute(aicb_scene *, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4]);
+/* Mutation::evaluate_light(epsilon) (space.rs:1496-1527): relax until the highest queued priority is
+ * <= Priority::from_difference(epsilon). */
+aicb_status aicb_light_evaluate(aicb_scene *, uint8_t epsilon, uint64_t *updates_done, uint8_t *max_diff,
+                                uint64_t *chart_node_visits_or_null);
 aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*cubes)[3], const uint16_t *new_ids,
                                           size_t n_edits, uint8_t epsilon, uint64_t *updates_done,
                                           uint8_t *max_diff);

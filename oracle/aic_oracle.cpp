@@ -1598,6 +1598,13 @@ void orc_pixel_ray(const aicb_camera *cam, uint32_t x, uint32_t y, int sample, d
     pixel_ray(*cam, x, y, sample, out, out + 3);
 }
 
+void orc_scene_block_sky(const orc_scene *s, uint8_t out[7][4]) {
+    for (int f = 0; f < 6; f++) {
+        out[f][0] = s->sky_faces[f].r; out[f][1] = s->sky_faces[f].g; out[f][2] = s->sky_faces[f].b; out[f][3] = s->sky_faces[f].status;
+    }
+    out[6][0] = s->sky_mean.r; out[6][1] = s->sky_mean.g; out[6][2] = s->sky_mean.b; out[6][3] = s->sky_mean.status;
+}
+
 int orc_hardware_threads(void) {
     unsigned n = std::thread::hardware_concurrency();
     return n ? (int)n : 1;

@@ -140,4 +140,23 @@ uint64_t orc_render_rowlist(const orc_scene *, const aicb_camera *, const aicb_o
 void orc_pixel_ray(const aicb_camera *, uint32_t x, uint32_t y, int sample /* -1 centre, 0..3 AA */,
                    double out_origin_dir[6]);
 int orc_hardware_threads(void);
+// BlockSky of a scene as texels: faces NX..PZ then mean (sky.rs:54-82)
+void orc_scene_block_sky(const orc_scene *, uint8_t out[7][4]);
+
+// ---- light propagation (oracle/aic_light.cpp) -----------------------------------
+typedef struct orc_light orc_light;
+size_t orc_light_chart(float *weights_or_null, uint32_t *children_or_null);  // flat chart (generator.rs), root = 0
+orc_light *orc_light_create(const aicb_scene_desc *);   // light field = desc.light or all NO_RAYS
+void orc_light_destroy(orc_light *);
+void orc_light_fast_evaluate(orc_light *);               // updater.rs:537-582
+void orc_light_set_cubes(orc_light *, const int32_t (*cubes)[3], const uint16_t *ids, size_t n);  // Mutation::set
+uint64_t orc_light_evaluate(orc_light *, uint8_t epsilon, uint64_t max_updates, uint8_t *max_diff_out);  // space.rs:1496-1527
+void orc_light_compute(orc_light *, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4]);  // compute_light only
+void orc_light_get(const orc_light *, uint8_t (*out)[4]);
+void orc_light_set_field(orc_light *, const uint8_t (*in)[4]);
+void orc_light_get_outside(const orc_light *, const int32_t cube[3], uint8_t out[4]);  // LightStorage::get incl. out of bounds
+void orc_light_set_pop_order(orc_light *, int order);  // 0 lowest cube index first (default), 1 highest first
+size_t orc_light_queue_len(const orc_light *);
+int orc_light_queue_peek(const orc_light *);
+uint64_t orc_light_node_visits(const orc_light *);
 }

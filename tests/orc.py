@@ -17,7 +17,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    src = [os.path.join(ROOT, "oracle", f) for f in ("aic_oracle.cpp", "aic_oracle.hpp")]
+    src = [os.path.join(ROOT, "oracle", f) for f in ("aic_oracle.cpp", "aic_light.cpp", "aic_oracle.hpp")]
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-B"], check=True, capture_output=True)
     L = C.CDLL(LIB_PATH)
@@ -57,6 +57,26 @@ def lib():
     L.orc_pixel_ray.argtypes = [C.POINTER(abi.CameraData), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.orc_pixel_ray.restype = None
     L.orc_hardware_threads.restype = C.c_int
+    L.orc_light_chart.restype = C.c_size_t
+    L.orc_light_chart.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_light_create.restype = C.c_void_p
+    L.orc_light_create.argtypes = [C.POINTER(abi.SceneDesc)]
+    L.orc_light_destroy.argtypes = [C.c_void_p]
+    L.orc_light_fast_evaluate.argtypes = [C.c_void_p]
+    L.orc_light_set_cubes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.orc_light_evaluate.restype = C.c_uint64
+    L.orc_light_evaluate.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64, C.c_void_p]
+    L.orc_light_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.orc_light_get.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_light_set_field.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_light_get_outside.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_light_set_pop_order.argtypes = [C.c_void_p, C.c_int]
+    L.orc_light_queue_len.restype = C.c_size_t
+    L.orc_light_queue_len.argtypes = [C.c_void_p]
+    L.orc_light_queue_peek.restype = C.c_int
+    L.orc_light_queue_peek.argtypes = [C.c_void_p]
+    L.orc_light_node_visits.restype = C.c_uint64
+    L.orc_light_node_visits.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -217,3 +237,73 @@ def ulp_diff(a, b):
 
 def max_ulp_diff(a, b):
     return int(ulp_diff(a, b).max()) if np.size(a) else 0
+
+
+def light_chart():
+    n = lib().orc_light_chart(None, None)
+    w = np.zeros((n, 6), dtype=np.float32)
+    ch = np.zeros((n, 6), dtype=np.uint32)
+    lib().orc_light_chart(w.ctypes.data, ch.ctypes.data)
+    return w, ch
+
+
+class OracleLight:
+    """Light propagation oracle over a Space (space/light/updater.rs restatement)."""
+
+    def __init__(self, space):
+        self.space = space
+        desc, keep = space.to_desc()
+        self.handle = lib().orc_light_create(C.byref(desc))
+        del keep
+        self.shape = space.size
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().orc_light_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_pop_order(self, order):
+        lib().orc_light_set_pop_order(self.handle, order)
+
+    def fast_evaluate(self):
+        lib().orc_light_fast_evaluate(self.handle)
+
+    def set_cubes(self, cubes, ids):
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        i = np.ascontiguousarray(ids, dtype=np.uint16)
+        lib().orc_light_set_cubes(self.handle, c.ctypes.data, i.ctypes.data, c.shape[0])
+
+    def evaluate(self, epsilon=0, max_updates=2**62):
+        md = C.c_uint8(0)
+        n = lib().orc_light_evaluate(self.handle, epsilon, max_updates, C.byref(md))
+        return int(n), int(md.value)
+
+    def compute(self, cubes):
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros((c.shape[0], 4), dtype=np.uint8)
+        lib().orc_light_compute(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data)
+        return out
+
+    def field(self):
+        out = np.zeros(self.shape + (4,), dtype=np.uint8)
+        lib().orc_light_get(self.handle, out.ctypes.data)
+        return out
+
+    def set_field(self, field):
+        f = np.ascontiguousarray(field, dtype=np.uint8)
+        lib().orc_light_set_field(self.handle, f.ctypes.data)
+
+    def get(self, cube):
+        c = np.array(cube, dtype=np.int32)
+        out = np.zeros(4, dtype=np.uint8)
+        lib().orc_light_get_outside(self.handle, c.ctypes.data, out.ctypes.data)
+        return tuple(int(v) for v in out)
+
+    def queue_len(self):
+        return int(lib().orc_light_queue_len(self.handle))
+
+    def queue_peek(self):
+        return int(lib().orc_light_queue_peek(self.handle))

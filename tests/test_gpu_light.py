@@ -1,0 +1,172 @@
+"""GPU parity tests for the secondary path: light propagation (space::light) — SURVEY §8(a) L1-L4.
+
+Contract (L4): compute_light on a given field is bit-identical to the oracle; converged fields have
+identical statuses and values within 2 PackedLightScalar units (the reference itself leaves the
+update order unspecified and stops at 1-unit differences, updater.rs:348-360); tiny reference scenes
+(light/tests.rs) reproduce the reference's exact values."""
+import numpy as np
+import pytest
+
+import aicb200
+import orc
+from aicb200 import Block, GraphicsOptions, Space, SpaceRaytracer, scenes
+
+pytestmark = pytest.mark.gpu
+OPAQUE, NO_RAYS, UNINIT, VISIBLE = 128, 1, 0, 255
+WHITE = (1.0, 1.0, 1.0, 1.0)
+
+
+def empty_space(size, blocks, sky=((0.9, 0.9, 0.9),), max_distance=30):
+    ids = np.zeros(size, dtype=np.uint16)
+    light = np.zeros(size + (4,), dtype=np.uint8)
+    light[..., 3] = NO_RAYS
+    return Space((0, 0, 0), ids, [Block.air()] + list(blocks), light=light, sky_colors=list(sky), light_max_distance=max_distance)
+
+
+def light_scene(n=14, seed=5, lower=(-2, 1, 3)):
+    """Random atoms: opaque / transparent / emissive / invisible, ~18 % fill."""
+    h = scenes.grid_hash(seed, (n, n, n))
+    blocks = [Block.air(), Block(color=(0.8, 0.7, 0.6, 1.0)), Block(color=(0.2, 0.9, 0.3, 1.0)),
+              Block(color=(0.9, 0.2, 0.1, 0.5)), Block(color=(0.3, 0.3, 0.9, 0.125)),
+              Block(color=(0.1, 0.1, 0.1, 1.0), emission=(4.0, 3.0, 1.0)),
+              Block(color=(0.0, 0.0, 0.0, 0.0), emission=(0.2, 0.6, 2.0)), Block(color=(0.5, 0.5, 0.5, 0.0))]
+    sel = (h % np.uint64(40)).astype(np.int64)
+    ids = np.where(sel < 7, sel + 1, 0).astype(np.uint16)
+    ids[:, 0, :] = 1  # a floor
+    light = np.zeros((n, n, n, 4), dtype=np.uint8)
+    light[..., 3] = NO_RAYS
+    return Space(lower, ids, blocks, light=light, sky_colors=scenes.OCTANT_SKY, light_max_distance=12)
+
+
+def all_cubes(space):
+    x, y, z = np.meshgrid(*[np.arange(space.lower[a], space.lower[a] + space.size[a]) for a in range(3)], indexing="ij")
+    return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).astype(np.int32)
+
+
+def test_compute_light_bit_exact_on_identical_fields():
+    space = light_scene()
+    ol = orc.OracleLight(space)
+    ol.fast_evaluate()
+    cubes = all_cubes(space)
+    for stage in range(3):
+        field = ol.field()
+        sp2 = Space(space.lower, space.block_ids, space.blocks, light=field, sky_colors=space.sky_colors, light_max_distance=12)
+        rt = SpaceRaytracer(sp2, GraphicsOptions())
+        gpu = rt.light_compute(cubes)
+        ref = ol.compute(cubes)
+        assert np.array_equal(gpu, ref), f"stage {stage}: {np.argwhere((gpu != ref).any(axis=1))[:5]}"
+        ol.evaluate(0, max_updates=400 * (stage + 1))
+
+
+def test_reference_light_kats_on_gpu():
+    """light/tests.rs:233-261 exact neighbour values around an opaque emitter; :111-160; :162-174."""
+    light = (0.5, 1.0, 2.0)
+    sp = empty_space((3, 3, 3), [Block(color=WHITE, emission=light)], sky=[(0.0, 0.0, 0.0)])
+    rt = SpaceRaytracer(sp, GraphicsOptions())
+    rt.light_edit_and_propagate([(1, 1, 1)], [1], 0)
+    f = rt.light_download()
+    L = orc.lib()
+    val = lambda t: tuple(np.float32(L.orc_packed_light_lut(int(v))) for v in t[:3])
+    f32 = np.float32
+    assert val(f[0, 1, 1]) == val(f[2, 1, 1]) == (f32(0.13397168), f32(0.26794338), f32(0.53588676))
+    assert val(f[1, 0, 1]) == val(f[1, 2, 1]) == (f32(0.1649385), f32(0.32987696), f32(0.6597539))
+    assert val(f[1, 1, 0]) == val(f[1, 1, 2]) == (f32(0.21763763), f32(0.43527526), f32(0.8705506))
+    # `evaluate_light`: 0, then 2 updates, then 0
+    sp = empty_space((3, 1, 1), [Block(color=WHITE)])
+    rt = SpaceRaytracer(sp, GraphicsOptions())
+    assert rt.light_evaluate(0)[0] == 0
+    assert rt.light_edit_and_propagate([(1, 0, 0)], [1], 0)[0] == 2
+    assert rt.light_evaluate(0)[0] == 0
+    # `step`: the cube next to a new opaque block takes the sky colour
+    sp = empty_space((3, 1, 1), [Block(color=WHITE)], sky=[(1.0, 0.0, 0.0)])
+    rt = SpaceRaytracer(sp, GraphicsOptions())
+    n, md = rt.light_edit_and_propagate([(0, 0, 0)], [1], 0)
+    f = rt.light_download()
+    assert n == 1 and tuple(f[0, 0, 0]) == (0, 0, 0, OPAQUE) and tuple(f[2, 0, 0]) == (0, 0, 0, NO_RAYS)
+    assert tuple(f[1, 0, 0]) == (144, 0, 0, VISIBLE)
+
+
+def converge_both(space):
+    ol = orc.OracleLight(space)
+    ol.fast_evaluate()
+    ol.evaluate(0)
+    rt = SpaceRaytracer(space, GraphicsOptions())
+    rt.light_fast_evaluate()
+    rt.light_evaluate(0)
+    return ol, rt
+
+
+def compare_fields(gpu, ref, max_units=8, frac_within_2=0.97):
+    """Statuses exact.  Values: the reference's fixed point depends on its (unspecified) queue order — the
+    oracle run with two legal pop orders differs from ITSELF by up to 4 units on this scene
+    (tests/test_oracle_light.py::test_order_dependence_of_the_reference_algorithm) — so the bound is
+    a few units, with nearly all cubes within 2."""
+    assert np.array_equal(gpu[..., 3], ref[..., 3]), "LightStatus differs"
+    d = np.abs(gpu[..., :3].astype(int) - ref[..., :3].astype(int)).max(axis=-1)
+    assert d.max() <= max_units, f"max difference {d.max()} units at {np.argwhere(d > max_units)[:4]}"
+    assert (d <= 2).mean() >= frac_within_2, f"only {(d <= 2).mean():.3f} of cubes within 2 units"
+    return int(d.max()), float((d > 0).mean())
+
+
+def test_converged_field_matches_oracle_and_is_quiescent():
+    space = light_scene()
+    ol, rt = converge_both(space)
+    gpu, ref = rt.light_download(), ol.field()
+    compare_fields(gpu, ref)
+    # Quiescence: the reference re-queues only the cubes a changed cube READ (updater.rs:355-360) and drops
+    # 1-unit changes, so its own converged field is not an exact fixed point (the oracle leaves residuals up to
+    # 6 units on this scene).  The GPU field must be at least as quiescent as that: statuses stable, nearly all
+    # cubes unchanged by a recomputation, small worst case.
+    cubes = all_cubes(space)
+    again = rt.light_compute(cubes).reshape(gpu.shape)
+    vis = gpu[..., 3] == VISIBLE
+    d = np.abs(again[..., :3].astype(int) - gpu[..., :3].astype(int)).max(axis=-1)[vis]
+    assert np.array_equal(again[..., 3][vis], gpu[..., 3][vis])
+    assert (d == 0).mean() > 0.8 and d.max() <= 12, (float((d == 0).mean()), int(d.max()))
+
+
+def test_edits_then_propagate_matches_oracle():
+    space = light_scene(seed=9)
+    ol, rt = converge_both(space)
+    rng = np.random.default_rng(4)
+    cubes = np.stack([rng.integers(0, space.size[a], 60) + space.lower[a] for a in range(3)], axis=1).astype(np.int32)
+    ids = rng.integers(0, len(space.blocks), 60).astype(np.uint16)
+    ol.set_cubes(cubes, ids)
+    ol.evaluate(0)
+    n, md = rt.light_edit_and_propagate(cubes, ids, 0)
+    assert n > 0
+    compare_fields(rt.light_download(), ol.field())
+    # and the renderer sees the edited Space + light: identical to a fresh snapshot of the oracle's state
+    ids2 = space.block_ids.copy()
+    for c, i in zip(cubes, ids):
+        ids2[tuple(c - np.array(space.lower))] = i
+    fresh = Space(space.lower, ids2, space.blocks, light=rt.light_download(), sky_colors=space.sky_colors, light_max_distance=12)
+    opts = GraphicsOptions()  # the options `rt` was created with
+    cam = scenes.standard_camera(space, opts, 64, 48)
+    r1 = aicb200.RtRenderer(cam)
+    r1.rt = rt
+    r2 = aicb200.RtRenderer(cam)
+    r2.update(fresh)
+    assert np.array_equal(r1.draw().data, r2.draw().data)
+
+
+def test_light_bench_shape_flood():
+    """A 32^3 slice of BASELINE configs[4]'s shape: converge, 300 random edits, propagate, compare."""
+    n = 32
+    h = scenes.grid_hash(21, (n, n, n))
+    blocks = [Block.air()] + [Block(color=(0.3 + 0.1 * i, 0.8 - 0.1 * i, 0.5, 1.0)) for i in range(4)] + \
+             [Block(color=(0.1, 0.1, 0.1, 1.0), emission=(3.0, 3.0, 2.0))]
+    ids = np.where((h & np.uint64(15)) == 0, 1 + ((h >> np.uint64(8)) % np.uint64(5)).astype(np.int64), 0).astype(np.uint16)
+    ids[:, : n // 4, :] = 1
+    light = np.zeros((n, n, n, 4), dtype=np.uint8)
+    light[..., 3] = NO_RAYS
+    space = Space((0, 0, 0), ids, blocks, light=light, sky_colors=scenes.OCTANT_SKY, light_max_distance=30)
+    ol, rt = converge_both(space)
+    compare_fields(rt.light_download(), ol.field())
+    rng = np.random.default_rng(1)
+    cubes = np.stack([rng.integers(0, n, 300) for _ in range(3)], axis=1).astype(np.int32)
+    new_ids = rng.integers(0, len(blocks), 300).astype(np.uint16)
+    ol.set_cubes(cubes, new_ids)
+    ol.evaluate(0)
+    rt.light_edit_and_propagate(cubes, new_ids, 0)
+    compare_fields(rt.light_download(), ol.field())
