@@ -143,7 +143,7 @@ static bool voxel_invisible(const aicb_voxel &v) {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
-typedef void (*kernel_fn)(const TraceParams);
+typedef void (*kernel_fn)(const TraceParams, uint32_t);
 
 template <bool V, int LC, bool AUX>
 static kernel_fn kernel_of() {
@@ -183,6 +183,16 @@ static uint32_t shard_rows(uint32_t fb_height, const aicb_shard *sh) {
         rows += end - begin;
     }
     return rows;
+}
+
+static aicb_status ensure(void **p, size_t *cur, size_t want) {
+    if (*cur >= want) return AICB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cur = 0;
+    CU(cudaMalloc(p, want));
+    *cur = want;
+    return AICB_OK;
 }
 
 struct Outputs {
@@ -255,7 +265,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.task_counter = ctx->d_tile_counter;
     {
         const char *e = getenv("AICB_REFILL_THRESHOLD");
-        int v = e ? atoi(e) : 16;
+        int v = e ? atoi(e) : 4;
         P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
     }
 
@@ -264,10 +274,32 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     sc->pending_rays = pixels * (P.antialias ? 4 : 1);
     sc->pending_out_bytes_per_pixel = out.srgb8 ? 4 : 16;
 
-    CU(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+    // ---- the three kernels of a frame, chunked so the ray stream stays bounded ---------------------------
+    P.n_samples = P.antialias ? 4 : 1;
+    const uint64_t total_tasks = (uint64_t)P.n_tasks * P.n_samples;
+    const uint64_t CHUNK = (uint64_t)8 << 20;  // tasks per chunk (a multiple of 32 * n_samples): 1.2 GB of ray records
+    const uint64_t chunk_cap = total_tasks < CHUNK ? total_tasks : CHUNK;
+    {
+        aicb_status st = ensure(&ctx->d_rays, &ctx->d_rays_bytes, chunk_cap * sizeof(RayRecord) + 16);
+        if (st != AICB_OK) return st;
+        st = ensure(&ctx->d_task_cb, &ctx->d_task_cb_bytes, chunk_cap * 16 + 16);
+        if (st != AICB_OK) return st;
+        if (aux) {
+            st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, chunk_cap * (8 + sizeof(aicb_hit) + 4) + 64);
+            if (st != AICB_OK) return st;
+        }
+    }
+    P.ray_records = (RayRecord *)ctx->d_rays;
+    P.task_cb = (float4 *)ctx->d_task_cb;
+    if (aux) {
+        char *b = (char *)ctx->d_task_aux;
+        P.task_depth = (double *)b;
+        P.task_hit = (aicb_hit *)(b + chunk_cap * 8);
+        P.task_steps = (uint32_t *)(b + chunk_cap * (8 + sizeof(aicb_hit)));
+    }
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
-    if ((uint64_t)P.tiles_x * P.tiles_y > 0) {
+    if (total_tasks > 0) {
         const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
         const int lc = opt->lighting_display == AICB_LIGHT_NONE ? LC_NONE
                        : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT : LC_INTERP);
@@ -275,10 +307,18 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         int blocks_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
-        uint64_t want = ((uint64_t)P.tiles_x * P.tiles_y + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
-        if (grid > want) grid = want;
-        k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P);
+        for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
+            const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
+            P.task_base = (uint32_t)base;
+            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+            gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
+            uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
+            uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
+            if (grid > want) grid = want;
+            k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
+            const uint32_t n_pixels = n / P.n_samples;
+            encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
+        }
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(ctx->ev1, stream));
@@ -309,15 +349,6 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
     return AICB_OK;
 }
 
-static aicb_status ensure(void **p, size_t *cur, size_t want) {
-    if (*cur >= want) return AICB_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *cur = 0;
-    CU(cudaMalloc(p, want));
-    *cur = want;
-    return AICB_OK;
-}
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -367,6 +398,9 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_aux) cudaFree(c->d_aux);
+    if (c->d_rays) cudaFree(c->d_rays);
+    if (c->d_task_cb) cudaFree(c->d_task_cb);
+    if (c->d_task_aux) cudaFree(c->d_task_aux);
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_counters) cudaFree(c->d_counters);

@@ -32,6 +32,13 @@ struct aicb_ctx {
     size_t d_out_bytes = 0;
     void *d_aux = nullptr;
     size_t d_aux_bytes = 0;
+    // per-task streams between gen -> trace -> encode (trace_kernel.cuh)
+    void *d_rays = nullptr;
+    size_t d_rays_bytes = 0;
+    void *d_task_cb = nullptr;
+    size_t d_task_cb_bytes = 0;
+    void *d_task_aux = nullptr;
+    size_t d_task_aux_bytes = 0;
     // light propagation: the static ray chart (space/light/chart), built and uploaded on first use
     LightChartNode *d_chart = nullptr;
     uint32_t chart_nodes = 0;

@@ -62,6 +62,21 @@ struct DeviceScene {
     uint32_t wide_cells;        // 0: u16 cells, 1: u32 cells
 };
 
+// One primary ray after trace_ray_impl's prologue (sr.rs:135-180) and Raycaster::new().within()
+// (raycast.rs:196-230): everything the marching kernel needs, 144 bytes = 9 x 16-byte loads.
+struct __align__(16) RayRecord {
+    double ox, oy, oz, dx, dy, dz;   // ray (direction already zeroed if |d| >= 1e100, raycast.rs:760-764)
+    double tdx, tdy, tdz;            // t_delta
+    double half_over_len;
+    double tmx, tmy, tmz, last_t;    // outer caster at its first in-bounds cube
+    double t_to_abs;                 // |d| of the original direction (sr.rs:146)
+    float t_to_view;                 // sr.rs:149-151
+    int rx, ry, rz;
+    uint32_t idx;
+    uint32_t flags;                  // face | running<<3 | valid<<4 | active<<5 | (sx+1)<<6 | (sy+1)<<8 | (sz+1)<<10 | sky octant<<12
+};
+static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
+
 struct TraceParams {
     DeviceScene scene;
     // camera
@@ -87,6 +102,14 @@ struct TraceParams {
     uint32_t tiles_x, tiles_y;
     uint32_t n_tasks;           // tiles_x * tiles_y * 32 (camera) or n_rays
     uint32_t out_full_frame;    // 1: outputs are indexed by framebuffer position (full-frame buffer, possibly peer memory)
+    uint32_t n_samples;         // rays per pixel task: 4 with AntialiasingOption::Always, else 1
+    uint32_t task_base;         // first task of the chunk being processed (tasks = pixel_task * n_samples + sample)
+    // per-task streams between the three kernels of a frame (HBM)
+    RayRecord *ray_records;     // gen -> trace
+    float4 *task_cb;            // trace -> encode: ColorBuf of each ray
+    double *task_depth;         // AUX only
+    aicb_hit *task_hit;         // AUX only
+    uint32_t *task_steps;       // AUX only
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
     uchar4 *out_srgb8;
@@ -564,35 +587,112 @@ enum LaneState : int { ST_IDLE = 0, ST_MARCH = 1, ST_EVENT = 2, ST_DONE = 3, ST_
 enum EventKind : int { EV_SURFACE = 0, EV_INVISIBLE = 1, EV_ENTER_BLOCK = 2 };
 enum EventPost : int { POST_CONTINUE = 0, POST_POP = 1, POST_FINISH = 2 };
 
-// The frame kernel (replaces the Rayon dispatch trace_scene_to_image_impl, renderer.rs:516-556, and
-// everything below it).
+// task -> pixel mapping shared by the three kernels: pixel tasks are tile-ordered (32 consecutive
+// pixel tasks = one 8x4 tile); returns false for the padding pixels of edge tiles.
+AICB_DEV bool task_pixel(const TraceParams &P, uint32_t pixel_task, uint32_t *px, uint32_t *py, size_t *out_index) {
+    if (P.rays) {
+        *px = *py = 0;
+        *out_index = pixel_task;
+        return pixel_task < P.n_rays;
+    }
+    const uint32_t tile = pixel_task >> 5, in_tile = pixel_task & 31;
+    const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    const uint32_t x = tx * TILE_W + (in_tile & (TILE_W - 1));
+    const uint32_t ly = ty * TILE_H + (in_tile / TILE_W);
+    uint32_t y = ly;
+    if (P.shard_count > 1) {  // local row -> framebuffer row (row-strip sharding)
+        const uint32_t strip_local = ly / P.strip_rows;
+        y = (strip_local * P.shard_count + P.shard_index) * P.strip_rows + ly % P.strip_rows;
+    }
+    *px = x;
+    *py = y;
+    *out_index = P.out_full_frame ? (size_t)y * P.fb_width + x : (size_t)ly * P.fb_width + x;
+    return x < P.fb_width && ly < P.local_rows;
+}
+
+// ======================================================================================================
+// Kernel 1 — ray generation: pixel -> NDC patch -> world ray (viewport.rs:104-113, renderer.rs:424-451,
+// camera_struct.rs:238-257), trace_ray_impl's prologue (sr.rs:135-180) and the outer
+// Raycaster::new().within(space bounds) (raycast.rs:196-230, 632-704).  One thread per ray, fully convergent.
+// ======================================================================================================
+static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunk_tasks) return;
+    const uint32_t task = P.task_base + i;
+    const uint32_t pixel_task = task / P.n_samples, sample = task % P.n_samples;
+    RayRecord rec;
+    uint32_t px, py;
+    size_t out_index;
+    const bool active = task_pixel(P, pixel_task, &px, &py, &out_index);
+    rec.flags = 0;
+    if (active) {
+        const DeviceScene &S = P.scene;
+        double o[3], d[3];
+        if (P.rays) {
+            const double *rp = P.rays + 6 * (size_t)pixel_task;
+            o[0] = rp[0]; o[1] = rp[1]; o[2] = rp[2]; d[0] = rp[3]; d[1] = rp[4]; d[2] = rp[5];
+        } else {
+            pixel_ray(P, px, py, P.n_samples == 4 ? (int)sample : -1, o, d);
+        }
+        // Sky::sample octant (sky.rs:32-41) and the t conversions (sr.rs:146-151) use the original direction
+        const uint32_t octant = ((d[0] >= 0.0) << 2) + ((d[1] >= 0.0) << 1) + (d[2] >= 0.0);
+        rec.t_to_abs = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        rec.t_to_view = (float)(rec.t_to_abs / P.view_distance);
+        // Parameters::new (raycast.rs:749-771)
+        if (!((fabs(d[0]) < 1e100) & (fabs(d[1]) < 1e100) & (fabs(d[2]) < 1e100))) { d[0] = d[1] = d[2] = 0.0; }
+        Ray r;
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+        r.sx = signum_101(d[0]); r.sy = signum_101(d[1]); r.sz = signum_101(d[2]);
+        r.tdx = 1.0 / fabs(d[0]); r.tdy = 1.0 / fabs(d[1]); r.tdz = 1.0 / fabs(d[2]);
+        r.half_over_len = 0.5 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        Level lv;
+        lv.lox = S.lo[0]; lv.loy = S.lo[1]; lv.loz = S.lo[2];
+        lv.nx = S.size[0]; lv.ny = S.size[1]; lv.nz = S.size[2];
+        lv.base = 0;
+        Caster c;
+        c.tmx = c.tmy = c.tmz = c.last_t = 0.0;
+        c.rx = c.ry = c.rz = 0;
+        c.face = 0;
+        c.idx = 0;
+        bool valid;
+        const bool running = caster_begin(c, r, o[0], o[1], o[2], lv, &valid);
+        rec.ox = r.ox; rec.oy = r.oy; rec.oz = r.oz; rec.dx = r.dx; rec.dy = r.dy; rec.dz = r.dz;
+        rec.tdx = r.tdx; rec.tdy = r.tdy; rec.tdz = r.tdz;
+        rec.half_over_len = r.half_over_len;
+        rec.tmx = c.tmx; rec.tmy = c.tmy; rec.tmz = c.tmz; rec.last_t = c.last_t;
+        rec.rx = c.rx; rec.ry = c.ry; rec.rz = c.rz;
+        rec.idx = c.idx;
+        rec.flags = ((uint32_t)c.face & 7u) | (running ? 8u : 0u) | (valid ? 16u : 0u) | 32u | ((uint32_t)(r.sx + 1) << 6) |
+                    ((uint32_t)(r.sy + 1) << 8) | ((uint32_t)(r.sz + 1) << 10) | (octant << 12);
+    }
+    // 9 x 16-byte stores
+    const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+    uint4 *dst = reinterpret_cast<uint4 *>(P.ray_records + i);
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst[k] = src[k];
+}
+
+// ======================================================================================================
+// Kernel 2 — the marching kernel (replaces SpaceRaytracer::trace_ray's loop, sr.rs:180-238, and the Rayon
+// dispatch, renderer.rs:516-556): persistent warps, lane refill from the ray stream, phase machine.
+// ======================================================================================================
 template <bool VOLUMETRIC, int LC, bool AUX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
-trace_kernel(const __grid_constant__ TraceParams P) {
-    __shared__ float s_tables[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_tables[i] = P.scene.tables[i];
+trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    __shared__ float s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
     __syncthreads();
-    const float *lut = s_tables;
-    const float *thr = s_tables + 256;
+    const float *lut = s_lut;
 
     const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
-    const bool explicit_rays = P.rays != nullptr;
-    const int n_samples = (!explicit_rays && P.antialias) ? 4 : 1;
 
     unsigned long long cubes_traced = 0;
     unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_texels = 0, n_blocks = 0;
 
-    // ---- per-lane task state ---------------------------------------------------------------------
     int st = ST_IDLE;
-    uint32_t task = 0;             // index into the tile-ordered task sequence
-    uint32_t px = 0, py = 0;       // framebuffer pixel of the task
-    size_t out_index = 0;
-    int sample = 0;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accT = 0.f;  // AA sums
-    uint32_t steps_total = 0;
-    AuxState<AUX> aa_aux;
-    bool aa_got = false;
+    uint32_t task = 0;  // index within the chunk
 
     // ---- per-ray state -----------------------------------------------------------------------------
     Ray r;
@@ -606,8 +706,9 @@ trace_kernel(const __grid_constant__ TraceParams P) {
     uint32_t steps = 0;
     double t_to_abs = 0.0;
     float t_to_view = 0.f;
-    bool have_fog = false;
-    float sky_r = 0.f, sky_g = 0.f, sky_b = 0.f, fog_blend = 0.f;
+    float sky_r = 0.f, sky_g = 0.f, sky_b = 0.f;
+    const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
+    const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
     bool have_last = false;
     PendingSurface last;
     AuxState<AUX> aux;
@@ -630,7 +731,7 @@ trace_kernel(const __grid_constant__ TraceParams P) {
     };
 
     for (;;) {
-        // =========================== REFILL: hand new tasks to idle lanes =============================
+        // =========================== REFILL: idle lanes load the next rays of the stream ================
         {
             const unsigned idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
             const unsigned running = __ballot_sync(0xffffffffu, st == ST_MARCH || st == ST_EVENT || st == ST_DONE);
@@ -642,155 +743,94 @@ trace_kernel(const __grid_constant__ TraceParams P) {
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (st == ST_IDLE) {
                     task = base + __popc(idle & ((1u << lane) - 1u));
-                    if (task >= P.n_tasks) {
+                    if (task >= n_chunk_tasks) {
                         st = ST_EXHAUSTED;
                     } else {
-                        bool active;
-                        if (explicit_rays) {
-                            active = task < P.n_rays;
-                            out_index = task;
-                        } else {
-                            const uint32_t tile = task >> 5, in_tile = task & 31;
-                            const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-                            px = tx * TILE_W + (in_tile & (TILE_W - 1));
-                            const uint32_t ly = ty * TILE_H + (in_tile / TILE_W);
-                            active = px < P.fb_width && ly < P.local_rows;
-                            out_index = (size_t)ly * P.fb_width + px;
-                            py = ly;
-                            if (P.shard_count > 1) {  // local row -> framebuffer row (row-strip sharding)
-                                uint32_t strip_local = ly / P.strip_rows;
-                                py = (strip_local * P.shard_count + P.shard_index) * P.strip_rows + ly % P.strip_rows;
-                            }
-                            if (P.out_full_frame) out_index = (size_t)py * P.fb_width + px;
+                        RayRecord rec;
+                        {
+                            const uint4 *src = reinterpret_cast<const uint4 *>(P.ray_records + task);
+                            uint4 *dst = reinterpret_cast<uint4 *>(&rec);
+#pragma unroll
+                            for (int k = 0; k < 9; k++) dst[k] = __ldg(src + k);
                         }
-                        if (active) {
-                            st = ST_DONE;  // "previous sample finished" -> the finalize phase starts sample 0
-                            sample = -1;
-                            acc0 = acc1 = acc2 = accT = 0.f;
-                            steps_total = 0;
-                            aa_got = false;
-                        }  // else: stays IDLE and simply takes another task next round
+                        if (rec.flags & 32u) {  // active pixel (edge tiles carry padding tasks)
+                            r.ox = rec.ox; r.oy = rec.oy; r.oz = rec.oz; r.dx = rec.dx; r.dy = rec.dy; r.dz = rec.dz;
+                            r.tdx = rec.tdx; r.tdy = rec.tdy; r.tdz = rec.tdz;
+                            r.half_over_len = rec.half_over_len;
+                            r.sx = (int)((rec.flags >> 6) & 3u) - 1; r.sy = (int)((rec.flags >> 8) & 3u) - 1;
+                            r.sz = (int)((rec.flags >> 10) & 3u) - 1;
+                            c.tmx = rec.tmx; c.tmy = rec.tmy; c.tmz = rec.tmz; c.last_t = rec.last_t;
+                            c.rx = rec.rx; c.ry = rec.ry; c.rz = rec.rz;
+                            c.idx = rec.idx;
+                            c.face = (int)(rec.flags & 7u);
+                            valid = (rec.flags & 16u) != 0;
+                            t_to_abs = rec.t_to_abs;
+                            t_to_view = rec.t_to_view;
+                            sky_r = sky_g = sky_b = 0.0f;
+                            if (P.include_sky) {  // Sky::sample (sky.rs:32-41)
+                                const int k = S.sky_kind ? (int)((rec.flags >> 12) & 7u) : 0;
+                                sky_r = S.sky_colors[k][0]; sky_g = S.sky_colors[k][1]; sky_b = S.sky_colors[k][2];
+                            }
+                            lr = lg = lb = 0.0f;
+                            T = 1.0f;
+                            steps = 0;
+                            have_last = false;
+                            inner = false;
+                            need_advance = false;
+                            nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
+                            if constexpr (AUX) {
+                                aux.depth = D_INF;
+                                aux.have_hit = false;
+                                aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
+                            }
+                            st = (rec.flags & 8u) ? ST_MARCH : ST_DONE;
+                        }  // else: stays IDLE and takes another task next round
                     }
                 }
             }
             if (__all_sync(0xffffffffu, st == ST_EXHAUSTED)) break;
         }
 
-        // =========================== FINALIZE / START: ray boundaries ================================
+        // =========================== FINALIZE: finish (sr.rs:658-693) and hand the ColorBuf on ========
         if (st == ST_DONE) {
-            if (sample >= 0) {
-                // ---- finish (sr.rs:658-693): the sky is an opaque hit at t = inf ----
-                if (P.include_sky) {
-                    lr = lr + (sky_r * 1.0f) * T;
-                    lg = lg + (sky_g * 1.0f) * T;
-                    lb = lb + (sky_b * 1.0f) * T;
-                    T = T * (1.0f - 1.0f);
-                }
-                if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
-                    float k = ps_clamped((float)steps);
-                    float red = ps_clamped(ps_mul(0.02f, k) * 1.0f);
-                    float green = ps_clamped(ps_mul(0.002f, k) * 1.0f);
-                    float rgba[4];
-                    colorbuf_to_rgba(lr, lg, lb, T, rgba);
-                    float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
-                    lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
-                    T = 0.0f;
-                }
-                steps_total += steps;
-                acc0 = acc0 + lr; acc1 = acc1 + lg; acc2 = acc2 + lb; accT = accT + T;
-                if constexpr (AUX) {
-                    n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
-                    n_texels += aux.n_texels; n_blocks += aux.n_blocks;
-                    if (sample == 0) {
-                        aa_aux = aux;
-                        aa_got = aux.have_hit;
-                    } else {
-                        double dmin = fmin(aa_aux.depth, aux.depth);  // DepthBuf::mean = min (accum.rs:284-297)
-                        if (!aa_got && aux.have_hit) { aa_aux = aux; aa_got = true; }
-                        aa_aux.depth = dmin;
-                    }
-                }
+            if (P.include_sky) {  // the sky is an opaque hit at t = inf
+                lr = lr + (sky_r * 1.0f) * T;
+                lg = lg + (sky_g * 1.0f) * T;
+                lb = lb + (sky_b * 1.0f) * T;
+                T = T * (1.0f - 1.0f);
             }
-            sample += 1;
-            if (sample >= n_samples) {
-                // ---- store the pixel ----
-                float l0 = acc0, l1 = acc1, l2 = acc2, tT = accT;
-                if (n_samples == 4) {  // ColorBuf::mean (raytracer_components.rs:97-102)
-                    l0 = acc0 / 4.0f; l1 = acc1 / 4.0f; l2 = acc2 / 4.0f; tT = accT / 4.0f;
-                }
-                cubes_traced += steps_total;
-                if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, thr, l0, l1, l2, tT);
-                if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
-                if constexpr (AUX) {
-                    if (P.out_depth) P.out_depth[out_index] = aa_aux.depth;
-                    if (P.out_steps) P.out_steps[out_index] = steps_total;
-                    if (P.out_hit) {
-                        aicb_hit h;
-                        if (aa_aux.have_hit) {
-                            h.cube[0] = aa_aux.hit_cube[0]; h.cube[1] = aa_aux.hit_cube[1]; h.cube[2] = aa_aux.hit_cube[2];
-                            h.voxel[0] = aa_aux.hit_voxel[0]; h.voxel[1] = aa_aux.hit_voxel[1]; h.voxel[2] = aa_aux.hit_voxel[2];
-                            h.resolution = aa_aux.hit_res;
-                            h.face = aa_aux.hit_face;
-                        } else {
-                            h.cube[0] = h.cube[1] = h.cube[2] = -1;
-                            h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
-                            h.resolution = -1;
-                            h.face = -1;
-                        }
-                        P.out_hit[out_index] = h;
-                    }
-                }
-                st = ST_IDLE;
-            } else {
-                // ---- start the next ray of this task: trace_ray_impl prologue (sr.rs:135-180) ----
-                double o[3], d[3];
-                if (explicit_rays) {
-                    const double *rp = P.rays + 6 * out_index;
-                    o[0] = rp[0]; o[1] = rp[1]; o[2] = rp[2]; d[0] = rp[3]; d[1] = rp[4]; d[2] = rp[5];
+            if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
+                float k = ps_clamped((float)steps);
+                float red = ps_clamped(ps_mul(0.02f, k) * 1.0f);
+                float green = ps_clamped(ps_mul(0.002f, k) * 1.0f);
+                float rgba[4];
+                colorbuf_to_rgba(lr, lg, lb, T, rgba);
+                float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
+                lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
+                T = 0.0f;
+            }
+            cubes_traced += steps;
+            P.task_cb[task] = make_float4(lr, lg, lb, T);
+            if constexpr (AUX) {
+                n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
+                n_texels += aux.n_texels; n_blocks += aux.n_blocks;
+                P.task_depth[task] = aux.depth;
+                P.task_steps[task] = steps;
+                aicb_hit h;
+                if (aux.have_hit) {
+                    h.cube[0] = aux.hit_cube[0]; h.cube[1] = aux.hit_cube[1]; h.cube[2] = aux.hit_cube[2];
+                    h.voxel[0] = aux.hit_voxel[0]; h.voxel[1] = aux.hit_voxel[1]; h.voxel[2] = aux.hit_voxel[2];
+                    h.resolution = aux.hit_res;
+                    h.face = aux.hit_face;
                 } else {
-                    pixel_ray(P, px, py, n_samples == 4 ? sample : -1, o, d);
+                    h.cube[0] = h.cube[1] = h.cube[2] = -1;
+                    h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
+                    h.resolution = -1;
+                    h.face = -1;
                 }
-                lr = lg = lb = 0.0f;
-                T = 1.0f;
-                steps = 0;
-                have_last = false;
-                inner = false;
-                if constexpr (AUX) {
-                    aux.depth = D_INF;
-                    aux.have_hit = false;
-                    aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
-                }
-                // Sky::sample (sky.rs:32-41)
-                sky_r = sky_g = sky_b = 0.0f;
-                if (P.include_sky) {
-                    int k = 0;
-                    if (S.sky_kind) k = ((d[0] >= 0.0) << 2) + ((d[1] >= 0.0) << 1) + (d[2] >= 0.0);
-                    sky_r = S.sky_colors[k][0]; sky_g = S.sky_colors[k][1]; sky_b = S.sky_colors[k][2];
-                }
-                t_to_abs = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                t_to_view = (float)(t_to_abs / P.view_distance);
-                have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
-                fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
-                // Parameters::new (raycast.rs:749-771)
-                r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
-                if (!((fabs(d[0]) < 1e100) & (fabs(d[1]) < 1e100) & (fabs(d[2]) < 1e100))) { d[0] = d[1] = d[2] = 0.0; }
-                r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
-                r.sx = signum_101(d[0]); r.sy = signum_101(d[1]); r.sz = signum_101(d[2]);
-                r.tdx = 1.0 / fabs(d[0]); r.tdy = 1.0 / fabs(d[1]); r.tdz = 1.0 / fabs(d[2]);
-                r.half_over_len = 0.5 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                Level lv;
-                lv.lox = S.lo[0]; lv.loy = S.lo[1]; lv.loz = S.lo[2];
-                lv.nx = S.size[0]; lv.ny = S.size[1]; lv.nz = S.size[2];
-                lv.base = 0;
-                nx = lv.nx; ny = lv.ny; nz = lv.nz;
-                Caster oc;
-                bool ovalid;
-                const bool running = caster_begin(oc, r, o[0], o[1], o[2], lv, &ovalid);
-                c = oc;
-                valid = ovalid;
-                need_advance = false;
-                st = running ? ST_MARCH : ST_DONE;
+                P.task_hit[task] = h;
             }
+            st = ST_IDLE;
         }
 
         // =========================== MARCH: cheap DDA steps until an event ===========================
@@ -1081,6 +1121,53 @@ trace_kernel(const __grid_constant__ TraceParams P) {
             atomicAdd(P.counters + 4, n_texels);
             atomicAdd(P.counters + 5, n_blocks);
         }
+    }
+}
+
+
+// ======================================================================================================
+// Kernel 3 — per pixel: ColorBuf::mean of the 4 sub-samples (raytracer_components.rs:97-102), the encoder of
+// draw_rgba (renderer.rs:287-291: Rgba::from(ColorBuf), post_process_color, to_srgb8), and the stores.
+// One thread per pixel task, fully convergent.
+// ======================================================================================================
+static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    __shared__ float s_thr[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_thr[i] = P.scene.tables[256 + i];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel task within the chunk
+    const uint32_t n_pixels = n_chunk_tasks / P.n_samples;
+    if (i >= n_pixels) return;
+    uint32_t px, py;
+    size_t out_index;
+    if (!task_pixel(P, P.task_base / P.n_samples + i, &px, &py, &out_index)) return;
+    const uint32_t t0 = i * P.n_samples;
+    float l0, l1, l2, tT;
+    if (P.n_samples == 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, aT = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 v = P.task_cb[t0 + k];
+            a0 = a0 + v.x; a1 = a1 + v.y; a2 = a2 + v.z; aT = aT + v.w;
+        }
+        l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f;
+    } else {
+        const float4 v = P.task_cb[t0];
+        l0 = v.x; l1 = v.y; l2 = v.z; tT = v.w;
+    }
+    if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);
+    if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
+    if (P.task_depth) {  // AUX outputs: DepthBuf::mean = min (accum.rs:284-297); first sub-sample with a hit
+        double dmin = P.task_depth[t0];
+        uint32_t steps = P.task_steps[t0];
+        aicb_hit h = P.task_hit[t0];
+        for (uint32_t k = 1; k < P.n_samples; k++) {
+            dmin = fmin(dmin, P.task_depth[t0 + k]);
+            steps += P.task_steps[t0 + k];
+            if (h.face < 0 && P.task_hit[t0 + k].face >= 0) h = P.task_hit[t0 + k];
+        }
+        if (P.out_depth) P.out_depth[out_index] = dmin;
+        if (P.out_steps) P.out_steps[out_index] = steps;
+        if (P.out_hit) P.out_hit[out_index] = h;
     }
 }
 

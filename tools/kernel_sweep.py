@@ -14,7 +14,7 @@ from aicb200 import scenes  # noqa: E402
 
 def main():
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2", "c1"]
-    thresholds = [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "4", "8", "12", "16", "24", "32"])]
+    thresholds = [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "2", "4", "8", "16", "32"])]
     for name in names:
         space, opts, w, h, desc = bench.make_workload(name)
         cam = scenes.standard_camera(space, opts, w, h)
