@@ -110,6 +110,7 @@ struct TraceParams {
     double *task_depth;         // AUX only
     aicb_hit *task_hit;         // AUX only
     uint32_t *task_steps;       // AUX only
+    uint32_t event_threshold;   // leave the MARCH phase once this many lanes wait with an event / finished ray
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
     uchar4 *out_srgb8;
@@ -572,12 +573,12 @@ struct AuxState<true> {
 };
 
 // A surface remembered between discovery and shading (Volumetric mode pairs it with the next
-// event's t, surface.rs:460-490).  Illumination depends only on geometry, so it is evaluated at
-// discovery and carried as three floats instead of carrying the intersection point.
+// event's t, surface.rs:460-490).  Illumination depends only on geometry (cube, face, intersection
+// point), so it is evaluated when the surface is shaded, never for surfaces that are not.
 struct PendingSurface {
     double t;
+    double ip[3];      // intersection point (only filled for interpolated lighting)
     uint32_t pal;      // global palette entry index
-    float illum[3];
     int cube[3];
     uint32_t packed;   // voxel x | y<<8 | z<<16 | face<<24
     int res;
@@ -833,156 +834,29 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             st = ST_IDLE;
         }
 
-        // =========================== MARCH: cheap DDA steps until an event ===========================
-        while (st == ST_MARCH) {
-            if (need_advance) {
-                if (!valid) {  // cannot step: the iterator ends without an exit step (raycast.rs:245-249)
-                    if (inner) { pop_level(); continue; }
-                    st = ST_DONE;
-                    break;
-                }
-                if (caster_step(c, r, nx, ny, nz)) {
-                    // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
-                    const double t = inner ? c.last_t * recip_pow2(res) : c.last_t;
-                    if (VOLUMETRIC && have_last) {
-                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = inner ? POST_POP : POST_FINISH;
-                        st = ST_EVENT;
-                        break;
-                    }
-                    if (count_stop()) { st = ST_DONE; break; }
-                    if (inner) { pop_level(); continue; }
-                    st = ST_DONE;
-                    break;
-                }
-            }
-            need_advance = true;
-            if (!inner) {
-                if constexpr (AUX) aux.n_outer++;
-                const uint32_t cell = S.wide_cells ? __ldg((const uint32_t *)S.cells + c.idx)
-                                                   : (uint32_t)__ldg((const uint16_t *)S.cells + c.idx);
-                const uint32_t ck = S.wide_cells ? (cell >> 16) : (cell >> 14);
-                if (ck == KIND_INVISIBLE) {
-                    if (VOLUMETRIC && have_last) {
-                        ev_kind = EV_INVISIBLE; ev_t = c.last_t; ev_post = POST_CONTINUE;
-                        st = ST_EVENT;
-                        break;
-                    }
-                    if (count_stop()) { st = ST_DONE; break; }
-                    continue;
-                }
-                ev_kind = (ck == KIND_SINGLE) ? EV_SURFACE : EV_ENTER_BLOCK;
-                ev_t = c.last_t;
-                ev_cell = S.wide_cells ? (cell & 0xffffu) : (cell & 0x3fffu);
-                ev_post = POST_CONTINUE;
-                st = ST_EVENT;
-                break;
-            } else {
-                if constexpr (AUX) aux.n_inner++;
-                const uint32_t v = __ldg(S.bricks + c.idx);
-                const double t = c.last_t * recip_pow2(res);  // surface.rs:385-386
-                if (v & 0x8000u) {
-                    if (VOLUMETRIC && have_last) {
-                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = POST_CONTINUE;
-                        st = ST_EVENT;
-                        break;
-                    }
-                    if (count_stop()) { st = ST_DONE; break; }
-                    continue;
-                }
-                ev_kind = EV_SURFACE; ev_t = t; ev_cell = v; ev_post = POST_CONTINUE;
-                st = ST_EVENT;
-                break;
-            }
-        }
-        __syncwarp();
-
-        // =========================== HEAVY: events =====================================================
-        // (1) DepthIter + the Volumetric loop (surface.rs:460-490, sr.rs:185-203) / the Surface loop (sr.rs:206-225)
-        bool do_span = false;
-        PendingSurface span;
-        double span_exit = 0.0;
-        if (st == ST_EVENT) {
-            bool stop;
-            if constexpr (VOLUMETRIC) {
-                do_span = have_last;
-                span = last;
-                span_exit = ev_t;
-                have_last = false;
-                stop = count_stop();
-                if (stop) do_span = false;
-            } else {
-                stop = count_stop();
-            }
-            if (stop) st = ST_DONE;
-        }
-        // (2) trace_through_span (sr.rs:720-740) with apply_transmittance (raytracer_components.rs:215-258)
-        float sh_r = 0.f, sh_g = 0.f, sh_b = 0.f, sh_a = 0.f, sh_er = 0.f, sh_eg = 0.f, sh_eb = 0.f;
-        bool do_shade = false;
-        PendingSurface shade_sf;
-        if constexpr (VOLUMETRIC) {
-            if (do_span) {
-                const float4 col = __ldg(S.palette + 2 * (size_t)span.pal);
-                const float4 emi = __ldg(S.palette + 2 * (size_t)span.pal + 1);
-                const float thickness = fmaxf((float)((span_exit - span.t) * t_to_abs), 0.0f);
-                float alpha, coeff;
-                sh_r = col.x; sh_g = col.y; sh_b = col.z;
-                if (thickness == 0.0f) {
-                    if (col.w == 1.0f) { alpha = col.w; coeff = 1.0f; }
-                    else { sh_r = sh_g = sh_b = 0.0f; alpha = 0.0f; coeff = 0.0f; }
-                } else if (col.w == 1.0f) {
-                    alpha = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
-                } else if (col.w == 0.0f) {
-                    alpha = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
-                } else {
-                    const float unit_t = 1.0f - col.w;
-                    const float depth_t = powf_exact(unit_t, thickness);
-                    alpha = zo_clamped(1.0f - depth_t);
-                    const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
-                    coeff = fmaxf(k, 0.0f);
-                }
-                const float k = ps_clamped(coeff);
-                sh_a = alpha;
-                sh_er = ps_mul(emi.x, k); sh_eg = ps_mul(emi.y, k); sh_eb = ps_mul(emi.z, k);
-                shade_sf = span;
-                do_shade = true;
-            }
-        }
-        // (3) surface discovery: build the Surface, evaluate compute_illumination (surface.rs:113-206)
-        PendingSurface sf;
-        const bool discover = st == ST_EVENT && ev_kind == EV_SURFACE;
-        if (discover) {
+        // =========================== MARCH: cheap DDA steps until the lane needs heavy work ===========
+        // Builds the Surface of the current cube / voxel (surface.rs:322-331, 399-409) without lighting it:
+        // illumination is a pure function of (cube, face, intersection point), so only those are recorded and
+        // the light is evaluated when (and if) the surface is actually shaded.
+        auto record_surface = [&](PendingSurface &sf, uint32_t cell_or_voxel, double t) {
             int cx, cy, cz;
             if (!inner) {
-                const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + ev_cell);
-                const uint4 b1 = __ldg(bp + 1);
-                sf.pal = b1.y;
+                const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + cell_or_voxel);
+                sf.pal = __ldg(bp + 1).y;
                 cx = c.rx + S.lo[0]; cy = c.ry + S.lo[1]; cz = c.rz + S.lo[2];
                 sf.packed = (uint32_t)c.face << 24;
                 sf.res = 1;
             } else {
-                sf.pal = pal_off + ev_cell;
+                sf.pal = pal_off + cell_or_voxel;
                 cx = saved.rx + S.lo[0]; cy = saved.ry + S.lo[1]; cz = saved.rz + S.lo[2];
                 const int vx = c.rx + (int)(int16_t)(blk0y & 0xffff), vy = c.ry + (int)(int16_t)(blk0y >> 16),
                           vz = c.rz + (int)(int16_t)(blk0z & 0xffff);
                 sf.packed = (uint32_t)vx | ((uint32_t)vy << 8) | ((uint32_t)vz << 16) | ((uint32_t)c.face << 24);
                 sf.res = res;
             }
-            sf.t = ev_t;
+            sf.t = t;
             sf.cube[0] = cx; sf.cube[1] = cy; sf.cube[2] = cz;
-            if constexpr (LC == LC_FLAT) {
-                int x = cx, y = cy, z = cz;
-                if (c.face != AICB_FACE_WITHIN) {
-                    const int dd = c.face >= AICB_FACE_PX ? 1 : -1;
-                    const int ax = (c.face - 1) % 3;
-                    if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
-                }
-                uint32_t tx = 0;
-                const uint32_t t = get_packed_light(S, x, y, z, tx);
-                if constexpr (AUX) aux.n_texels += tx;
-                sf.illum[0] = lut[t & 255];
-                sf.illum[1] = lut[(t >> 8) & 255];
-                sf.illum[2] = lut[(t >> 16) & 255];
-            } else if constexpr (LC == LC_INTERP) {
+            if constexpr (LC == LC_INTERP) {
                 double ip[3];
                 if (!inner) {
                     intersection_point(c, r, cx, cy, cz, r.ox, r.oy, r.oz, ip);
@@ -995,36 +869,156 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                     ip[1] = ip[1] * anti + (double)cy;
                     ip[2] = ip[2] * anti + (double)cz;
                 }
-                uint32_t tx = 0;
-                float il[3];
-                interpolated_light(S, lut, P.lighting, cx, cy, cz, c.face, ip[0], ip[1], ip[2], il, &tx);
-                sf.illum[0] = il[0]; sf.illum[1] = il[1]; sf.illum[2] = il[2];
-                if constexpr (AUX) aux.n_texels += tx;
-            } else {
-                sf.illum[0] = sf.illum[1] = sf.illum[2] = 1.0f;
+                sf.ip[0] = ip[0]; sf.ip[1] = ip[1]; sf.ip[2] = ip[2];
             }
-            if constexpr (VOLUMETRIC) {
-                last = sf;
-                have_last = true;
+        };
+        auto march_step = [&]() {
+            if (need_advance) {
+                if (!valid) {  // cannot step: the iterator ends without an exit step (raycast.rs:245-249)
+                    if (inner) { pop_level(); return; }
+                    st = ST_DONE;
+                    return;
+                }
+                if (caster_step(c, r, nx, ny, nz)) {
+                    // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
+                    const double t = inner ? c.last_t * recip_pow2(res) : c.last_t;
+                    if (VOLUMETRIC && have_last) {
+                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = inner ? POST_POP : POST_FINISH;
+                        st = ST_EVENT;
+                        return;
+                    }
+                    if (count_stop()) { st = ST_DONE; return; }
+                    if (inner) { pop_level(); return; }
+                    st = ST_DONE;
+                    return;
+                }
+            }
+            need_advance = true;
+            uint32_t word;
+            double t;
+            bool invisible, enter_block = false;
+            if (!inner) {
+                if constexpr (AUX) aux.n_outer++;
+                const uint32_t cell = S.wide_cells ? __ldg((const uint32_t *)S.cells + c.idx)
+                                                   : (uint32_t)__ldg((const uint16_t *)S.cells + c.idx);
+                const uint32_t ck = S.wide_cells ? (cell >> 16) : (cell >> 14);
+                word = S.wide_cells ? (cell & 0xffffu) : (cell & 0x3fffu);
+                t = c.last_t;
+                invisible = ck == KIND_INVISIBLE;
+                enter_block = ck == KIND_RECURSIVE;
             } else {
-                const float4 col = __ldg(S.palette + 2 * (size_t)sf.pal);
-                const float4 emi = __ldg(S.palette + 2 * (size_t)sf.pal + 1);
-                sh_r = col.x; sh_g = col.y; sh_b = col.z; sh_a = col.w;
-                sh_er = emi.x; sh_eg = emi.y; sh_eb = emi.z;
-                shade_sf = sf;
-                do_shade = true;
+                if constexpr (AUX) aux.n_inner++;
+                word = __ldg(S.bricks + c.idx);
+                t = c.last_t * recip_pow2(res);  // surface.rs:385-386
+                invisible = (word & 0x8000u) != 0;
+            }
+            if (invisible) {
+                if (VOLUMETRIC && have_last) {
+                    ev_kind = EV_INVISIBLE; ev_t = t; ev_post = POST_CONTINUE;
+                    st = ST_EVENT;
+                    return;
+                }
+                if (count_stop()) st = ST_DONE;
+                return;
+            }
+            ev_kind = enter_block ? EV_ENTER_BLOCK : EV_SURFACE;
+            ev_t = t;
+            ev_cell = word;
+            ev_post = POST_CONTINUE;
+            st = ST_EVENT;
+        };
+        for (;;) {
+            const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
+            if (!marching) break;
+            // only lanes that can make progress in the other phases count (idle lanes below the refill threshold cannot)
+            if (__popc(__ballot_sync(0xffffffffu, st == ST_EVENT || st == ST_DONE)) >= (int)P.event_threshold) break;
+            if (st == ST_MARCH) march_step();
+        }
+        __syncwarp();
+
+        // =========================== HEAVY: events =====================================================
+        // (1) DepthIter + the Volumetric loop (surface.rs:460-490, sr.rs:185-203) / the Surface loop (sr.rs:206-225):
+        //     decide which surface (if any) this event shades.
+        bool do_shade = false;
+        PendingSurface shade_sf;
+        double span_exit = 0.0;
+        if (st == ST_EVENT) {
+            bool stop;
+            if constexpr (VOLUMETRIC) {
+                do_shade = have_last;
+                shade_sf = last;
+                span_exit = ev_t;
+                have_last = false;
+                stop = count_stop();
+            } else {
+                stop = count_stop();
+                if (!stop && ev_kind == EV_SURFACE) {
+                    record_surface(shade_sf, ev_cell, ev_t);
+                    do_shade = true;
+                }
+            }
+            if (stop) {
+                do_shade = false;
+                st = ST_DONE;
             }
         }
-        // (4) Surface::to_light + trace_through_surface (surface.rs:73-106, sr.rs:697-717)
+        // (2) the one heavy shading routine: trace_through_span + apply_transmittance (sr.rs:720-740,
+        //     raytracer_components.rs:215-258; Volumetric only), compute_illumination (surface.rs:113-206),
+        //     Surface::to_light + trace_through_surface (surface.rs:73-106, sr.rs:697-717).
         if (do_shade) {
-            float cr = sh_r, cg = sh_g, cb = sh_b, ca = sh_a;
+            const float4 col = __ldg(S.palette + 2 * (size_t)shade_sf.pal);
+            const float4 emi = __ldg(S.palette + 2 * (size_t)shade_sf.pal + 1);
+            float cr = col.x, cg = col.y, cb = col.z, ca = col.w;
+            float er = emi.x, eg = emi.y, eb = emi.z;
+            if constexpr (VOLUMETRIC) {
+                const float thickness = fmaxf((float)((span_exit - shade_sf.t) * t_to_abs), 0.0f);
+                float alpha, coeff;
+                if (thickness == 0.0f) {
+                    if (col.w == 1.0f) { alpha = col.w; coeff = 1.0f; }
+                    else { cr = cg = cb = 0.0f; alpha = 0.0f; coeff = 0.0f; }
+                } else if (col.w == 1.0f) {
+                    alpha = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
+                } else if (col.w == 0.0f) {
+                    alpha = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
+                } else {
+                    const float unit_t = 1.0f - col.w;
+                    const float depth_t = powf_exact(unit_t, thickness);
+                    alpha = zo_clamped(1.0f - depth_t);
+                    const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
+                    coeff = fmaxf(k, 0.0f);
+                }
+                const float k = ps_clamped(coeff);
+                ca = alpha;
+                er = ps_mul(emi.x, k); eg = ps_mul(emi.y, k); eb = ps_mul(emi.z, k);
+            }
             if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
                 if (ca > P.threshold) { ca = 1.0f; } else { cr = cg = cb = ca = 0.0f; }
             }
-            if (!(ca == 0.0f && sh_er == 0.0f && sh_eg == 0.0f && sh_eb == 0.0f)) {
-                float orr = ps_mul(ps_mul(cr, shade_sf.illum[0]), ca) + sh_er;   // reflect + emission (color.rs:708-710)
-                float og = ps_mul(ps_mul(cg, shade_sf.illum[1]), ca) + sh_eg;
-                float ob = ps_mul(ps_mul(cb, shade_sf.illum[2]), ca) + sh_eb;
+            if (!(ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f)) {
+                float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
+                const int face = (int)(shade_sf.packed >> 24);
+                if constexpr (LC == LC_FLAT) {
+                    int x = shade_sf.cube[0], y = shade_sf.cube[1], z = shade_sf.cube[2];
+                    if (face != AICB_FACE_WITHIN) {
+                        const int dd = face >= AICB_FACE_PX ? 1 : -1;
+                        const int ax = (face - 1) % 3;
+                        if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
+                    }
+                    uint32_t tx = 0;
+                    const uint32_t t = get_packed_light(S, x, y, z, tx);
+                    if constexpr (AUX) aux.n_texels += tx;
+                    i0 = lut[t & 255]; i1 = lut[(t >> 8) & 255]; i2 = lut[(t >> 16) & 255];
+                } else if constexpr (LC == LC_INTERP) {
+                    uint32_t tx = 0;
+                    float il[3];
+                    interpolated_light(S, lut, P.lighting, shade_sf.cube[0], shade_sf.cube[1], shade_sf.cube[2], face,
+                                       shade_sf.ip[0], shade_sf.ip[1], shade_sf.ip[2], il, &tx);
+                    i0 = il[0]; i1 = il[1]; i2 = il[2];
+                    if constexpr (AUX) aux.n_texels += tx;
+                }
+                float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
+                float og = ps_mul(ps_mul(cg, i1), ca) + eg;
+                float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
                 float tr = 1.0f - ca;
                 if (have_fog) {  // distance_fog (sr.rs:745-768) + blend (surface.rs:97-100)
                     float rel = (float)shade_sf.t * t_to_view;
@@ -1056,6 +1050,13 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                         aux.hit_res = shade_sf.res;
                     }
                 }
+            }
+        }
+        // (3) Volumetric: the surface that raised this event becomes the pending one (surface.rs:467-476)
+        if constexpr (VOLUMETRIC) {
+            if (st == ST_EVENT && ev_kind == EV_SURFACE) {
+                record_surface(last, ev_cell, ev_t);
+                have_last = true;
             }
         }
         // (4b) the buffered DepthStep::EnterBlock is counted after the flushed span was traced

@@ -20,14 +20,17 @@ def main():
         cam = scenes.standard_camera(space, opts, w, h)
         r = aicb200.RtRenderer(cam)
         r.update(space)
-        for th in thresholds:
-            os.environ["AICB_REFILL_THRESHOLD"] = str(th)
-            ms = []
-            for i in range(6):
-                img = r.draw()
-                if i >= 2:
-                    ms.append(img.info.kernel_ms)
-            print(f"{name} refill_threshold={th:2d} kernel_ms={np.mean(ms):.3f} (min {np.min(ms):.3f})  Mrays/s={w * h / np.mean(ms) / 1e3:.0f}", flush=True)
+        events = [int(v) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["8"])]
+        for ev in events:
+            for th in thresholds:
+                os.environ["AICB_REFILL_THRESHOLD"] = str(th)
+                os.environ["AICB_EVENT_THRESHOLD"] = str(ev)
+                ms = []
+                for i in range(6):
+                    img = r.draw()
+                    if i >= 2:
+                        ms.append(img.info.kernel_ms)
+                print(f"{name} event_thr={ev:2d} refill_thr={th:2d} frame_ms={np.mean(ms):.3f} (min {np.min(ms):.3f})  Mrays/s={w * h / np.mean(ms) / 1e3:.0f}", flush=True)
 
 
 if __name__ == "__main__":
