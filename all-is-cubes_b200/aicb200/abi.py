@@ -3,8 +3,8 @@ import ctypes as C
 
 ABI_VERSION = 1
 
-OK, ERR_INVALID, ERR_OOM, ERR_CUDA, ERR_UNSUPPORTED, ERR_BUSY = range(6)
-STATUS_NAMES = {0: "OK", 1: "ERR_INVALID", 2: "ERR_OOM", 3: "ERR_CUDA", 4: "ERR_UNSUPPORTED", 5: "ERR_BUSY"}
+OK, ERR_INVALID, ERR_OOM, ERR_CUDA, ERR_UNSUPPORTED, ERR_BUSY, ERR_RETRY = range(7)
+STATUS_NAMES = {0: "OK", 1: "ERR_INVALID", 2: "ERR_OOM", 3: "ERR_CUDA", 4: "ERR_UNSUPPORTED", 5: "ERR_BUSY", 6: "ERR_RETRY"}
 
 FACE_WITHIN, FACE_NX, FACE_NY, FACE_NZ, FACE_PX, FACE_PY, FACE_PZ = range(7)
 FOG_NONE, FOG_ABRUPT, FOG_COMPROMISE, FOG_PHYSICAL = range(4)

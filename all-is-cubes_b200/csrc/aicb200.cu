@@ -280,12 +280,20 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     // ---- the three kernels of a frame, chunked so the ray stream stays bounded ---------------------------
     P.n_samples = P.antialias ? 4 : 1;
     const uint64_t total_tasks = (uint64_t)P.n_tasks * P.n_samples;
-    const uint64_t CHUNK = (uint64_t)8 << 20;  // tasks per chunk (a multiple of 32 * n_samples): 1.2 GB of ray records
+    const uint64_t CHUNK = (uint64_t)4 << 20;  // tasks per chunk (a multiple of 32 * n_samples): 0.6 GB of ray records
     const uint64_t chunk_cap = total_tasks < CHUNK ? total_tasks : CHUNK;
     {
         aicb_status st = ensure(&ctx->d_rays, &ctx->d_rays_bytes, chunk_cap * sizeof(RayRecord) + 16);
         if (st != AICB_OK) return st;
-        st = ensure(&ctx->d_task_cb, &ctx->d_task_cb_bytes, chunk_cap * 16 + 16);
+        st = ensure(&ctx->d_task_cb, &ctx->d_task_cb_bytes, chunk_cap * sizeof(TaskOut) + 16);
+        if (st != AICB_OK) return st;
+        uint64_t cap = chunk_cap * ctx->hits_per_task;
+        if (cap < (1u << 16)) cap = 1u << 16;
+        if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
+        P.hit_capacity = (uint32_t)cap;
+        st = ensure(&ctx->d_hits, &ctx->d_hits_bytes, cap * sizeof(HitRecord) + 64);
+        if (st != AICB_OK) return st;
+        st = ensure(&ctx->d_contrib, &ctx->d_contrib_bytes, cap * sizeof(float4) + 64);
         if (st != AICB_OK) return st;
         if (aux) {
             st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, chunk_cap * (8 + sizeof(aicb_hit) + 4) + 64);
@@ -293,12 +301,15 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         }
     }
     P.ray_records = (RayRecord *)ctx->d_rays;
-    P.task_cb = (float4 *)ctx->d_task_cb;
+    P.task_out = (TaskOut *)ctx->d_task_cb;
+    P.hits = (HitRecord *)ctx->d_hits;
+    P.hit_contrib = (float4 *)ctx->d_contrib;
+    P.hit_counter = ctx->d_tile_counter + 1;
+    P.overflow_flag = (unsigned int *)(ctx->d_counters + 7);
     if (aux) {
         char *b = (char *)ctx->d_task_aux;
         P.task_depth = (double *)b;
         P.task_hit = (aicb_hit *)(b + chunk_cap * 8);
-        P.task_steps = (uint32_t *)(b + chunk_cap * (8 + sizeof(aicb_hit)));
     }
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
@@ -313,12 +324,17 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;
-            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, 2 * sizeof(unsigned int), stream));
             gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
             uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
             uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
             if (grid > want) grid = want;
             k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
+            switch (lc) {
+                case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+                case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+                default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+            }
             const uint32_t n_pixels = n / P.n_samples;
             encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
         }
@@ -331,9 +347,14 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
 static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
     aicb_ctx *ctx = sc->ctx;
     CU(cudaEventSynchronize(ctx->ev1));
+    unsigned long long c[8];
+    CU(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    sc->pending = false;
+    if (c[7]) {  // the hit stream of some chunk overflowed: the frame is incomplete
+        if (ctx->hits_per_task < 1024) ctx->hits_per_task *= 4;
+        return fail(AICB_ERR_RETRY, "hit stream overflowed; its capacity has been raised - re-issue the render");
+    }
     if (info) {
-        unsigned long long c[8];
-        CU(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
         std::memset(info, 0, sizeof *info);
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -382,7 +403,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
-    CU(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_tile_counter, 4 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
     float lut[768];
@@ -403,6 +424,8 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_aux) cudaFree(c->d_aux);
     if (c->d_rays) cudaFree(c->d_rays);
     if (c->d_task_cb) cudaFree(c->d_task_cb);
+    if (c->d_hits) cudaFree(c->d_hits);
+    if (c->d_contrib) cudaFree(c->d_contrib);
     if (c->d_task_aux) cudaFree(c->d_task_aux);
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
@@ -661,11 +684,17 @@ aicb_status aicb_render_srgb8(aicb_scene *s, const aicb_camera *cam, const aicb_
     if (st != AICB_OK) return st;
     Outputs o;
     o.srgb8 = (uchar4 *)ctx->d_out;
-    st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
+    for (int attempt = 0;; attempt++) {
+        st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
+        if (st != AICB_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream));
+        st = finish(s, info);
+        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+    }
     if (st != AICB_OK) return st;
     if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return finish(s, info);
+    return AICB_OK;
 }
 
 static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, const aicb_shard *shard,
@@ -683,7 +712,13 @@ static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_
     o.depth = (double *)(base + off_depth);
     o.hit = (aicb_hit *)(base + off_hit);
     o.steps = (uint32_t *)(base + off_steps);
-    st = launch_trace(s, cam, opt, shard, d_rays, n_rays, o, true, ctx->stream);
+    for (int attempt = 0;; attempt++) {
+        st = launch_trace(s, cam, opt, shard, d_rays, n_rays, o, true, ctx->stream);
+        if (st != AICB_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream));
+        st = finish(s, info);
+        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+    }
     if (st != AICB_OK) return st;
     if (n) {
         if (out_cb) CU(cudaMemcpyAsync(out_cb, o.colorbuf, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -692,7 +727,7 @@ static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_
         if (steps) CU(cudaMemcpyAsync(steps, o.steps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    return finish(s, info);
+    return AICB_OK;
 }
 
 aicb_status aicb_render_colorbuf(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt,

@@ -35,8 +35,13 @@ struct aicb_ctx {
     // per-task streams between gen -> trace -> encode (trace_kernel.cuh)
     void *d_rays = nullptr;
     size_t d_rays_bytes = 0;
-    void *d_task_cb = nullptr;
+    void *d_task_cb = nullptr;   // TaskOut per task
     size_t d_task_cb_bytes = 0;
+    void *d_hits = nullptr;      // HitRecord stream (march -> shade -> encode)
+    size_t d_hits_bytes = 0;
+    void *d_contrib = nullptr;   // float4 per hit
+    size_t d_contrib_bytes = 0;
+    uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it
     void *d_task_aux = nullptr;
     size_t d_task_aux_bytes = 0;
     // light propagation: the static ray chart (space/light/chart), built and uploaded on first use

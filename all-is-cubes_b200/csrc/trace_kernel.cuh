@@ -77,6 +77,31 @@ struct __align__(16) RayRecord {
 };
 static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
 
+// One shaded surface of one ray, emitted by the marching kernel and lit by the shade kernel.
+// 64 bytes = 4 x 16-byte stores.  Everything the transmittance chain needs (alpha after the Volumetric
+// thickness rule and the threshold option, fog amount) is already resolved by the marcher; what is left is
+// compute_illumination (surface.rs:113-206) and the outgoing light of Surface::to_light (surface.rs:84-100).
+struct __align__(16) HitRecord {
+    double ip[3];        // intersection point (interpolated lighting only)
+    uint32_t pal;        // palette entry
+    int32_t cube[3];
+    float T_before;      // ColorBuf transmittance in front of this surface
+    float ca;            // alpha actually used
+    float coeff;         // emission coefficient of apply_transmittance (1 outside Volumetric mode)
+    float fa;            // distance-fog amount, or < 0 when fog is off
+    uint32_t flags;      // face | rgb_zeroed<<3 (Volumetric zero thickness / Threshold below the limit) | sky octant<<4
+    uint32_t next;       // next hit of the same ray (0xffffffff = none); the ray's first hit is in TaskOut
+};
+static_assert(sizeof(HitRecord) == 64, "HitRecord must be 64 bytes");
+
+// What the marching kernel hands to the encode kernel per ray (16 bytes).
+struct __align__(16) TaskOut {
+    uint32_t first_hit;  // index of the first HitRecord or 0xffffffff
+    float T;             // transmittance after the last surface (before the sky)
+    uint32_t steps;      // RaytraceInfo::cubes_traced of this ray
+    uint32_t flags;      // sky octant
+};
+
 struct TraceParams {
     DeviceScene scene;
     // camera
@@ -105,11 +130,15 @@ struct TraceParams {
     uint32_t n_samples;         // rays per pixel task: 4 with AntialiasingOption::Always, else 1
     uint32_t task_base;         // first task of the chunk being processed (tasks = pixel_task * n_samples + sample)
     // per-task streams between the three kernels of a frame (HBM)
-    RayRecord *ray_records;     // gen -> trace
-    float4 *task_cb;            // trace -> encode: ColorBuf of each ray
+    RayRecord *ray_records;     // gen -> march
+    TaskOut *task_out;          // march -> encode
+    HitRecord *hits;            // march -> shade
+    float4 *hit_contrib;        // shade -> encode: light of each hit already multiplied by T_before
+    unsigned int *hit_counter;  // hits emitted in this chunk
+    unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
+    uint32_t hit_capacity;
     double *task_depth;         // AUX only
     aicb_hit *task_hit;         // AUX only
-    uint32_t *task_steps;       // AUX only
     uint32_t event_threshold;   // leave the MARCH phase once this many lanes wait with an event / finished ray
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
@@ -681,16 +710,11 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
 template <bool VOLUMETRIC, int LC, bool AUX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
 trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
-    __shared__ float s_lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
-    __syncthreads();
-    const float *lut = s_lut;
-
     const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
 
     unsigned long long cubes_traced = 0;
-    unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_texels = 0, n_blocks = 0;
+    unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_blocks = 0;
 
     int st = ST_IDLE;
     uint32_t task = 0;  // index within the chunk
@@ -703,11 +727,11 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     uint32_t blk0y = 0, blk0z = 0;       // packed voxel bounds of the entered block (lo16|lo16, lo16|size16)
     uint32_t pal_off = 0;
     int res = 1;
-    float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.f;
+    float T = 1.f;
     uint32_t steps = 0;
+    uint32_t first_hit = 0xffffffffu, last_hit = 0xffffffffu, sky_octant = 0;
     double t_to_abs = 0.0;
     float t_to_view = 0.f;
-    float sky_r = 0.f, sky_g = 0.f, sky_b = 0.f;
     const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
     const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
     bool have_last = false;
@@ -767,12 +791,8 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                             valid = (rec.flags & 16u) != 0;
                             t_to_abs = rec.t_to_abs;
                             t_to_view = rec.t_to_view;
-                            sky_r = sky_g = sky_b = 0.0f;
-                            if (P.include_sky) {  // Sky::sample (sky.rs:32-41)
-                                const int k = S.sky_kind ? (int)((rec.flags >> 12) & 7u) : 0;
-                                sky_r = S.sky_colors[k][0]; sky_g = S.sky_colors[k][1]; sky_b = S.sky_colors[k][2];
-                            }
-                            lr = lg = lb = 0.0f;
+                            sky_octant = (rec.flags >> 12) & 7u;
+                            first_hit = last_hit = 0xffffffffu;
                             T = 1.0f;
                             steps = 0;
                             have_last = false;
@@ -792,31 +812,19 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             if (__all_sync(0xffffffffu, st == ST_EXHAUSTED)) break;
         }
 
-        // =========================== FINALIZE: finish (sr.rs:658-693) and hand the ColorBuf on ========
+        // =========================== FINALIZE: hand the ray's result to the encode kernel ================
         if (st == ST_DONE) {
-            if (P.include_sky) {  // the sky is an opaque hit at t = inf
-                lr = lr + (sky_r * 1.0f) * T;
-                lg = lg + (sky_g * 1.0f) * T;
-                lb = lb + (sky_b * 1.0f) * T;
-                T = T * (1.0f - 1.0f);
-            }
-            if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
-                float k = ps_clamped((float)steps);
-                float red = ps_clamped(ps_mul(0.02f, k) * 1.0f);
-                float green = ps_clamped(ps_mul(0.002f, k) * 1.0f);
-                float rgba[4];
-                colorbuf_to_rgba(lr, lg, lb, T, rgba);
-                float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
-                lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
-                T = 0.0f;
-            }
             cubes_traced += steps;
-            P.task_cb[task] = make_float4(lr, lg, lb, T);
+            TaskOut o;
+            o.first_hit = first_hit;
+            o.T = T;
+            o.steps = steps;
+            o.flags = sky_octant;
+            *reinterpret_cast<uint4 *>(P.task_out + task) = *reinterpret_cast<const uint4 *>(&o);
             if constexpr (AUX) {
                 n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
-                n_texels += aux.n_texels; n_blocks += aux.n_blocks;
+                n_blocks += aux.n_blocks;
                 P.task_depth[task] = aux.depth;
-                P.task_steps[task] = steps;
                 aicb_hit h;
                 if (aux.have_hit) {
                     h.cube[0] = aux.hit_cube[0]; h.cube[1] = aux.hit_cube[1]; h.cube[2] = aux.hit_cube[2];
@@ -962,81 +970,74 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 st = ST_DONE;
             }
         }
-        // (2) the one heavy shading routine: trace_through_span + apply_transmittance (sr.rs:720-740,
-        //     raytracer_components.rs:215-258; Volumetric only), compute_illumination (surface.rs:113-206),
-        //     Surface::to_light + trace_through_surface (surface.rs:73-106, sr.rs:697-717).
+        // (2) the sequential part of shading: apply_transmittance (sr.rs:720-740, raytracer_components.rs:215-258;
+        //     Volumetric only), limit_alpha, the invisibility test of Surface::to_light (surface.rs:78-82), the fog
+        //     amount (sr.rs:745-768) and the transmittance update of add_color_internal
+        //     (raytracer_components.rs:87-92).  The light itself is computed by shade_kernel from the HitRecord.
         if (do_shade) {
             const float4 col = __ldg(S.palette + 2 * (size_t)shade_sf.pal);
             const float4 emi = __ldg(S.palette + 2 * (size_t)shade_sf.pal + 1);
-            float cr = col.x, cg = col.y, cb = col.z, ca = col.w;
-            float er = emi.x, eg = emi.y, eb = emi.z;
+            float ca = col.w;
+            float coeff = 1.0f;
+            bool zeroed = false;
             if constexpr (VOLUMETRIC) {
                 const float thickness = fmaxf((float)((span_exit - shade_sf.t) * t_to_abs), 0.0f);
-                float alpha, coeff;
                 if (thickness == 0.0f) {
-                    if (col.w == 1.0f) { alpha = col.w; coeff = 1.0f; }
-                    else { cr = cg = cb = 0.0f; alpha = 0.0f; coeff = 0.0f; }
+                    if (col.w == 1.0f) { coeff = 1.0f; }
+                    else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
                 } else if (col.w == 1.0f) {
-                    alpha = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
+                    ca = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
                 } else if (col.w == 0.0f) {
-                    alpha = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
+                    ca = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
                 } else {
                     const float unit_t = 1.0f - col.w;
                     const float depth_t = powf_exact(unit_t, thickness);
-                    alpha = zo_clamped(1.0f - depth_t);
+                    ca = zo_clamped(1.0f - depth_t);
                     const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
                     coeff = fmaxf(k, 0.0f);
                 }
-                const float k = ps_clamped(coeff);
-                ca = alpha;
-                er = ps_mul(emi.x, k); eg = ps_mul(emi.y, k); eb = ps_mul(emi.z, k);
             }
+            const float kc = ps_clamped(coeff);
+            const float er = VOLUMETRIC ? ps_mul(emi.x, kc) : emi.x, eg = VOLUMETRIC ? ps_mul(emi.y, kc) : emi.y,
+                        eb = VOLUMETRIC ? ps_mul(emi.z, kc) : emi.z;
             if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
-                if (ca > P.threshold) { ca = 1.0f; } else { cr = cg = cb = ca = 0.0f; }
+                if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
             }
             if (!(ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f)) {
-                float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
-                const int face = (int)(shade_sf.packed >> 24);
-                if constexpr (LC == LC_FLAT) {
-                    int x = shade_sf.cube[0], y = shade_sf.cube[1], z = shade_sf.cube[2];
-                    if (face != AICB_FACE_WITHIN) {
-                        const int dd = face >= AICB_FACE_PX ? 1 : -1;
-                        const int ax = (face - 1) % 3;
-                        if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
-                    }
-                    uint32_t tx = 0;
-                    const uint32_t t = get_packed_light(S, x, y, z, tx);
-                    if constexpr (AUX) aux.n_texels += tx;
-                    i0 = lut[t & 255]; i1 = lut[(t >> 8) & 255]; i2 = lut[(t >> 16) & 255];
-                } else if constexpr (LC == LC_INTERP) {
-                    uint32_t tx = 0;
-                    float il[3];
-                    interpolated_light(S, lut, P.lighting, shade_sf.cube[0], shade_sf.cube[1], shade_sf.cube[2], face,
-                                       shade_sf.ip[0], shade_sf.ip[1], shade_sf.ip[2], il, &tx);
-                    i0 = il[0]; i1 = il[1]; i2 = il[2];
-                    if constexpr (AUX) aux.n_texels += tx;
-                }
-                float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
-                float og = ps_mul(ps_mul(cg, i1), ca) + eg;
-                float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
                 float tr = 1.0f - ca;
-                if (have_fog) {  // distance_fog (sr.rs:745-768) + blend (surface.rs:97-100)
+                float fa = -1.0f;
+                if (have_fog) {  // distance_fog (sr.rs:745-768)
                     float rel = (float)shade_sf.t * t_to_view;
                     rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
                     const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
                     const float fudged = fog_exponential / 0.79810348f;
                     const float p4 = (rel * rel) * (rel * rel);
-                    const float fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
-                    const float comp = 1.0f - fa;
-                    orr = ps_mul(orr, comp) + ps_mul(sky_r, fa);
-                    og = ps_mul(og, comp) + ps_mul(sky_g, fa);
-                    ob = ps_mul(ob, comp) + ps_mul(sky_b, fa);
-                    tr = tr * comp;
+                    fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
+                    tr = tr * (1.0f - fa);
                 }
-                // add_color_internal (raytracer_components.rs:87-92)
-                lr = lr + orr * T;
-                lg = lg + og * T;
-                lb = lb + ob * T;
+                // emit the hit
+                const uint32_t slot = atomicAdd(P.hit_counter, 1u);
+                if (slot < P.hit_capacity) {
+                    HitRecord h;
+                    if constexpr (LC == LC_INTERP) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
+                    else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
+                    h.pal = shade_sf.pal;
+                    h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
+                    h.T_before = T;
+                    h.ca = ca;
+                    h.coeff = coeff;
+                    h.fa = fa;
+                    h.flags = (shade_sf.packed >> 24) | (zeroed ? 8u : 0u) | (sky_octant << 4);
+                    h.next = 0xffffffffu;
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
+                    uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) dst[k] = src[k];
+                    if (last_hit != 0xffffffffu) P.hits[last_hit].next = slot; else first_hit = slot;
+                    last_hit = slot;
+                } else {
+                    *P.overflow_flag = 1u;  // the host re-runs the frame with a larger buffer
+                }
                 T = T * tr;
                 if constexpr (AUX) {
                     aux.depth = fmin(aux.depth, shade_sf.t);
@@ -1112,14 +1113,12 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             n_outer += __shfl_down_sync(0xffffffffu, n_outer, off);
             n_inner += __shfl_down_sync(0xffffffffu, n_inner, off);
             n_hits += __shfl_down_sync(0xffffffffu, n_hits, off);
-            n_texels += __shfl_down_sync(0xffffffffu, n_texels, off);
             n_blocks += __shfl_down_sync(0xffffffffu, n_blocks, off);
         }
         if (lane == 0) {
             atomicAdd(P.counters + 1, n_outer);
             atomicAdd(P.counters + 2, n_inner);
             atomicAdd(P.counters + 3, n_hits);
-            atomicAdd(P.counters + 4, n_texels);
             atomicAdd(P.counters + 5, n_blocks);
         }
     }
@@ -1127,14 +1126,81 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
 
 
 // ======================================================================================================
-// Kernel 3 — per pixel: ColorBuf::mean of the 4 sub-samples (raytracer_components.rs:97-102), the encoder of
-// draw_rgba (renderer.rs:287-291: Rgba::from(ColorBuf), post_process_color, to_srgb8), and the stores.
-// One thread per pixel task, fully convergent.
+// Kernel 3 — shading: one thread per HitRecord, fully convergent.  compute_illumination (surface.rs:113-206)
+// and the outgoing light of Surface::to_light (surface.rs:84-100); the result is stored already multiplied by
+// the transmittance in front of the surface, i.e. the addend of add_color_internal (raytracer_components.rs:90).
+// ======================================================================================================
+template <int LC>
+__global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ TraceParams P) {
+    __shared__ float s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    __syncthreads();
+    const DeviceScene &S = P.scene;
+    uint32_t n = *P.hit_counter;
+    if (n > P.hit_capacity) n = P.hit_capacity;
+    unsigned long long texels = 0;
+    const bool volumetric = P.transparency == AICB_TRANSPARENCY_VOLUMETRIC;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        HitRecord h;
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + i);
+            uint4 *dst = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst[k] = src[k];
+        }
+        const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
+        const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
+        const bool zeroed = (h.flags & 8u) != 0;
+        const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
+        const float ca = h.ca;
+        const float kc = ps_clamped(h.coeff);
+        const float er = volumetric ? ps_mul(emi.x, kc) : emi.x, eg = volumetric ? ps_mul(emi.y, kc) : emi.y,
+                    eb = volumetric ? ps_mul(emi.z, kc) : emi.z;
+        float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
+        const int face = (int)(h.flags & 7u);
+        if constexpr (LC == LC_FLAT) {
+            int x = h.cube[0], y = h.cube[1], z = h.cube[2];
+            if (face != AICB_FACE_WITHIN) {
+                const int dd = face >= AICB_FACE_PX ? 1 : -1;
+                const int ax = (face - 1) % 3;
+                if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
+            }
+            uint32_t tx = 0;
+            const uint32_t t = get_packed_light(S, x, y, z, tx);
+            texels += tx;
+            i0 = s_lut[t & 255]; i1 = s_lut[(t >> 8) & 255]; i2 = s_lut[(t >> 16) & 255];
+        } else if constexpr (LC == LC_INTERP) {
+            uint32_t tx = 0;
+            float il[3];
+            interpolated_light(S, s_lut, P.lighting, h.cube[0], h.cube[1], h.cube[2], face, h.ip[0], h.ip[1], h.ip[2], il, &tx);
+            i0 = il[0]; i1 = il[1]; i2 = il[2];
+            texels += tx;
+        }
+        float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
+        float og = ps_mul(ps_mul(cg, i1), ca) + eg;
+        float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
+        if (h.fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
+            const int k = S.sky_kind ? (int)((h.flags >> 4) & 7u) : 0;
+            const float comp = 1.0f - h.fa;
+            orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], h.fa);
+            og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], h.fa);
+            ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], h.fa);
+        }
+        P.hit_contrib[i] = make_float4(orr * h.T_before, og * h.T_before, ob * h.T_before, 0.0f);
+    }
+    if (texels) atomicAdd(P.counters + 4, texels);
+}
+
+// ======================================================================================================
+// Kernel 4 — per pixel: add_color_internal over the ray's hits in order (raytracer_components.rs:87-92),
+// finish (sr.rs:658-693: the sky; debug_pixel_cost), ColorBuf::mean of the 4 sub-samples
+// (raytracer_components.rs:97-102), the encoder of draw_rgba (renderer.rs:287-291) and the stores.
 // ======================================================================================================
 static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     __shared__ float s_thr[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_thr[i] = P.scene.tables[256 + i];
     __syncthreads();
+    const DeviceScene &S = P.scene;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel task within the chunk
     const uint32_t n_pixels = n_chunk_tasks / P.n_samples;
     if (i >= n_pixels) return;
@@ -1142,32 +1208,49 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
     size_t out_index;
     if (!task_pixel(P, P.task_base / P.n_samples + i, &px, &py, &out_index)) return;
     const uint32_t t0 = i * P.n_samples;
-    float l0, l1, l2, tT;
-    if (P.n_samples == 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, aT = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float4 v = P.task_cb[t0 + k];
-            a0 = a0 + v.x; a1 = a1 + v.y; a2 = a2 + v.z; aT = aT + v.w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, aT = 0.f;
+    uint32_t steps_total = 0;
+    for (uint32_t k = 0; k < P.n_samples; k++) {
+        TaskOut o;
+        *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + t0 + k);
+        float lr = 0.f, lg = 0.f, lb = 0.f, T = o.T;
+        for (uint32_t hi = o.first_hit; hi != 0xffffffffu; hi = P.hits[hi].next) {
+            const float4 c = P.hit_contrib[hi];
+            lr = lr + c.x; lg = lg + c.y; lb = lb + c.z;
         }
-        l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f;
-    } else {
-        const float4 v = P.task_cb[t0];
-        l0 = v.x; l1 = v.y; l2 = v.z; tT = v.w;
+        if (P.include_sky) {  // the sky is an opaque hit at t = inf
+            const int so = S.sky_kind ? (int)(o.flags & 7u) : 0;
+            lr = lr + (S.sky_colors[so][0] * 1.0f) * T;
+            lg = lg + (S.sky_colors[so][1] * 1.0f) * T;
+            lb = lb + (S.sky_colors[so][2] * 1.0f) * T;
+            T = T * (1.0f - 1.0f);
+        }
+        if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
+            float kk = ps_clamped((float)o.steps);
+            float red = ps_clamped(ps_mul(0.02f, kk) * 1.0f);
+            float green = ps_clamped(ps_mul(0.002f, kk) * 1.0f);
+            float rgba[4];
+            colorbuf_to_rgba(lr, lg, lb, T, rgba);
+            float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
+            lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
+            T = 0.0f;
+        }
+        steps_total += o.steps;
+        a0 = a0 + lr; a1 = a1 + lg; a2 = a2 + lb; aT = aT + T;
     }
+    float l0 = a0, l1 = a1, l2 = a2, tT = aT;
+    if (P.n_samples == 4) { l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f; }
     if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);
     if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
     if (P.task_depth) {  // AUX outputs: DepthBuf::mean = min (accum.rs:284-297); first sub-sample with a hit
         double dmin = P.task_depth[t0];
-        uint32_t steps = P.task_steps[t0];
         aicb_hit h = P.task_hit[t0];
         for (uint32_t k = 1; k < P.n_samples; k++) {
             dmin = fmin(dmin, P.task_depth[t0 + k]);
-            steps += P.task_steps[t0 + k];
             if (h.face < 0 && P.task_hit[t0 + k].face >= 0) h = P.task_hit[t0 + k];
         }
         if (P.out_depth) P.out_depth[out_index] = dmin;
-        if (P.out_steps) P.out_steps[out_index] = steps;
+        if (P.out_steps) P.out_steps[out_index] = steps_total;
         if (P.out_hit) P.out_hit[out_index] = h;
     }
 }
