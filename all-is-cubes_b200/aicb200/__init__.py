@@ -26,7 +26,7 @@ from .abi import (FOG_ABRUPT, FOG_COMPROMISE, FOG_NONE, FOG_PHYSICAL, LIGHT_COAR
                   TRANSPARENCY_THRESHOLD, TRANSPARENCY_VOLUMETRIC)
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libaicb200.so")
+LIB_PATH = os.environ.get("AICB200_LIB") or os.path.join(PKG_DIR, "libaicb200.so")  # override: kernel experiments only
 
 
 class AicbError(RuntimeError):

@@ -290,10 +290,13 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         uint64_t cap = chunk_cap * ctx->hits_per_task;
         if (cap < (1u << 16)) cap = 1u << 16;
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
+        cap &= ~(uint64_t)(HIT_BLOCK - 1);  // warps take whole blocks of the stream
         P.hit_capacity = (uint32_t)cap;
         st = ensure(&ctx->d_hits, &ctx->d_hits_bytes, cap * sizeof(HitRecord) + 64);
         if (st != AICB_OK) return st;
         st = ensure(&ctx->d_contrib, &ctx->d_contrib_bytes, cap * sizeof(float4) + 64);
+        if (st != AICB_OK) return st;
+        st = ensure(&ctx->d_bin_list, &ctx->d_bin_list_bytes, (size_t)N_BINS * chunk_cap * 4 + 64);
         if (st != AICB_OK) return st;
         if (aux) {
             st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, chunk_cap * (8 + sizeof(aicb_hit) + 4) + 64);
@@ -305,6 +308,9 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.hits = (HitRecord *)ctx->d_hits;
     P.hit_contrib = (float4 *)ctx->d_contrib;
     P.hit_counter = ctx->d_tile_counter + 1;
+    P.bin_count = ctx->d_tile_counter + 4;
+    P.bin_list = (uint32_t *)ctx->d_bin_list;
+    P.bin_stride = (uint32_t)chunk_cap;
     P.overflow_flag = (unsigned int *)(ctx->d_counters + 7);
     if (aux) {
         char *b = (char *)ctx->d_task_aux;
@@ -324,7 +330,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;
-            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, 2 * sizeof(unsigned int), stream));
+            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, 16 * sizeof(unsigned int), stream));
             gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
             uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
             uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
@@ -403,7 +409,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
-    CU(cudaMalloc(&c->d_tile_counter, 4 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_tile_counter, 16 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
     float lut[768];
@@ -426,6 +432,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_task_cb) cudaFree(c->d_task_cb);
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_contrib) cudaFree(c->d_contrib);
+    if (c->d_bin_list) cudaFree(c->d_bin_list);
     if (c->d_task_aux) cudaFree(c->d_task_aux);
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);

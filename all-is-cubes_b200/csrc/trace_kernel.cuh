@@ -134,7 +134,10 @@ struct TraceParams {
     TaskOut *task_out;          // march -> encode
     HitRecord *hits;            // march -> shade
     float4 *hit_contrib;        // shade -> encode: light of each hit already multiplied by T_before
-    unsigned int *hit_counter;  // hits emitted in this chunk
+    unsigned int *hit_counter;  // hit slots handed out in this chunk (in blocks of HIT_BLOCK)
+    uint32_t *bin_list;         // gen -> march: task ids of the rays that enter the space, binned by chord length
+    unsigned int *bin_count;    // [N_BINS] entries of each bin
+    uint32_t bin_stride;        // capacity of one bin's list
     unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
     uint32_t hit_capacity;
     double *task_depth;         // AUX only
@@ -159,7 +162,16 @@ struct TraceParams {
 constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (template)
 constexpr int TILE_W = 8, TILE_H = 4;
 constexpr int WARPS_PER_BLOCK = 4;
-constexpr int MIN_BLOCKS_PER_SM = 4;
+constexpr int N_BINS = 8;            // chord-length classes of the ray list (longest first)
+constexpr uint32_t HIT_BLOCK = 64;   // hit slots a warp takes from the stream at a time
+constexpr uint32_t HIT_DEAD = 0xffffffffu;  // HitRecord::pal of a slot that was handed out but never filled
+#ifndef AICB_MIN_BLOCKS
+#define AICB_MIN_BLOCKS 4
+#endif
+#ifndef AICB_STREAM_HINTS
+#define AICB_STREAM_HINTS 0
+#endif
+constexpr int MIN_BLOCKS_PER_SM = AICB_MIN_BLOCKS;
 
 
 constexpr double D_INF = __builtin_huge_val();
@@ -187,6 +199,23 @@ struct Level {
     int nx, ny, nz;    // sizes
     uint32_t base;
 };
+
+// The per-ray / per-hit streams are written once and read once: with AICB_STREAM_HINTS they bypass the
+// usual L2 retention (evict-first) so that the cell / brick volumes stay resident.
+AICB_DEV uint4 ld_stream(const uint4 *p) {
+#if AICB_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+AICB_DEV void st_stream(uint4 *p, uint4 v) {
+#if AICB_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 AICB_DEV int signum_101(double x) { return (x == 0.0 || x != x) ? 0 : (x < 0.0 ? -1 : 1); }
 
@@ -647,14 +676,17 @@ AICB_DEV bool task_pixel(const TraceParams &P, uint32_t pixel_task, uint32_t *px
 // ======================================================================================================
 static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_chunk_tasks) return;
+    const bool in_range = i < n_chunk_tasks;
     const uint32_t task = P.task_base + i;
     const uint32_t pixel_task = task / P.n_samples, sample = task % P.n_samples;
     RayRecord rec;
     uint32_t px, py;
     size_t out_index;
-    const bool active = task_pixel(P, pixel_task, &px, &py, &out_index);
+    const bool active = in_range && task_pixel(P, pixel_task, &px, &py, &out_index);
     rec.flags = 0;
+    bool running = false;
+    uint32_t octant = 0;
+    int bin = 0;
     if (active) {
         const DeviceScene &S = P.scene;
         double o[3], d[3];
@@ -665,7 +697,7 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
             pixel_ray(P, px, py, P.n_samples == 4 ? (int)sample : -1, o, d);
         }
         // Sky::sample octant (sky.rs:32-41) and the t conversions (sr.rs:146-151) use the original direction
-        const uint32_t octant = ((d[0] >= 0.0) << 2) + ((d[1] >= 0.0) << 1) + (d[2] >= 0.0);
+        octant = ((d[0] >= 0.0) << 2) + ((d[1] >= 0.0) << 1) + (d[2] >= 0.0);
         rec.t_to_abs = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         rec.t_to_view = (float)(rec.t_to_abs / P.view_distance);
         // Parameters::new (raycast.rs:749-771)
@@ -686,7 +718,7 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
         c.face = 0;
         c.idx = 0;
         bool valid;
-        const bool running = caster_begin(c, r, o[0], o[1], o[2], lv, &valid);
+        running = caster_begin(c, r, o[0], o[1], o[2], lv, &valid);
         rec.ox = r.ox; rec.oy = r.oy; rec.oz = r.oz; rec.dx = r.dx; rec.dy = r.dy; rec.dz = r.dz;
         rec.tdx = r.tdx; rec.tdy = r.tdy; rec.tdz = r.tdz;
         rec.half_over_len = r.half_over_len;
@@ -695,12 +727,62 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
         rec.idx = c.idx;
         rec.flags = ((uint32_t)c.face & 7u) | (running ? 8u : 0u) | (valid ? 16u : 0u) | 32u | ((uint32_t)(r.sx + 1) << 6) |
                     ((uint32_t)(r.sy + 1) << 8) | ((uint32_t)(r.sz + 1) << 10) | (octant << 12);
-    }
-    // 9 x 16-byte stores
-    const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
-    uint4 *dst = reinterpret_cast<uint4 *>(P.ray_records + i);
+        if (running) {
+            // Scheduling heuristic only (never affects results): the number of cube boundaries the ray's chord
+            // through the space bounds crosses, in f32.  Long rays are listed in early bins so that the marching
+            // kernel starts them first and the frame does not end on a few long serial chains.
+            const float lo3[3] = {(float)lv.lox, (float)lv.loy, (float)lv.loz};
+            const float n3[3] = {(float)lv.nx, (float)lv.ny, (float)lv.nz};
+            float tn = 0.0f, tf = 3.0e38f, l1 = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 9; k++) dst[k] = src[k];
+            for (int a = 0; a < 3; a++) {
+                const float da = (float)d[a], oa = (float)o[a];
+                if (da != 0.0f) {
+                    const float t0 = (lo3[a] - oa) / da, t1 = (lo3[a] + n3[a] - oa) / da;
+                    tn = fmaxf(tn, fminf(t0, t1));
+                    tf = fminf(tf, fmaxf(t0, t1));
+                    l1 += fabsf(da);
+                }
+            }
+            const float crossings = fmaxf(tf - tn, 0.0f) * l1;
+            const float frac = crossings / (n3[0] + n3[1] + n3[2]);
+            int q = (int)(frac * (float)N_BINS);
+            q = q < 0 ? 0 : (q > N_BINS - 1 ? N_BINS - 1 : q);
+            bin = N_BINS - 1 - q;
+        }
+    }
+    // Rays that enter the space go to the marching kernel through the binned list (warp-aggregated append); all
+    // others are complete already: nothing hit, transmittance 1, no steps.
+    const unsigned listed = __ballot_sync(0xffffffffu, running);
+    if (running) {
+        const unsigned peers = __match_any_sync(listed, bin);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(P.bin_count + bin, (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t slot = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+        P.bin_list[(size_t)bin * P.bin_stride + slot] = i;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+        uint4 *dst = reinterpret_cast<uint4 *>(P.ray_records + i);
+#pragma unroll
+        for (int k = 0; k < 9; k++) st_stream(dst + k, src[k]);
+    } else if (in_range) {
+        TaskOut o;
+        o.first_hit = 0xffffffffu;
+        o.T = 1.0f;
+        o.steps = 0;
+        o.flags = octant;
+        *reinterpret_cast<uint4 *>(P.task_out + i) = *reinterpret_cast<const uint4 *>(&o);
+        if (P.task_depth) {
+            P.task_depth[i] = D_INF;
+            aicb_hit h;
+            h.cube[0] = h.cube[1] = h.cube[2] = -1;
+            h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
+            h.resolution = -1;
+            h.face = -1;
+            P.task_hit[i] = h;
+        }
+    }
 }
 
 // ======================================================================================================
@@ -718,6 +800,19 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
 
     int st = ST_IDLE;
     uint32_t task = 0;  // index within the chunk
+
+    // the ray list: bins in order, longest chords first
+    __shared__ uint32_t s_bin_start[N_BINS + 1];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < N_BINS; b++) { s_bin_start[b] = acc; acc += P.bin_count[b]; }
+        s_bin_start[N_BINS] = acc;
+    }
+    __syncthreads();
+    const uint32_t n_listed = s_bin_start[N_BINS];
+    (void)n_chunk_tasks;
+    // this warp's block of the hit stream
+    uint32_t hit_base = 0xffffffffu, hit_used = 0;
 
     // ---- per-ray state -----------------------------------------------------------------------------
     Ray r;
@@ -767,18 +862,21 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 if (lane == leader) base = atomicAdd(P.task_counter, (unsigned)n);
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (st == ST_IDLE) {
-                    task = base + __popc(idle & ((1u << lane) - 1u));
-                    if (task >= n_chunk_tasks) {
+                    const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+                    if (k >= n_listed) {
                         st = ST_EXHAUSTED;
                     } else {
+                        int b = 0;
+                        while (k >= s_bin_start[b + 1]) b++;
+                        task = __ldg(P.bin_list + (size_t)b * P.bin_stride + (k - s_bin_start[b]));
                         RayRecord rec;
                         {
                             const uint4 *src = reinterpret_cast<const uint4 *>(P.ray_records + task);
                             uint4 *dst = reinterpret_cast<uint4 *>(&rec);
 #pragma unroll
-                            for (int k = 0; k < 9; k++) dst[k] = __ldg(src + k);
+                            for (int k = 0; k < 9; k++) dst[k] = ld_stream(src + k);
                         }
-                        if (rec.flags & 32u) {  // active pixel (edge tiles carry padding tasks)
+                        {
                             r.ox = rec.ox; r.oy = rec.oy; r.oz = rec.oz; r.dx = rec.dx; r.dy = rec.dy; r.dz = rec.dz;
                             r.tdx = rec.tdx; r.tdy = rec.tdy; r.tdz = rec.tdz;
                             r.half_over_len = rec.half_over_len;
@@ -804,8 +902,8 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                                 aux.have_hit = false;
                                 aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
                             }
-                            st = (rec.flags & 8u) ? ST_MARCH : ST_DONE;
-                        }  // else: stays IDLE and takes another task next round
+                            st = ST_MARCH;
+                        }
                     }
                 }
             }
@@ -974,6 +1072,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         //     Volumetric only), limit_alpha, the invisibility test of Surface::to_light (surface.rs:78-82), the fog
         //     amount (sr.rs:745-768) and the transmittance update of add_color_internal
         //     (raytracer_components.rs:87-92).  The light itself is computed by shade_kernel from the HitRecord.
+        bool emit = false;
+        float h_ca = 0.f, h_coeff = 0.f, h_fa = -1.0f, h_tr = 1.0f;
+        bool h_zeroed = false;
         if (do_shade) {
             const float4 col = __ldg(S.palette + 2 * (size_t)shade_sf.pal);
             const float4 emi = __ldg(S.palette + 2 * (size_t)shade_sf.pal + 1);
@@ -1015,42 +1116,65 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                     fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
                     tr = tr * (1.0f - fa);
                 }
-                // emit the hit
-                const uint32_t slot = atomicAdd(P.hit_counter, 1u);
-                if (slot < P.hit_capacity) {
-                    HitRecord h;
-                    if constexpr (LC == LC_INTERP) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
-                    else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
-                    h.pal = shade_sf.pal;
-                    h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
-                    h.T_before = T;
-                    h.ca = ca;
-                    h.coeff = coeff;
-                    h.fa = fa;
-                    h.flags = (shade_sf.packed >> 24) | (zeroed ? 8u : 0u) | (sky_octant << 4);
-                    h.next = 0xffffffffu;
-                    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
-                    uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) dst[k] = src[k];
-                    if (last_hit != 0xffffffffu) P.hits[last_hit].next = slot; else first_hit = slot;
-                    last_hit = slot;
-                } else {
-                    *P.overflow_flag = 1u;  // the host re-runs the frame with a larger buffer
+                emit = true;
+                h_ca = ca; h_coeff = coeff; h_fa = fa; h_tr = tr; h_zeroed = zeroed;
+            }
+        }
+        // emit the hits of this pass: slots come from the warp's block of the hit stream, a new block is taken
+        // (one atomic per HIT_BLOCK hits) when the current one cannot hold them all
+        {
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                const uint32_t n_emit = (uint32_t)__popc(em);
+                if (hit_base == 0xffffffffu || hit_used + n_emit > HIT_BLOCK) {
+                    if (hit_base != 0xffffffffu && hit_used + (uint32_t)lane < HIT_BLOCK)
+                        P.hits[hit_base + hit_used + lane].pal = HIT_DEAD;   // fewer than 32 slots are left over
+                    uint32_t nb = 0;
+                    if (lane == 0) nb = atomicAdd(P.hit_counter, HIT_BLOCK);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                    if (nb >= P.hit_capacity) {  // (the capacity is a multiple of HIT_BLOCK)
+                        if (lane == 0) *P.overflow_flag = 1u;  // the host re-runs the frame with a larger buffer
+                        nb = 0xffffffffu;
+                    }
+                    hit_base = nb;
+                    hit_used = 0;
                 }
-                T = T * tr;
-                if constexpr (AUX) {
-                    aux.depth = fmin(aux.depth, shade_sf.t);
-                    aux.n_hits++;
-                    if (!aux.have_hit) {
-                        aux.have_hit = true;
-                        aux.hit_cube[0] = shade_sf.cube[0]; aux.hit_cube[1] = shade_sf.cube[1]; aux.hit_cube[2] = shade_sf.cube[2];
-                        aux.hit_voxel[0] = shade_sf.packed & 255; aux.hit_voxel[1] = (shade_sf.packed >> 8) & 255;
-                        aux.hit_voxel[2] = (shade_sf.packed >> 16) & 255;
-                        aux.hit_face = shade_sf.packed >> 24;
-                        aux.hit_res = shade_sf.res;
+                if (emit) {
+                    if (hit_base != 0xffffffffu) {
+                        const uint32_t slot = hit_base + hit_used + (uint32_t)__popc(em & ((1u << lane) - 1u));
+                        HitRecord h;
+                        if constexpr (LC == LC_INTERP) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
+                        else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
+                        h.pal = shade_sf.pal;
+                        h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
+                        h.T_before = T;
+                        h.ca = h_ca;
+                        h.coeff = h_coeff;
+                        h.fa = h_fa;
+                        h.flags = (shade_sf.packed >> 24) | (h_zeroed ? 8u : 0u) | (sky_octant << 4);
+                        h.next = 0xffffffffu;
+                        const uint4 *src = reinterpret_cast<const uint4 *>(&h);
+                        uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) st_stream(dst + k, src[k]);
+                        if (last_hit != 0xffffffffu) P.hits[last_hit].next = slot; else first_hit = slot;
+                        last_hit = slot;
+                    }
+                    T = T * h_tr;
+                    if constexpr (AUX) {
+                        aux.depth = fmin(aux.depth, shade_sf.t);
+                        aux.n_hits++;
+                        if (!aux.have_hit) {
+                            aux.have_hit = true;
+                            aux.hit_cube[0] = shade_sf.cube[0]; aux.hit_cube[1] = shade_sf.cube[1]; aux.hit_cube[2] = shade_sf.cube[2];
+                            aux.hit_voxel[0] = shade_sf.packed & 255; aux.hit_voxel[1] = (shade_sf.packed >> 8) & 255;
+                            aux.hit_voxel[2] = (shade_sf.packed >> 16) & 255;
+                            aux.hit_face = shade_sf.packed >> 24;
+                            aux.hit_res = shade_sf.res;
+                        }
                     }
                 }
+                if (hit_base != 0xffffffffu) hit_used += n_emit;
             }
         }
         // (3) Volumetric: the surface that raised this event becomes the pending one (surface.rs:467-476)
@@ -1103,6 +1227,10 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         }
     }
 
+    // the unused rest of this warp's block of the hit stream
+    if (hit_base != 0xffffffffu)
+        for (uint32_t j = hit_used + lane; j < HIT_BLOCK; j += 32) P.hits[hit_base + j].pal = HIT_DEAD;
+
     // RaytraceInfo sum (renderer.rs:555): warp-reduce then one atomic per warp
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cubes_traced += __shfl_down_sync(0xffffffffu, cubes_traced, off);
@@ -1146,8 +1274,9 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
             const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + i);
             uint4 *dst = reinterpret_cast<uint4 *>(&h);
 #pragma unroll
-            for (int k = 0; k < 4; k++) dst[k] = src[k];
+            for (int k = 0; k < 4; k++) dst[k] = ld_stream(src + k);
         }
+        if (h.pal == HIT_DEAD) continue;
         const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
         const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
         const bool zeroed = (h.flags & 8u) != 0;
