@@ -3,6 +3,7 @@
 //
 // No CPU fallback lives here: every compute entry point needs a CUDA device and fails with
 // AICB_ERR_CUDA otherwise.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -145,16 +146,15 @@ static bool voxel_invisible(const aicb_voxel &v) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*kernel_fn)(const TraceParams, uint32_t);
 
-template <bool V, int LC, bool AUX>
+template <bool V, bool W, bool AUX>
 static kernel_fn kernel_of() {
-    return trace_kernel<V, LC, AUX>;
+    return trace_kernel<V, W, AUX>;
 }
 
-static kernel_fn select_kernel(bool volumetric, int lc, bool aux) {
-#define PICK(V, L, A) if (volumetric == V && lc == L && aux == A) return kernel_of<V, L, A>();
-    PICK(false, LC_NONE, false) PICK(false, LC_NONE, true) PICK(false, LC_FLAT, false) PICK(false, LC_FLAT, true)
-    PICK(false, LC_INTERP, false) PICK(false, LC_INTERP, true) PICK(true, LC_NONE, false) PICK(true, LC_NONE, true)
-    PICK(true, LC_FLAT, false) PICK(true, LC_FLAT, true) PICK(true, LC_INTERP, false) PICK(true, LC_INTERP, true)
+static kernel_fn select_kernel(bool volumetric, bool wide, bool aux) {
+#define PICK(V, W, A) if (volumetric == V && wide == W && aux == A) return kernel_of<V, W, A>();
+    PICK(false, false, false) PICK(false, false, true) PICK(false, true, false) PICK(false, true, true)
+    PICK(true, false, false) PICK(true, false, true) PICK(true, true, false) PICK(true, true, true)
 #undef PICK
     return nullptr;
 }
@@ -323,7 +323,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
         const int lc = opt->lighting_display == AICB_LIGHT_NONE ? LC_NONE
                        : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT : LC_INTERP);
-        kernel_fn k = select_kernel(volumetric, lc, aux);
+        kernel_fn k = select_kernel(volumetric, sc->ds.wide_cells != 0, aux);
         int blocks_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -331,18 +331,30 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;
             CU(cudaMemsetAsync(ctx->d_tile_counter, 0, 16 * sizeof(unsigned int), stream));
+            const bool prof = ctx->profile_kernels && base == 0;
+            if (prof) cudaEventRecord(ctx->ev_k[0], stream);
             gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
+            if (prof) cudaEventRecord(ctx->ev_k[1], stream);
             uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
             uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
             if (grid > want) grid = want;
+            if (prof) {
+                if (!ctx->d_debug) cudaMalloc(&ctx->d_debug, 4 * 8 * (size_t)ctx->num_sms * 64 * WARPS_PER_BLOCK);
+                P.debug_warp_times = (unsigned long long *)ctx->d_debug;
+                ctx->debug_warps = (uint32_t)grid * WARPS_PER_BLOCK;
+            }
             k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
+            P.debug_warp_times = nullptr;
+            if (prof) cudaEventRecord(ctx->ev_k[2], stream);
             switch (lc) {
                 case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
             }
+            if (prof) cudaEventRecord(ctx->ev_k[3], stream);
             const uint32_t n_pixels = n / P.n_samples;
             encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
+            if (prof) cudaEventRecord(ctx->ev_k[4], stream);
         }
         CU(cudaGetLastError());
     }
@@ -356,6 +368,24 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
     unsigned long long c[8];
     CU(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     sc->pending = false;
+    if (ctx->profile_kernels && sc->pending_rays) {  // AICB_PROFILE_KERNELS=1: per-kernel times of the first chunk
+        float t[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], ctx->ev_k[i], ctx->ev_k[i + 1]);
+        if (ctx->d_debug && ctx->debug_warps) {
+            std::vector<unsigned long long> w(4 * (size_t)ctx->debug_warps);
+            cudaMemcpy(w.data(), ctx->d_debug, w.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull, t1 = 0, passes = 0, rays = 0;
+            for (uint32_t i = 0; i < ctx->debug_warps; i++) { t0 = std::min(t0, w[4 * i]); t1 = std::max(t1, w[4 * i + 1]); passes += w[4 * i + 2]; rays += w[4 * i + 3]; }
+            std::vector<double> ends;
+            for (uint32_t i = 0; i < ctx->debug_warps; i++) ends.push_back((double)(w[4 * i + 1] - t0) * 1e-6);
+            std::sort(ends.begin(), ends.end());
+            auto q = [&](double f) { return ends[(size_t)(f * (ends.size() - 1))]; };
+            fprintf(stderr, "[aicb200] march warps %u: end times ms min %.3f p10 %.3f p50 %.3f p90 %.3f p99 %.3f max %.3f; passes/warp %.0f rays %llu\n",
+                    ctx->debug_warps, q(0), q(0.1), q(0.5), q(0.9), q(0.99), q(1.0), (double)passes / ctx->debug_warps, rays);
+        }
+        fprintf(stderr, "[aicb200] gen %.3f ms  march %.3f ms  shade %.3f ms  encode %.3f ms  (hits %llu)\n", t[0], t[1], t[2],
+                t[3], c[3]);
+    }
     if (c[7]) {  // the hit stream of some chunk overflowed: the frame is incomplete
         if (ctx->hits_per_task < 1024) ctx->hits_per_task *= 4;
         return fail(AICB_ERR_RETRY, "hit stream overflowed; its capacity has been raised - re-issue the render");
@@ -409,6 +439,8 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    c->profile_kernels = getenv("AICB_PROFILE_KERNELS") != nullptr;
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
     CU(cudaMalloc(&c->d_tile_counter, 16 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
@@ -433,6 +465,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_contrib) cudaFree(c->d_contrib);
     if (c->d_bin_list) cudaFree(c->d_bin_list);
+    if (c->d_debug) cudaFree(c->d_debug);
     if (c->d_task_aux) cudaFree(c->d_task_aux);
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
@@ -440,6 +473,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_tile_counter) cudaFree(c->d_tile_counter);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 5; i++) if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

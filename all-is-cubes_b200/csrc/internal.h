@@ -24,6 +24,10 @@ struct aicb_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // AICB_PROFILE_KERNELS
+    bool profile_kernels = false;
+    void *d_debug = nullptr;
+    uint32_t debug_warps = 0;
     unsigned int *d_tile_counter = nullptr;
     unsigned long long *d_counters = nullptr;
     float *d_lut = nullptr;

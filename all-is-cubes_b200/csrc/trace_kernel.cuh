@@ -30,9 +30,11 @@
 namespace aicb {
 
 // ---- device-side scene -------------------------------------------------------------------------
-constexpr uint32_t KIND_INVISIBLE = 0;  // AIR, or a single voxel that is fully transparent + non-emissive
-constexpr uint32_t KIND_SINGLE = 1;     // Evoxels::One, visible
-constexpr uint32_t KIND_RECURSIVE = 2;  // paletted brick
+// The kind sits in the top two bits of a u16 cell so that bit 15 means "nothing to see here" on both levels
+// (brick words carry the same flag): the marching loop tests one bit.
+constexpr uint32_t KIND_SINGLE = 0;     // Evoxels::One, visible
+constexpr uint32_t KIND_RECURSIVE = 1;  // paletted brick
+constexpr uint32_t KIND_INVISIBLE = 2;  // AIR, or a single voxel that is fully transparent + non-emissive
 
 // 32-byte block record, read as two uint4.
 struct BlockRec {
@@ -152,6 +154,7 @@ struct TraceParams {
     uint32_t *out_steps;
     unsigned long long *counters;  // [0] cubes_traced, [1] outer steps, [2] inner steps, [3] hits, [4] light texels, [5] blocks entered
     unsigned int *task_counter;
+    unsigned long long *debug_warp_times;  // AICB_PROFILE_KERNELS: per marching warp {start ns, end ns, passes, rays}
 };
 
 #ifdef __CUDACC__
@@ -327,36 +330,32 @@ AICB_NOINLINE bool caster_begin(Caster &c, const Ray &r, double ox, double oy, d
     return true;
 }
 
-// One State::step (raycast.rs:577-626) on the active caster, with incremental index update.
+// One State::step (raycast.rs:577-626) on the active caster, with incremental index update; select-based so that
+// lanes stepping along different axes stay converged.  Axis choice as the reference: x if t_max.x is strictly the
+// smallest, else y if t_max.y < t_max.z, else z.
 // Returns true if the new cube is outside the level (the "exit" step of raycast.rs:265-274).
 AICB_DEV bool caster_step(Caster &c, const Ray &r, int nx, int ny, int nz) {
-    bool exited;
-    if (c.tmx < c.tmy) {
-        if (c.tmx < c.tmz) {
-            c.last_t = c.tmx; c.rx += r.sx; c.tmx += r.tdx;
-            c.face = r.sx > 0 ? AICB_FACE_NX : AICB_FACE_PX;
-            c.idx += (uint32_t)(r.sx * ny * nz);
-            exited = (uint32_t)c.rx >= (uint32_t)nx;
-        } else {
-            c.last_t = c.tmz; c.rz += r.sz; c.tmz += r.tdz;
-            c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ;
-            c.idx += (uint32_t)r.sz;
-            exited = (uint32_t)c.rz >= (uint32_t)nz;
-        }
-    } else {
-        if (c.tmy < c.tmz) {
-            c.last_t = c.tmy; c.ry += r.sy; c.tmy += r.tdy;
-            c.face = r.sy > 0 ? AICB_FACE_NY : AICB_FACE_PY;
-            c.idx += (uint32_t)(r.sy * nz);
-            exited = (uint32_t)c.ry >= (uint32_t)ny;
-        } else {
-            c.last_t = c.tmz; c.rz += r.sz; c.tmz += r.tdz;
-            c.face = r.sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ;
-            c.idx += (uint32_t)r.sz;
-            exited = (uint32_t)c.rz >= (uint32_t)nz;
-        }
-    }
-    return exited;
+    const bool xy = c.tmx < c.tmy, xz = c.tmx < c.tmz, yz = c.tmy < c.tmz;
+    const bool ax = xy & xz;
+    const bool ay = !xy & yz;
+    const bool az = !(ax | ay);
+    const double tm = ax ? c.tmx : (ay ? c.tmy : c.tmz);
+    const double td = ax ? r.tdx : (ay ? r.tdy : r.tdz);
+    const double nt = tm + td;
+    c.last_t = tm;
+    c.tmx = ax ? nt : c.tmx;
+    c.tmy = ay ? nt : c.tmy;
+    c.tmz = az ? nt : c.tmz;
+    const int sg = ax ? r.sx : (ay ? r.sy : r.sz);
+    c.rx += ax ? sg : 0;
+    c.ry += ay ? sg : 0;
+    c.rz += az ? sg : 0;
+    const int stride = ax ? ny * nz : (ay ? nz : 1);
+    c.idx += (uint32_t)(sg * stride);
+    c.face = (ax ? AICB_FACE_NX : (ay ? AICB_FACE_NY : AICB_FACE_NZ)) + (sg > 0 ? 0 : 3);
+    const int pos = ax ? c.rx : (ay ? c.ry : c.rz);
+    const int lim = ax ? nx : (ay ? ny : nz);
+    return (uint32_t)pos >= (uint32_t)lim;
 }
 
 // RaycastStep::intersection_point (raycast.rs:409-439) for the caster's current (un-stepped)
@@ -643,7 +642,7 @@ struct PendingSurface {
 };
 
 enum LaneState : int { ST_IDLE = 0, ST_MARCH = 1, ST_EVENT = 2, ST_DONE = 3, ST_EXHAUSTED = 4 };
-enum EventKind : int { EV_SURFACE = 0, EV_INVISIBLE = 1, EV_ENTER_BLOCK = 2 };
+enum EventKind : int { EV_SURFACE = 0, EV_INVISIBLE = 1, EV_ENTER_BLOCK = 2, EV_EXIT = 3, EV_STUCK = 4 };
 enum EventPost : int { POST_CONTINUE = 0, POST_POP = 1, POST_FINISH = 2 };
 
 // task -> pixel mapping shared by the three kernels: pixel tasks are tile-ordered (32 consecutive
@@ -789,7 +788,7 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
 // Kernel 2 — the marching kernel (replaces SpaceRaytracer::trace_ray's loop, sr.rs:180-238, and the Rayon
 // dispatch, renderer.rs:516-556): persistent warps, lane refill from the ray stream, phase machine.
 // ======================================================================================================
-template <bool VOLUMETRIC, int LC, bool AUX>
+template <bool VOLUMETRIC, bool WIDE, bool AUX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
 trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     const DeviceScene &S = P.scene;
@@ -800,6 +799,8 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
 
     int st = ST_IDLE;
     uint32_t task = 0;  // index within the chunk
+    unsigned long long dbg_t0 = 0, dbg_passes = 0, dbg_rays = 0;
+    if (P.debug_warp_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
     // the ray list: bins in order, longest chords first
     __shared__ uint32_t s_bin_start[N_BINS + 1];
@@ -818,6 +819,8 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     Ray r;
     Caster c, saved;
     bool valid = false, saved_valid = false, inner = false, need_advance = false;
+    double t_scale = 1.0;                // 1 on the outer level, 1/resolution inside a block (surface.rs:385-386)
+    const bool want_ip = P.lighting >= AICB_LIGHT_COARSE;  // only interpolated lighting needs the intersection point
     int nx = 0, ny = 0, nz = 0;          // sizes of the active level
     uint32_t blk0y = 0, blk0z = 0;       // packed voxel bounds of the entered block (lo16|lo16, lo16|size16)
     uint32_t pal_off = 0;
@@ -844,6 +847,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     };
     auto pop_level = [&]() {
         inner = false;
+        t_scale = 1.0;
         c = saved;
         valid = saved_valid;
         nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
@@ -895,6 +899,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                             steps = 0;
                             have_last = false;
                             inner = false;
+                            t_scale = 1.0;
                             need_advance = false;
                             nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
                             if constexpr (AUX) {
@@ -910,9 +915,11 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             if (__all_sync(0xffffffffu, st == ST_EXHAUSTED)) break;
         }
 
+        dbg_passes++;
         // =========================== FINALIZE: hand the ray's result to the encode kernel ================
         if (st == ST_DONE) {
             cubes_traced += steps;
+            dbg_rays++;
             TaskOut o;
             o.first_hit = first_hit;
             o.T = T;
@@ -962,7 +969,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             }
             sf.t = t;
             sf.cube[0] = cx; sf.cube[1] = cy; sf.cube[2] = cz;
-            if constexpr (LC == LC_INTERP) {
+            if (want_ip) {
                 double ip[3];
                 if (!inner) {
                     intersection_point(c, r, cx, cy, cz, r.ox, r.oy, r.oz, ip);
@@ -978,49 +985,42 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 sf.ip[0] = ip[0]; sf.ip[1] = ip[1]; sf.ip[2] = ip[2];
             }
         };
+        // One DDA step and the classification of the cube / voxel it lands on.  Everything that is not "an empty
+        // cell, keep going" leaves the loop as an event; the rare cases (leaving the level, an iterator that cannot
+        // step) are events too so that the loop body stays small and converged.
         auto march_step = [&]() {
             if (need_advance) {
-                if (!valid) {  // cannot step: the iterator ends without an exit step (raycast.rs:245-249)
-                    if (inner) { pop_level(); return; }
-                    st = ST_DONE;
-                    return;
-                }
+                if (!valid) { ev_kind = EV_STUCK; st = ST_EVENT; return; }  // raycast.rs:245-249
                 if (caster_step(c, r, nx, ny, nz)) {
-                    // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
-                    const double t = inner ? c.last_t * recip_pow2(res) : c.last_t;
-                    if (VOLUMETRIC && have_last) {
-                        ev_kind = EV_INVISIBLE; ev_t = t; ev_post = inner ? POST_POP : POST_FINISH;
-                        st = ST_EVENT;
-                        return;
-                    }
-                    if (count_stop()) { st = ST_DONE; return; }
-                    if (inner) { pop_level(); return; }
-                    st = ST_DONE;
+                    ev_kind = EV_EXIT; ev_t = c.last_t * t_scale; st = ST_EVENT;
                     return;
                 }
             }
             need_advance = true;
             uint32_t word;
-            double t;
-            bool invisible, enter_block = false;
-            if (!inner) {
-                if constexpr (AUX) aux.n_outer++;
-                const uint32_t cell = S.wide_cells ? __ldg((const uint32_t *)S.cells + c.idx)
-                                                   : (uint32_t)__ldg((const uint16_t *)S.cells + c.idx);
-                const uint32_t ck = S.wide_cells ? (cell >> 16) : (cell >> 14);
-                word = S.wide_cells ? (cell & 0xffffu) : (cell & 0x3fffu);
-                t = c.last_t;
-                invisible = ck == KIND_INVISIBLE;
-                enter_block = ck == KIND_RECURSIVE;
+            bool invisible, enter_block;
+            if constexpr (WIDE) {
+                if (!inner) {
+                    const uint32_t cell = __ldg((const uint32_t *)S.cells + c.idx);
+                    word = cell & 0xffffu;
+                    invisible = (cell >> 16) == KIND_INVISIBLE;
+                    enter_block = (cell >> 16) == KIND_RECURSIVE;
+                } else {
+                    word = __ldg(S.bricks + c.idx);
+                    invisible = (word & 0x8000u) != 0;
+                    enter_block = false;
+                }
             } else {
-                if constexpr (AUX) aux.n_inner++;
-                word = __ldg(S.bricks + c.idx);
-                t = c.last_t * recip_pow2(res);  // surface.rs:385-386
-                invisible = (word & 0x8000u) != 0;
+                const uint16_t *vol = inner ? S.bricks : (const uint16_t *)S.cells;
+                const uint32_t w = __ldg(vol + c.idx);
+                invisible = (w & 0x8000u) != 0;
+                enter_block = !inner & ((w & 0x4000u) != 0);
+                word = inner ? w : (w & 0x3fffu);
             }
+            if constexpr (AUX) { if (inner) aux.n_inner++; else aux.n_outer++; }
             if (invisible) {
                 if (VOLUMETRIC && have_last) {
-                    ev_kind = EV_INVISIBLE; ev_t = t; ev_post = POST_CONTINUE;
+                    ev_kind = EV_INVISIBLE; ev_t = c.last_t * t_scale; ev_post = POST_CONTINUE;
                     st = ST_EVENT;
                     return;
                 }
@@ -1028,23 +1028,44 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 return;
             }
             ev_kind = enter_block ? EV_ENTER_BLOCK : EV_SURFACE;
-            ev_t = t;
+            ev_t = c.last_t * t_scale;
             ev_cell = word;
             ev_post = POST_CONTINUE;
             st = ST_EVENT;
         };
-        for (;;) {
-            const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
-            if (!marching) break;
-            // only lanes that can make progress in the other phases count (idle lanes below the refill threshold cannot)
-            if (__popc(__ballot_sync(0xffffffffu, st == ST_EVENT || st == ST_DONE)) >= (int)P.event_threshold) break;
-            if (st == ST_MARCH) march_step();
+        if (P.event_threshold >= 32) {
+            while (__any_sync(0xffffffffu, st == ST_MARCH)) {
+                if (st == ST_MARCH) march_step();
+            }
+        } else {
+            for (;;) {
+                const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
+                if (!marching) break;
+                // only lanes that can make progress in the other phases count (idle lanes below the refill threshold cannot)
+                if (__popc(__ballot_sync(0xffffffffu, st == ST_EVENT || st == ST_DONE)) >= (int)P.event_threshold) break;
+                if (st == ST_MARCH) march_step();
+            }
         }
         __syncwarp();
 
         // =========================== HEAVY: events =====================================================
         // (1) DepthIter + the Volumetric loop (surface.rs:460-490, sr.rs:185-203) / the Surface loop (sr.rs:206-225):
         //     decide which surface (if any) this event shades.
+        // (0) leaving the level / an iterator that cannot step
+        if (st == ST_EVENT && ev_kind == EV_STUCK) {   // ends without an exit step (raycast.rs:245-249)
+            if (inner) { pop_level(); st = ST_MARCH; } else { st = ST_DONE; }
+        }
+        if (st == ST_EVENT && ev_kind == EV_EXIT) {
+            // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
+            if (VOLUMETRIC && have_last) {
+                ev_kind = EV_INVISIBLE; ev_post = inner ? POST_POP : POST_FINISH;
+            } else if (count_stop() || !inner) {
+                st = ST_DONE;
+            } else {
+                pop_level();
+                st = ST_MARCH;
+            }
+        }
         bool do_shade = false;
         PendingSurface shade_sf;
         double span_exit = 0.0;
@@ -1143,7 +1164,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                     if (hit_base != 0xffffffffu) {
                         const uint32_t slot = hit_base + hit_used + (uint32_t)__popc(em & ((1u << lane) - 1u));
                         HitRecord h;
-                        if constexpr (LC == LC_INTERP) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
+                        if (want_ip) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
                         else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
                         h.pal = shade_sf.pal;
                         h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
@@ -1217,6 +1238,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 blk0y = b0.y; blk0z = b0.z;
                 pal_off = b1.y;
                 res = bres;
+                t_scale = recip_pow2(bres);
                 need_advance = false;
             }
         }
@@ -1227,6 +1249,15 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         }
     }
 
+    if (P.debug_warp_times) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        for (int off = 16; off > 0; off >>= 1) dbg_rays += __shfl_down_sync(0xffffffffu, dbg_rays, off);
+        if (lane == 0) {
+            unsigned long long *d = P.debug_warp_times + 4 * (size_t)(blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5));
+            d[0] = dbg_t0; d[1] = t1; d[2] = dbg_passes; d[3] = dbg_rays;
+        }
+    }
     // the unused rest of this warp's block of the hit stream
     if (hit_base != 0xffffffffu)
         for (uint32_t j = hit_used + lane; j < HIT_BLOCK; j += 32) P.hits[hit_base + j].pal = HIT_DEAD;
