@@ -432,25 +432,28 @@ AICB_DEV double rem_euclid1(double x) {
 }
 
 // get_interpolated_light (sr.rs:248-359). `lut` is the shared-memory copy of the decode table.
-AICB_NOINLINE void interpolated_light(const DeviceScene &s, const float *lut, uint32_t mode, int cube_x, int cube_y,
-                                      int cube_z, int face, double spx, double spy, double spz, float out[3],
-                                      uint32_t *texels_out) {
+// Written for the convergent shading kernel: no dynamically indexed arrays, and the (up to) eight texel loads of
+// the two layers are issued together before any of them is used.
+AICB_DEV void interpolated_light(const DeviceScene &s, const float *lut, uint32_t mode, int cube_x, int cube_y,
+                                 int cube_z, int face, double spx, double spy, double spz, float out[3],
+                                 uint32_t *texels_out) {
     const double eps = 0.5 / 256.0;
     const double sp[3] = {spx, spy, spz};
-    uint32_t texels = 0;
-    // Face::rotation_from_nz (face.rs:395-405): axis + sign of the images of +X and +Y
-    int a1, s1, a2, s2, an, sn;
-    switch (face) {
-        case AICB_FACE_NX: a1 = 1; s1 = 1;  a2 = 2; s2 = 1;  an = 0; sn = -1; break;  // RYZX
-        case AICB_FACE_NY: a1 = 2; s1 = 1;  a2 = 0; s2 = 1;  an = 1; sn = -1; break;  // RZXY
-        case AICB_FACE_NZ: a1 = 0; s1 = 1;  a2 = 1; s2 = 1;  an = 2; sn = -1; break;  // RXYZ
-        case AICB_FACE_PX: a1 = 1; s1 = -1; a2 = 2; s2 = 1;  an = 0; sn = 1;  break;  // RyZx
-        case AICB_FACE_PY: a1 = 2; s1 = 1;  a2 = 0; s2 = -1; an = 1; sn = 1;  break;  // RZxy
-        case AICB_FACE_PZ: a1 = 0; s1 = 1;  a2 = 1; s2 = -1; an = 2; sn = 1;  break;  // RXyz
-        default:           a1 = 0; s1 = 1;  a2 = 1; s2 = 1;  an = 2; sn = 0;  break;  // Within: IDENTITY, normal 0
-    }
-    double mix_1 = rem_euclid1((s1 > 0 ? sp[a1] : -sp[a1]) - 0.5);
-    double mix_2 = rem_euclid1((s2 > 0 ? sp[a2] : -sp[a2]) - 0.5);
+    // Face::rotation_from_nz (face.rs:395-405): axis + sign of the images of +X and +Y, and the normal
+    //   NX: RYZX   NY: RZXY   NZ: RXYZ   PX: RyZx   PY: RZxy   PZ: RXyz   Within: IDENTITY, normal 0
+    const bool within = face == AICB_FACE_WITHIN;
+    const int fa = within ? 2 : (face - 1) % 3;            // axis of the normal
+    const int a1 = fa == 0 ? 1 : (fa == 1 ? 2 : 0);
+    const int a2 = fa == 0 ? 2 : (fa == 1 ? 0 : 1);
+    const int an = fa;
+    const int sn = within ? 0 : (face >= AICB_FACE_PX ? 1 : -1);
+    int s1 = (face == AICB_FACE_PX) ? -1 : 1;
+    int s2 = (face == AICB_FACE_PY || face == AICB_FACE_PZ) ? -1 : 1;
+    const double sp1 = a1 == 0 ? sp[0] : (a1 == 1 ? sp[1] : sp[2]);
+    const double sp2 = a2 == 0 ? sp[0] : (a2 == 1 ? sp[1] : sp[2]);
+    const double spn = an == 0 ? sp[0] : (an == 1 ? sp[1] : sp[2]);
+    double mix_1 = rem_euclid1((s1 > 0 ? sp1 : -sp1) - 0.5);
+    double mix_2 = rem_euclid1((s2 > 0 ? sp2 : -sp2) - 0.5);
     if (mix_1 > 0.5) { mix_1 = 1.0 - mix_1; s1 = -s1; }
     if (mix_2 > 0.5) { mix_2 = 1.0 - mix_2; s2 = -s2; }
     if (mode == AICB_LIGHT_COARSE) {          // surface.rs:510-514
@@ -466,39 +469,63 @@ AICB_NOINLINE void interpolated_light(const DeviceScene &s, const float *lut, ui
     }
     const float m1 = (float)mix_1, m2 = (float)mix_2;
 
-    const int cube[3] = {cube_x, cube_y, cube_z};
-    double fdot_sp = sn == 0 ? 0.0 : (sn > 0 ? sp[an] : -sp[an]);
-    double ctr = (double)cube[an] + 0.5;
-    double fdot_c = sn == 0 ? 0.0 : (sn > 0 ? ctr : -ctr);
+    const int cube_n = an == 0 ? cube_x : (an == 1 ? cube_y : cube_z);
+    const double fdot_sp = sn == 0 ? 0.0 : (sn > 0 ? spn : -spn);
+    const double ctr = (double)cube_n + 0.5;
+    const double fdot_c = sn == 0 ? 0.0 : (sn > 0 ? ctr : -ctr);
     const double height_in_cube = fdot_sp - fdot_c + 0.5;
+    const bool two_layers = !(height_in_cube > (1.0 - eps));
 
-    const double lo1 = (double)s1 * -0.5, hi1 = (double)s1 * 0.5;
-    const double lo2 = (double)s2 * -0.5, hi2 = (double)s2 * 0.5;
-
-    float front[4], result[4];
-#pragma unroll 1
+    // the two candidate coordinates along each role: [0] = lo / front layer, [1] = hi / back layer
+    const double q1[2] = {sp1 + (double)s1 * -0.5, sp1 + (double)s1 * 0.5};
+    const double q2[2] = {sp2 + (double)s2 * -0.5, sp2 + (double)s2 * 0.5};
+    const double qn[2] = {sn != 0 ? spn + (double)sn * (1.0 - eps) : spn, sn != 0 ? spn + (double)sn * eps : spn};
+    bool ok1[2], ok2[2], okn[2];
+    int i1[2], i2[2], in_[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        ok1[j] = in_i32_range(q1[j]); i1[j] = __double2int_rd(q1[j]);
+        ok2[j] = in_i32_range(q2[j]); i2[j] = __double2int_rd(q2[j]);
+        okn[j] = in_i32_range(qn[j]); in_[j] = __double2int_rd(qn[j]);
+    }
+    // issue the loads: tex[layer][k], k: 0 near12, 1 near1far2, 2 near2far1, 3 far12
+    uint32_t tex[2][4];
+    uint32_t texels = 0;
+#pragma unroll
     for (int layer = 0; layer < 2; layer++) {
-        const double along = (layer == 0) ? (1.0 - eps) : eps;
-        double p[3] = {sp[0], sp[1], sp[2]};
-        if (sn != 0) p[an] = sp[an] + (double)sn * along;
-        const double b1 = p[a1], b2 = p[a2];
-        uint32_t tex[4];
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 4; k++) {
-            // k: 0 near12, 1 near1far2, 2 near2far1, 3 far12
-            p[a1] = b1 + ((k & 2) ? hi1 : lo1);
-            p[a2] = b2 + ((k & 1) ? hi2 : lo2);
-            if (in_i32_range(p[0]) & in_i32_range(p[1]) & in_i32_range(p[2]))
-                tex[k] = get_packed_light(s, __double2int_rd(p[0]), __double2int_rd(p[1]), __double2int_rd(p[2]), texels);
-            else
-                tex[k] = s.sky_mean;
+            const int j1 = (k >> 1) & 1, j2 = k & 1;
+            const int c1 = i1[j1], c2 = i2[j2], cn = in_[layer];
+            const int x = a1 == 0 ? c1 : (a2 == 0 ? c2 : cn);
+            const int y = a1 == 1 ? c1 : (a2 == 1 ? c2 : cn);
+            const int z = a1 == 2 ? c1 : (a2 == 2 ? c2 : cn);
+            uint32_t t = s.sky_mean;
+            if ((layer == 0 || two_layers) && (ok1[j1] & ok2[j2] & okn[layer])) {
+                const uint32_t dx = (uint32_t)(x - s.lo[0]), dy = (uint32_t)(y - s.lo[1]), dz = (uint32_t)(z - s.lo[2]);
+                if ((dx >= (uint32_t)s.size[0]) | (dy >= (uint32_t)s.size[1]) | (dz >= (uint32_t)s.size[2])) {
+                    t = light_outside(s, x, y, z);
+                } else if (s.light == nullptr) {
+                    t = TEXEL_ONE;
+                } else {
+                    texels++;
+                    t = __ldg(s.light + ((size_t)dx * s.size[1] + dy) * s.size[2] + dz);
+                }
+            }
+            tex[layer][k] = t;
         }
-        if ((tex[1] >> 24) != 255 && (tex[2] >> 24) != 255) tex[3] = tex[0];  // sr.rs:317-321
+    }
+    float front[4], result[4];
+#pragma unroll
+    for (int layer = 0; layer < 2; layer++) {
+        if (layer == 1 && !two_layers) break;
+        uint32_t t3 = tex[layer][3];
+        if ((tex[layer][1] >> 24) != 255 && (tex[layer][2] >> 24) != 255) t3 = tex[layer][0];  // sr.rs:317-321
         float v0[4], v1[4], v2[4], v3[4], cur[4];
-        texel_value_ao(lut, tex[0], v0);
-        texel_value_ao(lut, tex[1], v1);
-        texel_value_ao(lut, tex[2], v2);
-        texel_value_ao(lut, tex[3], v3);
+        texel_value_ao(lut, tex[layer][0], v0);
+        texel_value_ao(lut, tex[layer][1], v1);
+        texel_value_ao(lut, tex[layer][2], v2);
+        texel_value_ao(lut, t3, v3);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float ab = v0[i] + (v1[i] - v0[i]) * m2;
@@ -508,7 +535,6 @@ AICB_NOINLINE void interpolated_light(const DeviceScene &s, const float *lut, ui
         if (layer == 0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { front[i] = cur[i]; result[i] = cur[i]; }
-            if (height_in_cube > (1.0 - eps)) break;
         } else {
             const float h = (float)height_in_cube;
 #pragma unroll
