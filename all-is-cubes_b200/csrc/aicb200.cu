@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -157,6 +158,19 @@ static kernel_fn select_kernel(bool volumetric, bool wide, bool aux) {
     PICK(true, false, false) PICK(true, false, true) PICK(true, true, false) PICK(true, true, true)
 #undef PICK
     return nullptr;
+}
+
+// One edited cube of aicb_scene_update_cubes: linear index, encoded cell, optional light texel.
+struct CubeDelta {
+    uint32_t idx, cell, light, has_light;
+};
+
+static __global__ void scatter_cubes_kernel(const CubeDelta *ops, uint32_t n, uint32_t wide, void *cells, uint32_t *light) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CubeDelta op = ops[i];
+    if (wide) ((uint32_t *)cells)[op.idx] = op.cell; else ((uint16_t *)cells)[op.idx] = (uint16_t)op.cell;
+    if (op.has_light) light[op.idx] = op.light;
 }
 
 static aicb_status validate_options(const aicb_options *o) {
@@ -317,6 +331,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         P.task_depth = (double *)b;
         P.task_hit = (aicb_hit *)(b + chunk_cap * 8);
     }
+    if (stream != ctx->stream) CU(cudaStreamWaitEvent(stream, ctx->ev_delta, 0));  // pending cube edits
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     if (total_tasks > 0) {
@@ -441,6 +456,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaEventCreate(&c->ev1));
     c->profile_kernels = getenv("AICB_PROFILE_KERNELS") != nullptr;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
+    CU(cudaEventCreateWithFlags(&c->ev_delta, cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_tile_counter, 16 * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
@@ -466,6 +482,9 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_contrib) cudaFree(c->d_contrib);
     if (c->d_bin_list) cudaFree(c->d_bin_list);
     if (c->d_debug) cudaFree(c->d_debug);
+    if (c->h_delta) cudaFreeHost(c->h_delta);
+    if (c->d_delta) cudaFree(c->d_delta);
+    if (c->ev_delta) cudaEventDestroy(c->ev_delta);
     if (c->d_task_aux) cudaFree(c->d_task_aux);
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
@@ -658,29 +677,56 @@ uint64_t aicb_scene_device_bytes(const aicb_scene *s) { return s ? s->device_byt
 aicb_status aicb_scene_update_cubes(aicb_scene *s, const int32_t (*cubes)[3], const uint16_t *ids,
                                     const uint8_t (*light)[4], size_t n) {
     if (!s || (n && (!cubes || !ids))) return fail(AICB_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lock(s->ctx->mu);
-    CU(cudaSetDevice(s->ctx->device));
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return AICB_OK;
     const DeviceScene &ds = s->ds;
+    // validate everything before touching any state
     for (size_t i = 0; i < n; i++) {
         uint32_t dx = (uint32_t)(cubes[i][0] - ds.lo[0]), dy = (uint32_t)(cubes[i][1] - ds.lo[1]),
                  dz = (uint32_t)(cubes[i][2] - ds.lo[2]);
         if (dx >= (uint32_t)ds.size[0] || dy >= (uint32_t)ds.size[1] || dz >= (uint32_t)ds.size[2])
             return fail(AICB_ERR_INVALID, "cube out of bounds");
         if (ids[i] >= s->block_kind.size()) return fail(AICB_ERR_INVALID, "block id out of range");
-        size_t idx = ((size_t)dx * ds.size[1] + dy) * ds.size[2] + dz;
-        if (!s->h_ids.empty()) s->h_ids[idx] = ids[i];
-        if (ds.wide_cells) {
-            uint32_t cell = ids[i] | ((uint32_t)s->block_kind[ids[i]] << 16);
-            CU(cudaMemcpyAsync((uint32_t *)s->d_cells + idx, &cell, 4, cudaMemcpyHostToDevice, s->ctx->stream));
-        } else {
-            uint16_t cell = (uint16_t)(ids[i] | ((uint32_t)s->block_kind[ids[i]] << 14));
-            CU(cudaMemcpyAsync((uint16_t *)s->d_cells + idx, &cell, 2, cudaMemcpyHostToDevice, s->ctx->stream));
-        }
-        if (light && s->d_light)
-            CU(cudaMemcpyAsync(s->d_light + idx, light[i], 4, cudaMemcpyHostToDevice, s->ctx->stream));
-        CU(cudaStreamSynchronize(s->ctx->stream));  // source is a stack temporary
     }
-    return AICB_OK;
+    // one pinned staging buffer, one H2D copy, one scatter kernel per batch; a cube named twice keeps its
+    // last value (the scatter is parallel, so duplicates are resolved here)
+    const size_t need = n * sizeof(CubeDelta);
+    if (ctx->h_delta_bytes < need) {
+        if (ctx->h_delta) { cudaEventSynchronize(ctx->ev_delta); cudaFreeHost(ctx->h_delta); cudaFree(ctx->d_delta); }
+        ctx->h_delta = nullptr; ctx->d_delta = nullptr; ctx->h_delta_bytes = 0;
+        size_t cap = need < 65536 ? 65536 : need * 2;
+        CU(cudaMallocHost(&ctx->h_delta, cap));
+        CU(cudaMalloc(&ctx->d_delta, cap));
+        ctx->h_delta_bytes = cap;
+    }
+    CU(cudaEventSynchronize(ctx->ev_delta));  // the previous batch has left the staging buffer
+    CubeDelta *ops = (CubeDelta *)ctx->h_delta;
+    std::unordered_map<uint32_t, uint32_t> seen;
+    seen.reserve(n * 2);
+    uint32_t m = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t dx = (uint32_t)(cubes[i][0] - ds.lo[0]), dy = (uint32_t)(cubes[i][1] - ds.lo[1]),
+                       dz = (uint32_t)(cubes[i][2] - ds.lo[2]);
+        const size_t idx = ((size_t)dx * ds.size[1] + dy) * ds.size[2] + dz;
+        if (!s->h_ids.empty()) s->h_ids[idx] = ids[i];
+        CubeDelta op;
+        op.idx = (uint32_t)idx;
+        op.cell = ds.wide_cells ? (ids[i] | ((uint32_t)s->block_kind[ids[i]] << 16))
+                                : (ids[i] | ((uint32_t)s->block_kind[ids[i]] << 14));
+        op.has_light = (light && s->d_light) ? 1u : 0u;
+        op.light = 0;
+        if (op.has_light) std::memcpy(&op.light, light[i], 4);
+        auto it = seen.find(op.idx);
+        if (it == seen.end()) { seen.emplace(op.idx, m); ops[m++] = op; } else { ops[it->second] = op; }
+    }
+    CU(cudaMemcpyAsync(ctx->d_delta, ops, (size_t)m * sizeof(CubeDelta), cudaMemcpyHostToDevice, ctx->stream));
+    scatter_cubes_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>((const CubeDelta *)ctx->d_delta, m, ds.wide_cells, s->d_cells,
+                                                                   s->d_light);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev_delta, ctx->stream));  // renders on other streams wait for it (launch_trace)
+    return AICB_OK;  // stream-ordered before any later render of this context
 }
 
 aicb_status aicb_scene_upload_light(aicb_scene *s, const uint8_t (*light)[4], size_t n_texels) {
@@ -728,14 +774,13 @@ aicb_status aicb_render_srgb8(aicb_scene *s, const aicb_camera *cam, const aicb_
     for (int attempt = 0;; attempt++) {
         st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
         if (st != AICB_OK) return st;
+        // the copy is queued behind the frame: one host synchronisation per call
+        if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         st = finish(s, info);
         if (st != AICB_ERR_RETRY || attempt >= 5) break;
     }
-    if (st != AICB_OK) return st;
-    if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return AICB_OK;
+    return st;
 }
 
 static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, const aicb_shard *shard,

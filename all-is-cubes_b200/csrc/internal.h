@@ -26,6 +26,9 @@ struct aicb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // AICB_PROFILE_KERNELS
     bool profile_kernels = false;
+    void *h_delta = nullptr, *d_delta = nullptr;  // staging of aicb_scene_update_cubes batches (pinned / device)
+    size_t h_delta_bytes = 0;
+    cudaEvent_t ev_delta = nullptr;
     void *d_debug = nullptr;
     uint32_t debug_warps = 0;
     unsigned int *d_tile_counter = nullptr;

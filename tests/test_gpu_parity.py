@@ -335,6 +335,7 @@ def test_incremental_cube_update_equals_fresh_snapshot(mixed):
     new_ids = rng.integers(0, len(mixed.blocks), 50).astype(np.uint16)
     new_light = rng.integers(0, 255, (50, 4)).astype(np.uint8)
     new_light[:, 3] = 255
+    cubes[40:] = cubes[:10]   # cubes named twice in one batch keep their last value
     r.rt.update_cubes(cubes, new_ids, new_light)
     ids2 = mixed.block_ids.copy()
     light2 = mixed.light.copy()
