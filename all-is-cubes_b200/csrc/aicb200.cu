@@ -342,6 +342,10 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         int blocks_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        if (const char *e = getenv("AICB_BLOCKS_PER_SM")) {  // experiments: cap the resident marching blocks
+            int v = atoi(e);
+            if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v;
+        }
         for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;

@@ -824,7 +824,35 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_blocks = 0;
 
     int st = ST_IDLE;
-    uint32_t task = 0;  // index within the chunk
+
+    // Cold per-ray state lives in shared memory, one column per thread, so that the registers of the marching loop
+    // hold only what a DDA step touches (more resident warps); the HEAVY sections read what they need into
+    // short-lived locals.
+    __shared__ double sh_d[16][WARPS_PER_BLOCK * 32];
+    __shared__ uint32_t sh_w[17][WARPS_PER_BLOCK * 32];
+    const int tid = threadIdx.x;
+#define COLD_D(k) sh_d[k][tid]
+#define COLD_W(k) sh_w[k][tid]
+    // doubles: 0-2 origin, 3-5 direction, 6 half_over_len, 7-10 saved caster (t_max x/y/z, last_t), 11 pending t,
+    //          12-14 pending intersection point, 15 t_to_abs
+    // words:   0-4 saved caster (rx, ry, rz, face, idx), 5 saved valid, 6 pending pal, 7-9 pending cube, 10 pending packed,
+    //          11 pending res, 12 t_to_view, 13 first_hit, 14 last_hit, 15 task, 16 sky octant
+    auto load_ray = [&](Ray &rr, const Ray &hot) {
+        rr = hot;
+        rr.ox = COLD_D(0); rr.oy = COLD_D(1); rr.oz = COLD_D(2);
+        rr.dx = COLD_D(3); rr.dy = COLD_D(4); rr.dz = COLD_D(5);
+        rr.half_over_len = COLD_D(6);
+    };
+    auto store_pending = [&](const PendingSurface &sf) {
+        COLD_D(11) = sf.t; COLD_D(12) = sf.ip[0]; COLD_D(13) = sf.ip[1]; COLD_D(14) = sf.ip[2];
+        COLD_W(6) = sf.pal; COLD_W(7) = (uint32_t)sf.cube[0]; COLD_W(8) = (uint32_t)sf.cube[1]; COLD_W(9) = (uint32_t)sf.cube[2];
+        COLD_W(10) = sf.packed; COLD_W(11) = (uint32_t)sf.res;
+    };
+    auto load_pending = [&](PendingSurface &sf) {
+        sf.t = COLD_D(11); sf.ip[0] = COLD_D(12); sf.ip[1] = COLD_D(13); sf.ip[2] = COLD_D(14);
+        sf.pal = COLD_W(6); sf.cube[0] = (int)COLD_W(7); sf.cube[1] = (int)COLD_W(8); sf.cube[2] = (int)COLD_W(9);
+        sf.packed = COLD_W(10); sf.res = (int)COLD_W(11);
+    };
     unsigned long long dbg_t0 = 0, dbg_passes = 0, dbg_rays = 0;
     if (P.debug_warp_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
@@ -842,9 +870,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     uint32_t hit_base = 0xffffffffu, hit_used = 0;
 
     // ---- per-ray state -----------------------------------------------------------------------------
-    Ray r;
-    Caster c, saved;
-    bool valid = false, saved_valid = false, inner = false, need_advance = false;
+    Ray r;      // only t_delta and the signs are kept here (the DDA step); origin / direction are cold
+    Caster c;
+    bool valid = false, inner = false, need_advance = false;
     double t_scale = 1.0;                // 1 on the outer level, 1/resolution inside a block (surface.rs:385-386)
     const bool want_ip = P.lighting >= AICB_LIGHT_COARSE;  // only interpolated lighting needs the intersection point
     int nx = 0, ny = 0, nz = 0;          // sizes of the active level
@@ -853,13 +881,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     int res = 1;
     float T = 1.f;
     uint32_t steps = 0;
-    uint32_t first_hit = 0xffffffffu, last_hit = 0xffffffffu, sky_octant = 0;
-    double t_to_abs = 0.0;
-    float t_to_view = 0.f;
     const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
     const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
     bool have_last = false;
-    PendingSurface last;
     AuxState<AUX> aux;
     // event
     int ev_kind = 0, ev_post = 0;
@@ -874,8 +898,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     auto pop_level = [&]() {
         inner = false;
         t_scale = 1.0;
-        c = saved;
-        valid = saved_valid;
+        c.tmx = COLD_D(7); c.tmy = COLD_D(8); c.tmz = COLD_D(9); c.last_t = COLD_D(10);
+        c.rx = (int)COLD_W(0); c.ry = (int)COLD_W(1); c.rz = (int)COLD_W(2); c.face = (int)COLD_W(3); c.idx = COLD_W(4);
+        valid = COLD_W(5) != 0;
         nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
         need_advance = true;
     };
@@ -898,7 +923,8 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                     } else {
                         int b = 0;
                         while (k >= s_bin_start[b + 1]) b++;
-                        task = __ldg(P.bin_list + (size_t)b * P.bin_stride + (k - s_bin_start[b]));
+                        const uint32_t task = __ldg(P.bin_list + (size_t)b * P.bin_stride + (k - s_bin_start[b]));
+                        COLD_W(15) = task;
                         RayRecord rec;
                         {
                             const uint4 *src = reinterpret_cast<const uint4 *>(P.ray_records + task);
@@ -907,9 +933,10 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                             for (int k = 0; k < 9; k++) dst[k] = ld_stream(src + k);
                         }
                         {
-                            r.ox = rec.ox; r.oy = rec.oy; r.oz = rec.oz; r.dx = rec.dx; r.dy = rec.dy; r.dz = rec.dz;
+                            COLD_D(0) = rec.ox; COLD_D(1) = rec.oy; COLD_D(2) = rec.oz;
+                            COLD_D(3) = rec.dx; COLD_D(4) = rec.dy; COLD_D(5) = rec.dz;
                             r.tdx = rec.tdx; r.tdy = rec.tdy; r.tdz = rec.tdz;
-                            r.half_over_len = rec.half_over_len;
+                            COLD_D(6) = rec.half_over_len;
                             r.sx = (int)((rec.flags >> 6) & 3u) - 1; r.sy = (int)((rec.flags >> 8) & 3u) - 1;
                             r.sz = (int)((rec.flags >> 10) & 3u) - 1;
                             c.tmx = rec.tmx; c.tmy = rec.tmy; c.tmz = rec.tmz; c.last_t = rec.last_t;
@@ -917,10 +944,10 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                             c.idx = rec.idx;
                             c.face = (int)(rec.flags & 7u);
                             valid = (rec.flags & 16u) != 0;
-                            t_to_abs = rec.t_to_abs;
-                            t_to_view = rec.t_to_view;
-                            sky_octant = (rec.flags >> 12) & 7u;
-                            first_hit = last_hit = 0xffffffffu;
+                            COLD_D(15) = rec.t_to_abs;
+                            COLD_W(12) = __float_as_uint(rec.t_to_view);
+                            COLD_W(16) = (rec.flags >> 12) & 7u;
+                            COLD_W(13) = COLD_W(14) = 0xffffffffu;
                             T = 1.0f;
                             steps = 0;
                             have_last = false;
@@ -947,10 +974,11 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             cubes_traced += steps;
             dbg_rays++;
             TaskOut o;
-            o.first_hit = first_hit;
+            const uint32_t task = COLD_W(15);
+            o.first_hit = COLD_W(13);
             o.T = T;
             o.steps = steps;
-            o.flags = sky_octant;
+            o.flags = COLD_W(16);
             *reinterpret_cast<uint4 *>(P.task_out + task) = *reinterpret_cast<const uint4 *>(&o);
             if constexpr (AUX) {
                 n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
@@ -987,7 +1015,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 sf.res = 1;
             } else {
                 sf.pal = pal_off + cell_or_voxel;
-                cx = saved.rx + S.lo[0]; cy = saved.ry + S.lo[1]; cz = saved.rz + S.lo[2];
+                cx = (int)COLD_W(0) + S.lo[0]; cy = (int)COLD_W(1) + S.lo[1]; cz = (int)COLD_W(2) + S.lo[2];
                 const int vx = c.rx + (int)(int16_t)(blk0y & 0xffff), vy = c.ry + (int)(int16_t)(blk0y >> 16),
                           vz = c.rz + (int)(int16_t)(blk0z & 0xffff);
                 sf.packed = (uint32_t)vx | ((uint32_t)vy << 8) | ((uint32_t)vz << 16) | ((uint32_t)c.face << 24);
@@ -997,13 +1025,15 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             sf.cube[0] = cx; sf.cube[1] = cy; sf.cube[2] = cz;
             if (want_ip) {
                 double ip[3];
+                Ray rr;
+                load_ray(rr, r);
                 if (!inner) {
-                    intersection_point(c, r, cx, cy, cz, r.ox, r.oy, r.oz, ip);
+                    intersection_point(c, rr, cx, cy, cz, rr.ox, rr.oy, rr.oz, ip);
                 } else {
                     const double fres = (double)res, anti = recip_pow2(res);
                     const int vx = (int)(sf.packed & 255), vy = (int)((sf.packed >> 8) & 255), vz = (int)((sf.packed >> 16) & 255);
-                    intersection_point(c, r, vx, vy, vz, (r.ox - (double)cx) * fres, (r.oy - (double)cy) * fres,
-                                       (r.oz - (double)cz) * fres, ip);
+                    intersection_point(c, rr, vx, vy, vz, (rr.ox - (double)cx) * fres, (rr.oy - (double)cy) * fres,
+                                       (rr.oz - (double)cz) * fres, ip);
                     ip[0] = ip[0] * anti + (double)cx;  // surface.rs:406-407
                     ip[1] = ip[1] * anti + (double)cy;
                     ip[2] = ip[2] * anti + (double)cz;
@@ -1099,7 +1129,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             bool stop;
             if constexpr (VOLUMETRIC) {
                 do_shade = have_last;
-                shade_sf = last;
+                load_pending(shade_sf);
                 span_exit = ev_t;
                 have_last = false;
                 stop = count_stop();
@@ -1129,7 +1159,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             float coeff = 1.0f;
             bool zeroed = false;
             if constexpr (VOLUMETRIC) {
-                const float thickness = fmaxf((float)((span_exit - shade_sf.t) * t_to_abs), 0.0f);
+                const float thickness = fmaxf((float)((span_exit - shade_sf.t) * COLD_D(15)), 0.0f);
                 if (thickness == 0.0f) {
                     if (col.w == 1.0f) { coeff = 1.0f; }
                     else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
@@ -1155,7 +1185,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 float tr = 1.0f - ca;
                 float fa = -1.0f;
                 if (have_fog) {  // distance_fog (sr.rs:745-768)
-                    float rel = (float)shade_sf.t * t_to_view;
+                    float rel = (float)shade_sf.t * __uint_as_float(COLD_W(12));
                     rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
                     const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
                     const float fudged = fog_exponential / 0.79810348f;
@@ -1198,14 +1228,15 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                         h.ca = h_ca;
                         h.coeff = h_coeff;
                         h.fa = h_fa;
-                        h.flags = (shade_sf.packed >> 24) | (h_zeroed ? 8u : 0u) | (sky_octant << 4);
+                        h.flags = (shade_sf.packed >> 24) | (h_zeroed ? 8u : 0u) | (COLD_W(16) << 4);
                         h.next = 0xffffffffu;
                         const uint4 *src = reinterpret_cast<const uint4 *>(&h);
                         uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
 #pragma unroll
                         for (int k = 0; k < 4; k++) st_stream(dst + k, src[k]);
-                        if (last_hit != 0xffffffffu) P.hits[last_hit].next = slot; else first_hit = slot;
-                        last_hit = slot;
+                        const uint32_t prev_hit = COLD_W(14);
+                        if (prev_hit != 0xffffffffu) P.hits[prev_hit].next = slot; else COLD_W(13) = slot;
+                        COLD_W(14) = slot;
                     }
                     T = T * h_tr;
                     if constexpr (AUX) {
@@ -1227,7 +1258,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         // (3) Volumetric: the surface that raised this event becomes the pending one (surface.rs:467-476)
         if constexpr (VOLUMETRIC) {
             if (st == ST_EVENT && ev_kind == EV_SURFACE) {
-                record_surface(last, ev_cell, ev_t);
+                PendingSurface pending;
+                record_surface(pending, ev_cell, ev_t);
+                store_pending(pending);
                 have_last = true;
             }
         }
@@ -1253,10 +1286,13 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             const int cx = c.rx + S.lo[0], cy = c.ry + S.lo[1], cz = c.rz + S.lo[2];
             Caster ic;
             bool ivalid;
-            if (caster_begin(ic, r, (r.ox - (double)cx) * fres, (r.oy - (double)cy) * fres, (r.oz - (double)cz) * fres, in,
+            Ray rr;
+            load_ray(rr, r);
+            if (caster_begin(ic, rr, (rr.ox - (double)cx) * fres, (rr.oy - (double)cy) * fres, (rr.oz - (double)cz) * fres, in,
                              &ivalid)) {
-                saved = c;
-                saved_valid = valid;
+                COLD_D(7) = c.tmx; COLD_D(8) = c.tmy; COLD_D(9) = c.tmz; COLD_D(10) = c.last_t;
+                COLD_W(0) = (uint32_t)c.rx; COLD_W(1) = (uint32_t)c.ry; COLD_W(2) = (uint32_t)c.rz; COLD_W(3) = (uint32_t)c.face;
+                COLD_W(4) = c.idx; COLD_W(5) = valid ? 1u : 0u;
                 c = ic;
                 valid = ivalid;
                 inner = true;
