@@ -349,11 +349,12 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;
-            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, 16 * sizeof(unsigned int), stream));
-            const bool prof = ctx->profile_kernels && base == 0;
-            if (prof) cudaEventRecord(ctx->ev_k[0], stream);
+            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, (4 + N_BINS) * sizeof(unsigned int), stream));
+            const bool first = base == 0;  // stage times are reported for the first chunk
+            const bool prof = ctx->profile_kernels && first;
+            if (first) cudaEventRecord(ctx->ev_k[0], stream);
             gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
-            if (prof) cudaEventRecord(ctx->ev_k[1], stream);
+            if (first) cudaEventRecord(ctx->ev_k[1], stream);
             uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
             uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
             if (grid > want) grid = want;
@@ -364,16 +365,16 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
             }
             k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
             P.debug_warp_times = nullptr;
-            if (prof) cudaEventRecord(ctx->ev_k[2], stream);
+            if (first) cudaEventRecord(ctx->ev_k[2], stream);
             switch (lc) {
                 case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
             }
-            if (prof) cudaEventRecord(ctx->ev_k[3], stream);
+            if (first) cudaEventRecord(ctx->ev_k[3], stream);
             const uint32_t n_pixels = n / P.n_samples;
             encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
-            if (prof) cudaEventRecord(ctx->ev_k[4], stream);
+            if (first) cudaEventRecord(ctx->ev_k[4], stream);
         }
         CU(cudaGetLastError());
     }
@@ -414,6 +415,8 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         info->kernel_ms = ms;
+        if (sc->pending_rays)
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&info->stage_ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]);
         info->cubes_traced = c[0];
         info->rays = sc->pending_rays;
         for (int i = 0; i < 5; i++) info->counters[i] = c[1 + i];
@@ -461,7 +464,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     c->profile_kernels = getenv("AICB_PROFILE_KERNELS") != nullptr;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
     CU(cudaEventCreateWithFlags(&c->ev_delta, cudaEventDisableTiming));
-    CU(cudaMalloc(&c->d_tile_counter, 16 * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_tile_counter, (4 + N_BINS) * sizeof(unsigned int)));
     CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
     float lut[768];

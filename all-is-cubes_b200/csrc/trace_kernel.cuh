@@ -1408,7 +1408,8 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
             og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], h.fa);
             ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], h.fa);
         }
-        P.hit_contrib[i] = make_float4(orr * h.T_before, og * h.T_before, ob * h.T_before, 0.0f);
+        // .w carries the link to the ray's next hit so that the encode kernel reads one 16-byte record per hit
+        P.hit_contrib[i] = make_float4(orr * h.T_before, og * h.T_before, ob * h.T_before, __uint_as_float(h.next));
     }
     if (texels) atomicAdd(P.counters + 4, texels);
 }
@@ -1436,9 +1437,10 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
         TaskOut o;
         *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + t0 + k);
         float lr = 0.f, lg = 0.f, lb = 0.f, T = o.T;
-        for (uint32_t hi = o.first_hit; hi != 0xffffffffu; hi = P.hits[hi].next) {
+        for (uint32_t hi = o.first_hit; hi != 0xffffffffu;) {
             const float4 c = P.hit_contrib[hi];
             lr = lr + c.x; lg = lg + c.y; lb = lb + c.z;
+            hi = __float_as_uint(c.w);
         }
         if (P.include_sky) {  // the sky is an opaque hit at t = inf
             const int so = S.sky_kind ? (int)(o.flags & 7u) : 0;

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AICB_ABI_VERSION 1
+#define AICB_ABI_VERSION 2
 
 typedef enum aicb_status {
     AICB_OK = 0,
@@ -151,9 +151,10 @@ typedef struct aicb_render_info {
     uint64_t rays;                 /* primary rays traced (pixels * samples) */
     uint64_t algorithmic_bytes;    /* SURVEY §8(d) formula, from device counters */
     uint64_t counters[6];          /* outer steps, inner steps, surface hits, light texels, blocks entered, pixels */
-    float kernel_ms;               /* CUDA-event duration of the trace kernel on its stream */
+    float kernel_ms;               /* CUDA-event duration of the whole frame (all kernels) on its stream */
     uint16_t flaws;                /* Flaws bits (flaws.rs:20-91) */
     uint16_t _pad;
+    float stage_ms[4];             /* the frame's kernels (first chunk): ray generation, marching, shading, encode */
 } aicb_render_info;
 
 /* Per-pixel hit record: Position of the first non-exception Hit (hit.rs:92-101):
