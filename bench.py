@@ -382,6 +382,13 @@ def run_ours(args):
     march_bytes = 2 * ai.counters[0] + 2 * ai.counters[1] + 32 * ai.counters[2] + 32 * ai.counters[4]
     march_ms = stage_avg_ms[1]
     achieved = march_bytes / (march_ms * 1e-3) / 1e9
+    traffic = None   # DRAM bytes of the marching kernel per launch from the committed ncu --set full capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tr.get("workload") == args.workload and world == 1:
+            traffic = int(tr["traffic_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
     frame_achieved = alg_bytes / (kernel_avg_ms * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the public API ------------------------------------------------------
@@ -444,7 +451,7 @@ def run_ours(args):
                        "l2": "256 MiB buffer rewritten between timed steps", "scene_device_bytes": rt.device_bytes,
                        "cubes_traced_per_frame_this_rank": int(ai.cubes_traced)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "kernel": "trace_kernel (marching)", "kernel_ms": march_ms,
                          "algorithmic_bytes_per_launch": int(march_bytes),
                          "frame": {"kernels": ["gen_kernel", "trace_kernel", "shade_kernel", "encode_kernel"],
