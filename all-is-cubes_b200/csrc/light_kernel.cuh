@@ -48,6 +48,7 @@ struct LightParams {
     uint32_t max_distance;
     uint32_t priority;              // the round's priority level
     uint32_t epsilon_priority;
+    uint32_t priority_band;     // cubes whose queued priority is within this many levels of the round's maximum are updated together
 };
 
 #ifdef __CUDACC__
