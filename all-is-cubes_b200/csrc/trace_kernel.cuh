@@ -1411,7 +1411,10 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         // .w carries the link to the ray's next hit so that the encode kernel reads one 16-byte record per hit
         P.hit_contrib[i] = make_float4(orr * h.T_before, og * h.T_before, ob * h.T_before, __uint_as_float(h.next));
     }
-    if (texels) atomicAdd(P.counters + 4, texels);
+    // one atomic per warp: 150 K single-address atomics would cost more than the shading itself
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) texels += __shfl_down_sync(0xffffffffu, texels, off);
+    if ((threadIdx.x & 31) == 0 && texels) atomicAdd(P.counters + 4, texels);
 }
 
 // ======================================================================================================
