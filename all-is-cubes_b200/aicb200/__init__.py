@@ -65,6 +65,8 @@ def load_library() -> C.CDLL:
     lib.aicb_render_colorbuf.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
                                          C.POINTER(abi.Shard), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.POINTER(abi.RenderInfo)]
+    lib.aicb_render_rgba16f.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
+                                        C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.POINTER(abi.RenderInfo)]
     lib.aicb_render_srgb8_device.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
                                              C.POINTER(abi.Shard), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.aicb_render_srgb8_device_frame.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options),
@@ -569,6 +571,21 @@ class RtRenderer:
                          RenderInfo.from_abi(info))
 
     draw_rgba = draw
+
+    def draw_rgba16f(self, shard=None):
+        """The per-pixel colour raytrace_to_texture uploads (raytrace_to_texture.rs:645-661): premultiplied RGBA,
+        exposure applied, as float16 [h, w, 4]."""
+        rt = self._require()
+        n = self.pixel_count(shard)
+        w = self.camera.data.fb_width
+        out = np.empty((n, 4), dtype=np.float16)
+        info = abi.RenderInfo()
+        opt = rt.graphics_options.to_abi(True)
+        s = _shard_abi(shard)
+        _check(load_library().aicb_render_rgba16f(rt.handle, C.byref(self.camera.data), C.byref(opt),
+                                                  C.byref(s) if s else None, out.ctypes.data, n, C.byref(info)))
+        h = n // w if w else 0
+        return out.reshape(h, w, 4) if w else out.reshape(0, 0, 4)
 
     def draw_colorbuf(self, shard=None, want_depth=True, want_hit=True, want_steps=True):
         """RtRenderer::draw::<ColorBuf> (+DepthBuf, +Position) (renderer.rs:183-220)."""

@@ -116,6 +116,7 @@ EXPORTED_SYMBOLS = [
     "aicb_scene_device_bytes",
     "aicb_shard_pixel_count",
     "aicb_render_srgb8",
+    "aicb_render_rgba16f",
     "aicb_render_colorbuf",
     "aicb_render_srgb8_device",
     "aicb_render_srgb8_device_frame",

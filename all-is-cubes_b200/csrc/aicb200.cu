@@ -219,6 +219,7 @@ struct Outputs {
     bool full_frame = false;
     uchar4 *srgb8 = nullptr;
     float4 *colorbuf = nullptr;
+    uint2 *rgba16f = nullptr;
     double *depth = nullptr;
     aicb_hit *hit = nullptr;
     uint32_t *steps = nullptr;
@@ -278,6 +279,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.out_full_frame = out.full_frame ? 1 : 0;
     P.out_srgb8 = out.srgb8;
     P.out_colorbuf = out.colorbuf;
+    P.out_rgba16f = out.rgba16f;
     P.out_depth = out.depth;
     P.out_hit = out.hit;
     P.out_steps = out.steps;
@@ -295,7 +297,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     sc->pending = true;
     sc->pending_pixels = pixels;
     sc->pending_rays = pixels * (P.antialias ? 4 : 1);
-    sc->pending_out_bytes_per_pixel = out.srgb8 ? 4 : 16;
+    sc->pending_out_bytes_per_pixel = out.srgb8 ? 4 : (out.rgba16f ? 8 : 16);
 
     // ---- the three kernels of a frame, chunked so the ray stream stays bounded ---------------------------
     P.n_samples = P.antialias ? 4 : 1;
@@ -794,6 +796,29 @@ aicb_status aicb_render_srgb8(aicb_scene *s, const aicb_camera *cam, const aicb_
         if (st != AICB_OK) return st;
         // the copy is queued behind the frame: one host synchronisation per call
         if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        st = finish(s, info);
+        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+    }
+    return st;
+}
+
+aicb_status aicb_render_rgba16f(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, const aicb_shard *shard,
+                                uint16_t (*out)[4], size_t out_len, aicb_render_info *info) {
+    aicb_status st = check_render_args(s, cam, opt, shard, out_len);
+    if (st != AICB_OK) return st;
+    if (out_len && !out) return fail(AICB_ERR_INVALID, "out is NULL");
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    st = ensure(&ctx->d_out, &ctx->d_out_bytes, out_len * 8 + 16);
+    if (st != AICB_OK) return st;
+    Outputs o;
+    o.rgba16f = (uint2 *)ctx->d_out;
+    for (int attempt = 0;; attempt++) {
+        st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
+        if (st != AICB_OK) return st;
+        if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         st = finish(s, info);
         if (st != AICB_ERR_RETRY || attempt >= 5) break;

@@ -27,6 +27,10 @@
 
 #include "../../include/aicb200.h"
 
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#endif
+
 namespace aicb {
 
 // ---- device-side scene -------------------------------------------------------------------------
@@ -149,6 +153,7 @@ struct TraceParams {
     // outputs
     uchar4 *out_srgb8;
     float4 *out_colorbuf;
+    uint2 *out_rgba16f;         // premultiplied RGBA, 4 x f16 (raytrace_to_texture.rs:645-661)
     double *out_depth;
     aicb_hit *out_hit;
     uint32_t *out_steps;
@@ -1469,6 +1474,18 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
     if (P.n_samples == 4) { l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f; }
     if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);
     if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
+    if (P.out_rgba16f) {
+        // ColorBuf::into_premultiplied_rgba (raytracer_components.rs:70-77) scaled by the exposure and rounded to
+        // f16 as half::f16::from_f32 does (round to nearest even, overflow to infinity)
+        float a = 1.0f - tT;
+        a = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);   // clamp(0, 1): NaN passes through
+        const __half2 rg = __floats2half2_rn(l0 * P.exposure, l1 * P.exposure);
+        const __half2 ba = __floats2half2_rn(l2 * P.exposure, a);
+        uint2 packed;
+        packed.x = *reinterpret_cast<const uint32_t *>(&rg);
+        packed.y = *reinterpret_cast<const uint32_t *>(&ba);
+        P.out_rgba16f[out_index] = packed;
+    }
     if (P.task_depth) {  // AUX outputs: DepthBuf::mean = min (accum.rs:284-297); first sub-sample with a hit
         double dmin = P.task_depth[t0];
         aicb_hit h = P.task_hit[t0];

@@ -206,6 +206,14 @@ aicb_status aicb_render_srgb8(aicb_scene *, const aicb_camera *, const aicb_opti
                               const aicb_shard *shard_or_null,
                               uint8_t (*out)[4], size_t out_len, aicb_render_info *info_or_null);
 
+/* == the per-pixel colour of raytrace_to_texture (all-is-cubes-gpu/src/raytrace_to_texture.rs:645-661):
+ * ColorBuf::into_premultiplied_rgba (all-is-cubes/src/raytracer_components.rs:70-77) with the camera's exposure
+ * applied to r, g, b, rounded to IEEE binary16 like half::f16::from_f32; not tone-mapped (the caller's GPU
+ * postprocessing does that).  out[i] = {r, g, b, a} as raw f16 bits. */
+aicb_status aicb_render_rgba16f(aicb_scene *, const aicb_camera *, const aicb_options *,
+                                const aicb_shard *shard_or_null,
+                                uint16_t (*out)[4], size_t out_len, aicb_render_info *info_or_null);
+
 /* == draw::<ColorBuf> (+ DepthBuf, + Position): raw accumulators for parity and other callers.
  * out_colorbuf: light.xyz, transmittance (raytracer_components.rs:20-39).
  * depth_or_null: DepthBuf::depth (accum.rs:254-311) of the first Hit carrying a t_distance.

@@ -89,6 +89,30 @@ def test_antialiasing_and_debug_pixel_cost(mixed):
         assert np.abs(img.data.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
 
 
+def test_premultiplied_f16_output(mixed):
+    """raytrace_to_texture.rs:645-661: [f16(r * exposure), f16(g * exposure), f16(b * exposure), f16(alpha)] of
+    ColorBuf::into_premultiplied_rgba.  Exact against the same conversion of the GPU's own ColorBuf; within one
+    f16 ULP of the conversion of the oracle's ColorBuf (whose f32 channels may differ in the last bit)."""
+    for kw in (dict(), dict(exposure=2.5), dict(antialiasing_always=True)):
+        opts = GraphicsOptions(view_distance=40.0, **kw)
+        cam = scenes.standard_camera(mixed, opts, 64, 48)
+        r = RtRenderer(cam)
+        r.update(mixed)
+        got = r.draw_rgba16f().reshape(-1, 4)
+        exposure = np.float32(cam.data.exposure)
+
+        def convert(cb):
+            alpha = np.clip(np.float32(1.0) - cb[:, 3], np.float32(0.0), np.float32(1.0))
+            with np.errstate(over="ignore"):
+                return np.stack([(cb[:, 0] * exposure), (cb[:, 1] * exposure), (cb[:, 2] * exposure), alpha], axis=1).astype(np.float16)
+
+        own = convert(r.draw_colorbuf(want_depth=False, want_hit=False, want_steps=False)["colorbuf"])
+        assert np.array_equal(got.view(np.uint16), own.view(np.uint16))
+        ref = convert(orc.OracleScene(mixed).render(cam, opts)["colorbuf"])
+        d = np.abs(got.view(np.uint16).astype(int) - ref.view(np.uint16).astype(int))
+        assert d.max() <= 1
+
+
 def test_tone_mapping_and_exposure(mixed):
     for kw in (dict(tone_mapping=aicb200.TONE_REINHARD, maximum_intensity=1.0, exposure=2.0),
                dict(tone_mapping=aicb200.TONE_CLAMP, maximum_intensity=0.5, exposure=0.5)):
