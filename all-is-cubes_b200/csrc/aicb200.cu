@@ -16,7 +16,6 @@
 #include <cuda_runtime.h>
 
 #include "internal.h"
-#include "pool_kernel.cuh"
 
 using namespace aicb;
 
@@ -172,11 +171,6 @@ static __global__ void scatter_cubes_kernel(const CubeDelta *ops, uint32_t n, ui
     const CubeDelta op = ops[i];
     if (wide) ((uint32_t *)cells)[op.idx] = op.cell; else ((uint16_t *)cells)[op.idx] = (uint16_t)op.cell;
     if (op.has_light) light[op.idx] = op.light;
-}
-
-static kernel_fn select_pool_kernel(bool volumetric, bool wide) {
-    if (volumetric) return wide ? pool_kernel<true, true> : pool_kernel<true, false>;
-    return wide ? pool_kernel<false, true> : pool_kernel<false, false>;
 }
 
 static aicb_status validate_options(const aicb_options *o) {
@@ -346,14 +340,9 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
         const int lc = opt->lighting_display == AICB_LIGHT_NONE ? LC_NONE
                        : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT : LC_INTERP);
-        // AICB_SCHED=pool: the per-CTA ray pool scheduler (pool_kernel.cuh) for renders without AUX outputs
-        const char *sched = getenv("AICB_SCHED");
-        const bool pool = !aux && sched && std::strcmp(sched, "pool") == 0;
-        kernel_fn k = pool ? select_pool_kernel(volumetric, sc->ds.wide_cells != 0) : select_kernel(volumetric, sc->ds.wide_cells != 0, aux);
-        const size_t dyn_smem = pool ? POOL_SMEM_BYTES : 0;
-        if (pool) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        kernel_fn k = select_kernel(volumetric, sc->ds.wide_cells != 0, aux);
         int blocks_per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, dyn_smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         if (const char *e = getenv("AICB_BLOCKS_PER_SM")) {  // experiments: cap the resident marching blocks
             int v = atoi(e);
@@ -376,7 +365,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
                 P.debug_warp_times = (unsigned long long *)ctx->d_debug;
                 ctx->debug_warps = (uint32_t)grid * WARPS_PER_BLOCK;
             }
-            k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, dyn_smem, stream>>>(P, n);
+            k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
             P.debug_warp_times = nullptr;
             if (first) cudaEventRecord(ctx->ev_k[2], stream);
             switch (lc) {
