@@ -312,27 +312,21 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         if (st != AICB_OK) return st;
         st = ensure(&ctx->d_contrib, &ctx->d_contrib_bytes, cap * sizeof(float4) + 64);
         if (st != AICB_OK) return st;
+        st = ensure(&ctx->d_hit_link, &ctx->d_hit_link_bytes, cap * sizeof(HitLink) + 64);
+        if (st != AICB_OK) return st;
         st = ensure(&ctx->d_bin_list, &ctx->d_bin_list_bytes, (size_t)N_BINS * chunk_cap * 4 + 64);
         if (st != AICB_OK) return st;
-        if (aux) {
-            st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, chunk_cap * (8 + sizeof(aicb_hit) + 4) + 64);
-            if (st != AICB_OK) return st;
-        }
     }
     P.ray_records = (RayRecord *)ctx->d_rays;
     P.task_out = (TaskOut *)ctx->d_task_cb;
     P.hits = (HitRecord *)ctx->d_hits;
     P.hit_contrib = (float4 *)ctx->d_contrib;
+    P.hit_link = (HitLink *)ctx->d_hit_link;
     P.hit_counter = ctx->d_tile_counter + 1;
     P.bin_count = ctx->d_tile_counter + 4;
     P.bin_list = (uint32_t *)ctx->d_bin_list;
     P.bin_stride = (uint32_t)chunk_cap;
     P.overflow_flag = (unsigned int *)(ctx->d_counters + 7);
-    if (aux) {
-        char *b = (char *)ctx->d_task_aux;
-        P.task_depth = (double *)b;
-        P.task_hit = (aicb_hit *)(b + chunk_cap * 8);
-    }
     if (stream != ctx->stream) CU(cudaStreamWaitEvent(stream, ctx->ev_delta, 0));  // pending cube edits
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
@@ -489,6 +483,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_task_cb) cudaFree(c->d_task_cb);
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_contrib) cudaFree(c->d_contrib);
+    if (c->d_hit_link) cudaFree(c->d_hit_link);
     if (c->d_bin_list) cudaFree(c->d_bin_list);
     if (c->d_debug) cudaFree(c->d_debug);
     if (c->h_delta) cudaFreeHost(c->h_delta);

@@ -48,6 +48,8 @@ struct aicb_ctx {
     size_t d_hits_bytes = 0;
     void *d_contrib = nullptr;   // float4 per hit
     size_t d_contrib_bytes = 0;
+    void *d_hit_link = nullptr;  // HitLink per hit
+    size_t d_hit_link_bytes = 0;
     void *d_bin_list = nullptr;  // task ids of the rays that enter the space, per chord-length bin
     size_t d_bin_list_bytes = 0;
     uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it

@@ -84,28 +84,37 @@ struct __align__(16) RayRecord {
 static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
 
 // One shaded surface of one ray, emitted by the marching kernel and lit by the shade kernel.
-// 64 bytes = 4 x 16-byte stores.  Everything the transmittance chain needs (alpha after the Volumetric
-// thickness rule and the threshold option, fog amount) is already resolved by the marcher; what is left is
-// compute_illumination (surface.rs:113-206) and the outgoing light of Surface::to_light (surface.rs:84-100).
+// 64 bytes = 4 x 16-byte stores: the geometry of one surface the ray went through and the length of its span.
+// The marcher does not evaluate any colour or transmittance: apply_transmittance (f64 pow), the fog amount (f64
+// exp), the invisibility test and the illumination all happen in shade_kernel, convergently, and the transmittance
+// chain of the ray is multiplied up in order by encode_kernel.  The marcher only keeps an UPPER BOUND of the ray's
+// transmittance (a few f32 instructions per surface) to know when the ray is certainly finished.
 struct __align__(16) HitRecord {
     double ip[3];        // intersection point (interpolated lighting only)
+    double t;            // ray parameter where the surface was entered (Hit::t_distance; DepthBuf, fog)
     uint32_t pal;        // palette entry
     int32_t cube[3];
-    float T_before;      // ColorBuf transmittance in front of this surface
-    float ca;            // alpha actually used
-    float coeff;         // emission coefficient of apply_transmittance (1 outside Volumetric mode)
-    float fa;            // distance-fog amount, or < 0 when fog is off
-    uint32_t flags;      // face | rgb_zeroed<<3 (Volumetric zero thickness / Threshold below the limit) | sky octant<<4
-    uint32_t next;       // next hit of the same ray (0xffffffff = none); the ray's first hit is in TaskOut
+    uint32_t packed;     // voxel x | y<<8 | z<<16 | face<<24
+    float thickness;     // Volumetric: length of the span inside the surface's material (world units); else 0
+    float fog_rel;       // t relative to the view distance, as f32 (distance_fog, sr.rs:745-768)
+    uint32_t flags;      // sky octant | resolution<<8
 };
 static_assert(sizeof(HitRecord) == 64, "HitRecord must be 64 bytes");
+
+// Per hit, beside the record: the next hit of the same ray (0xffffffff = none) and the value of the ray's step
+// counter when the surface was shaded (the reference stops at the first counted step after the hit that brings the
+// transmittance under 1/256; encode_kernel needs the counter to restore that).
+struct HitLink {
+    uint32_t next;
+    uint32_t steps;
+};
 
 // What the marching kernel hands to the encode kernel per ray (16 bytes).
 struct __align__(16) TaskOut {
     uint32_t first_hit;  // index of the first HitRecord or 0xffffffff
-    float T;             // transmittance after the last surface (before the sky)
-    uint32_t steps;      // RaytraceInfo::cubes_traced of this ray
+    uint32_t steps;      // steps counted by the marcher (>= the reference's; see HitLink)
     uint32_t flags;      // sky octant
+    uint32_t _pad;
 };
 
 struct TraceParams {
@@ -139,15 +148,14 @@ struct TraceParams {
     RayRecord *ray_records;     // gen -> march
     TaskOut *task_out;          // march -> encode
     HitRecord *hits;            // march -> shade
-    float4 *hit_contrib;        // shade -> encode: light of each hit already multiplied by T_before
+    float4 *hit_contrib;        // shade -> encode: outgoing light of the hit (rgb) and its transmittance factor (< 0: skipped)
+    HitLink *hit_link;          // march -> encode
     unsigned int *hit_counter;  // hit slots handed out in this chunk (in blocks of HIT_BLOCK)
     uint32_t *bin_list;         // gen -> march: task ids of the rays that enter the space, binned by chord length
     unsigned int *bin_count;    // [N_BINS] entries of each bin
     uint32_t bin_stride;        // capacity of one bin's list
     unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
     uint32_t hit_capacity;
-    double *task_depth;         // AUX only
-    aicb_hit *task_hit;         // AUX only
     uint32_t event_threshold;   // leave the MARCH phase once this many lanes wait with an event / finished ray
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
@@ -651,13 +659,7 @@ template <bool AUX>
 struct AuxState {};
 template <>
 struct AuxState<true> {
-    double depth;
-    int hit_cube[3];
-    int hit_voxel[3];
-    int hit_res;
-    int hit_face;
-    bool have_hit;
-    uint32_t n_outer, n_inner, n_hits, n_texels, n_blocks;
+    uint32_t n_outer, n_inner, n_blocks;   // device counters of the roofline accounting
 };
 
 // A surface remembered between discovery and shading (Volumetric mode pairs it with the next
@@ -799,19 +801,10 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
     } else if (in_range) {
         TaskOut o;
         o.first_hit = 0xffffffffu;
-        o.T = 1.0f;
         o.steps = 0;
         o.flags = octant;
+        o._pad = 0;
         *reinterpret_cast<uint4 *>(P.task_out + i) = *reinterpret_cast<const uint4 *>(&o);
-        if (P.task_depth) {
-            P.task_depth[i] = D_INF;
-            aicb_hit h;
-            h.cube[0] = h.cube[1] = h.cube[2] = -1;
-            h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
-            h.resolution = -1;
-            h.face = -1;
-            P.task_hit[i] = h;
-        }
     }
 }
 
@@ -825,8 +818,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
 
-    unsigned long long cubes_traced = 0;
-    unsigned long long n_outer = 0, n_inner = 0, n_hits = 0, n_blocks = 0;
+    unsigned long long n_outer = 0, n_inner = 0, n_blocks = 0;
 
     int st = ST_IDLE;
 
@@ -884,10 +876,11 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     uint32_t blk0y = 0, blk0z = 0;       // packed voxel bounds of the entered block (lo16|lo16, lo16|size16)
     uint32_t pal_off = 0;
     int res = 1;
-    float T = 1.f;
+    // Upper bound of the ColorBuf transmittance (never below the exact value the encode kernel computes).  Once it is
+    // under 1/256 the ray is certainly finished (sr.rs:648-652); in the rare case that only the exact value is under
+    // the limit the marcher runs on and the encode kernel cuts the ray's hits and steps back (see HitLink).
+    float T_ub = 1.f;
     uint32_t steps = 0;
-    const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
-    const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
     bool have_last = false;
     AuxState<AUX> aux;
     // event
@@ -898,7 +891,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     auto count_stop = [&]() -> bool {  // count_step_should_stop (sr.rs:625-656)
         steps += 1;
         if (steps > 1000) return true;
-        return T < (1.0f / 256.0f);
+        return T_ub < (1.0f / 256.0f);
     };
     auto pop_level = [&]() {
         inner = false;
@@ -953,18 +946,14 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                             COLD_W(12) = __float_as_uint(rec.t_to_view);
                             COLD_W(16) = (rec.flags >> 12) & 7u;
                             COLD_W(13) = COLD_W(14) = 0xffffffffu;
-                            T = 1.0f;
+                            T_ub = 1.0f;
                             steps = 0;
                             have_last = false;
                             inner = false;
                             t_scale = 1.0;
                             need_advance = false;
                             nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
-                            if constexpr (AUX) {
-                                aux.depth = D_INF;
-                                aux.have_hit = false;
-                                aux.n_outer = aux.n_inner = aux.n_hits = aux.n_texels = aux.n_blocks = 0;
-                            }
+                            if constexpr (AUX) aux.n_outer = aux.n_inner = aux.n_blocks = 0;
                             st = ST_MARCH;
                         }
                     }
@@ -976,33 +965,15 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         dbg_passes++;
         // =========================== FINALIZE: hand the ray's result to the encode kernel ================
         if (st == ST_DONE) {
-            cubes_traced += steps;
             dbg_rays++;
             TaskOut o;
             const uint32_t task = COLD_W(15);
             o.first_hit = COLD_W(13);
-            o.T = T;
             o.steps = steps;
             o.flags = COLD_W(16);
+            o._pad = 0;
             *reinterpret_cast<uint4 *>(P.task_out + task) = *reinterpret_cast<const uint4 *>(&o);
-            if constexpr (AUX) {
-                n_outer += aux.n_outer; n_inner += aux.n_inner; n_hits += aux.n_hits;
-                n_blocks += aux.n_blocks;
-                P.task_depth[task] = aux.depth;
-                aicb_hit h;
-                if (aux.have_hit) {
-                    h.cube[0] = aux.hit_cube[0]; h.cube[1] = aux.hit_cube[1]; h.cube[2] = aux.hit_cube[2];
-                    h.voxel[0] = aux.hit_voxel[0]; h.voxel[1] = aux.hit_voxel[1]; h.voxel[2] = aux.hit_voxel[2];
-                    h.resolution = aux.hit_res;
-                    h.face = aux.hit_face;
-                } else {
-                    h.cube[0] = h.cube[1] = h.cube[2] = -1;
-                    h.voxel[0] = h.voxel[1] = h.voxel[2] = -1;
-                    h.resolution = -1;
-                    h.face = -1;
-                }
-                P.task_hit[task] = h;
-            }
+            if constexpr (AUX) { n_outer += aux.n_outer; n_inner += aux.n_inner; n_blocks += aux.n_blocks; }
             st = ST_IDLE;
         }
 
@@ -1150,61 +1121,30 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                 st = ST_DONE;
             }
         }
-        // (2) the sequential part of shading: apply_transmittance (sr.rs:720-740, raytracer_components.rs:215-258;
-        //     Volumetric only), limit_alpha, the invisibility test of Surface::to_light (surface.rs:78-82), the fog
-        //     amount (sr.rs:745-768) and the transmittance update of add_color_internal
-        //     (raytracer_components.rs:87-92).  The light itself is computed by shade_kernel from the HitRecord.
-        bool emit = false;
-        float h_ca = 0.f, h_coeff = 0.f, h_fa = -1.0f, h_tr = 1.0f;
-        bool h_zeroed = false;
+        // (2) the surface leaves the marcher as a HitRecord; all that is evaluated here is an upper bound of the factor
+        //     by which it multiplies the ray's transmittance (apply_transmittance, limit_alpha, fog: sr.rs:720-768,
+        //     graphics_options.rs:496-507, raytracer_components.rs:87-92 give the exact factor in shade_kernel).
+        float h_thickness = 0.0f;
         if (do_shade) {
-            const float4 col = __ldg(S.palette + 2 * (size_t)shade_sf.pal);
-            const float4 emi = __ldg(S.palette + 2 * (size_t)shade_sf.pal + 1);
-            float ca = col.w;
-            float coeff = 1.0f;
-            bool zeroed = false;
+            const float alpha = __ldg(&S.palette[2 * (size_t)shade_sf.pal].w);
+            float m_ub;   // >= (1 - alpha_used) * (1 - fog); 1 also covers a surface that turns out invisible
             if constexpr (VOLUMETRIC) {
-                const float thickness = fmaxf((float)((span_exit - shade_sf.t) * COLD_D(15)), 0.0f);
-                if (thickness == 0.0f) {
-                    if (col.w == 1.0f) { coeff = 1.0f; }
-                    else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
-                } else if (col.w == 1.0f) {
-                    ca = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
-                } else if (col.w == 0.0f) {
-                    ca = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
-                } else {
-                    const float unit_t = 1.0f - col.w;
-                    const float depth_t = powf_exact(unit_t, thickness);
-                    ca = zo_clamped(1.0f - depth_t);
-                    const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
-                    coeff = fmaxf(k, 0.0f);
-                }
+                h_thickness = fmaxf((float)((span_exit - shade_sf.t) * COLD_D(15)), 0.0f);
+                if (alpha == 1.0f) m_ub = 0.0f;                                  // alpha stays 1 for any thickness
+                else if (h_thickness == 0.0f || alpha == 0.0f) m_ub = 1.0f;
+                else m_ub = fminf(__powf(1.0f - alpha, h_thickness) * 1.001f + 1e-6f, 1.0f);
+            } else if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {
+                m_ub = (alpha > P.threshold) ? 0.0f : 1.0f;
+            } else {
+                m_ub = fminf((1.0f - alpha) * 1.000001f + 1e-7f, 1.0f);
+                if (alpha == 1.0f) m_ub = 0.0f;
             }
-            const float kc = ps_clamped(coeff);
-            const float er = VOLUMETRIC ? ps_mul(emi.x, kc) : emi.x, eg = VOLUMETRIC ? ps_mul(emi.y, kc) : emi.y,
-                        eb = VOLUMETRIC ? ps_mul(emi.z, kc) : emi.z;
-            if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
-                if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
-            }
-            if (!(ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f)) {
-                float tr = 1.0f - ca;
-                float fa = -1.0f;
-                if (have_fog) {  // distance_fog (sr.rs:745-768)
-                    float rel = (float)shade_sf.t * __uint_as_float(COLD_W(12));
-                    rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
-                    const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
-                    const float fudged = fog_exponential / 0.79810348f;
-                    const float p4 = (rel * rel) * (rel * rel);
-                    fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
-                    tr = tr * (1.0f - fa);
-                }
-                emit = true;
-                h_ca = ca; h_coeff = coeff; h_fa = fa; h_tr = tr; h_zeroed = zeroed;
-            }
+            T_ub = T_ub * m_ub * 1.000001f;
         }
         // emit the hits of this pass: slots come from the warp's block of the hit stream, a new block is taken
         // (one atomic per HIT_BLOCK hits) when the current one cannot hold them all
         {
+            const bool emit = do_shade;
             const unsigned em = __ballot_sync(0xffffffffu, emit);
             if (em) {
                 const uint32_t n_emit = (uint32_t)__popc(em);
@@ -1221,41 +1161,29 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                     hit_base = nb;
                     hit_used = 0;
                 }
-                if (emit) {
-                    if (hit_base != 0xffffffffu) {
-                        const uint32_t slot = hit_base + hit_used + (uint32_t)__popc(em & ((1u << lane) - 1u));
-                        HitRecord h;
-                        if (want_ip) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
-                        else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
-                        h.pal = shade_sf.pal;
-                        h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
-                        h.T_before = T;
-                        h.ca = h_ca;
-                        h.coeff = h_coeff;
-                        h.fa = h_fa;
-                        h.flags = (shade_sf.packed >> 24) | (h_zeroed ? 8u : 0u) | (COLD_W(16) << 4);
-                        h.next = 0xffffffffu;
-                        const uint4 *src = reinterpret_cast<const uint4 *>(&h);
-                        uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
+                if (emit && hit_base != 0xffffffffu) {
+                    const uint32_t slot = hit_base + hit_used + (uint32_t)__popc(em & ((1u << lane) - 1u));
+                    HitRecord h;
+                    if (want_ip) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
+                    else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
+                    h.t = shade_sf.t;
+                    h.pal = shade_sf.pal;
+                    h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
+                    h.packed = shade_sf.packed;
+                    h.thickness = h_thickness;
+                    h.fog_rel = (float)shade_sf.t * __uint_as_float(COLD_W(12));
+                    h.flags = COLD_W(16) | ((uint32_t)shade_sf.res << 8);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
+                    uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) st_stream(dst + k, src[k]);
-                        const uint32_t prev_hit = COLD_W(14);
-                        if (prev_hit != 0xffffffffu) P.hits[prev_hit].next = slot; else COLD_W(13) = slot;
-                        COLD_W(14) = slot;
-                    }
-                    T = T * h_tr;
-                    if constexpr (AUX) {
-                        aux.depth = fmin(aux.depth, shade_sf.t);
-                        aux.n_hits++;
-                        if (!aux.have_hit) {
-                            aux.have_hit = true;
-                            aux.hit_cube[0] = shade_sf.cube[0]; aux.hit_cube[1] = shade_sf.cube[1]; aux.hit_cube[2] = shade_sf.cube[2];
-                            aux.hit_voxel[0] = shade_sf.packed & 255; aux.hit_voxel[1] = (shade_sf.packed >> 8) & 255;
-                            aux.hit_voxel[2] = (shade_sf.packed >> 16) & 255;
-                            aux.hit_face = shade_sf.packed >> 24;
-                            aux.hit_res = shade_sf.res;
-                        }
-                    }
+                    for (int k = 0; k < 4; k++) st_stream(dst + k, src[k]);
+                    HitLink link;
+                    link.next = 0xffffffffu;
+                    link.steps = steps;
+                    *reinterpret_cast<uint2 *>(P.hit_link + slot) = *reinterpret_cast<const uint2 *>(&link);
+                    const uint32_t prev_hit = COLD_W(14);
+                    if (prev_hit != 0xffffffffu) P.hit_link[prev_hit].next = slot; else COLD_W(13) = slot;
+                    COLD_W(14) = slot;
                 }
                 if (hit_base != 0xffffffffu) hit_used += n_emit;
             }
@@ -1329,32 +1257,28 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     if (hit_base != 0xffffffffu)
         for (uint32_t j = hit_used + lane; j < HIT_BLOCK; j += 32) P.hits[hit_base + j].pal = HIT_DEAD;
 
-    // RaytraceInfo sum (renderer.rs:555): warp-reduce then one atomic per warp
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cubes_traced += __shfl_down_sync(0xffffffffu, cubes_traced, off);
-    if (lane == 0 && cubes_traced) atomicAdd(P.counters + 0, cubes_traced);
     if constexpr (AUX) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             n_outer += __shfl_down_sync(0xffffffffu, n_outer, off);
             n_inner += __shfl_down_sync(0xffffffffu, n_inner, off);
-            n_hits += __shfl_down_sync(0xffffffffu, n_hits, off);
             n_blocks += __shfl_down_sync(0xffffffffu, n_blocks, off);
         }
         if (lane == 0) {
             atomicAdd(P.counters + 1, n_outer);
             atomicAdd(P.counters + 2, n_inner);
-            atomicAdd(P.counters + 3, n_hits);
             atomicAdd(P.counters + 5, n_blocks);
         }
     }
 }
 
-
 // ======================================================================================================
-// Kernel 3 — shading: one thread per HitRecord, fully convergent.  compute_illumination (surface.rs:113-206)
-// and the outgoing light of Surface::to_light (surface.rs:84-100); the result is stored already multiplied by
-// the transmittance in front of the surface, i.e. the addend of add_color_internal (raytracer_components.rs:90).
+// Kernel 3 — shading: one thread per HitRecord, fully convergent.  Everything about a surface that does not depend
+// on the surfaces in front of it: apply_transmittance (sr.rs:720-740, raytracer_components.rs:215-258; Volumetric
+// only), limit_alpha (graphics_options.rs:496-507), the invisibility test of Surface::to_light (surface.rs:78-82),
+// compute_illumination (surface.rs:113-206), reflect + emission (color.rs:708-710), distance fog
+// (sr.rs:745-768, surface.rs:97-100).  Output per hit: the outgoing light and the factor by which the surface
+// multiplies the ray's transmittance (add_color_internal, raytracer_components.rs:87-92), or "skip".
 // ======================================================================================================
 template <int LC>
 __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ TraceParams P) {
@@ -1366,6 +1290,8 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
     if (n > P.hit_capacity) n = P.hit_capacity;
     unsigned long long texels = 0;
     const bool volumetric = P.transparency == AICB_TRANSPARENCY_VOLUMETRIC;
+    const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
+    const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         HitRecord h;
         {
@@ -1377,14 +1303,50 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         if (h.pal == HIT_DEAD) continue;
         const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
         const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
-        const bool zeroed = (h.flags & 8u) != 0;
-        const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
-        const float ca = h.ca;
-        const float kc = ps_clamped(h.coeff);
+        float ca = col.w;
+        float coeff = 1.0f;
+        bool zeroed = false;
+        if (volumetric) {
+            const float thickness = h.thickness;
+            if (thickness == 0.0f) {
+                if (col.w == 1.0f) { coeff = 1.0f; }
+                else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
+            } else if (col.w == 1.0f) {
+                ca = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
+            } else if (col.w == 0.0f) {
+                ca = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
+            } else {
+                const float unit_t = 1.0f - col.w;
+                const float depth_t = powf_exact(unit_t, thickness);
+                ca = zo_clamped(1.0f - depth_t);
+                const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
+                coeff = fmaxf(k, 0.0f);
+            }
+        }
+        const float kc = ps_clamped(coeff);
         const float er = volumetric ? ps_mul(emi.x, kc) : emi.x, eg = volumetric ? ps_mul(emi.y, kc) : emi.y,
                     eb = volumetric ? ps_mul(emi.z, kc) : emi.z;
+        if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
+            if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
+        }
+        if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) {   // nothing to see: the ray is not touched
+            P.hit_contrib[i] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+            continue;
+        }
+        float tr = 1.0f - ca;
+        float fa = -1.0f;
+        if (have_fog) {  // distance_fog (sr.rs:745-768)
+            float rel = h.fog_rel;
+            rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
+            const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
+            const float fudged = fog_exponential / 0.79810348f;
+            const float p4 = (rel * rel) * (rel * rel);
+            fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
+            tr = tr * (1.0f - fa);
+        }
+        const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
         float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
-        const int face = (int)(h.flags & 7u);
+        const int face = (int)(h.packed >> 24);
         if constexpr (LC == LC_FLAT) {
             int x = h.cube[0], y = h.cube[1], z = h.cube[2];
             if (face != AICB_FACE_WITHIN) {
@@ -1406,15 +1368,14 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
         float og = ps_mul(ps_mul(cg, i1), ca) + eg;
         float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
-        if (h.fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
-            const int k = S.sky_kind ? (int)((h.flags >> 4) & 7u) : 0;
-            const float comp = 1.0f - h.fa;
-            orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], h.fa);
-            og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], h.fa);
-            ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], h.fa);
+        if (fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
+            const int k = S.sky_kind ? (int)(h.flags & 7u) : 0;
+            const float comp = 1.0f - fa;
+            orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], fa);
+            og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], fa);
+            ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], fa);
         }
-        // .w carries the link to the ray's next hit so that the encode kernel reads one 16-byte record per hit
-        P.hit_contrib[i] = make_float4(orr * h.T_before, og * h.T_before, ob * h.T_before, __uint_as_float(h.next));
+        P.hit_contrib[i] = make_float4(orr, og, ob, tr);
     }
     // one atomic per warp: 150 K single-address atomics would cost more than the shading itself
 #pragma unroll
@@ -1423,7 +1384,8 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
 }
 
 // ======================================================================================================
-// Kernel 4 — per pixel: add_color_internal over the ray's hits in order (raytracer_components.rs:87-92),
+// Kernel 4 — per pixel: the ray's transmittance chain and add_color_internal over its hits in order
+// (raytracer_components.rs:87-92), count_step_should_stop's opacity cut (sr.rs:648-652) applied to the chain,
 // finish (sr.rs:658-693: the sky; debug_pixel_cost), ColorBuf::mean of the 4 sub-samples
 // (raytracer_components.rs:97-102), the encoder of draw_rgba (renderer.rs:287-291) and the stores.
 // ======================================================================================================
@@ -1434,68 +1396,109 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
     const DeviceScene &S = P.scene;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel task within the chunk
     const uint32_t n_pixels = n_chunk_tasks / P.n_samples;
-    if (i >= n_pixels) return;
-    uint32_t px, py;
-    size_t out_index;
-    if (!task_pixel(P, P.task_base / P.n_samples + i, &px, &py, &out_index)) return;
-    const uint32_t t0 = i * P.n_samples;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, aT = 0.f;
-    uint32_t steps_total = 0;
-    for (uint32_t k = 0; k < P.n_samples; k++) {
-        TaskOut o;
-        *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + t0 + k);
-        float lr = 0.f, lg = 0.f, lb = 0.f, T = o.T;
-        for (uint32_t hi = o.first_hit; hi != 0xffffffffu;) {
-            const float4 c = P.hit_contrib[hi];
-            lr = lr + c.x; lg = lg + c.y; lb = lb + c.z;
-            hi = __float_as_uint(c.w);
+    uint32_t px = 0, py = 0;
+    size_t out_index = 0;
+    const bool active = i < n_pixels && task_pixel(P, P.task_base / P.n_samples + i, &px, &py, &out_index);
+    unsigned long long cubes_traced = 0, n_hits = 0;
+    if (active) {
+        const uint32_t t0 = i * P.n_samples;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, aT = 0.f;
+        uint32_t steps_total = 0;
+        double depth = D_INF;          // DepthBuf::mean = min over the sub-samples (accum.rs:284-297)
+        uint32_t first_valid = 0xffffffffu;   // Position of the first surface hit: first sub-sample that has one
+        for (uint32_t k = 0; k < P.n_samples; k++) {
+            TaskOut o;
+            *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + t0 + k);
+            float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
+            uint32_t steps = o.steps;
+            uint32_t sample_first = 0xffffffffu;
+            for (uint32_t hi = o.first_hit; hi != 0xffffffffu;) {
+                const float4 c = P.hit_contrib[hi];
+                const HitLink link = P.hit_link[hi];
+                if (c.w >= 0.0f) {   // (a skipped surface leaves the ray untouched)
+                    lr = lr + c.x * T; lg = lg + c.y * T; lb = lb + c.z * T;
+                    T = T * c.w;
+                    n_hits++;
+                    if (sample_first == 0xffffffffu) sample_first = hi;
+                    if (T < (1.0f / 256.0f)) {
+                        // the reference stops at the first step it counts after this hit; the marcher, which only
+                        // had an upper bound of T, may have gone further
+                        if (steps > link.steps) steps = link.steps + 1;
+                        break;
+                    }
+                }
+                hi = link.next;
+            }
+            if (sample_first != 0xffffffffu) {
+                depth = fmin(depth, P.hits[sample_first].t);
+                if (first_valid == 0xffffffffu) first_valid = sample_first;
+            }
+            if (P.include_sky) {  // the sky is an opaque hit at t = inf
+                const int so = S.sky_kind ? (int)(o.flags & 7u) : 0;
+                lr = lr + (S.sky_colors[so][0] * 1.0f) * T;
+                lg = lg + (S.sky_colors[so][1] * 1.0f) * T;
+                lb = lb + (S.sky_colors[so][2] * 1.0f) * T;
+                T = T * (1.0f - 1.0f);
+            }
+            if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
+                float kk = ps_clamped((float)steps);
+                float red = ps_clamped(ps_mul(0.02f, kk) * 1.0f);
+                float green = ps_clamped(ps_mul(0.002f, kk) * 1.0f);
+                float rgba[4];
+                colorbuf_to_rgba(lr, lg, lb, T, rgba);
+                float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
+                lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
+                T = 0.0f;
+            }
+            steps_total += steps;
+            a0 = a0 + lr; a1 = a1 + lg; a2 = a2 + lb; aT = aT + T;
         }
-        if (P.include_sky) {  // the sky is an opaque hit at t = inf
-            const int so = S.sky_kind ? (int)(o.flags & 7u) : 0;
-            lr = lr + (S.sky_colors[so][0] * 1.0f) * T;
-            lg = lg + (S.sky_colors[so][1] * 1.0f) * T;
-            lb = lb + (S.sky_colors[so][2] * 1.0f) * T;
-            T = T * (1.0f - 1.0f);
+        cubes_traced = steps_total;
+        float l0 = a0, l1 = a1, l2 = a2, tT = aT;
+        if (P.n_samples == 4) { l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f; }
+        if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);
+        if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
+        if (P.out_rgba16f) {
+            // ColorBuf::into_premultiplied_rgba (raytracer_components.rs:70-77) scaled by the exposure and rounded to
+            // f16 as half::f16::from_f32 does (round to nearest even, overflow to infinity)
+            float a = 1.0f - tT;
+            a = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);   // clamp(0, 1): NaN passes through
+            const __half2 rg = __floats2half2_rn(l0 * P.exposure, l1 * P.exposure);
+            const __half2 ba = __floats2half2_rn(l2 * P.exposure, a);
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t *>(&rg);
+            packed.y = *reinterpret_cast<const uint32_t *>(&ba);
+            P.out_rgba16f[out_index] = packed;
         }
-        if (P.debug_pixel_cost) {  // ColorBuf::add for Exception::DebugOverrideRg (accum.rs:228-234)
-            float kk = ps_clamped((float)o.steps);
-            float red = ps_clamped(ps_mul(0.02f, kk) * 1.0f);
-            float green = ps_clamped(ps_mul(0.002f, kk) * 1.0f);
-            float rgba[4];
-            colorbuf_to_rgba(lr, lg, lb, T, rgba);
-            float lum = rgba[1] * 0.7152f + (rgba[0] * 0.2126f + rgba[2] * 0.0722f);
-            lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
-            T = 0.0f;
-        }
-        steps_total += o.steps;
-        a0 = a0 + lr; a1 = a1 + lg; a2 = a2 + lb; aT = aT + T;
-    }
-    float l0 = a0, l1 = a1, l2 = a2, tT = aT;
-    if (P.n_samples == 4) { l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f; }
-    if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);
-    if (P.out_colorbuf) P.out_colorbuf[out_index] = make_float4(l0, l1, l2, tT);
-    if (P.out_rgba16f) {
-        // ColorBuf::into_premultiplied_rgba (raytracer_components.rs:70-77) scaled by the exposure and rounded to
-        // f16 as half::f16::from_f32 does (round to nearest even, overflow to infinity)
-        float a = 1.0f - tT;
-        a = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);   // clamp(0, 1): NaN passes through
-        const __half2 rg = __floats2half2_rn(l0 * P.exposure, l1 * P.exposure);
-        const __half2 ba = __floats2half2_rn(l2 * P.exposure, a);
-        uint2 packed;
-        packed.x = *reinterpret_cast<const uint32_t *>(&rg);
-        packed.y = *reinterpret_cast<const uint32_t *>(&ba);
-        P.out_rgba16f[out_index] = packed;
-    }
-    if (P.task_depth) {  // AUX outputs: DepthBuf::mean = min (accum.rs:284-297); first sub-sample with a hit
-        double dmin = P.task_depth[t0];
-        aicb_hit h = P.task_hit[t0];
-        for (uint32_t k = 1; k < P.n_samples; k++) {
-            dmin = fmin(dmin, P.task_depth[t0 + k]);
-            if (h.face < 0 && P.task_hit[t0 + k].face >= 0) h = P.task_hit[t0 + k];
-        }
-        if (P.out_depth) P.out_depth[out_index] = dmin;
+        if (P.out_depth) P.out_depth[out_index] = depth;
         if (P.out_steps) P.out_steps[out_index] = steps_total;
-        if (P.out_hit) P.out_hit[out_index] = h;
+        if (P.out_hit) {
+            aicb_hit hh;
+            if (first_valid != 0xffffffffu) {
+                const HitRecord *hr = P.hits + first_valid;
+                const uint32_t packed = hr->packed;
+                hh.cube[0] = hr->cube[0]; hh.cube[1] = hr->cube[1]; hh.cube[2] = hr->cube[2];
+                hh.voxel[0] = (int)(packed & 255u); hh.voxel[1] = (int)((packed >> 8) & 255u); hh.voxel[2] = (int)((packed >> 16) & 255u);
+                hh.resolution = (int)(hr->flags >> 8);
+                hh.face = (int)(packed >> 24);
+            } else {
+                hh.cube[0] = hh.cube[1] = hh.cube[2] = -1;
+                hh.voxel[0] = hh.voxel[1] = hh.voxel[2] = -1;
+                hh.resolution = -1;
+                hh.face = -1;
+            }
+            P.out_hit[out_index] = hh;
+        }
+    }
+    // RaytraceInfo sum (renderer.rs:555) and the surface-hit counter: warp-reduce, one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cubes_traced += __shfl_down_sync(0xffffffffu, cubes_traced, off);
+        n_hits += __shfl_down_sync(0xffffffffu, n_hits, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cubes_traced) atomicAdd(P.counters + 0, cubes_traced);
+        if (n_hits) atomicAdd(P.counters + 3, n_hits);
     }
 }
 
