@@ -1429,7 +1429,7 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
                 }
                 hi = link.next;
             }
-            if (sample_first != 0xffffffffu) {
+            if (sample_first != 0xffffffffu && (P.out_depth || P.out_hit)) {
                 depth = fmin(depth, P.hits[sample_first].t);
                 if (first_valid == 0xffffffffu) first_valid = sample_first;
             }
