@@ -41,7 +41,10 @@ def text_images():
 
 def pngs():
     for name in ["transparent_one-surf-all", "transparent_one-vol-all", "emission-all", "emission_only-surf-all",
-                 "emission_only-vol-all", "emission_semi-surf-all", "emission_semi-vol-all", "debug_pixel_cost-ray"]:
+                 "emission_only-vol-all", "emission_semi-surf-all", "emission_semi-vol-all", "debug_pixel_cost-ray", "color_srgb_ramp-all", "furnace-Clear-Opaque-all",
+                 "furnace-Clear-Transparent-all", "furnace-Foggy-Opaque-all", "furnace-Foggy-Transparent-all",
+                 "fog-Abrupt-all", "fog-Compromise-all", "fog-Physical-all", "light_spread-None-all", "light_spread-Flat-all",
+                 "light_spread-Coarse-all", "light_spread-Linear-all", "light_spread-Smoothstep-all"]:
         im = np.array(Image.open(f"{REF}/test-renderers/expected/renderers/{name}.png").convert("RGBA"))
         np.save(f"{OUT}/png_{name}.npy", im)
 
