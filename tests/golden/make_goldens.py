@@ -44,7 +44,9 @@ def pngs():
                  "emission_only-vol-all", "emission_semi-surf-all", "emission_semi-vol-all", "debug_pixel_cost-ray", "color_srgb_ramp-all", "furnace-Clear-Opaque-all",
                  "furnace-Clear-Transparent-all", "furnace-Foggy-Opaque-all", "furnace-Foggy-Transparent-all",
                  "fog-Abrupt-all", "fog-Compromise-all", "fog-Physical-all", "light_spread-None-all", "light_spread-Flat-all",
-                 "light_spread-Coarse-all", "light_spread-Linear-all", "light_spread-Smoothstep-all"]:
+                 "light_spread-Coarse-all", "light_spread-Linear-all", "light_spread-Smoothstep-all", "tone_map-Clamp-1.0-0.5-all",
+                 "tone_map-Clamp-1.0-2.0-all", "tone_map-Reinhard-0.5-0.5-all", "tone_map-Reinhard-1.0-0.5-all",
+                 "tone_map-Reinhard-1.0-2.0-all"]:
         im = np.array(Image.open(f"{REF}/test-renderers/expected/renderers/{name}.png").convert("RGBA"))
         np.save(f"{OUT}/png_{name}.npy", im)
 

