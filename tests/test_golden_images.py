@@ -300,3 +300,16 @@ def test_tone_map(tone_mapping_universe, tmo, max_intensity, exposure):
     cam.set_view_transform((0.0, 0.0, 0.0, 1.0), eye)
     img = orc.OracleScene(space).render(cam, opts)["srgb8"].reshape(320, 256, 4)
     check_threshold(img, golden(f"tone_map-{tmo}-{max_intensity}-{exposure}-all"), [(1, 256 * 320), (3, 500), (10, 500)])
+
+
+def test_debug_pixel_cost(fog_universe):
+    """cases/src/lib.rs:286-294: GraphicsOptions::debug_pixel_cost over the fog universe (UNALTERED_COLORS: no lighting,
+    so nothing order-dependent is involved): red / green encode the per-pixel `cubes_traced`, blue a fifth of the
+    luminance (accum.rs:228-234).  The reference's threshold as is.  This pins count_step_should_stop's counting."""
+    opts = GraphicsOptions.unaltered_colors()
+    opts.debug_pixel_cost = True
+    cam = Camera(opts, Viewport((128.0, 96.0), (128, 96)))
+    cam.look_at_y_up((0.0, 10.0, 0.0), (0.4, 10.0, -1.0))
+    img = orc.OracleScene(fog_universe).render(cam, opts)["srgb8"].reshape(96, 128, 4)
+    max_diff, n_diff = check_threshold(img, golden("debug_pixel_cost-ray"), [(2, 500), (15, 100)])
+    print(f"debug_pixel_cost: max diff {max_diff}, {n_diff} pixels differ")
