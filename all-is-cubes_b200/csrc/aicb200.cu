@@ -293,10 +293,19 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     sc->pending_rays = pixels * (P.antialias ? 4 : 1);
     sc->pending_out_bytes_per_pixel = out.srgb8 ? 4 : (out.rgba16f ? 8 : 16);
 
-    // ---- the three kernels of a frame, chunked so the ray stream stays bounded ---------------------------
+    // ---- the four kernels of a frame, chunked so the per-frame streams stay bounded ---------------------------
     P.n_samples = P.antialias ? 4 : 1;
     const uint64_t total_tasks = (uint64_t)P.n_tasks * P.n_samples;
-    const uint64_t CHUNK = (uint64_t)4 << 20;  // tasks per chunk (a multiple of 32 * n_samples): 0.6 GB of ray records
+    // Tasks per chunk (a multiple of 32 * n_samples): at most 4 M (0.6 GB of ray records); fewer when the hit stream
+    // has been enlarged after an overflow, so that the per-frame streams stay within ~8 GB however deep the scene is.
+    uint64_t CHUNK = (uint64_t)4 << 20;
+    {
+        const uint64_t per_task = sizeof(RayRecord) + sizeof(TaskOut) + 4 * N_BINS +
+                                  (uint64_t)ctx->hits_per_task * (sizeof(HitRecord) + sizeof(float4) + sizeof(HitLink));
+        uint64_t fit = ((uint64_t)8 << 30) / per_task;
+        if (fit < (1u << 17)) fit = 1u << 17;
+        if (fit < CHUNK) CHUNK = fit & ~(uint64_t)127;
+    }
     const uint64_t chunk_cap = total_tasks < CHUNK ? total_tasks : CHUNK;
     {
         aicb_status st = ensure(&ctx->d_rays, &ctx->d_rays_bytes, chunk_cap * sizeof(RayRecord) + 16);
