@@ -1,24 +1,25 @@
-// trace_kernel.cuh — the per-ray device code of libaicb200: a from-scratch sm_100a
-// implementation of all-is-cubes' SpaceRaytracer::trace_ray (sr.rs:135-238) and its pixel
-// dispatch (renderer.rs:424-451, 516-556).
+// trace_kernel.cuh — the device code of libaicb200's raytracer: a from-scratch sm_100a implementation of
+// all-is-cubes' SpaceRaytracer::trace_ray (sr.rs:135-238) and its pixel dispatch (renderer.rs:424-451, 516-556).
 //
-// Design (B200-first, not a translation):
-//  * persistent warps; every lane owns one pixel task at a time and pulls the next one from a
-//    global counter when it finishes (tile-ordered: 32 consecutive tasks = one 8x4 pixel tile), so
-//    a warp never idles behind its slowest ray;
-//  * the warp runs a synchronous phase machine — REFILL (ray setup) | MARCH (cheap DDA steps
-//    until the lane reaches an event) | HEAVY (span shading, surface lighting, block entry) |
-//    FINALIZE (sky, encode, store) — so that lanes executing expensive code execute the SAME
-//    expensive code; the heavy math is out of line with one call site each (i-cache);
-//  * the two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is walked
-//    by ONE unified Amanatides–Woo DDA whose state lives in registers; entering a recursive block
-//    pushes the outer state and re-initialises the same DDA on the brick;
-//  * cell words carry their classification in the top bits (invisible / single / recursive;
-//    voxel invisible), so an empty step costs exactly one dependent 2-byte load;
-//  * all ray geometry is f64 and all colour is f32, operation for operation as the reference
-//    (compiled with -fmad=false: Rust never contracts to FMA); powf/expf are evaluated in f64 and
-//    rounded once; the sRGB8 encode is a search in a 255-entry threshold table built on the host
-//    with the platform powf (bit-identical to what the reference computes on that host).
+// Design (B200-first, not a translation).  One frame = four kernels on one stream:
+//  * gen_kernel (one thread per ray, convergent): pixel -> world ray, Raycaster::new().within(space bounds); rays that
+//    miss the space are finished here, the others are listed by chord length (longest first);
+//  * trace_kernel (persistent warps): every lane owns one ray at a time and takes the next one from the list when it
+//    finishes.  The warp runs a synchronous phase machine — REFILL | FINALIZE | MARCH (a select-based, branch-free
+//    Amanatides–Woo DDA step in f64, one dependent 2-byte load and one bit test per step) | HEAVY (surfaces, span logic,
+//    block entry) — so that lanes executing expensive code execute the SAME expensive code.  It evaluates no colour:
+//    surfaces leave it as 64-byte hit records, and of the transmittance it keeps only an upper bound (to know when the
+//    ray is certainly opaque);
+//  * shade_kernel (one thread per hit record, convergent): apply_transmittance (f64 pow), fog (f64 exp), the
+//    invisibility test and compute_illumination;
+//  * encode_kernel (one thread per pixel): the exact transmittance chain in ray order, the opacity cut, sky, tone
+//    mapping, sRGB8.
+//  The two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is walked by ONE unified DDA;
+//  entering a recursive block pushes the outer state (shared memory) and re-initialises the same DDA on the brick.
+//  Cell words carry their classification in the top bits (bit 15 = nothing to see, on both levels).
+//  All ray geometry is f64 and all colour is f32, operation for operation as the reference (compiled with
+//  -fmad=false: Rust never contracts to FMA); powf/expf are evaluated in f64 and rounded once; the sRGB8 encode is a
+//  search in a 255-entry threshold table built on the host with the platform powf.
 //
 // Every function cites the reference lines it reproduces.
 #pragma once
