@@ -57,6 +57,7 @@ def load_library() -> C.CDLL:
     lib.aicb_scene_device_bytes.argtypes = [C.c_void_p]
     lib.aicb_scene_device_bytes.restype = C.c_uint64
     lib.aicb_scene_update_cubes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_scene_update_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.aicb_scene_upload_light.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.aicb_shard_pixel_count.argtypes = [C.POINTER(abi.CameraData), C.POINTER(abi.Shard)]
     lib.aicb_shard_pixel_count.restype = C.c_size_t
@@ -334,25 +335,7 @@ class Space:
         d.light = self.light.ctypes.data if self.light is not None else None
         arr = (abi.BlockDesc * len(self.blocks))()
         for i, b in enumerate(self.blocks):
-            bd = arr[i]
-            bd.resolution = b.resolution
-            bd.is_air = 1 if b.is_air else 0
-            bd.voxel_bounds.lower[:] = b.voxel_lower
-            bd.voxel_bounds.size[:] = b.voxel_size
-            if b.indices is not None:
-                bd.indices = b.indices.ctypes.data
-                bd.n_indices = b.indices.size
-            else:
-                bd.indices = None
-                bd.n_indices = 0
-            bd.palette = b.palette.ctypes.data
-            bd.n_palette = b.palette.shape[0]
-            bd.light_opaque_faces = b.light_opaque_faces
-            bd.light_visible = 1 if b.light_visible else 0
-            for f in range(6):
-                bd.light_face_colors[f][:] = b.light_face_colors[f]
-            bd.light_color[:] = b.light_color
-            bd.light_emission[:] = b.light_emission
+            fill_block_desc(arr[i], b)
             keep.append(b)
         d.blocks = arr
         d.n_blocks = len(self.blocks)
@@ -363,6 +346,28 @@ class Space:
         keep.append(arr)
         keep.append(self)
         return d, keep
+
+
+def fill_block_desc(bd, b):
+    """Block -> aicb_block_desc (the arrays stay owned by `b`)."""
+    bd.resolution = b.resolution
+    bd.is_air = 1 if b.is_air else 0
+    bd.voxel_bounds.lower[:] = b.voxel_lower
+    bd.voxel_bounds.size[:] = b.voxel_size
+    if b.indices is not None:
+        bd.indices = b.indices.ctypes.data
+        bd.n_indices = b.indices.size
+    else:
+        bd.indices = None
+        bd.n_indices = 0
+    bd.palette = b.palette.ctypes.data
+    bd.n_palette = b.palette.shape[0]
+    bd.light_opaque_faces = b.light_opaque_faces
+    bd.light_visible = 1 if b.light_visible else 0
+    for f in range(6):
+        bd.light_face_colors[f][:] = b.light_face_colors[f]
+    bd.light_color[:] = b.light_color
+    bd.light_emission[:] = b.light_emission
 
 
 def light_chart():
@@ -485,6 +490,14 @@ class SpaceRaytracer:
         lt = None if light is None else np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
         _check(load_library().aicb_scene_update_cubes(self.handle, c.ctypes.data, ids.ctypes.data,
                                                       lt.ctypes.data if lt is not None else None, c.shape[0]))
+
+    def update_blocks(self, indices, blocks):
+        """SpaceChange::BlockEvaluation / BlockIndex: new definitions for existing block indices."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint16)
+        arr = (abi.BlockDesc * len(blocks))()
+        for i, b in enumerate(blocks):
+            fill_block_desc(arr[i], b)
+        _check(load_library().aicb_scene_update_blocks(self.handle, idx.ctypes.data, arr, len(blocks)))
 
     # ---- light propagation (space::light; SURVEY 8(a) L1-L4) ----
     def light_fast_evaluate(self):

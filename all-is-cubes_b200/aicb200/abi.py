@@ -111,6 +111,7 @@ EXPORTED_SYMBOLS = [
     "aicb_last_error",
     "aicb_scene_create",
     "aicb_scene_update_cubes",
+    "aicb_scene_update_blocks",
     "aicb_scene_upload_light",
     "aicb_scene_destroy",
     "aicb_scene_device_bytes",

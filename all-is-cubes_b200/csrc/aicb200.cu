@@ -37,6 +37,7 @@ static aicb_status cuda_fail(cudaError_t e, const char *what) { return aicb_cuda
 
 void aicb_light_scene_init(aicb_scene *s, const aicb_scene_desc *d);   // light.cu
 aicb_status aicb_light_scene_upload(aicb_scene *s, const aicb_scene_desc *d);
+aicb_status aicb_light_blocks_update(aicb_scene *s, const uint16_t *indices, const aicb_block_desc *descs, size_t n);
 void aicb_light_scene_free(aicb_scene *s);
 void aicb_light_ctx_free(aicb_ctx *c);
 
@@ -647,6 +648,8 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
         CUS(cudaMemcpy(s->d_blocks, recs.data(), recs.size() * sizeof(BlockRec), cudaMemcpyHostToDevice));
         s->device_bytes += recs.size() * sizeof(BlockRec);
     }
+    s->n_bricks = bricks.size();
+    s->n_palette = palette.size();
     if (!bricks.empty()) {
         CUS(cudaMalloc(&s->d_bricks, bricks.size() * 2));
         CUS(cudaMemcpy(s->d_bricks, bricks.data(), bricks.size() * 2, cudaMemcpyHostToDevice));
@@ -740,6 +743,155 @@ aicb_status aicb_scene_update_cubes(aicb_scene *s, const int32_t (*cubes)[3], co
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev_delta, ctx->stream));  // renders on other streams wait for it (launch_trace)
     return AICB_OK;  // stream-ordered before any later render of this context
+}
+
+// == SpaceChange::BlockEvaluation / BlockIndex (space.rs:1062-1100; UpdatingSpaceRaytracer::update handles them in
+// updating.rs:128-150 by re-running TracingBlock::from_block for the changed indices): replace the definition of
+// existing block indices.  New voxel data is appended to the brick pool and the palette (the replaced ranges are
+// reclaimed by the next aicb_scene_create); cubes that hold a block whose classification changed are re-encoded.
+// Does not queue light updates: call aicb_light_evaluate afterwards if the change affects light.
+aicb_status aicb_scene_update_blocks(aicb_scene *s, const uint16_t *indices, const aicb_block_desc *descs, size_t n) {
+    if (!s || (n && (!indices || !descs))) return fail(AICB_ERR_INVALID, "NULL argument");
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return AICB_OK;
+    const size_t n_blocks = s->block_kind.size();
+    std::vector<BlockRec> recs(n);
+    std::vector<uint8_t> kinds(n);
+    std::vector<uint16_t> bricks;
+    std::vector<float4> palette;
+    for (size_t i = 0; i < n; i++) {
+        if (indices[i] >= n_blocks) return fail(AICB_ERR_INVALID, "block index out of range (new indices need a new scene)");
+        const aicb_block_desc &b = descs[i];
+        BlockRec &r = recs[i];
+        std::memset(&r, 0, sizeof r);
+        const uint32_t res = b.resolution;
+        if (res == 0 || (res & (res - 1)) || res > 128) return fail(AICB_ERR_INVALID, "block resolution must be 1..128, power of 2");
+        static const aicb_voxel AIR_VOXEL = {{0, 0, 0, 0}, {0, 0, 0}, 0};
+        auto push_voxel = [&](const aicb_voxel &v) {
+            palette.push_back(make_float4(v.rgba[0], v.rgba[1], v.rgba[2], v.rgba[3]));
+            palette.push_back(make_float4(v.emission[0], v.emission[1], v.emission[2], 0.0f));
+        };
+        bool single = false;
+        aicb_voxel sv = AIR_VOXEL;
+        uint64_t nvox = 0;
+        if (b.indices == nullptr) {
+            single = true;
+            if (b.n_palette) {
+                if (!b.palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+                sv = b.palette[0];
+            }
+        } else {
+            nvox = (uint64_t)b.voxel_bounds.size[0] * b.voxel_bounds.size[1] * b.voxel_bounds.size[2];
+            if (nvox != b.n_indices) return fail(AICB_ERR_INVALID, "n_indices does not match voxel_bounds");
+            for (int a = 0; a < 3; a++) {
+                int64_t lo = b.voxel_bounds.lower[a], hi = lo + (int64_t)b.voxel_bounds.size[a];
+                if (lo < 0 || hi > (int64_t)res) return fail(AICB_ERR_INVALID, "voxel_bounds must lie within [0, resolution)^3");
+            }
+            if (!b.palette && b.n_palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+            for (size_t k = 0; k < b.n_indices; k++)
+                if (b.indices[k] >= b.n_palette) return fail(AICB_ERR_INVALID, "voxel index out of palette range");
+            if (res == 1) {  // single_voxel_or_palette (voxel_storage.rs:371-383)
+                single = true;
+                sv = (nvox == 1 && b.voxel_bounds.lower[0] == 0 && b.voxel_bounds.lower[1] == 0 && b.voxel_bounds.lower[2] == 0)
+                         ? b.palette[b.indices[0]]
+                         : AIR_VOXEL;
+            }
+        }
+        // offsets are relative to the appended ranges for now; the bases are added below
+        if (b.is_air) {
+            kinds[i] = KIND_INVISIBLE;
+            r.kind_res = KIND_INVISIBLE | (1u << 8);
+        } else if (single) {
+            kinds[i] = voxel_invisible(sv) ? KIND_INVISIBLE : KIND_SINGLE;
+            r.kind_res = kinds[i] | (1u << 8);
+            r.pal_off = (uint32_t)(palette.size() / 2);
+            r.vsize[0] = r.vsize[1] = r.vsize[2] = 1;
+            push_voxel(sv);
+        } else {
+            if (b.n_palette > 32768) return fail(AICB_ERR_UNSUPPORTED, "block palettes above 32768 entries are not supported");
+            kinds[i] = KIND_RECURSIVE;
+            r.kind_res = KIND_RECURSIVE | (res << 8);
+            for (int a = 0; a < 3; a++) {
+                r.vlo[a] = (int16_t)b.voxel_bounds.lower[a];
+                r.vsize[a] = (uint16_t)b.voxel_bounds.size[a];
+            }
+            r.brick_off = (uint32_t)bricks.size();
+            r.pal_off = (uint32_t)(palette.size() / 2);
+            for (size_t k = 0; k < b.n_indices; k++) {
+                uint16_t v = b.indices[k];
+                bricks.push_back((uint16_t)(v | (voxel_invisible(b.palette[v]) ? 0x8000u : 0u)));
+            }
+            for (size_t k = 0; k < b.n_palette; k++) push_voxel(b.palette[k]);
+        }
+    }
+    // ---- grow the brick pool and the palette, then patch the block table --------------------------------
+    CU(cudaDeviceSynchronize());   // nothing (on any stream) may still be reading the arrays that are replaced
+    if (s->n_bricks + bricks.size() > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
+    if (!bricks.empty()) {
+        uint16_t *nb = nullptr;
+        CU(cudaMalloc(&nb, (s->n_bricks + bricks.size()) * 2));
+        if (s->n_bricks) CU(cudaMemcpy(nb, s->d_bricks, s->n_bricks * 2, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(nb + s->n_bricks, bricks.data(), bricks.size() * 2, cudaMemcpyHostToDevice));
+        if (s->d_bricks) cudaFree(s->d_bricks);
+        s->d_bricks = nb;
+        s->ds.bricks = nb;
+        s->device_bytes += bricks.size() * 2;
+    }
+    if (!palette.empty()) {
+        float4 *np = nullptr;
+        CU(cudaMalloc(&np, (s->n_palette + palette.size()) * sizeof(float4)));
+        if (s->n_palette) CU(cudaMemcpy(np, s->d_palette, s->n_palette * sizeof(float4), cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(np + s->n_palette, palette.data(), palette.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (s->d_palette) cudaFree(s->d_palette);
+        s->d_palette = np;
+        s->ds.palette = np;
+        s->device_bytes += palette.size() * sizeof(float4);
+    }
+    std::vector<uint8_t> kind_changed(n_blocks, 0);
+    bool any_kind_changed = false;
+    for (size_t i = 0; i < n; i++) {
+        BlockRec &r = recs[i];
+        if (kinds[i] == KIND_RECURSIVE) r.brick_off += (uint32_t)s->n_bricks;
+        if (kinds[i] != KIND_INVISIBLE || !descs[i].is_air) r.pal_off += (uint32_t)(s->n_palette / 2);
+        CU(cudaMemcpy(s->d_blocks + indices[i], &r, sizeof r, cudaMemcpyHostToDevice));
+        if (s->block_kind[indices[i]] != kinds[i]) {
+            kind_changed[indices[i]] = 1;
+            any_kind_changed = true;
+            s->block_kind[indices[i]] = kinds[i];
+        }
+    }
+    s->n_bricks += bricks.size();
+    s->n_palette += palette.size();
+    // ---- cubes whose block changed its classification carry the kind in their cell word -------------------
+    if (any_kind_changed) {
+        if (s->h_ids.size() != s->volume) return fail(AICB_ERR_INVALID, "scene has no host mirror of its block ids");
+        std::vector<CubeDelta> ops;
+        for (size_t idx = 0; idx < s->volume; idx++) {
+            const uint16_t id = s->h_ids[idx];
+            if (!kind_changed[id]) continue;
+            CubeDelta op;
+            op.idx = (uint32_t)idx;
+            op.cell = s->ds.wide_cells ? (id | ((uint32_t)s->block_kind[id] << 16)) : (id | ((uint32_t)s->block_kind[id] << 14));
+            op.light = 0;
+            op.has_light = 0;
+            ops.push_back(op);
+        }
+        if (!ops.empty()) {
+            CubeDelta *d_ops = nullptr;
+            CU(cudaMalloc(&d_ops, ops.size() * sizeof(CubeDelta)));
+            cudaError_t e = cudaMemcpy(d_ops, ops.data(), ops.size() * sizeof(CubeDelta), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                scatter_cubes_kernel<<<(unsigned)((ops.size() + 127) / 128), 128, 0, ctx->stream>>>(d_ops, (uint32_t)ops.size(),
+                                                                                              s->ds.wide_cells, s->d_cells, s->d_light);
+                e = cudaStreamSynchronize(ctx->stream);
+            }
+            cudaFree(d_ops);
+            if (e != cudaSuccess) return cuda_fail(e, "re-encoding cells");
+        }
+    }
+    return aicb_light_blocks_update(s, indices, descs, n);
 }
 
 aicb_status aicb_scene_upload_light(aicb_scene *s, const uint8_t (*light)[4], size_t n_texels) {

@@ -72,6 +72,7 @@ struct aicb_scene {
     aicb::BlockRec *d_blocks = nullptr;
     uint16_t *d_bricks = nullptr;
     float4 *d_palette = nullptr;
+    size_t n_bricks = 0, n_palette = 0;   // elements in d_bricks / d_palette (aicb_scene_update_blocks appends)
     // state of the last asynchronous render
     bool pending = false;
     uint64_t pending_rays = 0;

@@ -364,6 +364,26 @@ aicb_status aicb_light_scene_upload(aicb_scene *s, const aicb_scene_desc *d) {
     return AICB_OK;
 }
 
+// the light-side records of replaced block definitions (aicb_scene_update_blocks)
+aicb_status aicb_light_blocks_update(aicb_scene *s, const uint16_t *indices, const aicb_block_desc *descs, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        const aicb_block_desc &b = descs[i];
+        LightBlockDev o;
+        std::memset(&o, 0, sizeof o);
+        std::memcpy(o.face_color[0], b.light_color, 16);
+        for (int f = 0; f < 6; f++) std::memcpy(o.face_color[f + 1], b.light_face_colors[f], 16);
+        std::memcpy(o.emission, b.light_emission, 12);
+        uint32_t fl = b.light_opaque_faces & 0x3f;
+        if (fl == 0x3f) fl |= LB_ALL_OPAQUE;
+        if (b.light_visible) fl |= LB_VISIBLE;
+        if (!(b.light_emission[0] == 0.0f && b.light_emission[1] == 0.0f && b.light_emission[2] == 0.0f)) fl |= LB_EMISSIVE;
+        o.flags = fl;
+        if (indices[i] < s->h_block_light.size()) s->h_block_light[indices[i]] = fl;
+        if (s->d_light_blocks) CU(cudaMemcpy(s->d_light_blocks + indices[i], &o, sizeof o, cudaMemcpyHostToDevice));
+    }
+    return AICB_OK;
+}
+
 void aicb_light_scene_free(aicb_scene *s) {
     if (s->d_light_blocks) cudaFree(s->d_light_blocks);
     if (s->d_pending) cudaFree(s->d_pending);
