@@ -190,8 +190,7 @@ def _converged(lower, ids, blocks, sky):
     return Space(lower, ids, blocks, light=ol.field(), sky_colors=sky, light_max_distance=30)
 
 
-@pytest.fixture(scope="module")
-def light_spread_universe():
+def build_light_spread_universe():
     """cases/src/lib.rs:1409-1441: a grey back wall, two emissive blocks (10, 5, 0) and a diagonal of dark pillars."""
     ids = np.zeros((20, 20, 5), dtype=np.uint16)
     ab = srgb8_to_linear((0x3d, 0x3d, 0x3d))   # palette::ALMOST_BLACK
@@ -221,8 +220,7 @@ def test_light_spread(light_spread_universe, name, lighting):
     check_threshold(img, golden(f"light_spread-{name}-all"), [(7, 128 * 96)])
 
 
-@pytest.fixture(scope="module")
-def fog_universe():
+def build_fog_universe():
     """cases/src/lib.rs:1354-1406: a 60x20x60 hall: green floor, pink right wall, dark pillars each with a strongly
     emissive lamp (40, 0.05, 0.05) in front of it."""
     ids = np.zeros((60, 20, 60), dtype=np.uint16)
@@ -258,8 +256,7 @@ def test_fog(fog_universe, name, fog):
     check_threshold(img, golden(f"fog-{name}-all"), [(2, 2000), (15, 100)])
 
 
-@pytest.fixture(scope="module")
-def tone_mapping_universe():
+def build_tone_mapping_universe():
     """cases/src/lib.rs:1503-1597: a dark slab with 10 x 13 compartments, each holding a white block that emits one of
     13 hues at one of 10 luminances (1/64 .. 128) and lights the back wall of its compartment; black sky."""
     ramp = [1 / 64, 1 / 32, 1 / 16, 1 / 4, 1.0, 4.0, 16.0, 32.0, 64.0, 128.0]
@@ -313,3 +310,18 @@ def test_debug_pixel_cost(fog_universe):
     img = orc.OracleScene(fog_universe).render(cam, opts)["srgb8"].reshape(96, 128, 4)
     max_diff, n_diff = check_threshold(img, golden("debug_pixel_cost-ray"), [(2, 500), (15, 100)])
     print(f"debug_pixel_cost: max diff {max_diff}, {n_diff} pixels differ")
+
+
+@pytest.fixture(scope="module")
+def light_spread_universe():
+    return build_light_spread_universe()
+
+
+@pytest.fixture(scope="module")
+def fog_universe():
+    return build_fog_universe()
+
+
+@pytest.fixture(scope="module")
+def tone_mapping_universe():
+    return build_tone_mapping_universe()
