@@ -190,8 +190,7 @@ aicb_status aicb_scene_update_cubes(aicb_scene *, const int32_t (*cubes)[3], con
 /* SpaceChange::BlockEvaluation / BlockIndex (space.rs:1062-1100; updating.rs:128-150): new definitions for EXISTING
  * block indices (an index beyond the table needs a new scene).  Voxel data is appended to the device pools; cubes
  * holding a block whose classification (invisible / single voxel / voxel brick) changed are re-encoded.  Light is not
- * re-propagated (call aicb_light_evaluate).  Written at the end of round 1 without GPU access: its GPU test
- * (tests/test_gpu_parity.py::test_block_definition_update_equals_fresh_snapshot) is opt-in until first verified. */
+ * re-propagated (call aicb_light_evaluate).  GPU test: tests/test_gpu_parity.py::test_block_definition_update_equals_fresh_snapshot. */
 aicb_status aicb_scene_update_blocks(aicb_scene *, const uint16_t *indices, const aicb_block_desc *descs, size_t n);
 /* Whole light volume replaced (after light propagation on the host or on another rank). */
 aicb_status aicb_scene_upload_light(aicb_scene *, const uint8_t (*light)[4], size_t n_texels);

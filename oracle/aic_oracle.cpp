@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -739,6 +740,27 @@ struct ColorBuf {
     float transmittance;
 };
 
+// The two f32 transcendentals of the per-ray path: f32::powf (raytracer_components.rs:233) and f32::exp (sr.rs:751).
+// Rust's std calls the platform libm; mode 0 does the same (glibc powf / expf).  Mode 1 ("cr") evaluates in f64 and
+// rounds once, which is what the CUDA path does: it is the correctly rounded result except when the f64 value lies
+// within an f64 ULP or two of an f32 rounding boundary (probability ~1e-8 per call).  The parity tests compare the
+// GPU with mode 1 exactly (0 ULP) and bound mode 0 against mode 1 per call (<= 1 ULP), so that a libm difference
+// cannot hide a kernel difference.  Selected by orc_set_libm() / ORC_LIBM=cr.
+static std::atomic<int> g_libm_mode{-1};
+static int libm_mode() {
+    int m = g_libm_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = std::getenv("ORC_LIBM");
+        m = (e && std::strcmp(e, "cr") == 0) ? 1 : 0;
+        g_libm_mode.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+static inline float orc_powf_mode(float x, float y) {
+    return libm_mode() ? (float)std::pow((double)x, (double)y) : std::pow(x, y);
+}
+static inline float orc_expf_mode(float x) { return libm_mode() ? (float)std::exp((double)x) : std::exp(x); }
+
 // apply_transmittance (raytracer_components.rs:215-258)
 static void apply_transmittance(const float color[4], float thickness_in, float out_color[4], float *coeff) {
     float thickness = rmaxf(thickness_in, 0.0f);
@@ -753,7 +775,7 @@ static void apply_transmittance(const float color[4], float thickness_in, float 
         return;
     }
     float unit_t = 1.0f - color[3];
-    float depth_t = std::pow(unit_t, thickness);  // f32::powf -> libm powf
+    float depth_t = orc_powf_mode(unit_t, thickness);  // f32::powf -> libm powf (or the round-once mode)
     float alpha = zo_clamped(1.0f - depth_t);
     out_color[0] = color[0];
     out_color[1] = color[1];
@@ -955,7 +977,7 @@ struct Tracer {
     bool distance_fog(double t_distance, float *amount) const {
         if (!have_fog) return false;
         float rel = rclampf((float)t_distance * t_to_view_distance, 0.0f, 1.0f);
-        float fog_exponential = 1.0f - std::exp(-1.6f * rel);
+        float fog_exponential = 1.0f - orc_expf_mode(-1.6f * rel);
         float fog_exp_fudged = fog_exponential / 0.79810348f;
         float p4 = (rel * rel) * (rel * rel);  // powi(4)
         *amount = zo_clamped(fog_exp_fudged * (1.0f - fog_blend) + p4 * fog_blend);
@@ -1604,6 +1626,12 @@ void orc_scene_block_sky(const orc_scene *s, uint8_t out[7][4]) {
     }
     out[6][0] = s->sky_mean.r; out[6][1] = s->sky_mean.g; out[6][2] = s->sky_mean.b; out[6][3] = s->sky_mean.status;
 }
+
+// libm mode of the two per-ray transcendentals: 0 = platform powf/expf (what Rust's std calls), 1 = f64 + one rounding.
+void orc_set_libm(int mode) { g_libm_mode.store(mode ? 1 : 0, std::memory_order_relaxed); }
+int orc_get_libm(void) { return libm_mode(); }
+float orc_powf(float x, float y, int mode) { return mode ? (float)std::pow((double)x, (double)y) : std::pow(x, y); }
+float orc_expf(float x, int mode) { return mode ? (float)std::exp((double)x) : std::exp(x); }
 
 int orc_hardware_threads(void) {
     unsigned n = std::thread::hardware_concurrency();

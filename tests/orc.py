@@ -57,6 +57,13 @@ def lib():
     L.orc_pixel_ray.argtypes = [C.POINTER(abi.CameraData), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.orc_pixel_ray.restype = None
     L.orc_hardware_threads.restype = C.c_int
+    L.orc_set_libm.argtypes = [C.c_int]
+    L.orc_set_libm.restype = None
+    L.orc_get_libm.restype = C.c_int
+    L.orc_powf.restype = C.c_float
+    L.orc_powf.argtypes = [C.c_float, C.c_float, C.c_int]
+    L.orc_expf.restype = C.c_float
+    L.orc_expf.argtypes = [C.c_float, C.c_int]
     L.orc_light_chart.restype = C.c_size_t
     L.orc_light_chart.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_light_create.restype = C.c_void_p
@@ -79,6 +86,19 @@ def lib():
     L.orc_light_node_visits.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+LIBM_PLATFORM, LIBM_CR = 0, 1
+
+
+def set_libm(mode):
+    """How the oracle evaluates f32::powf (raytracer_components.rs:233) and f32::exp (sr.rs:751): LIBM_PLATFORM = glibc
+    powf / expf (what Rust's std calls on this host), LIBM_CR = in f64, rounded once (what the CUDA path does)."""
+    lib().orc_set_libm(int(mode))
+
+
+def get_libm():
+    return int(lib().orc_get_libm())
 
 
 FACES = ["Within", "NX", "NY", "NZ", "PX", "PY", "PZ"]

@@ -1,8 +1,7 @@
 """The scenes of tests/test_golden_images.py (restated from the reference's test-renderers suite) through the CUDA path.
 
-Written at the end of round 1 after the GPU budget was spent, so the whole module is opt-in until its first run on a
-B200: AICB_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_golden.py -m gpu.  The CUDA path is already held to the
-oracle on other scenes (tests/test_gpu_parity.py); these cases add the reference's own expected images on top."""
+The CUDA path is held to the oracle on other scenes (tests/test_gpu_parity.py); these cases add the reference's own
+expected images on top, and the same bit-exact comparison against the oracle (f64-rounded-once powf / expf)."""
 import os
 
 import numpy as np
@@ -14,9 +13,15 @@ from aicb200 import Camera, GraphicsOptions, RtRenderer, Space, SpaceRaytracer, 
 from test_golden_images import (build_fog_universe, build_light_spread_universe, build_tone_mapping_universe,
                                 check_threshold, golden)
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("AICB_TEST_UNVERIFIED"),
-                                 reason="not yet run on a GPU (round-1 budget spent); set AICB_TEST_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _oracle_rounds_once():
+    prev = orc.get_libm()
+    orc.set_libm(orc.LIBM_CR)
+    yield
+    orc.set_libm(prev)
 
 
 def gpu_and_oracle(space, cam, opts):
@@ -25,9 +30,10 @@ def gpu_and_oracle(space, cam, opts):
     img = r.draw().data
     ref = orc.OracleScene(space).render(cam, opts)
     h, w = img.shape[:2]
-    assert np.abs(img.reshape(-1, 4).astype(int) - ref["srgb8"].astype(int)).max() <= 1
+    assert np.array_equal(img.reshape(-1, 4), ref["srgb8"])
     aux = r.draw_colorbuf()
     assert np.array_equal(aux["hit"], ref["hit"]) and np.array_equal(aux["steps"], ref["steps"])
+    assert orc.max_ulp_diff(aux["colorbuf"], ref["colorbuf"]) == 0
     return img
 
 
