@@ -143,6 +143,89 @@ static bool voxel_invisible(const aicb_voxel &v) {
     return v.rgba[3] == 0.0f && v.emission[0] == 0.0f && v.emission[1] == 0.0f && v.emission[2] == 0.0f;
 }
 
+// TracingBlock::from_block (sr.rs:579-587) for one block definition: its 32-byte record, classification, brick words
+// and palette entries (appended to `bricks` / `palette`; the record's offsets are relative to those vectors), plus
+// what the marching kernel needs of each surface: {alpha, an upper bound of log2(1 - alpha)} per palette entry.
+// Shared by aicb_scene_create and aicb_scene_update_blocks.
+static const aicb_voxel AIR_VOXEL = {{0, 0, 0, 0}, {0, 0, 0}, 0};
+
+static float2 surface_entry(float alpha) {
+    float l2a;
+    if (alpha >= 1.0f) l2a = -INFINITY;
+    else if (!(alpha > 0.0f)) l2a = 0.0f;
+    else {
+        const float unit_t = 1.0f - alpha;   // the f32 value apply_transmittance raises to the span's thickness
+        l2a = std::nextafterf((float)std::log2((double)unit_t), INFINITY);
+        if (l2a > 0.0f) l2a = 0.0f;
+    }
+    return make_float2(alpha, l2a);
+}
+
+static aicb_status flatten_block(const aicb_block_desc &b, BlockRec &r, uint8_t &kind, std::vector<uint16_t> &bricks,
+                                 std::vector<float4> &palette, std::vector<float2> &pal_tab) {
+    std::memset(&r, 0, sizeof r);
+    const uint32_t res = b.resolution;
+    if (res == 0 || (res & (res - 1)) || res > 128) return fail(AICB_ERR_INVALID, "block resolution must be 1..128, power of 2");
+    auto push_voxel = [&](const aicb_voxel &v) {
+        palette.push_back(make_float4(v.rgba[0], v.rgba[1], v.rgba[2], v.rgba[3]));
+        palette.push_back(make_float4(v.emission[0], v.emission[1], v.emission[2], 0.0f));
+        pal_tab.push_back(surface_entry(v.rgba[3]));
+    };
+    bool single = false;
+    aicb_voxel sv = AIR_VOXEL;
+    if (b.indices == nullptr) {
+        single = true;
+        if (b.n_palette) {
+            if (!b.palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+            sv = b.palette[0];
+        }
+    } else {
+        const uint64_t nvox = (uint64_t)b.voxel_bounds.size[0] * b.voxel_bounds.size[1] * b.voxel_bounds.size[2];
+        if (nvox != b.n_indices) return fail(AICB_ERR_INVALID, "n_indices does not match voxel_bounds");
+        for (int a = 0; a < 3; a++) {
+            int64_t lo = b.voxel_bounds.lower[a], hi = lo + (int64_t)b.voxel_bounds.size[a];
+            if (lo < 0 || hi > (int64_t)res) return fail(AICB_ERR_INVALID, "voxel_bounds must lie within [0, resolution)^3");
+        }
+        if (!b.palette && b.n_palette) return fail(AICB_ERR_INVALID, "palette is NULL");
+        for (size_t k = 0; k < b.n_indices; k++)
+            if (b.indices[k] >= b.n_palette) return fail(AICB_ERR_INVALID, "voxel index out of palette range");
+        if (res == 1) {
+            // single_voxel_or_palette (voxel_storage.rs:371-383)
+            single = true;
+            sv = (nvox == 1 && b.voxel_bounds.lower[0] == 0 && b.voxel_bounds.lower[1] == 0 && b.voxel_bounds.lower[2] == 0)
+                     ? b.palette[b.indices[0]]
+                     : AIR_VOXEL;
+        }
+    }
+    if (b.is_air) {
+        kind = KIND_INVISIBLE;
+        r.kind_res = KIND_INVISIBLE | (1u << 8);
+    } else if (single) {
+        kind = voxel_invisible(sv) ? KIND_INVISIBLE : KIND_SINGLE;
+        r.kind_res = kind | (1u << 8);
+        r.pal_off = (uint32_t)(palette.size() / 2);
+        r.vsize[0] = r.vsize[1] = r.vsize[2] = 1;
+        push_voxel(sv);
+    } else {
+        if (b.n_palette > 32768) return fail(AICB_ERR_UNSUPPORTED, "block palettes above 32768 entries are not supported");
+        kind = KIND_RECURSIVE;
+        r.kind_res = KIND_RECURSIVE | (res << 8);
+        for (int a = 0; a < 3; a++) {
+            r.vlo[a] = (int16_t)b.voxel_bounds.lower[a];
+            r.vsize[a] = (uint16_t)b.voxel_bounds.size[a];
+        }
+        if (bricks.size() + b.n_indices > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
+        r.brick_off = (uint32_t)bricks.size();
+        r.pal_off = (uint32_t)(palette.size() / 2);
+        for (size_t k = 0; k < b.n_indices; k++) {
+            uint16_t v = b.indices[k];
+            bricks.push_back((uint16_t)(v | (voxel_invisible(b.palette[v]) ? 0x8000u : 0u)));
+        }
+        for (size_t k = 0; k < b.n_palette; k++) push_voxel(b.palette[k]);
+    }
+    return AICB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
@@ -282,10 +365,10 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.task_counter = ctx->d_tile_counter;
     {
         const char *e = getenv("AICB_REFILL_THRESHOLD");
-        int v = e ? atoi(e) : 12;
+        int v = e ? atoi(e) : 1;
         P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         const char *e2 = getenv("AICB_EVENT_THRESHOLD");
-        int v2 = e2 ? atoi(e2) : 32;
+        int v2 = e2 ? atoi(e2) : 12;
         P.event_threshold = (uint32_t)(v2 < 1 ? 1 : (v2 > 32 ? 32 : v2));
     }
 
@@ -302,7 +385,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     uint64_t CHUNK = (uint64_t)4 << 20;
     {
         const uint64_t per_task = sizeof(RayRecord) + sizeof(TaskOut) + 4 * N_BINS +
-                                  (uint64_t)ctx->hits_per_task * (sizeof(HitRecord) + sizeof(float4) + sizeof(HitLink));
+                                  (uint64_t)ctx->hits_per_task * (sizeof(HitRecord) + sizeof(ShadedHit));
         uint64_t fit = ((uint64_t)8 << 30) / per_task;
         if (fit < (1u << 17)) fit = 1u << 17;
         if (fit < CHUNK) CHUNK = fit & ~(uint64_t)127;
@@ -316,13 +399,11 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         uint64_t cap = chunk_cap * ctx->hits_per_task;
         if (cap < (1u << 16)) cap = 1u << 16;
         if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
-        cap &= ~(uint64_t)(HIT_BLOCK - 1);  // warps take whole blocks of the stream
+        cap &= ~(uint64_t)(HIT_CHUNK - 1);  // lanes take whole chunks of the stream
         P.hit_capacity = (uint32_t)cap;
         st = ensure(&ctx->d_hits, &ctx->d_hits_bytes, cap * sizeof(HitRecord) + 64);
         if (st != AICB_OK) return st;
-        st = ensure(&ctx->d_contrib, &ctx->d_contrib_bytes, cap * sizeof(float4) + 64);
-        if (st != AICB_OK) return st;
-        st = ensure(&ctx->d_hit_link, &ctx->d_hit_link_bytes, cap * sizeof(HitLink) + 64);
+        st = ensure(&ctx->d_contrib, &ctx->d_contrib_bytes, cap * sizeof(ShadedHit) + 64);
         if (st != AICB_OK) return st;
         st = ensure(&ctx->d_bin_list, &ctx->d_bin_list_bytes, (size_t)N_BINS * chunk_cap * 4 + 64);
         if (st != AICB_OK) return st;
@@ -330,8 +411,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.ray_records = (RayRecord *)ctx->d_rays;
     P.task_out = (TaskOut *)ctx->d_task_cb;
     P.hits = (HitRecord *)ctx->d_hits;
-    P.hit_contrib = (float4 *)ctx->d_contrib;
-    P.hit_link = (HitLink *)ctx->d_hit_link;
+    P.shaded = (ShadedHit *)ctx->d_contrib;
     P.hit_counter = ctx->d_tile_counter + 1;
     P.bin_count = ctx->d_tile_counter + 4;
     P.bin_list = (uint32_t *)ctx->d_bin_list;
@@ -493,7 +573,6 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_task_cb) cudaFree(c->d_task_cb);
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_contrib) cudaFree(c->d_contrib);
-    if (c->d_hit_link) cudaFree(c->d_hit_link);
     if (c->d_bin_list) cudaFree(c->d_bin_list);
     if (c->d_debug) cudaFree(c->d_debug);
     if (c->h_delta) cudaFreeHost(c->h_delta);
@@ -529,73 +608,16 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
     if (volume && d->n_blocks == 0) return fail(AICB_ERR_INVALID, "non-empty space with an empty block table");
 
     // ---- flatten the block table --------------------------------------------------------------
+    if (d->n_blocks && !d->blocks) return fail(AICB_ERR_INVALID, "blocks is NULL");
     std::vector<BlockRec> recs(d->n_blocks);
     std::vector<uint8_t> kinds(d->n_blocks);
     std::vector<uint16_t> bricks;
     std::vector<float4> palette;
+    std::vector<float2> pal_tab, blk_tab(d->n_blocks);
     for (size_t i = 0; i < d->n_blocks; i++) {
-        const aicb_block_desc &b = d->blocks[i];
-        BlockRec &r = recs[i];
-        std::memset(&r, 0, sizeof r);
-        const uint32_t res = b.resolution;
-        if (res == 0 || (res & (res - 1)) || res > 128) return fail(AICB_ERR_INVALID, "block resolution must be 1..128, power of 2");
-        auto push_voxel = [&](const aicb_voxel &v) {
-            palette.push_back(make_float4(v.rgba[0], v.rgba[1], v.rgba[2], v.rgba[3]));
-            palette.push_back(make_float4(v.emission[0], v.emission[1], v.emission[2], 0.0f));
-        };
-        static const aicb_voxel AIR_VOXEL = {{0, 0, 0, 0}, {0, 0, 0}, 0};
-        bool single = false;
-        aicb_voxel sv = AIR_VOXEL;
-        if (b.indices == nullptr) {
-            single = true;
-            if (b.n_palette) {
-                if (!b.palette) return fail(AICB_ERR_INVALID, "palette is NULL");
-                sv = b.palette[0];
-            }
-        } else {
-            uint64_t nvox = (uint64_t)b.voxel_bounds.size[0] * b.voxel_bounds.size[1] * b.voxel_bounds.size[2];
-            if (nvox != b.n_indices) return fail(AICB_ERR_INVALID, "n_indices does not match voxel_bounds");
-            for (int a = 0; a < 3; a++) {
-                int64_t lo = b.voxel_bounds.lower[a], hi = lo + (int64_t)b.voxel_bounds.size[a];
-                if (lo < 0 || hi > (int64_t)res) return fail(AICB_ERR_INVALID, "voxel_bounds must lie within [0, resolution)^3");
-            }
-            if (!b.palette && b.n_palette) return fail(AICB_ERR_INVALID, "palette is NULL");
-            for (size_t k = 0; k < b.n_indices; k++)
-                if (b.indices[k] >= b.n_palette) return fail(AICB_ERR_INVALID, "voxel index out of palette range");
-            if (res == 1) {
-                // single_voxel_or_palette (voxel_storage.rs:371-383)
-                single = true;
-                sv = (nvox == 1 && b.voxel_bounds.lower[0] == 0 && b.voxel_bounds.lower[1] == 0 && b.voxel_bounds.lower[2] == 0)
-                         ? b.palette[b.indices[0]]
-                         : AIR_VOXEL;
-            }
-        }
-        if (b.is_air) {
-            kinds[i] = KIND_INVISIBLE;
-            r.kind_res = KIND_INVISIBLE | (1u << 8);
-        } else if (single) {
-            kinds[i] = voxel_invisible(sv) ? KIND_INVISIBLE : KIND_SINGLE;
-            r.kind_res = kinds[i] | (1u << 8);
-            r.pal_off = (uint32_t)(palette.size() / 2);
-            r.vsize[0] = r.vsize[1] = r.vsize[2] = 1;
-            push_voxel(sv);
-        } else {
-            if (b.n_palette > 32768) return fail(AICB_ERR_UNSUPPORTED, "block palettes above 32768 entries are not supported");
-            kinds[i] = KIND_RECURSIVE;
-            r.kind_res = KIND_RECURSIVE | (res << 8);
-            for (int a = 0; a < 3; a++) {
-                r.vlo[a] = (int16_t)b.voxel_bounds.lower[a];
-                r.vsize[a] = (uint16_t)b.voxel_bounds.size[a];
-            }
-            if (bricks.size() + b.n_indices > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
-            r.brick_off = (uint32_t)bricks.size();
-            r.pal_off = (uint32_t)(palette.size() / 2);
-            for (size_t k = 0; k < b.n_indices; k++) {
-                uint16_t v = b.indices[k];
-                bricks.push_back((uint16_t)(v | (voxel_invisible(b.palette[v]) ? 0x8000u : 0u)));
-            }
-            for (size_t k = 0; k < b.n_palette; k++) push_voxel(b.palette[k]);
-        }
+        aicb_status fst = flatten_block(d->blocks[i], recs[i], kinds[i], bricks, palette, pal_tab);
+        if (fst != AICB_OK) return fst;
+        blk_tab[i] = kinds[i] == KIND_SINGLE ? pal_tab[recs[i].pal_off] : make_float2(0.0f, 0.0f);
     }
 
     aicb_scene *s = new aicb_scene();
@@ -659,6 +681,14 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
         CUS(cudaMalloc(&s->d_palette, palette.size() * sizeof(float4)));
         CUS(cudaMemcpy(s->d_palette, palette.data(), palette.size() * sizeof(float4), cudaMemcpyHostToDevice));
         s->device_bytes += palette.size() * sizeof(float4);
+        CUS(cudaMalloc(&s->d_pal_tab, pal_tab.size() * sizeof(float2)));
+        CUS(cudaMemcpy(s->d_pal_tab, pal_tab.data(), pal_tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        s->device_bytes += pal_tab.size() * sizeof(float2);
+    }
+    if (!blk_tab.empty()) {
+        CUS(cudaMalloc(&s->d_blk_tab, blk_tab.size() * sizeof(float2)));
+        CUS(cudaMemcpy(s->d_blk_tab, blk_tab.data(), blk_tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        s->device_bytes += blk_tab.size() * sizeof(float2);
     }
 #undef CUS
     ds.cells = s->d_cells;
@@ -666,6 +696,8 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
     ds.blocks = s->d_blocks;
     ds.bricks = s->d_bricks;
     ds.palette = s->d_palette;
+    ds.blk_tab = s->d_blk_tab;
+    ds.pal_tab = s->d_pal_tab;
     ds.tables = ctx->d_lut;
     build_block_sky(d->sky, &ds);
     {
@@ -684,6 +716,8 @@ void aicb_scene_destroy(aicb_scene *s) {
     if (s->d_blocks) cudaFree(s->d_blocks);
     if (s->d_bricks) cudaFree(s->d_bricks);
     if (s->d_palette) cudaFree(s->d_palette);
+    if (s->d_pal_tab) cudaFree(s->d_pal_tab);
+    if (s->d_blk_tab) cudaFree(s->d_blk_tab);
     aicb_light_scene_free(s);
     delete s;
 }
@@ -761,104 +795,78 @@ aicb_status aicb_scene_update_blocks(aicb_scene *s, const uint16_t *indices, con
     std::vector<uint8_t> kinds(n);
     std::vector<uint16_t> bricks;
     std::vector<float4> palette;
+    std::vector<float2> pal_tab;
+    // validate and flatten everything before touching any state
     for (size_t i = 0; i < n; i++) {
         if (indices[i] >= n_blocks) return fail(AICB_ERR_INVALID, "block index out of range (new indices need a new scene)");
-        const aicb_block_desc &b = descs[i];
-        BlockRec &r = recs[i];
-        std::memset(&r, 0, sizeof r);
-        const uint32_t res = b.resolution;
-        if (res == 0 || (res & (res - 1)) || res > 128) return fail(AICB_ERR_INVALID, "block resolution must be 1..128, power of 2");
-        static const aicb_voxel AIR_VOXEL = {{0, 0, 0, 0}, {0, 0, 0}, 0};
-        auto push_voxel = [&](const aicb_voxel &v) {
-            palette.push_back(make_float4(v.rgba[0], v.rgba[1], v.rgba[2], v.rgba[3]));
-            palette.push_back(make_float4(v.emission[0], v.emission[1], v.emission[2], 0.0f));
-        };
-        bool single = false;
-        aicb_voxel sv = AIR_VOXEL;
-        uint64_t nvox = 0;
-        if (b.indices == nullptr) {
-            single = true;
-            if (b.n_palette) {
-                if (!b.palette) return fail(AICB_ERR_INVALID, "palette is NULL");
-                sv = b.palette[0];
-            }
-        } else {
-            nvox = (uint64_t)b.voxel_bounds.size[0] * b.voxel_bounds.size[1] * b.voxel_bounds.size[2];
-            if (nvox != b.n_indices) return fail(AICB_ERR_INVALID, "n_indices does not match voxel_bounds");
-            for (int a = 0; a < 3; a++) {
-                int64_t lo = b.voxel_bounds.lower[a], hi = lo + (int64_t)b.voxel_bounds.size[a];
-                if (lo < 0 || hi > (int64_t)res) return fail(AICB_ERR_INVALID, "voxel_bounds must lie within [0, resolution)^3");
-            }
-            if (!b.palette && b.n_palette) return fail(AICB_ERR_INVALID, "palette is NULL");
-            for (size_t k = 0; k < b.n_indices; k++)
-                if (b.indices[k] >= b.n_palette) return fail(AICB_ERR_INVALID, "voxel index out of palette range");
-            if (res == 1) {  // single_voxel_or_palette (voxel_storage.rs:371-383)
-                single = true;
-                sv = (nvox == 1 && b.voxel_bounds.lower[0] == 0 && b.voxel_bounds.lower[1] == 0 && b.voxel_bounds.lower[2] == 0)
-                         ? b.palette[b.indices[0]]
-                         : AIR_VOXEL;
-            }
+        aicb_status fst = flatten_block(descs[i], recs[i], kinds[i], bricks, palette, pal_tab);
+        if (fst != AICB_OK) return fst;
+    }
+    if (s->n_bricks + bricks.size() > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
+    bool any_kind_changed = false;
+    for (size_t i = 0; i < n; i++) any_kind_changed |= s->block_kind[indices[i]] != kinds[i];
+    if (any_kind_changed && s->h_ids.size() != s->volume)
+        return fail(AICB_ERR_INVALID, "scene has no host mirror of its block ids");
+    CU(cudaDeviceSynchronize());   // nothing (on any stream) may still be reading the arrays that are replaced
+
+    // ---- grow the pools: the new arrays are complete before any pointer of the scene changes ----------------
+    const size_t n_pal_old = s->n_palette / 2;   // palette entries (2 x float4 each)
+    uint16_t *nb = nullptr;
+    float4 *np = nullptr;
+    float2 *nt = nullptr;
+    auto grow = [&]() -> cudaError_t {
+        cudaError_t e;
+        if (!bricks.empty()) {
+            if ((e = cudaMalloc(&nb, (s->n_bricks + bricks.size()) * 2)) != cudaSuccess) return e;
+            if (s->n_bricks && (e = cudaMemcpy(nb, s->d_bricks, s->n_bricks * 2, cudaMemcpyDeviceToDevice)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(nb + s->n_bricks, bricks.data(), bricks.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         }
-        // offsets are relative to the appended ranges for now; the bases are added below
-        if (b.is_air) {
-            kinds[i] = KIND_INVISIBLE;
-            r.kind_res = KIND_INVISIBLE | (1u << 8);
-        } else if (single) {
-            kinds[i] = voxel_invisible(sv) ? KIND_INVISIBLE : KIND_SINGLE;
-            r.kind_res = kinds[i] | (1u << 8);
-            r.pal_off = (uint32_t)(palette.size() / 2);
-            r.vsize[0] = r.vsize[1] = r.vsize[2] = 1;
-            push_voxel(sv);
-        } else {
-            if (b.n_palette > 32768) return fail(AICB_ERR_UNSUPPORTED, "block palettes above 32768 entries are not supported");
-            kinds[i] = KIND_RECURSIVE;
-            r.kind_res = KIND_RECURSIVE | (res << 8);
-            for (int a = 0; a < 3; a++) {
-                r.vlo[a] = (int16_t)b.voxel_bounds.lower[a];
-                r.vsize[a] = (uint16_t)b.voxel_bounds.size[a];
-            }
-            r.brick_off = (uint32_t)bricks.size();
-            r.pal_off = (uint32_t)(palette.size() / 2);
-            for (size_t k = 0; k < b.n_indices; k++) {
-                uint16_t v = b.indices[k];
-                bricks.push_back((uint16_t)(v | (voxel_invisible(b.palette[v]) ? 0x8000u : 0u)));
-            }
-            for (size_t k = 0; k < b.n_palette; k++) push_voxel(b.palette[k]);
+        if (!palette.empty()) {
+            if ((e = cudaMalloc(&np, (s->n_palette + palette.size()) * sizeof(float4))) != cudaSuccess) return e;
+            if (s->n_palette && (e = cudaMemcpy(np, s->d_palette, s->n_palette * sizeof(float4), cudaMemcpyDeviceToDevice)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(np + s->n_palette, palette.data(), palette.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&nt, (n_pal_old + pal_tab.size()) * sizeof(float2))) != cudaSuccess) return e;
+            if (n_pal_old && (e = cudaMemcpy(nt, s->d_pal_tab, n_pal_old * sizeof(float2), cudaMemcpyDeviceToDevice)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(nt + n_pal_old, pal_tab.data(), pal_tab.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    {
+        const cudaError_t e = grow();
+        if (e != cudaSuccess) {
+            if (nb) cudaFree(nb);
+            if (np) cudaFree(np);
+            if (nt) cudaFree(nt);
+            return cuda_fail(e, "growing the brick pool / palette");
         }
     }
-    // ---- grow the brick pool and the palette, then patch the block table --------------------------------
-    CU(cudaDeviceSynchronize());   // nothing (on any stream) may still be reading the arrays that are replaced
-    if (s->n_bricks + bricks.size() > 0xffffffffull) return fail(AICB_ERR_INVALID, "brick pool exceeds 2^32 voxels");
-    if (!bricks.empty()) {
-        uint16_t *nb = nullptr;
-        CU(cudaMalloc(&nb, (s->n_bricks + bricks.size()) * 2));
-        if (s->n_bricks) CU(cudaMemcpy(nb, s->d_bricks, s->n_bricks * 2, cudaMemcpyDeviceToDevice));
-        CU(cudaMemcpy(nb + s->n_bricks, bricks.data(), bricks.size() * 2, cudaMemcpyHostToDevice));
+    if (nb) {
         if (s->d_bricks) cudaFree(s->d_bricks);
         s->d_bricks = nb;
         s->ds.bricks = nb;
         s->device_bytes += bricks.size() * 2;
     }
-    if (!palette.empty()) {
-        float4 *np = nullptr;
-        CU(cudaMalloc(&np, (s->n_palette + palette.size()) * sizeof(float4)));
-        if (s->n_palette) CU(cudaMemcpy(np, s->d_palette, s->n_palette * sizeof(float4), cudaMemcpyDeviceToDevice));
-        CU(cudaMemcpy(np + s->n_palette, palette.data(), palette.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (np) {
         if (s->d_palette) cudaFree(s->d_palette);
+        if (s->d_pal_tab) cudaFree(s->d_pal_tab);
         s->d_palette = np;
         s->ds.palette = np;
-        s->device_bytes += palette.size() * sizeof(float4);
+        s->d_pal_tab = nt;
+        s->ds.pal_tab = nt;
+        s->device_bytes += palette.size() * sizeof(float4) + pal_tab.size() * sizeof(float2);
     }
+    // ---- patch the block table ------------------------------------------------------------------------------
     std::vector<uint8_t> kind_changed(n_blocks, 0);
-    bool any_kind_changed = false;
     for (size_t i = 0; i < n; i++) {
         BlockRec &r = recs[i];
+        float2 bt = make_float2(0.0f, 0.0f);
+        if (kinds[i] == KIND_SINGLE) bt = pal_tab[r.pal_off];
         if (kinds[i] == KIND_RECURSIVE) r.brick_off += (uint32_t)s->n_bricks;
-        if (kinds[i] != KIND_INVISIBLE || !descs[i].is_air) r.pal_off += (uint32_t)(s->n_palette / 2);
+        if (kinds[i] != KIND_INVISIBLE || !descs[i].is_air) r.pal_off += (uint32_t)n_pal_old;
         CU(cudaMemcpy(s->d_blocks + indices[i], &r, sizeof r, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->d_blk_tab + indices[i], &bt, sizeof bt, cudaMemcpyHostToDevice));
         if (s->block_kind[indices[i]] != kinds[i]) {
             kind_changed[indices[i]] = 1;
-            any_kind_changed = true;
             s->block_kind[indices[i]] = kinds[i];
         }
     }
@@ -866,7 +874,6 @@ aicb_status aicb_scene_update_blocks(aicb_scene *s, const uint16_t *indices, con
     s->n_palette += palette.size();
     // ---- cubes whose block changed its classification carry the kind in their cell word -------------------
     if (any_kind_changed) {
-        if (s->h_ids.size() != s->volume) return fail(AICB_ERR_INVALID, "scene has no host mirror of its block ids");
         std::vector<CubeDelta> ops;
         for (size_t idx = 0; idx < s->volume; idx++) {
             const uint16_t id = s->h_ids[idx];

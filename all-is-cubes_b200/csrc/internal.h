@@ -46,10 +46,8 @@ struct aicb_ctx {
     size_t d_task_cb_bytes = 0;
     void *d_hits = nullptr;      // HitRecord stream (march -> shade -> encode)
     size_t d_hits_bytes = 0;
-    void *d_contrib = nullptr;   // float4 per hit
+    void *d_contrib = nullptr;   // ShadedHit per hit (shade -> encode)
     size_t d_contrib_bytes = 0;
-    void *d_hit_link = nullptr;  // HitLink per hit
-    size_t d_hit_link_bytes = 0;
     void *d_bin_list = nullptr;  // task ids of the rays that enter the space, per chord-length bin
     size_t d_bin_list_bytes = 0;
     uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it
@@ -72,6 +70,8 @@ struct aicb_scene {
     aicb::BlockRec *d_blocks = nullptr;
     uint16_t *d_bricks = nullptr;
     float4 *d_palette = nullptr;
+    float2 *d_pal_tab = nullptr;   // per palette entry: {alpha, log2(1 - alpha) bound} (marching kernel)
+    float2 *d_blk_tab = nullptr;   // per block id: the same pair for single-voxel blocks
     size_t n_bricks = 0, n_palette = 0;   // elements in d_bricks / d_palette (aicb_scene_update_blocks appends)
     // state of the last asynchronous render
     bool pending = false;

@@ -5,13 +5,17 @@
 //  * gen_kernel (one thread per ray, convergent): pixel -> world ray, Raycaster::new().within(space bounds); rays that
 //    miss the space are finished here, the others are listed by chord length (longest first);
 //  * trace_kernel (persistent warps): every lane owns one ray at a time and takes the next one from the list when it
-//    finishes.  The warp runs a synchronous phase machine — REFILL | FINALIZE | MARCH (a select-based, branch-free
-//    Amanatides–Woo DDA step in f64, one dependent 2-byte load and one bit test per step) | HEAVY (surfaces, span logic,
-//    block entry) — so that lanes executing expensive code execute the SAME expensive code.  It evaluates no colour:
-//    surfaces leave it as 64-byte hit records, and of the transmittance it keeps only an upper bound (to know when the
-//    ray is certainly opaque);
-//  * shade_kernel (one thread per hit record, convergent): apply_transmittance (f64 pow), fog (f64 exp), the
-//    invisibility test and compute_illumination;
+//    finishes.  The hot loop does, for every lane, ONE Amanatides–Woo DDA step in f64 (select-based, branch-free), one
+//    dependent 2-byte load, the step count / opacity test, and — predicated, in the same iteration — the two cheap
+//    things a ray can meet: the end of a Volumetric span (an 8-byte store into the pending hit record) and a visible
+//    surface (a 64-byte hit record written to the lane's own chunk of the hit stream).  Only a change of level
+//    (entering a recursive block: Raycaster::within on the brick; leaving one) and the end of a ray park the lane; the
+//    warp serves parked lanes together once enough of them wait.  The kernel evaluates no colour: of the transmittance
+//    it keeps only an upper bound, in the log domain (one multiply-add per span), to know when the ray is certainly
+//    opaque;
+//  * shade_kernel (one thread per hit record, convergent): cube / voxel coordinates and the intersection point from
+//    the recorded caster state, apply_transmittance (f64 pow), fog (f64 exp), the invisibility test and
+//    compute_illumination;
 //  * encode_kernel (one thread per pixel): the exact transmittance chain in ray order, the opacity cut, sky, tone
 //    mapping, sRGB8.
 //  The two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is walked by ONE unified DDA;
@@ -60,6 +64,8 @@ struct DeviceScene {
     const BlockRec *blocks;
     const uint16_t *bricks;     // palette index | invisible<<15
     const float4 *palette;      // 2 x float4 per entry: rgba, emission
+    const float2 *blk_tab;      // per block id (single-voxel blocks): {alpha, upper bound of log2(1 - alpha)}
+    const float2 *pal_tab;      // per palette entry: the same pair (what the marching kernel needs of a surface)
     const float *tables;        // [0,256): PackedLight decode LUT (data.rs:301-354); [256,512): sRGB8 thresholds;
                                 // [512,768): PackedLight quantiser thresholds (light kernels)
     uint32_t sky_faces[6];      // BlockSky faces NX..PZ as texels (sky.rs:54-82)
@@ -84,36 +90,43 @@ struct __align__(16) RayRecord {
 };
 static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
 
-// One shaded surface of one ray, emitted by the marching kernel and lit by the shade kernel.
-// 64 bytes = 4 x 16-byte stores: the geometry of one surface the ray went through and the length of its span.
-// The marcher does not evaluate any colour or transmittance: apply_transmittance (f64 pow), the fog amount (f64
-// exp), the invisibility test and the illumination all happen in shade_kernel, convergently, and the transmittance
-// chain of the ray is multiplied up in order by encode_kernel.  The marcher only keeps an UPPER BOUND of the ray's
-// transmittance (a few f32 instructions per surface) to know when the ray is certainly finished.
+// One surface of one ray, emitted by the marching kernel and lit by the shade kernel: 64 bytes = 4 x 16-byte stores.
+// It is the caster's state at the surface, not a derived geometry: cube / voxel coordinates, the intersection point
+// (raycast.rs:409-439) and the palette entry are recovered from it by shade_kernel, convergently.  The marcher
+// evaluates no colour or transmittance: apply_transmittance (f64 pow), the fog amount (f64 exp), the invisibility
+// test and the illumination all happen in shade_kernel, and the transmittance chain of the ray is multiplied up in
+// order by encode_kernel.
 struct __align__(16) HitRecord {
-    double ip[3];        // intersection point (interpolated lighting only)
-    double t;            // ray parameter where the surface was entered (Hit::t_distance; DepthBuf, fog)
-    uint32_t pal;        // palette entry
-    int32_t cube[3];
-    uint32_t packed;     // voxel x | y<<8 | z<<16 | face<<24
-    float thickness;     // Volumetric: length of the span inside the surface's material (world units); else 0
-    float fog_rel;       // t relative to the view distance, as f32 (distance_fog, sr.rs:745-768)
-    uint32_t flags;      // sky octant | resolution<<8
+    double tmx, tmy, tmz;   // State::t_max of the level the surface is on (unscaled)
+    double last_t;          // State::last_t_distance of that level: Hit::t_distance = last_t / resolution
+    uint32_t word;          // outer level: block id | HIT_WORD_BLOCK; inner level: palette entry (global index)
+    uint32_t cell;          // linear index of the Space cube
+    uint32_t vidx;          // inner level: index of the voxel in the brick pool
+    uint32_t flags;         // face | inner<<3 | log2(resolution)<<4
+    float thickness;        // Volumetric: length of the span inside the surface's material (world units), written when
+                            // the span is closed; Surface / Threshold: 0; < 0: the surface was never shaded
+    uint32_t steps;         // the ray's step counter when the surface was shaded (the reference stops at the first
+                            // counted step after the hit that brings the transmittance under 1/256; encode_kernel
+                            // needs the counter to restore that when the marcher's bound let the ray run on)
+    uint32_t task;          // the ray: index of its RayRecord in the chunk
+    uint32_t next;          // next hit of the same ray (HIT_NONE = none)
 };
 static_assert(sizeof(HitRecord) == 64, "HitRecord must be 64 bytes");
 
-// Per hit, beside the record: the next hit of the same ray (0xffffffff = none) and the value of the ray's step
-// counter when the surface was shaded (the reference stops at the first counted step after the hit that brings the
-// transmittance under 1/256; encode_kernel needs the counter to restore that).
-struct HitLink {
+// What shade_kernel leaves per hit for encode_kernel: one 32-byte sector.
+struct __align__(32) ShadedHit {
+    float r, g, b;       // outgoing light of the surface
+    float factor;        // what it multiplies the ray's transmittance by (< 0: surface invisible / never shaded, skip)
     uint32_t next;
     uint32_t steps;
+    uint32_t _pad[2];
 };
+static_assert(sizeof(ShadedHit) == 32, "ShadedHit must be 32 bytes");
 
 // What the marching kernel hands to the encode kernel per ray (16 bytes).
 struct __align__(16) TaskOut {
     uint32_t first_hit;  // index of the first HitRecord or 0xffffffff
-    uint32_t steps;      // steps counted by the marcher (>= the reference's; see HitLink)
+    uint32_t steps;      // steps counted by the marcher (>= the reference's; see HitRecord::steps)
     uint32_t flags;      // sky octant
     uint32_t _pad;
 };
@@ -149,15 +162,14 @@ struct TraceParams {
     RayRecord *ray_records;     // gen -> march
     TaskOut *task_out;          // march -> encode
     HitRecord *hits;            // march -> shade
-    float4 *hit_contrib;        // shade -> encode: outgoing light of the hit (rgb) and its transmittance factor (< 0: skipped)
-    HitLink *hit_link;          // march -> encode
-    unsigned int *hit_counter;  // hit slots handed out in this chunk (in blocks of HIT_BLOCK)
+    ShadedHit *shaded;          // shade -> encode
+    unsigned int *hit_counter;  // hit slots handed out in this chunk (in chunks of HIT_CHUNK per lane)
     uint32_t *bin_list;         // gen -> march: task ids of the rays that enter the space, binned by chord length
     unsigned int *bin_count;    // [N_BINS] entries of each bin
     uint32_t bin_stride;        // capacity of one bin's list
     unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
     uint32_t hit_capacity;
-    uint32_t event_threshold;   // leave the MARCH phase once this many lanes wait with an event / finished ray
+    uint32_t event_threshold;   // leave the marching loop once this many lanes wait (parked at a level switch, finished, idle)
     uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
     // outputs
     uchar4 *out_srgb8;
@@ -180,8 +192,9 @@ constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (templ
 constexpr int TILE_W = 8, TILE_H = 4;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int N_BINS = 8;            // chord-length classes of the ray list (longest first)
-constexpr uint32_t HIT_BLOCK = 64;   // hit slots a warp takes from the stream at a time
-constexpr uint32_t HIT_DEAD = 0xffffffffu;  // HitRecord::pal of a slot that was handed out but never filled
+constexpr uint32_t HIT_CHUNK = 16;   // hit slots a lane takes from the stream at a time (one atomic per chunk)
+constexpr uint32_t HIT_NONE = 0xffffffffu;
+constexpr uint32_t HIT_WORD_BLOCK = 0x80000000u;  // HitRecord::word holds a block id (outer level), not a palette entry
 #ifndef AICB_MIN_BLOCKS
 #define AICB_MIN_BLOCKS 4
 #endif
@@ -663,21 +676,8 @@ struct AuxState<true> {
     uint32_t n_outer, n_inner, n_blocks;   // device counters of the roofline accounting
 };
 
-// A surface remembered between discovery and shading (Volumetric mode pairs it with the next
-// event's t, surface.rs:460-490).  Illumination depends only on geometry (cube, face, intersection
-// point), so it is evaluated when the surface is shaded, never for surfaces that are not.
-struct PendingSurface {
-    double t;
-    double ip[3];      // intersection point (only filled for interpolated lighting)
-    uint32_t pal;      // global palette entry index
-    int cube[3];
-    uint32_t packed;   // voxel x | y<<8 | z<<16 | face<<24
-    int res;
-};
-
-enum LaneState : int { ST_IDLE = 0, ST_MARCH = 1, ST_EVENT = 2, ST_DONE = 3, ST_EXHAUSTED = 4 };
-enum EventKind : int { EV_SURFACE = 0, EV_INVISIBLE = 1, EV_ENTER_BLOCK = 2, EV_EXIT = 3, EV_STUCK = 4 };
-enum EventPost : int { POST_CONTINUE = 0, POST_POP = 1, POST_FINISH = 2 };
+// A lane is marching, parked (waiting for the warp to serve its level switch / to take its result), or has no ray.
+enum LaneState : int { ST_IDLE = 0, ST_MARCH = 1, ST_ENTER = 2, ST_POP = 3, ST_DONE = 4, ST_EXHAUSTED = 5 };
 
 // task -> pixel mapping shared by the three kernels: pixel tasks are tile-ordered (32 consecutive
 // pixel tasks = one 8x4 tile); returns false for the padding pixels of edge tiles.
@@ -811,46 +811,38 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
 
 // ======================================================================================================
 // Kernel 2 — the marching kernel (replaces SpaceRaytracer::trace_ray's loop, sr.rs:180-238, and the Rayon
-// dispatch, renderer.rs:516-556): persistent warps, lane refill from the ray stream, phase machine.
+// dispatch, renderer.rs:516-556): persistent warps, lane refill from the ray list.
+//
+// One iteration of the hot loop is, for every marching lane (no divergent branch up to the surface case):
+//   State::step (raycast.rs:577-626)           select the axis with the smallest t_max, add t_delta, move the index
+//   bounds (raycast.rs:265-274)                per-axis counters of the steps left inside the level: one sign test
+//   SurfaceIter / VoxelSurfaceIter lookup      one dependent 2-byte load; bit 15 = nothing to see
+//   count_step_should_stop (sr.rs:625-656)     step counter, log-domain upper bound of the transmittance
+//   DepthIter span end (surface.rs:460-490)    Volumetric: thickness of the pending surface's span -> its hit record
+//   visible surface (surface.rs:322-331,399)   a 64-byte hit record into the lane's chunk of the hit stream
+// A lane parks when it has to change level (EnterBlock: Raycaster::within on the brick, raycast.rs:458-476; leaving
+// the brick) or when its ray is finished; parked lanes are served together once `event_threshold` lanes wait.
 // ======================================================================================================
 template <bool VOLUMETRIC, bool WIDE, bool AUX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
 trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
+    constexpr float F_NEG_INF = -__builtin_huge_valf();
+    constexpr int COUNTER_STATIC = 0x3fffffff;   // steps left along an axis the ray does not move on
 
     unsigned long long n_outer = 0, n_inner = 0, n_blocks = 0;
 
-    int st = ST_IDLE;
-
     // Cold per-ray state lives in shared memory, one column per thread, so that the registers of the marching loop
-    // hold only what a DDA step touches (more resident warps); the HEAVY sections read what they need into
-    // short-lived locals.
-    __shared__ double sh_d[16][WARPS_PER_BLOCK * 32];
-    __shared__ uint32_t sh_w[17][WARPS_PER_BLOCK * 32];
+    // hold only what a DDA step touches; the level switches read what they need into short-lived locals.
+    __shared__ double sh_d[12][WARPS_PER_BLOCK * 32];
+    __shared__ uint32_t sh_w[11][WARPS_PER_BLOCK * 32];
     const int tid = threadIdx.x;
 #define COLD_D(k) sh_d[k][tid]
 #define COLD_W(k) sh_w[k][tid]
-    // doubles: 0-2 origin, 3-5 direction, 6 half_over_len, 7-10 saved caster (t_max x/y/z, last_t), 11 pending t,
-    //          12-14 pending intersection point, 15 t_to_abs
-    // words:   0-4 saved caster (rx, ry, rz, face, idx), 5 saved valid, 6 pending pal, 7-9 pending cube, 10 pending packed,
-    //          11 pending res, 12 t_to_view, 13 first_hit, 14 last_hit, 15 task, 16 sky octant
-    auto load_ray = [&](Ray &rr, const Ray &hot) {
-        rr = hot;
-        rr.ox = COLD_D(0); rr.oy = COLD_D(1); rr.oz = COLD_D(2);
-        rr.dx = COLD_D(3); rr.dy = COLD_D(4); rr.dz = COLD_D(5);
-        rr.half_over_len = COLD_D(6);
-    };
-    auto store_pending = [&](const PendingSurface &sf) {
-        COLD_D(11) = sf.t; COLD_D(12) = sf.ip[0]; COLD_D(13) = sf.ip[1]; COLD_D(14) = sf.ip[2];
-        COLD_W(6) = sf.pal; COLD_W(7) = (uint32_t)sf.cube[0]; COLD_W(8) = (uint32_t)sf.cube[1]; COLD_W(9) = (uint32_t)sf.cube[2];
-        COLD_W(10) = sf.packed; COLD_W(11) = (uint32_t)sf.res;
-    };
-    auto load_pending = [&](PendingSurface &sf) {
-        sf.t = COLD_D(11); sf.ip[0] = COLD_D(12); sf.ip[1] = COLD_D(13); sf.ip[2] = COLD_D(14);
-        sf.pal = COLD_W(6); sf.cube[0] = (int)COLD_W(7); sf.cube[1] = (int)COLD_W(8); sf.cube[2] = (int)COLD_W(9);
-        sf.packed = COLD_W(10); sf.res = (int)COLD_W(11);
-    };
+    // doubles: 0-2 origin, 3-5 direction, 6 half_over_len, 7 t_to_abs, 8-10 outer t_max while inside a block, 11 outer last_t
+    // words:   0 outer index (= the Space cube of the entered block), 1-3 outer step counters, 4 outer face, 5 outer valid,
+    //          6 task, 7 first hit, 8 sky octant, 9 palette offset of the entered block, 10 log2(resolution) of it
     unsigned long long dbg_t0 = 0, dbg_passes = 0, dbg_rays = 0;
     if (P.debug_warp_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
@@ -864,52 +856,178 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     __syncthreads();
     const uint32_t n_listed = s_bin_start[N_BINS];
     (void)n_chunk_tasks;
-    // this warp's block of the hit stream
-    uint32_t hit_base = 0xffffffffu, hit_used = 0;
 
-    // ---- per-ray state -----------------------------------------------------------------------------
-    Ray r;      // only t_delta and the signs are kept here (the DDA step); origin / direction are cold
-    Caster c;
-    bool valid = false, inner = false, need_advance = false;
+    // ---- per-ray state (registers) ---------------------------------------------------------------------
+    int st = ST_IDLE;
+    double tmx = 0.0, tmy = 0.0, tmz = 0.0, last_t = 0.0;   // State::t_max, last_t_distance of the active level
+    double tdx = 0.0, tdy = 0.0, tdz = 0.0;                 // t_delta (raycast.rs:769)
     double t_scale = 1.0;                // 1 on the outer level, 1/resolution inside a block (surface.rs:385-386)
-    const bool want_ip = P.lighting >= AICB_LIGHT_COARSE;  // only interpolated lighting needs the intersection point
-    int nx = 0, ny = 0, nz = 0;          // sizes of the active level
-    uint32_t blk0y = 0, blk0z = 0;       // packed voxel bounds of the entered block (lo16|lo16, lo16|size16)
-    uint32_t pal_off = 0;
-    int res = 1;
-    // Upper bound of the ColorBuf transmittance (never below the exact value the encode kernel computes).  Once it is
-    // under 1/256 the ray is certainly finished (sr.rs:648-652); in the rare case that only the exact value is under
-    // the limit the marcher runs on and the encode kernel cuts the ray's hits and steps back (see HitLink).
-    float T_ub = 1.f;
+    uint32_t idx = 0;                    // linear index of the current cube (cells) / voxel (brick pool)
+    int stx = 0, sty = 0, stz = 0;       // signed index strides of the active level
+    int cx = 0, cy = 0, cz = 0;          // steps left inside the level along each axis (< 0: outside)
+    int fcx = 0, fcy = 0, fcz = 0;       // the face entered by a step along each axis (from the direction's signs)
+    int face = 0;                        // Face7 through which the current cube was entered
+    uint32_t sbits = 0;                  // (sx+1) | (sy+1)<<2 | (sz+1)<<4
+    bool valid = false, inner = false, need_advance = false, have_pending = false;
+    // Upper bound of log2 of the ColorBuf transmittance (never below the exact value the encode kernel computes).
+    // Once it is under -8 the ray is certainly finished (sr.rs:648-652); in the rare case that only the exact value is
+    // under 1/256 the marcher runs on and the encode kernel cuts the ray's hits and steps back (HitRecord::steps).
+    float L = 0.0f;
     uint32_t steps = 0;
-    bool have_last = false;
+    double pend_t = 0.0;                 // Volumetric: entry t of the surface whose span is open (surface.rs:467-476)
+    uint32_t pend_slot = HIT_NONE;
+    float pend_l2a = 0.0f;
+    uint32_t last_slot = HIT_NONE;       // the ray's latest hit record (its `next` is patched by the following one)
+    uint32_t chunk_base = HIT_NONE, chunk_used = HIT_CHUNK;   // this lane's chunk of the hit stream
+    uint32_t ev_word = 0;
     AuxState<AUX> aux;
-    // event
-    int ev_kind = 0, ev_post = 0;
-    double ev_t = 0.0;
-    uint32_t ev_cell = 0;
+    bool list_exhausted = false;         // warp-uniform: the ray list has run out (tail of the frame)
 
-    auto count_stop = [&]() -> bool {  // count_step_should_stop (sr.rs:625-656)
-        steps += 1;
-        if (steps > 1000) return true;
-        return T_ub < (1.0f / 256.0f);
+    // log-domain bound of one transmittance factor.  Exact factor (shade_kernel): 1 - clamp(1 - (f32)pow(u, th)) with
+    // u = 1 - alpha, i.e. <= u^th (1 + 2^-23) + 2^-24; with u^th >= 2^-8.5 that is <= u^th * 2^(3.3e-5).  l2a >= log2(u)
+    // (host, rounded up); the f32 product and sum add < 2e-6.  A factor under 2^-8.5 makes the ray opaque by itself.
+    auto bound_factor = [&](float p) { L = (p < -8.5f) ? F_NEG_INF : L + (p + 1e-4f); };
+
+    // State::step (raycast.rs:577-626) on the active level, select-based so that lanes stepping along different axes
+    // stay converged.  Axis choice as the reference: x if t_max.x is strictly the smallest, else y if
+    // t_max.y < t_max.z, else z.  Returns true if the new cube is outside the level (raycast.rs:265-274).
+    auto advance = [&]() -> bool {
+        const bool xy = tmx < tmy, xz = tmx < tmz, yz = tmy < tmz;
+        const bool ax = xy & xz;
+        const bool ay = !xy & yz;
+        const bool axy = ax | ay;
+        const double tm = ax ? tmx : (ay ? tmy : tmz);
+        const double td = ax ? tdx : (ay ? tdy : tdz);
+        const double nt = tm + td;
+        last_t = tm;
+        tmx = ax ? nt : tmx;
+        tmy = ay ? nt : tmy;
+        tmz = axy ? tmz : nt;
+        idx += (uint32_t)(ax ? stx : (ay ? sty : stz));
+        face = ax ? fcx : (ay ? fcy : fcz);
+        cx -= ax ? 1 : 0;
+        cy -= ay ? 1 : 0;
+        cz -= axy ? 0 : 1;
+        return (cx | cy | cz) < 0;
     };
-    auto pop_level = [&]() {
-        inner = false;
-        t_scale = 1.0;
-        c.tmx = COLD_D(7); c.tmy = COLD_D(8); c.tmz = COLD_D(9); c.last_t = COLD_D(10);
-        c.rx = (int)COLD_W(0); c.ry = (int)COLD_W(1); c.rz = (int)COLD_W(2); c.face = (int)COLD_W(3); c.idx = COLD_W(4);
-        valid = COLD_W(5) != 0;
-        nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
+
+    // A visible surface (surface.rs:322-331, 399-409): its hit record goes to the lane's chunk of the hit stream.
+    auto emit_surface = [&](uint32_t word, double t_now) {
+        const uint32_t entry = inner ? COLD_W(9) + word : word;
+        const float2 te = __ldg((inner ? S.pal_tab : S.blk_tab) + entry);
+        if (chunk_used == HIT_CHUNK) {   // one atomic per HIT_CHUNK hits of this lane
+            const uint32_t nb = atomicAdd(P.hit_counter, HIT_CHUNK);
+            if (nb + HIT_CHUNK > P.hit_capacity) {   // (the capacity is a multiple of HIT_CHUNK)
+                *P.overflow_flag = 1u;               // the host re-runs the frame with a larger buffer
+                chunk_base = HIT_NONE;
+            } else {
+                chunk_base = nb;
+            }
+            chunk_used = 0;
+        }
+        uint32_t slot = HIT_NONE;
+        if (chunk_base != HIT_NONE) {
+            slot = chunk_base + chunk_used;
+            chunk_used++;
+            uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
+            st_stream(dst, make_uint4((uint32_t)__double2loint(tmx), (uint32_t)__double2hiint(tmx),
+                                      (uint32_t)__double2loint(tmy), (uint32_t)__double2hiint(tmy)));
+            st_stream(dst + 1, make_uint4((uint32_t)__double2loint(tmz), (uint32_t)__double2hiint(tmz),
+                                          (uint32_t)__double2loint(last_t), (uint32_t)__double2hiint(last_t)));
+            st_stream(dst + 2, make_uint4(inner ? entry : (word | HIT_WORD_BLOCK), inner ? COLD_W(0) : idx, idx,
+                                          (uint32_t)face | (inner ? (8u | (COLD_W(10) << 4)) : 0u)));
+            st_stream(dst + 3, make_uint4(__float_as_uint(VOLUMETRIC ? -1.0f : 0.0f), steps, COLD_W(6), HIT_NONE));
+            if (last_slot != HIT_NONE) P.hits[last_slot].next = slot; else COLD_W(7) = slot;
+            last_slot = slot;
+        }
+        if constexpr (VOLUMETRIC) {   // the span is closed by the next step (surface.rs:467-476)
+            pend_slot = slot;
+            pend_t = t_now;
+            pend_l2a = te.y;
+            have_pending = true;
+        } else if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {   // limit_alpha (graphics_options.rs:496-507)
+            if (te.x > P.threshold) L = F_NEG_INF;
+        } else {
+            bound_factor(te.y);
+        }
+    };
+
+    // One step of the ray: advance, look at the cube / voxel, count, close the open span, classify.
+    auto step = [&]() {
+        bool left = false;
+        if (need_advance) {
+            if (!valid) {   // the iterator ends without an exit step (raycast.rs:245-249)
+                st = inner ? ST_POP : ST_DONE;
+                return;
+            }
+            left = advance();
+        }
         need_advance = true;
+        uint32_t w = 0;
+        if (!left) {
+            if constexpr (WIDE) {
+                if (!inner) {
+                    const uint32_t cell = __ldg((const uint32_t *)S.cells + idx);   // id | kind<<16
+                    w = (cell & 0x3fffu) | ((cell >> 2) & 0xc000u);                  // only ids < 16384 keep their bits here
+                    ev_word = cell & 0xffffu;
+                } else {
+                    w = __ldg(S.bricks + idx);
+                }
+            } else {
+                w = __ldg((inner ? S.bricks : (const uint16_t *)S.cells) + idx);
+            }
+            if constexpr (AUX) { if (inner) aux.n_inner++; else aux.n_outer++; }
+        }
+        const double t_now = last_t * t_scale;
+        // count_step_should_stop (sr.rs:625-656): every TraceStep / DepthStep is counted before it is looked at
+        steps += 1;
+        if ((steps > 1000u) | (L < -8.0f)) { st = ST_DONE; return; }
+        if constexpr (VOLUMETRIC) {
+            if (have_pending) {   // DepthIter: this step's t ends the pending surface's span (surface.rs:460-490)
+                const float th = fmaxf((float)((t_now - pend_t) * COLD_D(7)), 0.0f);   // sr.rs:720-731
+                if (pend_slot != HIT_NONE)
+                    *reinterpret_cast<uint2 *>(&P.hits[pend_slot].thickness) = make_uint2(__float_as_uint(th), steps);
+                bound_factor(pend_l2a == F_NEG_INF ? F_NEG_INF : th * pend_l2a);
+                have_pending = false;
+            }
+        }
+        if (left) {   // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
+            st = inner ? ST_POP : ST_DONE;
+            return;
+        }
+        if (w & 0x8000u) return;   // nothing to see here
+        if (!inner && (w & 0x4000u)) {   // TraceStep::EnterBlock (surface.rs:334-352)
+            if constexpr (VOLUMETRIC) {
+                // the buffered DepthStep::EnterBlock is counted after the flushed span (surface.rs:478-488)
+                steps += 1;
+                if ((steps > 1000u) | (L < -8.0f)) { st = ST_DONE; return; }
+            }
+            if constexpr (!WIDE) ev_word = w & 0x3fffu;
+            st = ST_ENTER;
+            return;
+        }
+        if constexpr (WIDE) emit_surface(inner ? w : ev_word, t_now);
+        else emit_surface(inner ? w : (w & 0x3fffu), t_now);
     };
 
     for (;;) {
-        // =========================== REFILL: idle lanes load the next rays of the stream ================
+        dbg_passes++;
+        // =========================== FINALIZE: hand the ray's result to the encode kernel ================
+        if (st == ST_DONE) {
+            dbg_rays++;
+            TaskOut o;
+            o.first_hit = COLD_W(7);
+            o.steps = steps;
+            o.flags = COLD_W(8);
+            o._pad = 0;
+            *reinterpret_cast<uint4 *>(P.task_out + COLD_W(6)) = *reinterpret_cast<const uint4 *>(&o);
+            if constexpr (AUX) { n_outer += aux.n_outer; n_inner += aux.n_inner; n_blocks += aux.n_blocks; }
+            st = ST_IDLE;
+        }
+        // =========================== REFILL: idle lanes take the next rays of the list ====================
         {
             const unsigned idle = __ballot_sync(0xffffffffu, st == ST_IDLE);
-            const unsigned running = __ballot_sync(0xffffffffu, st == ST_MARCH || st == ST_EVENT || st == ST_DONE);
-            if (idle && (running == 0 || __popc(idle) >= (int)P.refill_threshold)) {
+            if (idle && !list_exhausted) {
                 const int n = __popc(idle);
                 uint32_t base = 0;
                 const int leader = __ffs(idle) - 1;
@@ -923,292 +1041,54 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                         int b = 0;
                         while (k >= s_bin_start[b + 1]) b++;
                         const uint32_t task = __ldg(P.bin_list + (size_t)b * P.bin_stride + (k - s_bin_start[b]));
-                        COLD_W(15) = task;
                         RayRecord rec;
                         {
                             const uint4 *src = reinterpret_cast<const uint4 *>(P.ray_records + task);
                             uint4 *dst = reinterpret_cast<uint4 *>(&rec);
 #pragma unroll
-                            for (int k = 0; k < 9; k++) dst[k] = ld_stream(src + k);
+                            for (int q = 0; q < 9; q++) dst[q] = ld_stream(src + q);
                         }
-                        {
-                            COLD_D(0) = rec.ox; COLD_D(1) = rec.oy; COLD_D(2) = rec.oz;
-                            COLD_D(3) = rec.dx; COLD_D(4) = rec.dy; COLD_D(5) = rec.dz;
-                            r.tdx = rec.tdx; r.tdy = rec.tdy; r.tdz = rec.tdz;
-                            COLD_D(6) = rec.half_over_len;
-                            r.sx = (int)((rec.flags >> 6) & 3u) - 1; r.sy = (int)((rec.flags >> 8) & 3u) - 1;
-                            r.sz = (int)((rec.flags >> 10) & 3u) - 1;
-                            c.tmx = rec.tmx; c.tmy = rec.tmy; c.tmz = rec.tmz; c.last_t = rec.last_t;
-                            c.rx = rec.rx; c.ry = rec.ry; c.rz = rec.rz;
-                            c.idx = rec.idx;
-                            c.face = (int)(rec.flags & 7u);
-                            valid = (rec.flags & 16u) != 0;
-                            COLD_D(15) = rec.t_to_abs;
-                            COLD_W(12) = __float_as_uint(rec.t_to_view);
-                            COLD_W(16) = (rec.flags >> 12) & 7u;
-                            COLD_W(13) = COLD_W(14) = 0xffffffffu;
-                            T_ub = 1.0f;
-                            steps = 0;
-                            have_last = false;
-                            inner = false;
-                            t_scale = 1.0;
-                            need_advance = false;
-                            nx = S.size[0]; ny = S.size[1]; nz = S.size[2];
-                            if constexpr (AUX) aux.n_outer = aux.n_inner = aux.n_blocks = 0;
-                            st = ST_MARCH;
-                        }
+                        COLD_W(6) = task;
+                        COLD_D(0) = rec.ox; COLD_D(1) = rec.oy; COLD_D(2) = rec.oz;
+                        COLD_D(3) = rec.dx; COLD_D(4) = rec.dy; COLD_D(5) = rec.dz;
+                        COLD_D(6) = rec.half_over_len;
+                        COLD_D(7) = rec.t_to_abs;
+                        COLD_W(7) = HIT_NONE;
+                        COLD_W(8) = (rec.flags >> 12) & 7u;
+                        tdx = rec.tdx; tdy = rec.tdy; tdz = rec.tdz;
+                        tmx = rec.tmx; tmy = rec.tmy; tmz = rec.tmz; last_t = rec.last_t;
+                        sbits = (rec.flags >> 6) & 0x3fu;
+                        const int sx = (int)(sbits & 3u) - 1, sy = (int)((sbits >> 2) & 3u) - 1, sz = (int)((sbits >> 4) & 3u) - 1;
+                        fcx = sx > 0 ? AICB_FACE_NX : AICB_FACE_PX;
+                        fcy = sy > 0 ? AICB_FACE_NY : AICB_FACE_PY;
+                        fcz = sz > 0 ? AICB_FACE_NZ : AICB_FACE_PZ;
+                        stx = sx * (S.size[1] * S.size[2]); sty = sy * S.size[2]; stz = sz;
+                        cx = sx > 0 ? S.size[0] - 1 - rec.rx : (sx < 0 ? rec.rx : COUNTER_STATIC);
+                        cy = sy > 0 ? S.size[1] - 1 - rec.ry : (sy < 0 ? rec.ry : COUNTER_STATIC);
+                        cz = sz > 0 ? S.size[2] - 1 - rec.rz : (sz < 0 ? rec.rz : COUNTER_STATIC);
+                        idx = rec.idx;
+                        face = (int)(rec.flags & 7u);
+                        valid = (rec.flags & 16u) != 0;
+                        L = 0.0f;
+                        steps = 0;
+                        have_pending = false;
+                        pend_slot = HIT_NONE;
+                        last_slot = HIT_NONE;
+                        inner = false;
+                        t_scale = 1.0;
+                        need_advance = false;
+                        if constexpr (AUX) aux.n_outer = aux.n_inner = aux.n_blocks = 0;
+                        st = ST_MARCH;
                     }
                 }
+                if (__any_sync(0xffffffffu, st == ST_EXHAUSTED)) list_exhausted = true;
             }
-            if (__all_sync(0xffffffffu, st == ST_EXHAUSTED)) break;
+            if (__all_sync(0xffffffffu, st == ST_EXHAUSTED || st == ST_IDLE)) break;
         }
-
-        dbg_passes++;
-        // =========================== FINALIZE: hand the ray's result to the encode kernel ================
-        if (st == ST_DONE) {
-            dbg_rays++;
-            TaskOut o;
-            const uint32_t task = COLD_W(15);
-            o.first_hit = COLD_W(13);
-            o.steps = steps;
-            o.flags = COLD_W(16);
-            o._pad = 0;
-            *reinterpret_cast<uint4 *>(P.task_out + task) = *reinterpret_cast<const uint4 *>(&o);
-            if constexpr (AUX) { n_outer += aux.n_outer; n_inner += aux.n_inner; n_blocks += aux.n_blocks; }
-            st = ST_IDLE;
-        }
-
-        // =========================== MARCH: cheap DDA steps until the lane needs heavy work ===========
-        // Builds the Surface of the current cube / voxel (surface.rs:322-331, 399-409) without lighting it:
-        // illumination is a pure function of (cube, face, intersection point), so only those are recorded and
-        // the light is evaluated when (and if) the surface is actually shaded.
-        auto record_surface = [&](PendingSurface &sf, uint32_t cell_or_voxel, double t) {
-            int cx, cy, cz;
-            if (!inner) {
-                const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + cell_or_voxel);
-                sf.pal = __ldg(bp + 1).y;
-                cx = c.rx + S.lo[0]; cy = c.ry + S.lo[1]; cz = c.rz + S.lo[2];
-                sf.packed = (uint32_t)c.face << 24;
-                sf.res = 1;
-            } else {
-                sf.pal = pal_off + cell_or_voxel;
-                cx = (int)COLD_W(0) + S.lo[0]; cy = (int)COLD_W(1) + S.lo[1]; cz = (int)COLD_W(2) + S.lo[2];
-                const int vx = c.rx + (int)(int16_t)(blk0y & 0xffff), vy = c.ry + (int)(int16_t)(blk0y >> 16),
-                          vz = c.rz + (int)(int16_t)(blk0z & 0xffff);
-                sf.packed = (uint32_t)vx | ((uint32_t)vy << 8) | ((uint32_t)vz << 16) | ((uint32_t)c.face << 24);
-                sf.res = res;
-            }
-            sf.t = t;
-            sf.cube[0] = cx; sf.cube[1] = cy; sf.cube[2] = cz;
-            if (want_ip) {
-                double ip[3];
-                Ray rr;
-                load_ray(rr, r);
-                if (!inner) {
-                    intersection_point(c, rr, cx, cy, cz, rr.ox, rr.oy, rr.oz, ip);
-                } else {
-                    const double fres = (double)res, anti = recip_pow2(res);
-                    const int vx = (int)(sf.packed & 255), vy = (int)((sf.packed >> 8) & 255), vz = (int)((sf.packed >> 16) & 255);
-                    intersection_point(c, rr, vx, vy, vz, (rr.ox - (double)cx) * fres, (rr.oy - (double)cy) * fres,
-                                       (rr.oz - (double)cz) * fres, ip);
-                    ip[0] = ip[0] * anti + (double)cx;  // surface.rs:406-407
-                    ip[1] = ip[1] * anti + (double)cy;
-                    ip[2] = ip[2] * anti + (double)cz;
-                }
-                sf.ip[0] = ip[0]; sf.ip[1] = ip[1]; sf.ip[2] = ip[2];
-            }
-        };
-        // One DDA step and the classification of the cube / voxel it lands on.  Everything that is not "an empty
-        // cell, keep going" leaves the loop as an event; the rare cases (leaving the level, an iterator that cannot
-        // step) are events too so that the loop body stays small and converged.
-        auto march_step = [&]() {
-            if (need_advance) {
-                if (!valid) { ev_kind = EV_STUCK; st = ST_EVENT; return; }  // raycast.rs:245-249
-                if (caster_step(c, r, nx, ny, nz)) {
-                    ev_kind = EV_EXIT; ev_t = c.last_t * t_scale; st = ST_EVENT;
-                    return;
-                }
-            }
-            need_advance = true;
-            uint32_t word;
-            bool invisible, enter_block;
-            if constexpr (WIDE) {
-                if (!inner) {
-                    const uint32_t cell = __ldg((const uint32_t *)S.cells + c.idx);
-                    word = cell & 0xffffu;
-                    invisible = (cell >> 16) == KIND_INVISIBLE;
-                    enter_block = (cell >> 16) == KIND_RECURSIVE;
-                } else {
-                    word = __ldg(S.bricks + c.idx);
-                    invisible = (word & 0x8000u) != 0;
-                    enter_block = false;
-                }
-            } else {
-                const uint16_t *vol = inner ? S.bricks : (const uint16_t *)S.cells;
-                const uint32_t w = __ldg(vol + c.idx);
-                invisible = (w & 0x8000u) != 0;
-                enter_block = !inner & ((w & 0x4000u) != 0);
-                word = inner ? w : (w & 0x3fffu);
-            }
-            if constexpr (AUX) { if (inner) aux.n_inner++; else aux.n_outer++; }
-            if (invisible) {
-                if (VOLUMETRIC && have_last) {
-                    ev_kind = EV_INVISIBLE; ev_t = c.last_t * t_scale; ev_post = POST_CONTINUE;
-                    st = ST_EVENT;
-                    return;
-                }
-                if (count_stop()) st = ST_DONE;
-                return;
-            }
-            ev_kind = enter_block ? EV_ENTER_BLOCK : EV_SURFACE;
-            ev_t = c.last_t * t_scale;
-            ev_cell = word;
-            ev_post = POST_CONTINUE;
-            st = ST_EVENT;
-        };
-        if (P.event_threshold >= 32) {
-            while (__any_sync(0xffffffffu, st == ST_MARCH)) {
-                if (st == ST_MARCH) march_step();
-            }
-        } else {
-            for (;;) {
-                const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
-                if (!marching) break;
-                // only lanes that can make progress in the other phases count (idle lanes below the refill threshold cannot)
-                if (__popc(__ballot_sync(0xffffffffu, st == ST_EVENT || st == ST_DONE)) >= (int)P.event_threshold) break;
-                if (st == ST_MARCH) march_step();
-            }
-        }
-        __syncwarp();
-
-        // =========================== HEAVY: events =====================================================
-        // (1) DepthIter + the Volumetric loop (surface.rs:460-490, sr.rs:185-203) / the Surface loop (sr.rs:206-225):
-        //     decide which surface (if any) this event shades.
-        // (0) leaving the level / an iterator that cannot step
-        if (st == ST_EVENT && ev_kind == EV_STUCK) {   // ends without an exit step (raycast.rs:245-249)
-            if (inner) { pop_level(); st = ST_MARCH; } else { st = ST_DONE; }
-        }
-        if (st == ST_EVENT && ev_kind == EV_EXIT) {
-            // exit step: TraceStep::Invisible at this t (surface.rs:296-301, 388-393)
-            if (VOLUMETRIC && have_last) {
-                ev_kind = EV_INVISIBLE; ev_post = inner ? POST_POP : POST_FINISH;
-            } else if (count_stop() || !inner) {
-                st = ST_DONE;
-            } else {
-                pop_level();
-                st = ST_MARCH;
-            }
-        }
-        bool do_shade = false;
-        PendingSurface shade_sf;
-        double span_exit = 0.0;
-        if (st == ST_EVENT) {
-            bool stop;
-            if constexpr (VOLUMETRIC) {
-                do_shade = have_last;
-                load_pending(shade_sf);
-                span_exit = ev_t;
-                have_last = false;
-                stop = count_stop();
-            } else {
-                stop = count_stop();
-                if (!stop && ev_kind == EV_SURFACE) {
-                    record_surface(shade_sf, ev_cell, ev_t);
-                    do_shade = true;
-                }
-            }
-            if (stop) {
-                do_shade = false;
-                st = ST_DONE;
-            }
-        }
-        // (2) the surface leaves the marcher as a HitRecord; all that is evaluated here is an upper bound of the factor
-        //     by which it multiplies the ray's transmittance (apply_transmittance, limit_alpha, fog: sr.rs:720-768,
-        //     graphics_options.rs:496-507, raytracer_components.rs:87-92 give the exact factor in shade_kernel).
-        float h_thickness = 0.0f;
-        if (do_shade) {
-            const float alpha = __ldg(&S.palette[2 * (size_t)shade_sf.pal].w);
-            float m_ub;   // >= (1 - alpha_used) * (1 - fog); 1 also covers a surface that turns out invisible
-            if constexpr (VOLUMETRIC) {
-                h_thickness = fmaxf((float)((span_exit - shade_sf.t) * COLD_D(15)), 0.0f);
-                if (alpha == 1.0f) m_ub = 0.0f;                                  // alpha stays 1 for any thickness
-                else if (h_thickness == 0.0f || alpha == 0.0f) m_ub = 1.0f;
-                else m_ub = fminf(__powf(1.0f - alpha, h_thickness) * 1.001f + 1e-6f, 1.0f);
-            } else if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {
-                m_ub = (alpha > P.threshold) ? 0.0f : 1.0f;
-            } else {
-                m_ub = fminf((1.0f - alpha) * 1.000001f + 1e-7f, 1.0f);
-                if (alpha == 1.0f) m_ub = 0.0f;
-            }
-            T_ub = T_ub * m_ub * 1.000001f;
-        }
-        // emit the hits of this pass: slots come from the warp's block of the hit stream, a new block is taken
-        // (one atomic per HIT_BLOCK hits) when the current one cannot hold them all
-        {
-            const bool emit = do_shade;
-            const unsigned em = __ballot_sync(0xffffffffu, emit);
-            if (em) {
-                const uint32_t n_emit = (uint32_t)__popc(em);
-                if (hit_base == 0xffffffffu || hit_used + n_emit > HIT_BLOCK) {
-                    if (hit_base != 0xffffffffu && hit_used + (uint32_t)lane < HIT_BLOCK)
-                        P.hits[hit_base + hit_used + lane].pal = HIT_DEAD;   // fewer than 32 slots are left over
-                    uint32_t nb = 0;
-                    if (lane == 0) nb = atomicAdd(P.hit_counter, HIT_BLOCK);
-                    nb = __shfl_sync(0xffffffffu, nb, 0);
-                    if (nb >= P.hit_capacity) {  // (the capacity is a multiple of HIT_BLOCK)
-                        if (lane == 0) *P.overflow_flag = 1u;  // the host re-runs the frame with a larger buffer
-                        nb = 0xffffffffu;
-                    }
-                    hit_base = nb;
-                    hit_used = 0;
-                }
-                if (emit && hit_base != 0xffffffffu) {
-                    const uint32_t slot = hit_base + hit_used + (uint32_t)__popc(em & ((1u << lane) - 1u));
-                    HitRecord h;
-                    if (want_ip) { h.ip[0] = shade_sf.ip[0]; h.ip[1] = shade_sf.ip[1]; h.ip[2] = shade_sf.ip[2]; }
-                    else { h.ip[0] = h.ip[1] = h.ip[2] = 0.0; }
-                    h.t = shade_sf.t;
-                    h.pal = shade_sf.pal;
-                    h.cube[0] = shade_sf.cube[0]; h.cube[1] = shade_sf.cube[1]; h.cube[2] = shade_sf.cube[2];
-                    h.packed = shade_sf.packed;
-                    h.thickness = h_thickness;
-                    h.fog_rel = (float)shade_sf.t * __uint_as_float(COLD_W(12));
-                    h.flags = COLD_W(16) | ((uint32_t)shade_sf.res << 8);
-                    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
-                    uint4 *dst = reinterpret_cast<uint4 *>(P.hits + slot);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) st_stream(dst + k, src[k]);
-                    HitLink link;
-                    link.next = 0xffffffffu;
-                    link.steps = steps;
-                    *reinterpret_cast<uint2 *>(P.hit_link + slot) = *reinterpret_cast<const uint2 *>(&link);
-                    const uint32_t prev_hit = COLD_W(14);
-                    if (prev_hit != 0xffffffffu) P.hit_link[prev_hit].next = slot; else COLD_W(13) = slot;
-                    COLD_W(14) = slot;
-                }
-                if (hit_base != 0xffffffffu) hit_used += n_emit;
-            }
-        }
-        // (3) Volumetric: the surface that raised this event becomes the pending one (surface.rs:467-476)
-        if constexpr (VOLUMETRIC) {
-            if (st == ST_EVENT && ev_kind == EV_SURFACE) {
-                PendingSurface pending;
-                record_surface(pending, ev_cell, ev_t);
-                store_pending(pending);
-                have_last = true;
-            }
-        }
-        // (4b) the buffered DepthStep::EnterBlock is counted after the flushed span was traced
-        //      (surface.rs:478-488, sr.rs:185-203): its opacity test sees that span.
-        if constexpr (VOLUMETRIC) {
-            if (st == ST_EVENT && ev_kind == EV_ENTER_BLOCK) {
-                if (count_stop()) st = ST_DONE;
-            }
-        }
-        // (5) recursive_raycast (raycast.rs:458-476) + TraceStep::EnterBlock (surface.rs:334-352)
-        if (st == ST_EVENT && ev_kind == EV_ENTER_BLOCK) {
+        // =========================== recursive_raycast (raycast.rs:458-476) + TraceStep::EnterBlock ======
+        if (st == ST_ENTER) {
             if constexpr (AUX) aux.n_blocks++;
-            const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + ev_cell);
+            const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + ev_word);
             const uint4 b0 = __ldg(bp);
             const uint4 b1 = __ldg(bp + 1);
             const int bres = (int)(b0.x >> 8);
@@ -1217,32 +1097,65 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             in.nx = (int)(b0.z >> 16); in.ny = (int)(b0.w & 0xffff); in.nz = (int)(b0.w >> 16);
             in.base = b1.x;
             const double fres = (double)bres;
-            const int cx = c.rx + S.lo[0], cy = c.ry + S.lo[1], cz = c.rz + S.lo[2];
+            // the Space cube of this block, from its linear index
+            const uint32_t nyz = (uint32_t)S.size[1] * (uint32_t)S.size[2];
+            const uint32_t qx = idx / nyz, rem = idx - qx * nyz;
+            const uint32_t qy = rem / (uint32_t)S.size[2], qz = rem - qy * (uint32_t)S.size[2];
+            const int ccx = (int)qx + S.lo[0], ccy = (int)qy + S.lo[1], ccz = (int)qz + S.lo[2];
+            Ray rr;
+            rr.ox = COLD_D(0); rr.oy = COLD_D(1); rr.oz = COLD_D(2);
+            rr.dx = COLD_D(3); rr.dy = COLD_D(4); rr.dz = COLD_D(5);
+            rr.tdx = tdx; rr.tdy = tdy; rr.tdz = tdz;
+            rr.half_over_len = COLD_D(6);
+            rr.sx = (int)(sbits & 3u) - 1; rr.sy = (int)((sbits >> 2) & 3u) - 1; rr.sz = (int)((sbits >> 4) & 3u) - 1;
             Caster ic;
             bool ivalid;
-            Ray rr;
-            load_ray(rr, r);
-            if (caster_begin(ic, rr, (rr.ox - (double)cx) * fres, (rr.oy - (double)cy) * fres, (rr.oz - (double)cz) * fres, in,
+            if (caster_begin(ic, rr, (rr.ox - (double)ccx) * fres, (rr.oy - (double)ccy) * fres, (rr.oz - (double)ccz) * fres, in,
                              &ivalid)) {
-                COLD_D(7) = c.tmx; COLD_D(8) = c.tmy; COLD_D(9) = c.tmz; COLD_D(10) = c.last_t;
-                COLD_W(0) = (uint32_t)c.rx; COLD_W(1) = (uint32_t)c.ry; COLD_W(2) = (uint32_t)c.rz; COLD_W(3) = (uint32_t)c.face;
-                COLD_W(4) = c.idx; COLD_W(5) = valid ? 1u : 0u;
-                c = ic;
+                COLD_D(8) = tmx; COLD_D(9) = tmy; COLD_D(10) = tmz; COLD_D(11) = last_t;
+                COLD_W(0) = idx; COLD_W(1) = (uint32_t)cx; COLD_W(2) = (uint32_t)cy; COLD_W(3) = (uint32_t)cz;
+                COLD_W(4) = (uint32_t)face; COLD_W(5) = valid ? 1u : 0u;
+                COLD_W(9) = b1.y;
+                COLD_W(10) = (uint32_t)(31 - __clz(bres));
+                tmx = ic.tmx; tmy = ic.tmy; tmz = ic.tmz; last_t = ic.last_t;
+                idx = ic.idx;
+                face = ic.face;
                 valid = ivalid;
+                cx = rr.sx > 0 ? in.nx - 1 - ic.rx : (rr.sx < 0 ? ic.rx : COUNTER_STATIC);
+                cy = rr.sy > 0 ? in.ny - 1 - ic.ry : (rr.sy < 0 ? ic.ry : COUNTER_STATIC);
+                cz = rr.sz > 0 ? in.nz - 1 - ic.rz : (rr.sz < 0 ? ic.rz : COUNTER_STATIC);
+                stx = rr.sx * (in.ny * in.nz); sty = rr.sy * in.nz; stz = rr.sz;
                 inner = true;
-                nx = in.nx; ny = in.ny; nz = in.nz;
-                blk0y = b0.y; blk0z = b0.z;
-                pal_off = b1.y;
-                res = bres;
                 t_scale = recip_pow2(bres);
                 need_advance = false;
             }
+            st = ST_MARCH;
         }
-        // (6) what the event's producer wanted next
-        if (st == ST_EVENT) {
-            if (ev_post == POST_POP) pop_level();
-            st = (ev_post == POST_FINISH) ? ST_DONE : ST_MARCH;
+        // =========================== back to the Space level ==============================================
+        if (st == ST_POP) {
+            tmx = COLD_D(8); tmy = COLD_D(9); tmz = COLD_D(10); last_t = COLD_D(11);
+            idx = COLD_W(0); cx = (int)COLD_W(1); cy = (int)COLD_W(2); cz = (int)COLD_W(3);
+            face = (int)COLD_W(4);
+            valid = COLD_W(5) != 0;
+            const int sx = (int)(sbits & 3u) - 1, sy = (int)((sbits >> 2) & 3u) - 1, sz = (int)((sbits >> 4) & 3u) - 1;
+            stx = sx * (S.size[1] * S.size[2]); sty = sy * S.size[2]; stz = sz;
+            inner = false;
+            t_scale = 1.0;
+            need_advance = true;
+            st = ST_MARCH;
         }
+        // =========================== MARCH ================================================================
+        {
+            const int n_off = __popc(__ballot_sync(0xffffffffu, st == ST_EXHAUSTED || (list_exhausted && st == ST_IDLE)));
+            const int thr = list_exhausted ? 1 : (int)P.event_threshold;
+            for (;;) {
+                const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
+                if (!marching) break;
+                if (32 - __popc(marching) - n_off >= thr) break;   // enough lanes wait for the warp
+                if (st == ST_MARCH) step();
+            }
+        }
+        __syncwarp();
     }
 
     if (P.debug_warp_times) {
@@ -1254,9 +1167,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             d[0] = dbg_t0; d[1] = t1; d[2] = dbg_passes; d[3] = dbg_rays;
         }
     }
-    // the unused rest of this warp's block of the hit stream
-    if (hit_base != 0xffffffffu)
-        for (uint32_t j = hit_used + lane; j < HIT_BLOCK; j += 32) P.hits[hit_base + j].pal = HIT_DEAD;
+    // the unused rest of this lane's chunk of the hit stream: never shaded
+    if (chunk_base != HIT_NONE)
+        for (uint32_t j = chunk_used; j < HIT_CHUNK; j++) P.hits[chunk_base + j].thickness = -2.0f;
 
     if constexpr (AUX) {
 #pragma unroll
@@ -1271,15 +1184,55 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             atomicAdd(P.counters + 5, n_blocks);
         }
     }
+#undef COLD_D
+#undef COLD_W
+}
+
+// Position of a hit (hit.rs:92-101) from its record: Space cube, voxel, resolution, face, and the palette entry.
+struct HitGeom {
+    int cube[3];
+    int voxel[3];
+    int res;
+    int face;
+    uint32_t pal;
+};
+AICB_DEV void decode_hit(const DeviceScene &S, const HitRecord &h, HitGeom &g) {
+    const uint32_t nz = (uint32_t)S.size[2], nyz = (uint32_t)S.size[1] * nz;
+    const uint32_t qx = h.cell / nyz, rem = h.cell - qx * nyz;
+    const uint32_t qy = rem / nz, qz = rem - qy * nz;
+    g.cube[0] = (int)qx + S.lo[0]; g.cube[1] = (int)qy + S.lo[1]; g.cube[2] = (int)qz + S.lo[2];
+    g.face = (int)(h.flags & 7u);
+    if (h.flags & 8u) {
+        const uint32_t id = S.wide_cells ? (__ldg((const uint32_t *)S.cells + h.cell) & 0xffffu)
+                                         : ((uint32_t)__ldg((const uint16_t *)S.cells + h.cell) & 0x3fffu);
+        const uint4 *bp = reinterpret_cast<const uint4 *>(S.blocks + id);
+        const uint4 b0 = __ldg(bp);
+        const uint32_t brick_off = __ldg(bp + 1).x;
+        const uint32_t vny = b0.w & 0xffffu, vnz = b0.w >> 16;
+        const uint32_t local = h.vidx - brick_off;
+        const uint32_t vx = local / (vny * vnz), vrem = local - vx * (vny * vnz);
+        const uint32_t vy = vrem / vnz, vz = vrem - vy * vnz;
+        g.voxel[0] = (int)vx + (int)(int16_t)(b0.y & 0xffff);
+        g.voxel[1] = (int)vy + (int)(int16_t)(b0.y >> 16);
+        g.voxel[2] = (int)vz + (int)(int16_t)(b0.z & 0xffff);
+        g.res = 1 << ((h.flags >> 4) & 15u);
+        g.pal = h.word;
+    } else {
+        g.voxel[0] = g.voxel[1] = g.voxel[2] = 0;
+        g.res = 1;
+        g.pal = __ldg(reinterpret_cast<const uint4 *>(S.blocks + (h.word & 0xffffu)) + 1).y;
+    }
 }
 
 // ======================================================================================================
 // Kernel 3 — shading: one thread per HitRecord, fully convergent.  Everything about a surface that does not depend
-// on the surfaces in front of it: apply_transmittance (sr.rs:720-740, raytracer_components.rs:215-258; Volumetric
-// only), limit_alpha (graphics_options.rs:496-507), the invisibility test of Surface::to_light (surface.rs:78-82),
-// compute_illumination (surface.rs:113-206), reflect + emission (color.rs:708-710), distance fog
-// (sr.rs:745-768, surface.rs:97-100).  Output per hit: the outgoing light and the factor by which the surface
-// multiplies the ray's transmittance (add_color_internal, raytracer_components.rs:87-92), or "skip".
+// on the surfaces in front of it: its position (cube, voxel, face) and intersection point (raycast.rs:409-439,
+// surface.rs:406-407) from the recorded caster state, apply_transmittance (sr.rs:720-740,
+// raytracer_components.rs:215-258; Volumetric only), limit_alpha (graphics_options.rs:496-507), the invisibility
+// test of Surface::to_light (surface.rs:78-82), compute_illumination (surface.rs:113-206), reflect + emission
+// (color.rs:708-710), distance fog (sr.rs:745-768, surface.rs:97-100).  Output per hit: the outgoing light and the
+// factor by which the surface multiplies the ray's transmittance (add_color_internal,
+// raytracer_components.rs:87-92), or "skip".
 // ======================================================================================================
 template <int LC>
 __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ TraceParams P) {
@@ -1301,9 +1254,22 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
 #pragma unroll
             for (int k = 0; k < 4; k++) dst[k] = ld_stream(src + k);
         }
-        if (h.pal == HIT_DEAD) continue;
-        const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
-        const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
+        ShadedHit out;
+        out.r = out.g = out.b = 0.0f;
+        out.factor = -1.0f;
+        out.next = h.next;
+        out.steps = h.steps;
+        out._pad[0] = out._pad[1] = 0;
+        uint4 *outp = reinterpret_cast<uint4 *>(P.shaded + i);
+        if (!(h.thickness >= 0.0f)) {   // a chunk slot that was never filled, or a surface whose ray stopped before shading it
+            outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+            outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
+            continue;
+        }
+        HitGeom g;
+        decode_hit(S, h, g);
+        const float4 col = __ldg(S.palette + 2 * (size_t)g.pal);
+        const float4 emi = __ldg(S.palette + 2 * (size_t)g.pal + 1);
         float ca = col.w;
         float coeff = 1.0f;
         bool zeroed = false;
@@ -1331,13 +1297,18 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
             if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
         }
         if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) {   // nothing to see: the ray is not touched
-            P.hit_contrib[i] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+            outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+            outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
             continue;
         }
+        // what the shading needs of the ray
+        const RayRecord *rp = P.ray_records + h.task;
+        const uint32_t rflags = __ldg(&rp->flags);
+        const double t_scale = recip_pow2(g.res);
         float tr = 1.0f - ca;
         float fa = -1.0f;
         if (have_fog) {  // distance_fog (sr.rs:745-768)
-            float rel = h.fog_rel;
+            float rel = (float)(h.last_t * t_scale) * __ldg(&rp->t_to_view);
             rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
             const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
             const float fudged = fog_exponential / 0.79810348f;
@@ -1347,9 +1318,9 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         }
         const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
         float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
-        const int face = (int)(h.packed >> 24);
+        const int face = g.face;
         if constexpr (LC == LC_FLAT) {
-            int x = h.cube[0], y = h.cube[1], z = h.cube[2];
+            int x = g.cube[0], y = g.cube[1], z = g.cube[2];
             if (face != AICB_FACE_WITHIN) {
                 const int dd = face >= AICB_FACE_PX ? 1 : -1;
                 const int ax = (face - 1) % 3;
@@ -1360,9 +1331,32 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
             texels += tx;
             i0 = s_lut[t & 255]; i1 = s_lut[(t >> 8) & 255]; i2 = s_lut[(t >> 16) & 255];
         } else if constexpr (LC == LC_INTERP) {
+            // RaycastStep::intersection_point (raycast.rs:409-439) of the level the surface is on, brought to
+            // Space coordinates (surface.rs:406-407)
+            Ray rr;
+            {
+                const double2 *q = reinterpret_cast<const double2 *>(rp);
+                const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                rr.ox = q0.x; rr.oy = q0.y; rr.oz = q1.x; rr.dx = q1.y; rr.dy = q2.x; rr.dz = q2.y;
+            }
+            rr.sx = (int)((rflags >> 6) & 3u) - 1; rr.sy = (int)((rflags >> 8) & 3u) - 1; rr.sz = (int)((rflags >> 10) & 3u) - 1;
+            Caster c;
+            c.tmx = h.tmx; c.tmy = h.tmy; c.tmz = h.tmz; c.last_t = h.last_t;
+            c.face = face;
+            double ip[3];
+            if (!(h.flags & 8u)) {
+                intersection_point(c, rr, g.cube[0], g.cube[1], g.cube[2], rr.ox, rr.oy, rr.oz, ip);
+            } else {
+                const double fres = (double)g.res;
+                intersection_point(c, rr, g.voxel[0], g.voxel[1], g.voxel[2], (rr.ox - (double)g.cube[0]) * fres,
+                                   (rr.oy - (double)g.cube[1]) * fres, (rr.oz - (double)g.cube[2]) * fres, ip);
+                ip[0] = ip[0] * t_scale + (double)g.cube[0];
+                ip[1] = ip[1] * t_scale + (double)g.cube[1];
+                ip[2] = ip[2] * t_scale + (double)g.cube[2];
+            }
             uint32_t tx = 0;
             float il[3];
-            interpolated_light(S, s_lut, P.lighting, h.cube[0], h.cube[1], h.cube[2], face, h.ip[0], h.ip[1], h.ip[2], il, &tx);
+            interpolated_light(S, s_lut, P.lighting, g.cube[0], g.cube[1], g.cube[2], face, ip[0], ip[1], ip[2], il, &tx);
             i0 = il[0]; i1 = il[1]; i2 = il[2];
             texels += tx;
         }
@@ -1370,13 +1364,15 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         float og = ps_mul(ps_mul(cg, i1), ca) + eg;
         float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
         if (fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
-            const int k = S.sky_kind ? (int)(h.flags & 7u) : 0;
+            const int k = S.sky_kind ? (int)((rflags >> 12) & 7u) : 0;
             const float comp = 1.0f - fa;
             orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], fa);
             og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], fa);
             ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], fa);
         }
-        P.hit_contrib[i] = make_float4(orr, og, ob, tr);
+        out.r = orr; out.g = og; out.b = ob; out.factor = tr;
+        outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+        outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
     }
     // one atomic per warp: 150 K single-address atomics would cost more than the shading itself
 #pragma unroll
@@ -1414,24 +1410,29 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
             uint32_t steps = o.steps;
             uint32_t sample_first = 0xffffffffu;
             for (uint32_t hi = o.first_hit; hi != 0xffffffffu;) {
-                const float4 c = P.hit_contrib[hi];
-                const HitLink link = P.hit_link[hi];
-                if (c.w >= 0.0f) {   // (a skipped surface leaves the ray untouched)
-                    lr = lr + c.x * T; lg = lg + c.y * T; lb = lb + c.z * T;
-                    T = T * c.w;
+                ShadedHit c;
+                {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(P.shaded + hi);
+                    reinterpret_cast<uint4 *>(&c)[0] = src[0];
+                    reinterpret_cast<uint4 *>(&c)[1] = src[1];
+                }
+                if (c.factor >= 0.0f) {   // (a skipped surface leaves the ray untouched)
+                    lr = lr + c.r * T; lg = lg + c.g * T; lb = lb + c.b * T;
+                    T = T * c.factor;
                     n_hits++;
                     if (sample_first == 0xffffffffu) sample_first = hi;
                     if (T < (1.0f / 256.0f)) {
                         // the reference stops at the first step it counts after this hit; the marcher, which only
                         // had an upper bound of T, may have gone further
-                        if (steps > link.steps) steps = link.steps + 1;
+                        if (steps > c.steps) steps = c.steps + 1;
                         break;
                     }
                 }
-                hi = link.next;
+                hi = c.next;
             }
             if (sample_first != 0xffffffffu && (P.out_depth || P.out_hit)) {
-                depth = fmin(depth, P.hits[sample_first].t);
+                const HitRecord *hr = P.hits + sample_first;   // Hit::t_distance = last_t / resolution (surface.rs:385-386)
+                depth = fmin(depth, hr->last_t * recip_pow2(1 << ((hr->flags >> 4) & 15u)));
                 if (first_valid == 0xffffffffu) first_valid = sample_first;
             }
             if (P.include_sky) {  // the sky is an opaque hit at t = inf
@@ -1476,12 +1477,18 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
         if (P.out_hit) {
             aicb_hit hh;
             if (first_valid != 0xffffffffu) {
-                const HitRecord *hr = P.hits + first_valid;
-                const uint32_t packed = hr->packed;
-                hh.cube[0] = hr->cube[0]; hh.cube[1] = hr->cube[1]; hh.cube[2] = hr->cube[2];
-                hh.voxel[0] = (int)(packed & 255u); hh.voxel[1] = (int)((packed >> 8) & 255u); hh.voxel[2] = (int)((packed >> 16) & 255u);
-                hh.resolution = (int)(hr->flags >> 8);
-                hh.face = (int)(packed >> 24);
+                HitRecord hr;
+                {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + first_valid);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) reinterpret_cast<uint4 *>(&hr)[q] = src[q];
+                }
+                HitGeom g;
+                decode_hit(S, hr, g);
+                hh.cube[0] = g.cube[0]; hh.cube[1] = g.cube[1]; hh.cube[2] = g.cube[2];
+                hh.voxel[0] = g.voxel[0]; hh.voxel[1] = g.voxel[1]; hh.voxel[2] = g.voxel[2];
+                hh.resolution = g.res;
+                hh.face = g.face;
             } else {
                 hh.cube[0] = hh.cube[1] = hh.cube[2] = -1;
                 hh.voxel[0] = hh.voxel[1] = hh.voxel[2] = -1;

@@ -25,12 +25,15 @@ def main():
             for th in thresholds:
                 os.environ["AICB_REFILL_THRESHOLD"] = str(th)
                 os.environ["AICB_EVENT_THRESHOLD"] = str(ev)
-                ms = []
+                ms, stages = [], []
                 for i in range(6):
                     img = r.draw()
                     if i >= 2:
                         ms.append(img.info.kernel_ms)
-                print(f"{name} event_thr={ev:2d} refill_thr={th:2d} frame_ms={np.mean(ms):.3f} (min {np.min(ms):.3f})  Mrays/s={w * h / np.mean(ms) / 1e3:.0f}", flush=True)
+                        stages.append([float(v) for v in img.info.stage_ms])
+                st = np.mean(np.array(stages), axis=0)
+                print(f"{name} event_thr={ev:2d} refill_thr={th:2d} frame_ms={np.mean(ms):.3f} (min {np.min(ms):.3f})  "
+                      f"gen/march/shade/encode {st[0]:.3f}/{st[1]:.3f}/{st[2]:.3f}/{st[3]:.3f}  Mrays/s={w * h / np.mean(ms) / 1e3:.0f}", flush=True)
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@ def main():
         workloads = sys.argv[2]
         for name in sys.argv[3:]:
             env = dict(os.environ, AICB200_LIB=os.path.join(OUT, f"lib_{name}.so"))
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kernel_sweep.py"), workloads, "16", "32"],
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kernel_sweep.py"), workloads, "1", os.environ.get("SWEEP_EV", "12")],
                                env=env, capture_output=True, text=True, timeout=300)
             for line in r.stdout.splitlines():
                 print(f"[{name}] {line}", flush=True)
