@@ -424,11 +424,12 @@ class RenderInfo:
     counters: tuple
     kernel_ms: float
     flaws: int
+    stage_ms: tuple = (0.0, 0.0, 0.0, 0.0)   # ray generation, marching, shading, encode (first chunk)
 
     @staticmethod
     def from_abi(i: abi.RenderInfo) -> "RenderInfo":
         return RenderInfo(int(i.cubes_traced), int(i.rays), int(i.algorithmic_bytes), tuple(int(c) for c in i.counters),
-                          float(i.kernel_ms), int(i.flaws))
+                          float(i.kernel_ms), int(i.flaws), tuple(float(v) for v in i.stage_ms))
 
 
 @dataclasses.dataclass

@@ -161,6 +161,17 @@ static float2 surface_entry(float alpha) {
     return make_float2(alpha, l2a);
 }
 
+// blk_tab entry of a block: what the marching kernel needs of a single-voxel surface on the Space level.
+// `pal_off` indexes `pal_tab`; `pal_base` is added to it for the device-wide palette index.
+static float4 block_entry(uint8_t kind, uint32_t pal_off, const std::vector<float2> &pal_tab, uint32_t pal_base) {
+    if (kind != KIND_SINGLE) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float2 e = pal_tab[pal_off];
+    const uint32_t pal = pal_off + pal_base;
+    float palf;
+    std::memcpy(&palf, &pal, 4);
+    return make_float4(e.x, e.y, palf, 0.0f);
+}
+
 static aicb_status flatten_block(const aicb_block_desc &b, BlockRec &r, uint8_t &kind, std::vector<uint16_t> &bricks,
                                  std::vector<float4> &palette, std::vector<float2> &pal_tab) {
     std::memset(&r, 0, sizeof r);
@@ -368,7 +379,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         int v = e ? atoi(e) : 1;
         P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         const char *e2 = getenv("AICB_EVENT_THRESHOLD");
-        int v2 = e2 ? atoi(e2) : 12;
+        int v2 = e2 ? atoi(e2) : 24;
         P.event_threshold = (uint32_t)(v2 < 1 ? 1 : (v2 > 32 ? 32 : v2));
     }
 
@@ -613,11 +624,12 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
     std::vector<uint8_t> kinds(d->n_blocks);
     std::vector<uint16_t> bricks;
     std::vector<float4> palette;
-    std::vector<float2> pal_tab, blk_tab(d->n_blocks);
+    std::vector<float2> pal_tab;
+    std::vector<float4> blk_tab(d->n_blocks);
     for (size_t i = 0; i < d->n_blocks; i++) {
         aicb_status fst = flatten_block(d->blocks[i], recs[i], kinds[i], bricks, palette, pal_tab);
         if (fst != AICB_OK) return fst;
-        blk_tab[i] = kinds[i] == KIND_SINGLE ? pal_tab[recs[i].pal_off] : make_float2(0.0f, 0.0f);
+        blk_tab[i] = block_entry(kinds[i], recs[i].pal_off, pal_tab, 0);
     }
 
     aicb_scene *s = new aicb_scene();
@@ -686,9 +698,9 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
         s->device_bytes += pal_tab.size() * sizeof(float2);
     }
     if (!blk_tab.empty()) {
-        CUS(cudaMalloc(&s->d_blk_tab, blk_tab.size() * sizeof(float2)));
-        CUS(cudaMemcpy(s->d_blk_tab, blk_tab.data(), blk_tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        s->device_bytes += blk_tab.size() * sizeof(float2);
+        CUS(cudaMalloc(&s->d_blk_tab, blk_tab.size() * sizeof(float4)));
+        CUS(cudaMemcpy(s->d_blk_tab, blk_tab.data(), blk_tab.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        s->device_bytes += blk_tab.size() * sizeof(float4);
     }
 #undef CUS
     ds.cells = s->d_cells;
@@ -859,8 +871,7 @@ aicb_status aicb_scene_update_blocks(aicb_scene *s, const uint16_t *indices, con
     std::vector<uint8_t> kind_changed(n_blocks, 0);
     for (size_t i = 0; i < n; i++) {
         BlockRec &r = recs[i];
-        float2 bt = make_float2(0.0f, 0.0f);
-        if (kinds[i] == KIND_SINGLE) bt = pal_tab[r.pal_off];
+        const float4 bt = block_entry(kinds[i], r.pal_off, pal_tab, (uint32_t)n_pal_old);
         if (kinds[i] == KIND_RECURSIVE) r.brick_off += (uint32_t)s->n_bricks;
         if (kinds[i] != KIND_INVISIBLE || !descs[i].is_air) r.pal_off += (uint32_t)n_pal_old;
         CU(cudaMemcpy(s->d_blocks + indices[i], &r, sizeof r, cudaMemcpyHostToDevice));

@@ -71,7 +71,7 @@ struct aicb_scene {
     uint16_t *d_bricks = nullptr;
     float4 *d_palette = nullptr;
     float2 *d_pal_tab = nullptr;   // per palette entry: {alpha, log2(1 - alpha) bound} (marching kernel)
-    float2 *d_blk_tab = nullptr;   // per block id: the same pair for single-voxel blocks
+    float4 *d_blk_tab = nullptr;   // per block id: that pair and the palette entry of single-voxel blocks
     size_t n_bricks = 0, n_palette = 0;   // elements in d_bricks / d_palette (aicb_scene_update_blocks appends)
     // state of the last asynchronous render
     bool pending = false;

@@ -64,8 +64,8 @@ struct DeviceScene {
     const BlockRec *blocks;
     const uint16_t *bricks;     // palette index | invisible<<15
     const float4 *palette;      // 2 x float4 per entry: rgba, emission
-    const float2 *blk_tab;      // per block id (single-voxel blocks): {alpha, upper bound of log2(1 - alpha)}
-    const float2 *pal_tab;      // per palette entry: the same pair (what the marching kernel needs of a surface)
+    const float4 *blk_tab;      // per block id (single-voxel blocks): {alpha, upper bound of log2(1 - alpha), palette entry (bits), -}
+    const float2 *pal_tab;      // per palette entry: {alpha, log2 bound} (what the marching kernel needs of a surface)
     const float *tables;        // [0,256): PackedLight decode LUT (data.rs:301-354); [256,512): sRGB8 thresholds;
                                 // [512,768): PackedLight quantiser thresholds (light kernels)
     uint32_t sky_faces[6];      // BlockSky faces NX..PZ as texels (sky.rs:54-82)
@@ -99,7 +99,7 @@ static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
 struct __align__(16) HitRecord {
     double tmx, tmy, tmz;   // State::t_max of the level the surface is on (unscaled)
     double last_t;          // State::last_t_distance of that level: Hit::t_distance = last_t / resolution
-    uint32_t word;          // outer level: block id | HIT_WORD_BLOCK; inner level: palette entry (global index)
+    uint32_t pal;           // palette entry (global index)
     uint32_t cell;          // linear index of the Space cube
     uint32_t vidx;          // inner level: index of the voxel in the brick pool
     uint32_t flags;         // face | inner<<3 | log2(resolution)<<4
@@ -109,7 +109,7 @@ struct __align__(16) HitRecord {
                             // counted step after the hit that brings the transmittance under 1/256; encode_kernel
                             // needs the counter to restore that when the marcher's bound let the ray run on)
     uint32_t task;          // the ray: index of its RayRecord in the chunk
-    uint32_t next;          // next hit of the same ray (HIT_NONE = none)
+    uint32_t next;          // in the last slot of a chunk: where the ray's hits continue (the first slot of another chunk)
 };
 static_assert(sizeof(HitRecord) == 64, "HitRecord must be 64 bytes");
 
@@ -128,7 +128,7 @@ struct __align__(16) TaskOut {
     uint32_t first_hit;  // index of the first HitRecord or 0xffffffff
     uint32_t steps;      // steps counted by the marcher (>= the reference's; see HitRecord::steps)
     uint32_t flags;      // sky octant
-    uint32_t _pad;
+    uint32_t n_hits;     // hit records of this ray (consecutive slots; the last slot of a chunk links to the next chunk)
 };
 
 struct TraceParams {
@@ -192,11 +192,13 @@ constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (templ
 constexpr int TILE_W = 8, TILE_H = 4;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int N_BINS = 8;            // chord-length classes of the ray list (longest first)
-constexpr uint32_t HIT_CHUNK = 16;   // hit slots a lane takes from the stream at a time (one atomic per chunk)
+#ifndef AICB_HIT_CHUNK
+#define AICB_HIT_CHUNK 8
+#endif
+constexpr uint32_t HIT_CHUNK = AICB_HIT_CHUNK;   // hit slots a lane takes from the stream at a time (one atomic per chunk)
 constexpr uint32_t HIT_NONE = 0xffffffffu;
-constexpr uint32_t HIT_WORD_BLOCK = 0x80000000u;  // HitRecord::word holds a block id (outer level), not a palette entry
 #ifndef AICB_MIN_BLOCKS
-#define AICB_MIN_BLOCKS 4
+#define AICB_MIN_BLOCKS 5
 #endif
 #ifndef AICB_STREAM_HINTS
 #define AICB_STREAM_HINTS 0
@@ -249,8 +251,23 @@ AICB_DEV void st_stream(uint4 *p, uint4 v) {
 
 AICB_DEV int signum_101(double x) { return (x == 0.0 || x != x) ? 0 : (x < 0.0 ? -1 : 1); }
 
-// scale_to_integer_step (raycast.rs:797-819). fmod(s, 1) == s - trunc(s) exactly.
-AICB_DEV double scale_to_integer_step(double s, double ds) {
+// a / b, correctly rounded, given rb = RN(1 / b): two Newton corrections with exact remainders (Markstein: with a
+// correctly rounded reciprocal and a faithful quotient, q + (a - b q) rb rounds to RN(a / b)).  The ray's t_delta IS
+// RN(1 / |direction|) (raycast.rs:769), so the divisions by the direction in Raycaster::within / fast_forward /
+// scale_to_integer_step cost five FP64 instructions instead of a division routine.  Outside a generous exponent
+// window (where an intermediate could leave the normal range) the real division is used.
+AICB_DEV double div_known_recip(double a, double b, double rb) {
+    const double ab = fabs(b);
+    if (!((ab >= 0x1p-400) & (ab <= 0x1p400) & (fabs(a) <= 0x1p200))) return a / b;
+    const double q0 = a * rb;
+    const double r0 = fma(-b, q0, a);
+    const double q1 = fma(r0, rb, q0);
+    const double r1 = fma(-b, q1, a);
+    return fma(r1, rb, q1);
+}
+
+// scale_to_integer_step (raycast.rs:797-819). fmod(s, 1) == s - trunc(s) exactly.  rds = RN(1 / |ds|).
+AICB_DEV double scale_to_integer_step(double s, double ds, double rds) {
     if (ds == 0.0 && !(s != s)) return D_INF;
     if (ds < 0.0) {
         s = -s;
@@ -258,7 +275,7 @@ AICB_DEV double scale_to_integer_step(double s, double ds) {
     }
     double r = s - trunc(s);
     if (r < 0.0) r = r + 1.0;
-    return (1.0 - r) / ds;
+    return div_known_recip(1.0 - r, ds, rds);
 }
 
 // 1 / res for res = 2^k (Resolution::recip_f64): exact, no division
@@ -305,9 +322,9 @@ AICB_NOINLINE bool caster_begin(Caster &c, const Ray &r, double ox, double oy, d
     // fast_forward: (plane - origin) / direction per moving axis; the dot products with an axis
     // normal reduce exactly to this quotient.
     double max_t = 0.0;
-    if (r.sx != 0) max_t = fmax(max_t, ((double)(r.sx < 0 ? lv.lox + lv.nx : lv.lox) - ox) / r.dx);
-    if (r.sy != 0) max_t = fmax(max_t, ((double)(r.sy < 0 ? lv.loy + lv.ny : lv.loy) - oy) / r.dy);
-    if (r.sz != 0) max_t = fmax(max_t, ((double)(r.sz < 0 ? lv.loz + lv.nz : lv.loz) - oz) / r.dz);
+    if (r.sx != 0) max_t = fmax(max_t, div_known_recip((double)(r.sx < 0 ? lv.lox + lv.nx : lv.lox) - ox, r.dx, r.sx < 0 ? -r.tdx : r.tdx));
+    if (r.sy != 0) max_t = fmax(max_t, div_known_recip((double)(r.sy < 0 ? lv.loy + lv.ny : lv.loy) - oy, r.dy, r.sy < 0 ? -r.tdy : r.tdy));
+    if (r.sz != 0) max_t = fmax(max_t, div_known_recip((double)(r.sz < 0 ? lv.loz + lv.nz : lv.loz) - oz, r.dz, r.sz < 0 ? -r.tdz : r.tdz));
 
     double px = ox, py = oy, pz = oz, t0 = 0.0;
     if (max_t > 0.0) {
@@ -320,9 +337,9 @@ AICB_NOINLINE bool caster_begin(Caster &c, const Ray &r, double ox, double oy, d
         t0 = t_start;
     }
     int cx = __double2int_rd(px), cy = __double2int_rd(py), cz = __double2int_rd(pz);
-    c.tmx = scale_to_integer_step(px, r.dx) + t0;
-    c.tmy = scale_to_integer_step(py, r.dy) + t0;
-    c.tmz = scale_to_integer_step(pz, r.dz) + t0;
+    c.tmx = scale_to_integer_step(px, r.dx, r.tdx) + t0;
+    c.tmy = scale_to_integer_step(py, r.dy, r.tdy) + t0;
+    c.tmz = scale_to_integer_step(pz, r.dz, r.tdz) + t0;
     c.last_t = t0;
     c.face = AICB_FACE_WITHIN;
     const bool ok = tmax_valid(c, r);
@@ -389,11 +406,9 @@ AICB_DEV bool caster_step(Caster &c, const Ray &r, int nx, int ny, int nz) {
 // state (cube given in absolute coordinates of its level), against that level's ray origin.
 AICB_DEV void intersection_point(const Caster &c, const Ray &r, int cx, int cy, int cz, double ox, double oy, double oz,
                                  double ip[3]) {
-    if (c.face == AICB_FACE_WITHIN) {
-        ip[0] = ox; ip[1] = oy; ip[2] = oz;
-        return;
-    }
-    const int fa = (c.face - 1) % 3;
+    // select-based (the face axis differs between the lanes of the shading kernel)
+    const bool within = c.face == AICB_FACE_WITHIN;
+    const int fa = within ? -1 : (c.face - 1) % 3;
     const double tm[3] = {c.tmx, c.tmy, c.tmz};
     const double d[3] = {r.dx, r.dy, r.dz};
     const double o[3] = {ox, oy, oz};
@@ -401,16 +416,12 @@ AICB_DEV void intersection_point(const Caster &c, const Ray &r, int cx, int cy, 
     const int cu[3] = {cx, cy, cz};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        double p = (double)cu[a];
-        if (a == fa) {
-            if (s[a] < 0) p += 1.0;
-        } else if (s[a] == 0) {
-            p = o[a];
-        } else {
-            double off = (tm[a] - c.last_t) * d[a];
-            p += (s[a] > 0) ? (1.0 - rclamp01(off)) : rclamp01(-off);
-        }
-        ip[a] = p;
+        const double base = (double)cu[a];
+        const double off = (tm[a] - c.last_t) * d[a];
+        const double p_face = s[a] < 0 ? base + 1.0 : base;
+        const double p_other = base + ((s[a] > 0) ? (1.0 - rclamp01(off)) : rclamp01(-off));
+        const double p = (a == fa) ? p_face : (s[a] == 0 ? o[a] : p_other);
+        ip[a] = within ? o[a] : p;
     }
 }
 
@@ -804,7 +815,7 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
         o.first_hit = 0xffffffffu;
         o.steps = 0;
         o.flags = octant;
-        o._pad = 0;
+        o.n_hits = 0;
         *reinterpret_cast<uint4 *>(P.task_out + i) = *reinterpret_cast<const uint4 *>(&o);
     }
 }
@@ -835,14 +846,15 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
 
     // Cold per-ray state lives in shared memory, one column per thread, so that the registers of the marching loop
     // hold only what a DDA step touches; the level switches read what they need into short-lived locals.
-    __shared__ double sh_d[12][WARPS_PER_BLOCK * 32];
-    __shared__ uint32_t sh_w[11][WARPS_PER_BLOCK * 32];
+    __shared__ double sh_d[13][WARPS_PER_BLOCK * 32];
+    __shared__ uint32_t sh_w[13][WARPS_PER_BLOCK * 32];
     const int tid = threadIdx.x;
 #define COLD_D(k) sh_d[k][tid]
 #define COLD_W(k) sh_w[k][tid]
     // doubles: 0-2 origin, 3-5 direction, 6 half_over_len, 7 t_to_abs, 8-10 outer t_max while inside a block, 11 outer last_t
     // words:   0 outer index (= the Space cube of the entered block), 1-3 outer step counters, 4 outer face, 5 outer valid,
-    //          6 task, 7 first hit, 8 sky octant, 9 palette offset of the entered block, 10 log2(resolution) of it
+    //          6 task, 7 first hit, 8 sky octant, 9 palette offset of the entered block, 10 log2(resolution) of it,
+    //          11 pending surface's slot, 12 its log2(1 - alpha) bound;  double 12: its entry t
     unsigned long long dbg_t0 = 0, dbg_passes = 0, dbg_rays = 0;
     if (P.debug_warp_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
@@ -872,12 +884,11 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     // Upper bound of log2 of the ColorBuf transmittance (never below the exact value the encode kernel computes).
     // Once it is under -8 the ray is certainly finished (sr.rs:648-652); in the rare case that only the exact value is
     // under 1/256 the marcher runs on and the encode kernel cuts the ray's hits and steps back (HitRecord::steps).
+    // count_step_should_stop is then ONE compare per step: steps > step_limit, with step_limit = 1000 (sr.rs:639-643)
+    // until the bound says "opaque", 0 from then on.
     float L = 0.0f;
-    uint32_t steps = 0;
-    double pend_t = 0.0;                 // Volumetric: entry t of the surface whose span is open (surface.rs:467-476)
-    uint32_t pend_slot = HIT_NONE;
-    float pend_l2a = 0.0f;
-    uint32_t last_slot = HIT_NONE;       // the ray's latest hit record (its `next` is patched by the following one)
+    uint32_t steps = 0, step_limit = 1000u;
+    uint32_t n_hits = 0;                 // hit records of the current ray (consecutive slots of this lane's chunks)
     uint32_t chunk_base = HIT_NONE, chunk_used = HIT_CHUNK;   // this lane's chunk of the hit stream
     uint32_t ev_word = 0;
     AuxState<AUX> aux;
@@ -886,7 +897,10 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     // log-domain bound of one transmittance factor.  Exact factor (shade_kernel): 1 - clamp(1 - (f32)pow(u, th)) with
     // u = 1 - alpha, i.e. <= u^th (1 + 2^-23) + 2^-24; with u^th >= 2^-8.5 that is <= u^th * 2^(3.3e-5).  l2a >= log2(u)
     // (host, rounded up); the f32 product and sum add < 2e-6.  A factor under 2^-8.5 makes the ray opaque by itself.
-    auto bound_factor = [&](float p) { L = (p < -8.5f) ? F_NEG_INF : L + (p + 1e-4f); };
+    auto bound_factor = [&](float p) {
+        L = (p < -8.5f) ? F_NEG_INF : L + (p + 1e-4f);
+        step_limit = (L < -8.0f) ? 0u : 1000u;
+    };
 
     // State::step (raycast.rs:577-626) on the active level, select-based so that lanes stepping along different axes
     // stay converged.  Axis choice as the reference: x if t_max.x is strictly the smallest, else y if
@@ -912,15 +926,25 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     };
 
     // A visible surface (surface.rs:322-331, 399-409): its hit record goes to the lane's chunk of the hit stream.
-    auto emit_surface = [&](uint32_t word, double t_now) {
-        const uint32_t entry = inner ? COLD_W(9) + word : word;
-        const float2 te = __ldg((inner ? S.pal_tab : S.blk_tab) + entry);
+    auto emit_surface = [&](uint32_t word) {
+        uint32_t entry;   // palette entry of the surface, and what the transmittance bound needs of it
+        float2 te;
+        if (inner) {
+            entry = COLD_W(9) + word;
+            te = __ldg(S.pal_tab + entry);
+        } else {
+            const float4 t4 = __ldg(S.blk_tab + word);
+            te = make_float2(t4.x, t4.y);
+            entry = __float_as_uint(t4.z);
+        }
         if (chunk_used == HIT_CHUNK) {   // one atomic per HIT_CHUNK hits of this lane
             const uint32_t nb = atomicAdd(P.hit_counter, HIT_CHUNK);
             if (nb + HIT_CHUNK > P.hit_capacity) {   // (the capacity is a multiple of HIT_CHUNK)
                 *P.overflow_flag = 1u;               // the host re-runs the frame with a larger buffer
                 chunk_base = HIT_NONE;
             } else {
+                // a ray's records are consecutive slots; the last slot of a chunk says where they continue
+                if (chunk_base != HIT_NONE && n_hits != 0) P.hits[chunk_base + HIT_CHUNK - 1].next = nb;
                 chunk_base = nb;
             }
             chunk_used = 0;
@@ -934,16 +958,16 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                                       (uint32_t)__double2loint(tmy), (uint32_t)__double2hiint(tmy)));
             st_stream(dst + 1, make_uint4((uint32_t)__double2loint(tmz), (uint32_t)__double2hiint(tmz),
                                           (uint32_t)__double2loint(last_t), (uint32_t)__double2hiint(last_t)));
-            st_stream(dst + 2, make_uint4(inner ? entry : (word | HIT_WORD_BLOCK), inner ? COLD_W(0) : idx, idx,
+            st_stream(dst + 2, make_uint4(entry, inner ? COLD_W(0) : idx, idx,
                                           (uint32_t)face | (inner ? (8u | (COLD_W(10) << 4)) : 0u)));
             st_stream(dst + 3, make_uint4(__float_as_uint(VOLUMETRIC ? -1.0f : 0.0f), steps, COLD_W(6), HIT_NONE));
-            if (last_slot != HIT_NONE) P.hits[last_slot].next = slot; else COLD_W(7) = slot;
-            last_slot = slot;
+            if (n_hits == 0) COLD_W(7) = slot;
+            n_hits++;
         }
         if constexpr (VOLUMETRIC) {   // the span is closed by the next step (surface.rs:467-476)
-            pend_slot = slot;
-            pend_t = t_now;
-            pend_l2a = te.y;
+            COLD_W(11) = slot;
+            COLD_W(12) = __float_as_uint(te.y);
+            COLD_D(12) = last_t * t_scale;
             have_pending = true;
         } else if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {   // limit_alpha (graphics_options.rs:496-507)
             if (te.x > P.threshold) L = F_NEG_INF;
@@ -978,13 +1002,14 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             }
             if constexpr (AUX) { if (inner) aux.n_inner++; else aux.n_outer++; }
         }
-        const double t_now = last_t * t_scale;
         // count_step_should_stop (sr.rs:625-656): every TraceStep / DepthStep is counted before it is looked at
         steps += 1;
-        if ((steps > 1000u) | (L < -8.0f)) { st = ST_DONE; return; }
+        if (steps > step_limit) { st = ST_DONE; return; }
         if constexpr (VOLUMETRIC) {
             if (have_pending) {   // DepthIter: this step's t ends the pending surface's span (surface.rs:460-490)
-                const float th = fmaxf((float)((t_now - pend_t) * COLD_D(7)), 0.0f);   // sr.rs:720-731
+                const float th = fmaxf((float)((last_t * t_scale - COLD_D(12)) * COLD_D(7)), 0.0f);   // sr.rs:720-731
+                const uint32_t pend_slot = COLD_W(11);
+                const float pend_l2a = __uint_as_float(COLD_W(12));
                 if (pend_slot != HIT_NONE)
                     *reinterpret_cast<uint2 *>(&P.hits[pend_slot].thickness) = make_uint2(__float_as_uint(th), steps);
                 bound_factor(pend_l2a == F_NEG_INF ? F_NEG_INF : th * pend_l2a);
@@ -1000,14 +1025,14 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             if constexpr (VOLUMETRIC) {
                 // the buffered DepthStep::EnterBlock is counted after the flushed span (surface.rs:478-488)
                 steps += 1;
-                if ((steps > 1000u) | (L < -8.0f)) { st = ST_DONE; return; }
+                if (steps > step_limit) { st = ST_DONE; return; }
             }
             if constexpr (!WIDE) ev_word = w & 0x3fffu;
             st = ST_ENTER;
             return;
         }
-        if constexpr (WIDE) emit_surface(inner ? w : ev_word, t_now);
-        else emit_surface(inner ? w : (w & 0x3fffu), t_now);
+        if constexpr (WIDE) emit_surface(inner ? w : ev_word);
+        else emit_surface(inner ? w : (w & 0x3fffu));
     };
 
     for (;;) {
@@ -1019,7 +1044,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
             o.first_hit = COLD_W(7);
             o.steps = steps;
             o.flags = COLD_W(8);
-            o._pad = 0;
+            o.n_hits = n_hits;
             *reinterpret_cast<uint4 *>(P.task_out + COLD_W(6)) = *reinterpret_cast<const uint4 *>(&o);
             if constexpr (AUX) { n_outer += aux.n_outer; n_inner += aux.n_inner; n_blocks += aux.n_blocks; }
             st = ST_IDLE;
@@ -1071,9 +1096,9 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                         valid = (rec.flags & 16u) != 0;
                         L = 0.0f;
                         steps = 0;
+                        step_limit = 1000u;
+                        n_hits = 0;
                         have_pending = false;
-                        pend_slot = HIT_NONE;
-                        last_slot = HIT_NONE;
                         inner = false;
                         t_scale = 1.0;
                         need_advance = false;
@@ -1216,12 +1241,11 @@ AICB_DEV void decode_hit(const DeviceScene &S, const HitRecord &h, HitGeom &g) {
         g.voxel[1] = (int)vy + (int)(int16_t)(b0.y >> 16);
         g.voxel[2] = (int)vz + (int)(int16_t)(b0.z & 0xffff);
         g.res = 1 << ((h.flags >> 4) & 15u);
-        g.pal = h.word;
     } else {
         g.voxel[0] = g.voxel[1] = g.voxel[2] = 0;
         g.res = 1;
-        g.pal = __ldg(reinterpret_cast<const uint4 *>(S.blocks + (h.word & 0xffffu)) + 1).y;
     }
+    g.pal = h.pal;
 }
 
 // ======================================================================================================
@@ -1246,7 +1270,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
     const bool volumetric = P.transparency == AICB_TRANSPARENCY_VOLUMETRIC;
     const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
     const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    auto shade_one = [&](const uint32_t i) {
         HitRecord h;
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + i);
@@ -1264,7 +1288,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         if (!(h.thickness >= 0.0f)) {   // a chunk slot that was never filled, or a surface whose ray stopped before shading it
             outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
             outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
-            continue;
+            return;
         }
         HitGeom g;
         decode_hit(S, h, g);
@@ -1299,7 +1323,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) {   // nothing to see: the ray is not touched
             outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
             outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
-            continue;
+            return;
         }
         // what the shading needs of the ray
         const RayRecord *rp = P.ray_records + h.task;
@@ -1373,6 +1397,46 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         out.r = orr; out.g = og; out.b = ob; out.factor = tr;
         outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
         outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
+    };
+
+    // The hit stream holds slots that were never shaded (the unused tail of each lane's last chunk, surfaces whose ray
+    // stopped before their span closed: a quarter of the slots of the bench frame).  Each warp scans its slots 32 at
+    // a time, answers the dead ones on the spot, and queues the live ones until it has 32 of them to shade together.
+    __shared__ uint32_t s_queue[4][64];
+    uint32_t *queue = s_queue[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t queued = 0, base = warp * 32u;
+    for (;;) {
+        while (queued < 32u && base < n) {
+            const uint32_t slot = base + lane;
+            base += n_warps * 32u;
+            bool live = false;
+            if (slot < n) {
+                live = __ldg(&P.hits[slot].thickness) >= 0.0f;
+                if (!live) {   // encode_kernel may still walk over it (the last, never shaded surface of a ray)
+                    ShadedHit out;
+                    out.r = out.g = out.b = 0.0f;
+                    out.factor = -1.0f;
+                    out.next = P.hits[slot].next;
+                    out.steps = 0;
+                    out._pad[0] = out._pad[1] = 0;
+                    uint4 *outp = reinterpret_cast<uint4 *>(P.shaded + slot);
+                    outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+                    outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (live) queue[queued + __popc(m & ((1u << lane) - 1u))] = slot;
+            queued += __popc(m);
+            __syncwarp();
+        }
+        if (queued == 0u) break;
+        const uint32_t take_n = queued < 32u ? queued : 32u;
+        queued -= take_n;
+        const uint32_t take = lane < take_n ? queue[queued + lane] : HIT_NONE;
+        __syncwarp();
+        if (take != HIT_NONE) shade_one(take);
     }
     // one atomic per warp: 150 K single-address atomics would cost more than the shading itself
 #pragma unroll
@@ -1409,7 +1473,8 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
             float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
             uint32_t steps = o.steps;
             uint32_t sample_first = 0xffffffffu;
-            for (uint32_t hi = o.first_hit; hi != 0xffffffffu;) {
+            uint32_t hi = o.first_hit;
+            for (uint32_t hk = 0; hk < o.n_hits; hk++) {
                 ShadedHit c;
                 {
                     const uint4 *src = reinterpret_cast<const uint4 *>(P.shaded + hi);
@@ -1428,7 +1493,7 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
                         break;
                     }
                 }
-                hi = c.next;
+                hi = ((hi + 1u) & (HIT_CHUNK - 1u)) ? hi + 1u : c.next;   // consecutive slots; chunks are linked
             }
             if (sample_first != 0xffffffffu && (P.out_depth || P.out_hit)) {
                 const HitRecord *hr = P.hits + sample_first;   // Hit::t_distance = last_t / resolution (surface.rs:385-386)
