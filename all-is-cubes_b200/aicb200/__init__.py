@@ -105,6 +105,43 @@ def load_library() -> C.CDLL:
     return lib
 
 
+# The camera matrices (host-only code, all-is-cubes_b200/host/camera.cpp) are reached through the C ABI of
+# libaicb200.so by default.  bench.py's reference arm must not load the product library at all, so the same host
+# source is also compiled into the oracle library under orc_* names; use_camera_library() points Camera at it.
+_camera_lib = None
+_camera_prefix = "aicb_"
+
+
+def use_camera_library(lib, prefix: str):
+    """Route Camera / eye_for_look_at through another shared library exporting <prefix>camera_look_at,
+    <prefix>camera_from_view, <prefix>eye_for_look_at, <prefix>camera_project_ndc (same signatures)."""
+    global _camera_lib, _camera_prefix
+    for name in ("camera_look_at", "camera_from_view"):
+        fn = getattr(lib, prefix + name)
+        fn.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_double,
+                       C.c_uint32, C.c_uint32, C.c_float, C.POINTER(abi.CameraData)]
+        fn.restype = C.c_int
+    fn = getattr(lib, prefix + "eye_for_look_at")
+    fn.argtypes = [C.POINTER(abi.Aab), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    fn.restype = None
+    fn = getattr(lib, prefix + "camera_project_ndc")
+    fn.argtypes = [C.POINTER(abi.CameraData), C.c_double, C.c_double, C.POINTER(C.c_double)]
+    fn.restype = None
+    _camera_lib, _camera_prefix = lib, prefix
+
+
+def _cam(name: str):
+    lib = _camera_lib if _camera_lib is not None else load_library()
+    return getattr(lib, _camera_prefix + name)
+
+
+def _check_cam(status: int):
+    if status != abi.OK:
+        if _camera_lib is not None:
+            raise AicbError(status, "camera construction failed")
+        _check(status)
+
+
 def _check(status: int):
     if status != abi.OK:
         raise AicbError(status, load_library().aicb_last_error().decode("utf-8", "replace"))
@@ -179,10 +216,9 @@ class Camera:
         self._compute()
 
     def _compute(self):
-        lib = load_library()
         q = (C.c_double * 4)(*self._rotation)
         t = (C.c_double * 3)(*self._translation)
-        _check(lib.aicb_camera_from_view(q, t, self.options.fov_y, self.options.view_distance,
+        _check_cam(_cam("camera_from_view")(q, t, self.options.fov_y, self.options.view_distance,
                                          float(self.viewport.nominal_size[0]), float(self.viewport.nominal_size[1]),
                                          self.viewport.framebuffer_size[0], self.viewport.framebuffer_size[1],
                                          self.options.exposure, C.byref(self.data)))
@@ -194,10 +230,9 @@ class Camera:
 
     def look_at_y_up(self, eye: Sequence[float], target: Sequence[float]):
         """camera_struct.rs:459-471"""
-        lib = load_library()
         e = (C.c_double * 3)(*[float(v) for v in eye])
         t = (C.c_double * 3)(*[float(v) for v in target])
-        _check(lib.aicb_camera_look_at(e, t, self.options.fov_y, self.options.view_distance,
+        _check_cam(_cam("camera_look_at")(e, t, self.options.fov_y, self.options.view_distance,
                                        float(self.viewport.nominal_size[0]), float(self.viewport.nominal_size[1]),
                                        self.viewport.framebuffer_size[0], self.viewport.framebuffer_size[1],
                                        self.options.exposure, C.byref(self.data)))
@@ -205,7 +240,7 @@ class Camera:
     def project_ndc_into_world(self, x: float, y: float) -> np.ndarray:
         """camera_struct.rs:238-257 -> [ox,oy,oz,dx,dy,dz]"""
         out = (C.c_double * 6)()
-        load_library().aicb_camera_project_ndc(C.byref(self.data), x, y, out)
+        _cam("camera_project_ndc")(C.byref(self.data), x, y, out)
         return np.array(out[:], dtype=np.float64)
 
     @property
@@ -220,7 +255,7 @@ def eye_for_look_at(bounds_lower, bounds_size, direction) -> np.ndarray:
     b.size[:] = [int(v) for v in bounds_size]
     d = (C.c_double * 3)(*[float(v) for v in direction])
     out = (C.c_double * 3)()
-    load_library().aicb_eye_for_look_at(C.byref(b), d, out)
+    _cam("eye_for_look_at")(C.byref(b), d, out)
     return np.array(out[:], dtype=np.float64)
 
 

@@ -79,14 +79,15 @@ struct DeviceScene {
 // (raycast.rs:196-230): everything the marching kernel needs, 144 bytes = 9 x 16-byte loads.
 struct __align__(16) RayRecord {
     double ox, oy, oz, dx, dy, dz;   // ray (direction already zeroed if |d| >= 1e100, raycast.rs:760-764)
+    float t_to_view;                 // sr.rs:149-151
+    uint32_t flags;                  // face | running<<3 | valid<<4 | active<<5 | (sx+1)<<6 | (sy+1)<<8 | (sz+1)<<10 | sky octant<<12
+                                     // (the first 64 bytes are what the shading kernel reads of a ray)
     double tdx, tdy, tdz;            // t_delta
     double half_over_len;
     double tmx, tmy, tmz, last_t;    // outer caster at its first in-bounds cube
     double t_to_abs;                 // |d| of the original direction (sr.rs:146)
-    float t_to_view;                 // sr.rs:149-151
     int rx, ry, rz;
     uint32_t idx;
-    uint32_t flags;                  // face | running<<3 | valid<<4 | active<<5 | (sx+1)<<6 | (sy+1)<<8 | (sz+1)<<10 | sky octant<<12
 };
 static_assert(sizeof(RayRecord) == 144, "RayRecord must be 144 bytes");
 
@@ -648,8 +649,9 @@ AICB_DEV void project_ndc(const TraceParams &P, double x, double y, double z, do
     double hy = x * m[1] + y * m[5] + z * m[9] + m[13];
     double hz = x * m[2] + y * m[6] + z * m[10] + m[14];
     double hw = x * m[3] + y * m[7] + z * m[11] + m[15];
-    if (hw > 0.0) {
-        out[0] = hx / hw; out[1] = hy / hw; out[2] = hz / hw;
+    if (hw > 0.0) {   // three quotients by the same w: one division for RN(1 / w), then exact quotients from it
+        const double rw = 1.0 / hw;
+        out[0] = div_known_recip(hx, hw, rw); out[1] = div_known_recip(hy, hw, rw); out[2] = div_known_recip(hz, hw, rw);
     } else {
         out[0] = out[1] = out[2] = __longlong_as_double(0x7ff8000000000000LL);
     }
@@ -1278,6 +1280,19 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
 #pragma unroll
             for (int k = 0; k < 4; k++) dst[k] = ld_stream(src + k);
         }
+        // everything the shading reads through the record is requested now, before any of it is needed
+        const RayRecord *rp = P.ray_records + h.task;
+        const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
+        const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
+        const uint2 rmeta = __ldg(reinterpret_cast<const uint2 *>(&rp->t_to_view));   // t_to_view, flags
+        const uint32_t rflags = rmeta.y;
+        Ray rr;
+        rr.ox = rr.oy = rr.oz = rr.dx = rr.dy = rr.dz = 0.0;
+        if constexpr (LC == LC_INTERP) {
+            const double2 *q = reinterpret_cast<const double2 *>(rp);
+            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            rr.ox = q0.x; rr.oy = q0.y; rr.oz = q1.x; rr.dx = q1.y; rr.dy = q2.x; rr.dz = q2.y;
+        }
         ShadedHit out;
         out.r = out.g = out.b = 0.0f;
         out.factor = -1.0f;
@@ -1285,15 +1300,8 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         out.steps = h.steps;
         out._pad[0] = out._pad[1] = 0;
         uint4 *outp = reinterpret_cast<uint4 *>(P.shaded + i);
-        if (!(h.thickness >= 0.0f)) {   // a chunk slot that was never filled, or a surface whose ray stopped before shading it
-            outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
-            outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
-            return;
-        }
         HitGeom g;
         decode_hit(S, h, g);
-        const float4 col = __ldg(S.palette + 2 * (size_t)g.pal);
-        const float4 emi = __ldg(S.palette + 2 * (size_t)g.pal + 1);
         float ca = col.w;
         float coeff = 1.0f;
         bool zeroed = false;
@@ -1325,14 +1333,11 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
             outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
             return;
         }
-        // what the shading needs of the ray
-        const RayRecord *rp = P.ray_records + h.task;
-        const uint32_t rflags = __ldg(&rp->flags);
         const double t_scale = recip_pow2(g.res);
         float tr = 1.0f - ca;
         float fa = -1.0f;
         if (have_fog) {  // distance_fog (sr.rs:745-768)
-            float rel = (float)(h.last_t * t_scale) * __ldg(&rp->t_to_view);
+            float rel = (float)(h.last_t * t_scale) * __uint_as_float(rmeta.x);
             rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
             const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
             const float fudged = fog_exponential / 0.79810348f;
@@ -1357,12 +1362,6 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
         } else if constexpr (LC == LC_INTERP) {
             // RaycastStep::intersection_point (raycast.rs:409-439) of the level the surface is on, brought to
             // Space coordinates (surface.rs:406-407)
-            Ray rr;
-            {
-                const double2 *q = reinterpret_cast<const double2 *>(rp);
-                const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-                rr.ox = q0.x; rr.oy = q0.y; rr.oz = q1.x; rr.dx = q1.y; rr.dy = q2.x; rr.dz = q2.y;
-            }
             rr.sx = (int)((rflags >> 6) & 3u) - 1; rr.sy = (int)((rflags >> 8) & 3u) - 1; rr.sz = (int)((rflags >> 10) & 3u) - 1;
             Caster c;
             c.tmx = h.tmx; c.tmy = h.tmy; c.tmz = h.tmz; c.last_t = h.last_t;

@@ -17,7 +17,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    src = [os.path.join(ROOT, "oracle", f) for f in ("aic_oracle.cpp", "aic_light.cpp", "aic_oracle.hpp")]
+    src = [os.path.join(ROOT, "oracle", f) for f in ("aic_oracle.cpp", "aic_light.cpp", "aic_oracle.hpp", "Makefile")]
+    src.append(os.path.join(ROOT, "all-is-cubes_b200", "host", "camera.cpp"))
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-B"], check=True, capture_output=True)
     L = C.CDLL(LIB_PATH)
