@@ -17,6 +17,7 @@ aicb_status aicb_cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 struct LightChartNode;  // light_kernel.cuh
+struct LightNodePre;    // light_kernel.cuh
 struct LightBlockDev;   // light_kernel.cuh
 
 struct aicb_ctx {
@@ -55,6 +56,7 @@ struct aicb_ctx {
     size_t d_task_aux_bytes = 0;
     // light propagation: the static ray chart (space/light/chart), built and uploaded on first use
     LightChartNode *d_chart = nullptr;
+    LightNodePre *d_chart_pre = nullptr;   // the same chart in depth-first preorder (the lockstep walk)
     uint32_t chart_nodes = 0;
     std::mutex mu;
 };
@@ -87,5 +89,6 @@ struct aicb_scene {
     uint32_t *d_new_light = nullptr;        // computed texels of one round
     uint8_t *d_diff = nullptr;              // difference_priority of one round
     uint32_t *d_scalars = nullptr;          // [0] list length, [1] max priority, [2] max diff, [3] updates
+    uint32_t *d_tile_max = nullptr;         // per LIGHT_TILE cubes: upper bound of the queued priorities
     uint32_t light_max_distance = 0;
 };

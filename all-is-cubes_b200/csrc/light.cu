@@ -89,9 +89,53 @@ std::vector<LightChartNode> build_chart() {
     return flat;
 }
 
+// The chart in depth-first preorder, as the lockstep walk (light_kernel.cuh) steps through it: children in Face6
+// order (the order walk_ray_tree recurses in, updater.rs:500), each node with its depth, its cube relative to the
+// origin, the direction of the step from its parent and the index one past its last descendant.
+std::vector<LightNodePre> build_chart_preorder(const std::vector<LightChartNode> &flat) {
+    std::vector<LightNodePre> pre;
+    pre.reserve(flat.size());
+    struct Item { uint32_t node; int8_t rel[3]; uint8_t depth; uint8_t dir; uint32_t slot; uint8_t next_child; };
+    std::vector<Item> stack;
+    stack.push_back(Item{0, {0, 0, 0}, 0, 0, 0, 0});
+    while (!stack.empty()) {
+        Item &it = stack.back();
+        if (it.next_child == 0) {   // first visit: emit the node
+            it.slot = (uint32_t)pre.size();
+            LightNodePre n;
+            std::memcpy(n.w, flat[it.node].w, sizeof n.w);
+            n.rel[0] = it.rel[0]; n.rel[1] = it.rel[1]; n.rel[2] = it.rel[2];
+            n.depth = it.depth;
+            n.end_dir = (uint32_t)it.dir << 29;
+            pre.push_back(n);
+        }
+        int f = it.next_child;
+        while (f < 6 && flat[it.node].child[f] == 0) f++;
+        if (f < 6) {
+            it.next_child = (uint8_t)(f + 1);
+            Item c;
+            c.node = flat[it.node].child[f];
+            c.rel[0] = it.rel[0]; c.rel[1] = it.rel[1]; c.rel[2] = it.rel[2];
+            c.rel[f % 3] = (int8_t)(c.rel[f % 3] + ((f < 3) ? -1 : 1));
+            c.depth = (uint8_t)(it.depth + 1);
+            c.dir = (uint8_t)f;
+            c.slot = 0;
+            c.next_child = 0;
+            stack.push_back(c);   // (invalidates `it`)
+        } else {
+            pre[it.slot].end_dir |= (uint32_t)pre.size();
+            stack.pop_back();
+        }
+    }
+    return pre;
+}
+
 aicb_status ensure_chart(aicb_ctx *ctx) {
     if (ctx->d_chart) return AICB_OK;
     std::vector<LightChartNode> chart = build_chart();
+    std::vector<LightNodePre> pre = build_chart_preorder(chart);
+    CU(cudaMalloc(&ctx->d_chart_pre, pre.size() * sizeof(LightNodePre)));
+    CU(cudaMemcpy(ctx->d_chart_pre, pre.data(), pre.size() * sizeof(LightNodePre), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&ctx->d_chart, chart.size() * sizeof(LightChartNode)));
     CU(cudaMemcpy(ctx->d_chart, chart.data(), chart.size() * sizeof(LightChartNode), cudaMemcpyHostToDevice));
     ctx->chart_nodes = (uint32_t)chart.size();
@@ -101,14 +145,31 @@ aicb_status ensure_chart(aicb_ctx *ctx) {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void k_find_max(const LightParams P) {
-    uint32_t m = 0;
+// The queue: one priority byte per cube (0 = not queued) and, per LIGHT_TILE cubes, an upper bound of the tile's
+// highest byte (raised with every insert, recomputed by whoever scans the tile).  Finding the round's priority reads
+// the tile bounds only; gathering reads only the tiles that can hold a cube of the round.
+__global__ void __launch_bounds__(256) k_tile_rebuild(const LightParams P, uint32_t n_tiles) {
+    __shared__ uint32_t s_max[8];
     const uint32_t n_words = (P.volume + 3) / 4;
-    const uint32_t *w = (const uint32_t *)P.pending;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
-        uint32_t v = w[i];
-        m = max(m, max(max(v & 255u, (v >> 8) & 255u), max((v >> 16) & 255u, v >> 24)));
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t w = tile * (LIGHT_TILE / 4) + threadIdx.x;
+        const uint32_t v = w < n_words ? ((const uint32_t *)P.pending)[w] : 0u;
+        uint32_t m = max(max(v & 255u, (v >> 8) & 255u), max((v >> 16) & 255u, v >> 24));
+        for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int i = 0; i < 8; i++) t = max(t, s_max[i]);
+            P.tile_max[tile] = t;
+        }
+        __syncthreads();
     }
+}
+
+__global__ void k_find_max(const LightParams P, uint32_t n_tiles) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += gridDim.x * blockDim.x) m = max(m, P.tile_max[i]);
     for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(P.scalars + 1, m);
 }
@@ -117,36 +178,84 @@ __global__ void k_find_max(const LightParams P) {
 // (accumulated), [3] cube updates (accumulated), [4..5] chart nodes visited (64-bit, accumulated).
 // A round's kernels read the round's priority and count from device memory, so rounds are queued back to back
 // without a host round trip; a round whose priority is already <= epsilon does nothing.
-__global__ void k_gather(const LightParams P) {
+// One block per tile: the cubes of a tile reach the list in index order (block-wide scan), so 32 consecutive list
+// entries are neighbours along z — what the lockstep walk wants.
+__global__ void __launch_bounds__(256) k_gather(const LightParams P, uint32_t n_tiles) {
+    __shared__ uint32_t s_part[8], s_max[8], s_base;
     const uint32_t prio = P.scalars[1];
     if (prio <= P.epsilon_priority) return;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.volume; i += gridDim.x * blockDim.x) {
-        const uint32_t p = P.pending[i];
-        if (p > P.epsilon_priority && p + P.priority_band >= prio) {   // the round's priority band (0 = one level)
-            P.pending[i] = 0;
-            P.list[atomicAdd(P.scalars + 0, 1u)] = i;
+    const uint32_t n_words = (P.volume + 3) / 4;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t tm = P.tile_max[tile];
+        if (tm <= P.epsilon_priority || tm + P.priority_band < prio) continue;   // (block-uniform)
+        const uint32_t w = tile * (LIGHT_TILE / 4) + threadIdx.x;
+        uint32_t v = w < n_words ? ((uint32_t *)P.pending)[w] : 0u;
+        uint32_t sel = 0, cnt = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t p = (v >> (8 * k)) & 255u;
+            if (p > P.epsilon_priority && p + P.priority_band >= prio && w * 4 + k < P.volume) { sel |= 1u << k; cnt++; }
         }
+        // exclusive scan of cnt over the block
+        uint32_t inc = cnt;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)lane >= off) inc += t;
+        }
+        if (lane == 31) s_part[wid] = inc;
+        // what stays queued in this tile
+        uint32_t rest = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) if (!(sel & (1u << k))) rest = max(rest, (v >> (8 * k)) & 255u);
+        for (int off = 16; off > 0; off >>= 1) rest = max(rest, __shfl_down_sync(0xffffffffu, rest, off));
+        if (lane == 0) s_max[wid] = rest;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0, m = 0;
+            for (int i = 0; i < 8; i++) { const uint32_t c = s_part[i]; s_part[i] = total; total += c; m = max(m, s_max[i]); }
+            s_base = total ? atomicAdd(P.scalars + 0, total) : 0u;
+            P.tile_max[tile] = m;
+        }
+        __syncthreads();
+        if (cnt) {
+            uint32_t at = s_base + s_part[wid] + inc - cnt;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                if (sel & (1u << k)) { P.list[at++] = w * 4 + k; v &= ~(255u << (8 * k)); }
+            ((uint32_t *)P.pending)[w] = v;
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(64) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
+__global__ void __launch_bounds__(128) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
     __shared__ float s_lut[256];
+    __shared__ uint32_t s_path[4][LIGHT_MAX_DEPTH];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
     __syncthreads();
     if (!explicit_cubes) n = P.scalars[0];   // the round's list
     unsigned long long total_visits = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int x, y, z;
-        if (explicit_cubes) {
-            x = explicit_cubes[3 * i]; y = explicit_cubes[3 * i + 1]; z = explicit_cubes[3 * i + 2];
-        } else {
-            cube_of(P.scene, P.list[i], x, y, z);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {   // one warp per 32 consecutive list entries
+        const uint32_t i = base + lane;
+        const bool active = i < n;
+        int x = 0, y = 0, z = 0;
+        if (active) {
+            if (explicit_cubes) {
+                x = explicit_cubes[3 * i]; y = explicit_cubes[3 * i + 1]; z = explicit_cubes[3 * i + 2];
+            } else {
+                cube_of(P.scene, P.list[i], x, y, z);
+            }
         }
         uint32_t visits = 0;
-        P.new_light[i] = compute_light<false>(P, s_lut, x, y, z, 0, &visits);
+        const uint32_t nv = compute_light_lockstep<false>(P, s_lut, s_path[threadIdx.x >> 5], active, x, y, z, 0, &visits);
+        if (active) P.new_light[i] = nv;
         total_visits += visits;
     }
-    if (total_visits) atomicAdd(reinterpret_cast<unsigned long long *>(P.scalars + 4), total_visits);
+    for (int off = 16; off > 0; off >>= 1) total_visits += __shfl_down_sync(0xffffffffu, total_visits, off);
+    if (lane == 0 && total_visits) atomicAdd(reinterpret_cast<unsigned long long *>(P.scalars + 4), total_visits);
 }
 
 // apply_light_update (updater.rs:295-363) minus the dependency re-queue (k_mark)
@@ -184,14 +293,19 @@ __global__ void k_apply(const LightParams P) {
 
 // the dependency re-queue of apply_light_update (updater.rs:355-360): re-walk the chart, raising the
 // queue priority of every cube whose light was read
-__global__ void __launch_bounds__(64) k_mark(const LightParams P) {
+__global__ void __launch_bounds__(128) k_mark(const LightParams P) {
+    __shared__ uint32_t s_path[4][LIGHT_MAX_DEPTH];
     const uint32_t n = P.scalars[0];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int d = P.diff[i];
-        if (d <= 1) continue;
-        int x, y, z;
-        cube_of(P.scene, P.list[i], x, y, z);
-        compute_light<true>(P, P.scene.tables, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
+        const uint32_t i = base + lane;
+        const int d = i < n ? (int)P.diff[i] : 0;
+        const bool active = d > 1;   // apply_light_update re-queues only when the packed difference exceeds 1
+        if (!__any_sync(0xffffffffu, active)) continue;
+        int x = 0, y = 0, z = 0;
+        if (active) cube_of(P.scene, P.list[i], x, y, z);
+        compute_light_lockstep<true>(P, P.scene.tables, s_path[threadIdx.x >> 5], active, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
     }
 }
 
@@ -257,6 +371,9 @@ LightParams make_params(aicb_scene *s) {
     P.scene = s->ds;
     P.blocks = s->d_light_blocks;
     P.chart = s->ctx->d_chart;
+    P.chart_pre = s->ctx->d_chart_pre;
+    P.chart_nodes = s->ctx->chart_nodes;
+    P.tile_max = s->d_tile_max;
     P.pending = s->d_pending;
     P.list = s->d_list;
     P.new_light = s->d_new_light;
@@ -285,6 +402,7 @@ aicb_status ensure_light_state(aicb_scene *s) {
         CU(cudaMalloc(&s->d_new_light, s->volume * 4 + 16));
         CU(cudaMalloc(&s->d_diff, s->volume + 16));
         CU(cudaMalloc(&s->d_scalars, 8 * 4));
+        CU(cudaMalloc(&s->d_tile_max, ((s->volume + LIGHT_TILE - 1) / LIGHT_TILE + 1) * 4));
         s->device_bytes += s->volume * 10;
     }
     return AICB_OK;
@@ -304,19 +422,21 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
         P.priority_band = e ? (uint32_t)atoi(e) : 16u;
     }
     const int blocks = ctx->num_sms * 8;
-    const int wide = ctx->num_sms * 32;   // 64-thread blocks of the per-cube kernels (grid-stride over the round's list)
+    const int wide = ctx->num_sms * 8;    // 128-thread blocks of the lockstep kernels (one warp per 32 list entries, grid-stride)
+    const uint32_t n_tiles = (uint32_t)((s->volume + LIGHT_TILE - 1) / LIGHT_TILE);
     uint64_t total = 0, visits = 0;
     uint32_t maxd = 0;
     CU(cudaMemsetAsync(s->d_scalars, 0, 8 * 4, st));
+    k_tile_rebuild<<<blocks, 256, 0, st>>>(P, n_tiles);   // (fast_evaluate / edits write the priority bytes directly)
     const int ROUNDS_PER_SYNC = 8;
     for (int batch = 0; batch < 100000; batch++) {
         for (int round = 0; round < ROUNDS_PER_SYNC; round++) {
             CU(cudaMemsetAsync(s->d_scalars, 0, 2 * 4, st));   // this round's count and priority
-            k_find_max<<<blocks, 256, 0, st>>>(P);
-            k_gather<<<blocks, 256, 0, st>>>(P);
-            k_compute<<<wide, 64, 0, st>>>(P, 0, nullptr);
-            k_apply<<<wide, 64, 0, st>>>(P);
-            k_mark<<<wide, 64, 0, st>>>(P);
+            k_find_max<<<16, 256, 0, st>>>(P, n_tiles);
+            k_gather<<<blocks, 256, 0, st>>>(P, n_tiles);
+            k_compute<<<wide, 128, 0, st>>>(P, 0, nullptr);
+            k_apply<<<wide, 128, 0, st>>>(P);
+            k_mark<<<wide, 128, 0, st>>>(P);
         }
         uint32_t h[8];
         CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
@@ -391,10 +511,12 @@ void aicb_light_scene_free(aicb_scene *s) {
     if (s->d_new_light) cudaFree(s->d_new_light);
     if (s->d_diff) cudaFree(s->d_diff);
     if (s->d_scalars) cudaFree(s->d_scalars);
+    if (s->d_tile_max) cudaFree(s->d_tile_max);
 }
 
 void aicb_light_ctx_free(aicb_ctx *c) {
     if (c->d_chart) cudaFree(c->d_chart);
+    if (c->d_chart_pre) cudaFree(c->d_chart_pre);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,7 +559,7 @@ aicb_status aicb_light_compute(aicb_scene *s, const int32_t (*cubes)[3], size_t 
     int32_t *d_cubes = nullptr;
     CU(cudaMalloc(&d_cubes, n * 12));
     CU(cudaMemcpy(d_cubes, cubes, n * 12, cudaMemcpyHostToDevice));
-    k_compute<<<(unsigned)((n + 63) / 64), 64, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
+    k_compute<<<(unsigned)((n + 127) / 128), 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
     cudaError_t e = cudaMemcpyAsync(out, s->d_new_light, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
     cudaFree(d_cubes);

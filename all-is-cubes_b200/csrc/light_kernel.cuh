@@ -3,12 +3,20 @@
 //
 // Design: the reference pops one cube at a time from a priority queue (32 at a time with threads,
 // updater.rs:211-252) and recomputes its light by a depth-first walk over a static ray chart
-// (walk_ray_tree, updater.rs:427-529).  Here the queue is a per-cube priority byte in HBM; one round
-// = all cubes of the highest queued priority: gather -> compute (one thread per cube, explicit-stack
-// DFS reproducing the recursion's f32 summation order exactly) -> apply (store, fill uninitialised
-// neighbours, re-queue dependencies by re-walking the chart).  compute_light on a given field is
-// bit-identical to the reference; the relaxation order differs (batch = one priority level), which
-// the reference leaves unspecified (queue.rs:226-246) — parity contract SURVEY §8(a) L4.
+// (walk_ray_tree, updater.rs:427-529).  Here the queue is a per-cube priority byte in HBM with a per-tile
+// maximum beside it; one round = the cubes within a band of the highest queued priority:
+// gather (tiles in index order, so the list is spatially sorted) -> compute -> apply (store, fill uninitialised
+// neighbours) -> mark (re-queue the dependencies of the cubes that changed).
+//
+// compute: ONE WARP WALKS THE CHART FOR 32 NEIGHBOURING CUBES IN LOCKSTEP.  The chart is a static prefix tree; in
+// depth-first preorder every lane would visit a subsequence of the same node sequence.  So the warp steps through
+// the nodes in preorder — node record, depth and weights are warp-uniform, one broadcast load — and a lane takes
+// part in a node iff its own walk would enter it (its frame of the parent is alive); a subtree that no lane of the
+// warp enters is skipped through the node's `subtree_end`.  Control flow is uniform, the cell / light loads of
+// neighbouring cubes coalesce, and every lane's f32 additions happen in exactly the reference's depth-first order,
+// so compute_light on a given field stays bit-identical to the reference (the old one-thread-per-cube walk diverged
+// on every node).  The relaxation order differs from the reference's (batch = a priority band), which the
+// reference leaves unspecified (queue.rs:226-246) — parity contract SURVEY §8(a) L4.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -20,6 +28,15 @@ struct LightChartNode {
     float w[6];
     uint32_t child[6];
 };
+
+// The same chart in depth-first preorder (children in Face6 order NX,NY,NZ,PX,PY,PZ, updater.rs:500), 32 bytes.
+struct LightNodePre {
+    float w[6];
+    int8_t rel[3];        // the node's cube relative to the origin cube
+    uint8_t depth;
+    uint32_t end_dir;     // index one past the node's last descendant | direction (0..5) of the step from its parent << 29
+};
+static_assert(sizeof(LightNodePre) == 32, "LightNodePre must be 32 bytes");
 
 // The EvaluatedBlock members light reads (evaluated.rs:189-272), 128 bytes.
 struct LightBlockDev {
@@ -34,11 +51,15 @@ constexpr int LIGHT_MAX_DEPTH = 224;  // longest chart path is 219 (rays end at 
 
 constexpr uint32_t TX_OPAQUE = 128u << 24, TX_NO_RAYS = 1u << 24, TX_UNINIT = 0u;
 constexpr int PRIO_NEWLY_VISIBLE = 250, PRIO_ESTIMATED = 200;
+constexpr uint32_t LIGHT_TILE = 1024;   // cubes per queue tile (256 words of pending bytes: one 256-thread block)
 
 struct LightParams {
     aicb::DeviceScene scene;        // cells, light, sky faces, tables (LUT)
     const LightBlockDev *blocks;
     const LightChartNode *chart;
+    const LightNodePre *chart_pre;
+    uint32_t chart_nodes;
+    uint32_t *tile_max;             // per LIGHT_TILE cubes: an upper bound of the tile's highest queued priority
     uint8_t *pending;
     uint32_t *list;
     uint32_t *new_light;
@@ -118,7 +139,8 @@ __device__ __forceinline__ int difference_priority(uint32_t a, uint32_t b) {  //
 
 // LightUpdateQueue::insert (queue.rs:107-133): raise the queued priority of a cube (never lowers it).
 // The queue is one byte per cube; the byte is updated with a CAS on its containing word.
-__device__ __forceinline__ void raise_pending(uint8_t *pending, uint32_t idx, uint32_t prio) {
+__device__ __forceinline__ void raise_pending(uint8_t *pending, uint32_t *tile_max, uint32_t idx, uint32_t prio) {
+    if (tile_max[idx / LIGHT_TILE] < prio) atomicMax(tile_max + idx / LIGHT_TILE, prio);
     uint32_t *wp = (uint32_t *)(pending + (idx & ~3u));
     const uint32_t shift = (idx & 3u) * 8u;
     uint32_t old = *wp;
@@ -132,7 +154,7 @@ __device__ __forceinline__ void raise_pending(uint8_t *pending, uint32_t idx, ui
 // light_needs_update (updater.rs:107-111)
 __device__ __forceinline__ void mark_dependency(const LightParams &P, int x, int y, int z, uint32_t prio) {
     uint32_t idx;
-    if (cube_index(P.scene, x, y, z, &idx)) raise_pending(P.pending, idx, prio);
+    if (cube_index(P.scene, x, y, z, &idx)) raise_pending(P.pending, P.tile_max, idx, prio);
 }
 
 struct Frame {
@@ -362,6 +384,192 @@ __device__ uint32_t compute_light(const LightParams &P, const float *lut, int ox
         }
     }
     if (visits_out) *visits_out = visits;
+    // LightBuffer::finish (updater.rs:932-944)
+    const float scale = ps_clamped(1.0f / fmaxf(acc.total, 1.0f));
+    if (acc.total > 0.0f)
+        return scalar_in_t(S.tables, ps_mul(acc.in0, scale)) | (scalar_in_t(S.tables, ps_mul(acc.in1, scale)) << 8) |
+               (scalar_in_t(S.tables, ps_mul(acc.in2, scale)) << 16) | (255u << 24);
+    return origin_opaque ? TX_OPAQUE : TX_NO_RAYS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// compute_light (updater.rs:368-418) with walk_ray_tree (:427-529) and LightBuffer::traverse (:760-884) for the 32
+// cubes of a warp in lockstep (see the header).  Warp-collective: every lane calls it; `active` = this lane has a
+// cube.  `path` = LIGHT_MAX_DEPTH words of shared memory per warp (the node index at each depth of the current
+// path).  MARK as in compute_light.  Per-lane state of the walk: `ld`, the depth of the lane's deepest live frame
+// (-1: only the call of the root is pending; -2: the lane does not walk), and its frames (alpha after traverse(),
+// ray_bundle_weight, the children's weight so far, light_ahead_cache) indexed by depth — the depth is warp-uniform,
+// so these local-memory accesses are coalesced.
+template <bool MARK>
+__device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lut, uint32_t *path, bool active, int ox,
+                                           int oy, int oz, uint32_t mark_priority, uint32_t *visits_out) {
+    const DeviceScene &S = P.scene;
+    Accum acc = {0.f, 0.f, 0.f, 0.f};
+    uint32_t oidx;
+    uint32_t oflags = 0;
+    const LightBlockDev *ob = nullptr;
+    if (active && cube_index(S, ox, oy, oz, &oidx)) {
+        ob = &P.blocks[block_id_at(S, oidx)];
+        oflags = __ldg(&ob->flags);
+    }
+    const bool origin_opaque = (oflags & LB_ALL_OPAQUE) != 0;
+    uint32_t visits = 0;
+    float dw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active && origin_opaque) {
+        if (oflags & LB_EMISSIVE) {  // !opaque_for_light_computation: add_weighted_light(emission, 1.0)
+            acc.in0 = acc.in0 + ps_mul(__ldg(&ob->emission[0]), 1.0f);
+            acc.in1 = acc.in1 + ps_mul(__ldg(&ob->emission[1]), 1.0f);
+            acc.in2 = acc.in2 + ps_mul(__ldg(&ob->emission[2]), 1.0f);
+            acc.total += 1.0f;
+        }
+    } else if (active) {
+        if (oflags & LB_VISIBLE) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) dw[f] = 1.0f;
+        } else {  // directions_to_seek_light (updater.rs:669-690)
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                const int s = (f < 3) ? -1 : 1, a = f % 3;
+                const uint32_t toward = flags_at(P, ox + (a == 0 ? s : 0), oy + (a == 1 ? s : 0), oz + (a == 2 ? s : 0));
+                const uint32_t away = flags_at(P, ox - (a == 0 ? s : 0), oy - (a == 1 ? s : 0), oz - (a == 2 ? s : 0));
+                dw[f] = ((away & LB_VISIBLE) || (toward & LB_EMISSIVE)) ? 1.0f : 0.0f;
+            }
+        }
+    }
+    int ld = (active && !origin_opaque) ? -1 : -2;
+    if (__any_sync(0xffffffffu, ld == -1)) {
+        float f_alpha[LIGHT_MAX_DEPTH], f_bundle[LIGHT_MAX_DEPTH], f_csum[LIGHT_MAX_DEPTH];
+        uint32_t f_ahead[LIGHT_MAX_DEPTH];
+        uint8_t f_have[LIGHT_MAX_DEPTH];
+        const int max_d2 = (int)(P.max_distance * P.max_distance);
+        const int lane = threadIdx.x & 31;
+        // all children of the frame at depth k are done (updater.rs:518-528): the rest of its bundle ends here
+        auto pop_level = [&](int k) {
+            const uint4 *np = reinterpret_cast<const uint4 *>(P.chart_pre + path[k]);
+            const uint4 a = __ldg(np);
+            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(np + 1));
+            if (ld == k) {
+                if (!MARK) {
+                    const float cw[6] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+                                         __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y)};
+                    end_of_ray(P, lut, acc, f_alpha[k], fmaxf(f_bundle[k] - f_csum[k], 0.0f), cw);
+                }
+                ld = k - 1;
+            }
+        };
+        uint32_t n = 0;
+        int top = -1;   // deepest depth of the current path that holds a frame of some lane
+        for (;;) {
+            const uint4 *np = reinterpret_cast<const uint4 *>(P.chart_pre + n);
+            const uint4 na = __ldg(np), nb = __ldg(np + 1);
+            const int d = (int)(nb.z >> 24);
+            for (int k = top; k >= d; k--) pop_level(k);
+            top = d - 1;
+            const uint32_t end_dir = nb.w;
+            const int relx = (int)(int8_t)(nb.z & 255u), rely = (int)(int8_t)((nb.z >> 8) & 255u), relz = (int)(int8_t)((nb.z >> 16) & 255u);
+            const bool too_far = relx * relx + rely * rely + relz * relz > max_d2;   // updater.rs:452-455, exact in integers
+            bool pushed = false;
+            if (ld == d - 1) {   // this lane's walk enters the node
+                visits++;
+                const float cw[6] = {__uint_as_float(na.x), __uint_as_float(na.y), __uint_as_float(na.z),
+                                     __uint_as_float(na.w), __uint_as_float(nb.x), __uint_as_float(nb.y)};
+                float prod[6];
+#pragma unroll
+                for (int f = 0; f < 6; f++) prod[f] = cw[f] * dw[f];
+                const float bundle = fm_sum(prod);
+                const float e_alpha = d == 0 ? 1.0f : f_alpha[d - 1];
+                if (bundle > 0.0f) {
+                    const int e_x = ox + relx, e_y = oy + rely, e_z = oz + relz;
+                    uint32_t cidx;
+                    if (too_far || !cube_index(S, e_x, e_y, e_z, &cidx)) {
+                        if (!MARK) end_of_ray(P, lut, acc, e_alpha, bundle, cw);
+                    } else {
+                        // ---- LightBuffer::traverse ----
+                        const int dir = (int)(end_dir >> 29);
+                        const int e_face = d == 0 ? 0 : ((dir < 3) ? dir + 3 : dir - 3) + 1;
+                        const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
+                        const uint32_t fl = __ldg(&ev->flags);
+                        float alpha = e_alpha;
+                        bool have_ahead = false;
+                        uint32_t ahead = 0;
+                        if (fl & LB_VISIBLE) {
+                            const bool hit_opaque_face = (e_face == 0) ? ((fl & LB_ALL_OPAQUE) != 0) : (((fl >> (e_face - 1)) & 1u) != 0);
+                            if (hit_opaque_face && e_face == 0) {
+                                alpha = 0.0f;  // (direction weights are zeroed too; nothing reads them afterwards)
+                            } else {
+                                float col[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) col[i] = __ldg(&ev->face_color[e_face][i]);
+#pragma unroll
+                                for (int i = 0; i < 3; i++) col[i] = col[i] > 1.0f ? 1.0f : col[i];  // Rgba::clamp
+                                const float hit_alpha = col[3];
+                                const float kw = ps_clamped(fm_sum(prod));
+                                if (hit_alpha > 0.0f && e_face != 0) {
+                                    int lx = e_x, ly = e_y, lz = e_z;  // hit.adjacent(): the cube the ray came from
+                                    const int ax = (e_face - 1) % 3, sgn = (e_face >= 4) ? 1 : -1;
+                                    if (ax == 0) lx += sgn; else if (ax == 1) ly += sgn; else lz += sgn;
+                                    if (MARK) mark_dependency(P, lx, ly, lz, mark_priority);
+                                    if (!MARK) {
+                                        const bool e_have_prev = d > 0 && f_have[d - 1] != 0;
+                                        const uint32_t stored = e_have_prev ? f_ahead[d - 1] : light_get(P, lx, ly, lz);
+                                        const float ka = ps_clamped(alpha);
+                                        float lf[3];
+                                        lf[0] = __ldg(&ev->emission[0]) + ps_mul(ps_mul(col[0], lut[stored & 255]), hit_alpha);
+                                        lf[1] = __ldg(&ev->emission[1]) + ps_mul(ps_mul(col[1], lut[(stored >> 8) & 255]), hit_alpha);
+                                        lf[2] = __ldg(&ev->emission[2]) + ps_mul(ps_mul(col[2], lut[(stored >> 16) & 255]), hit_alpha);
+                                        acc.in0 = acc.in0 + ps_mul(ps_mul(lf[0], ka), kw);
+                                        acc.in1 = acc.in1 + ps_mul(ps_mul(lf[1], ka), kw);
+                                        acc.in2 = acc.in2 + ps_mul(ps_mul(lf[2], ka), kw);
+                                    }
+                                    if (hit_opaque_face) alpha = 0.0f; else alpha *= 1.0f - hit_alpha;
+                                }
+                                if (hit_alpha < 1.0f) {
+                                    if (MARK) mark_dependency(P, e_x, e_y, e_z, mark_priority);
+                                    if (!MARK) {
+                                        float sv0 = 0.f, sv1 = 0.f, sv2 = 0.f;
+                                        if (e_face != 0) {
+                                            ahead = S.light[cidx];
+                                            have_ahead = true;
+                                            sv0 = lut[ahead & 255]; sv1 = lut[(ahead >> 8) & 255]; sv2 = lut[(ahead >> 16) & 255];
+                                        }
+                                        const float kh = ps_clamped(hit_alpha), ka = ps_clamped(alpha);
+                                        const float l0 = __ldg(&ev->emission[0]) + ps_mul(sv0, kh);
+                                        const float l1 = __ldg(&ev->emission[1]) + ps_mul(sv1, kh);
+                                        const float l2 = __ldg(&ev->emission[2]) + ps_mul(sv2, kh);
+                                        acc.in0 = acc.in0 + ps_mul(ps_mul(l0, ka), kw);
+                                        acc.in1 = acc.in1 + ps_mul(ps_mul(l1, ka), kw);
+                                        acc.in2 = acc.in2 + ps_mul(ps_mul(l2, ka), kw);
+                                    }
+                                    alpha *= 1.0f - hit_alpha;
+                                }
+                            }
+                        }
+                        if (!(alpha > 0.0f)) {
+                            if (!MARK) end_of_ray(P, lut, acc, alpha, bundle, cw);
+                        } else {
+                            f_alpha[d] = alpha; f_bundle[d] = bundle; f_csum[d] = 0.0f;
+                            f_ahead[d] = ahead; f_have[d] = have_ahead ? 1 : 0;
+                            ld = d;
+                            pushed = true;
+                        }
+                    }
+                }
+                if (d > 0) f_csum[d - 1] += bundle;   // the call returns its bundle weight (updater.rs:514, 528)
+            }
+            if (__any_sync(0xffffffffu, pushed)) {
+                if (lane == 0) path[d] = n;
+                __syncwarp();
+                top = d;
+                n = n + 1;                       // a child if there is one, else the pops above end the frame
+            } else {
+                n = end_dir & 0x1fffffffu;       // nobody is inside: skip the subtree
+            }
+            if (n >= P.chart_nodes) break;
+        }
+        for (int k = top; k >= 0; k--) pop_level(k);
+    }
+    if (visits_out) *visits_out = visits;
+    if (!active) return 0u;
     // LightBuffer::finish (updater.rs:932-944)
     const float scale = ps_clamped(1.0f / fmaxf(acc.total, 1.0f));
     if (acc.total > 0.0f)

@@ -893,7 +893,7 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     uint32_t n_hits = 0;                 // hit records of the current ray (consecutive slots of this lane's chunks)
     uint32_t chunk_base = HIT_NONE, chunk_used = HIT_CHUNK;   // this lane's chunk of the hit stream
     uint32_t ev_word = 0;
-    AuxState<AUX> aux;
+    AuxState<AUX> aux{};
     bool list_exhausted = false;         // warp-uniform: the ray list has run out (tail of the frame)
 
     // log-domain bound of one transmittance factor.  Exact factor (shade_kernel): 1 - clamp(1 - (f32)pow(u, th)) with
