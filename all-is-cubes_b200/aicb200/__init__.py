@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     lib.aicb_light_edit_and_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8,
                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
     lib.aicb_light_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_light_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.aicb_light_chart.argtypes = [C.c_void_p, C.c_void_p]
     lib.aicb_light_chart.restype = C.c_uint32
     lib.aicb_light_fast_evaluate.argtypes = [C.c_void_p]
@@ -561,6 +562,13 @@ class SpaceRaytracer:
         _check(load_library().aicb_light_edit_and_propagate(self.handle, c.ctypes.data, ids.ctypes.data, c.shape[0], epsilon,
                                                             C.byref(n), C.byref(md)))
         return int(n.value), int(md.value)
+
+    def light_stats(self) -> dict:
+        """Counters of the last propagation: cube updates, chart node visits, rounds, device seconds."""
+        out = (C.c_uint64 * 4)()
+        _check(load_library().aicb_light_stats(self.handle, out))
+        return {"cube_updates": int(out[0]), "chart_node_visits": int(out[1]), "rounds": int(out[2]),
+                "device_seconds": int(out[3]) * 1e-6}
 
     def light_download(self) -> np.ndarray:
         out = np.zeros(self.space.size + (4,), dtype=np.uint8)

@@ -137,4 +137,5 @@ EXPORTED_SYMBOLS = [
     "aicb_light_evaluate",
     "aicb_light_edit_and_propagate",
     "aicb_light_download",
+    "aicb_light_stats",
 ]

@@ -157,6 +157,30 @@ def config_c2(n=256, seed=3, n_voxel_blocks=64, with_light=False):
     return Space((0, 0, 0), ids, blocks, light=light)
 
 
+def config_c4(n=256, seed=4):
+    """BASELINE configs[4]: the C1 layout with res-1 blocks — ground slab of opaque blocks for
+    y < n/4, 1/16 of the cubes above it opaque (one in fifteen of them an emitter) — LightPhysics::Rays{30},
+    Sky::Octants as content/testing.rs:124-137, light all NO_RAYS (to be converged by the light kernels)."""
+    h = grid_hash(seed, (n, n, n))
+    pal = make_palette(seed, 14)
+    blocks = [Block.air()] + [Block(color=tuple(pal[i, :4])) for i in range(14)] + \
+             [Block(color=(0.1, 0.1, 0.1, 1.0), emission=(4.0, 3.5, 2.0))]
+    ids = np.where((h & U64(15)) == 0, 1 + ((h >> U64(8)) % U64(15)).astype(np.int64), 0).astype(np.uint16)
+    ids[:, : n // 4, :] = 1 + ((h[:, : n // 4, :] >> U64(8)) % U64(14)).astype(np.uint16)
+    light = np.zeros((n, n, n, 4), dtype=np.uint8)
+    light[..., 3] = 1
+    return Space((0, 0, 0), ids, blocks, light=light, sky_colors=OCTANT_SKY, light_max_distance=30)
+
+
+def c4_edits(space, n_edits, batch):
+    """The `batch`-th set of random block edits of C4: cubes from the ground surface upwards, any block of the table."""
+    n = space.size[0]
+    rng = np.random.default_rng(7 + batch)
+    cubes = np.stack([rng.integers(0, n, n_edits), rng.integers(n // 4 - 2, n, n_edits), rng.integers(0, n, n_edits)],
+                     axis=1).astype(np.int32)
+    return cubes, rng.integers(0, len(space.blocks), n_edits).astype(np.uint16)
+
+
 def small_mixed_scene(n=12, seed=7, lower=(-3, 2, -5), with_light=True, octant_sky=True):
     """A small Space exercising every code path: AIR, opaque / transparent / emissive /
     invisible-but-not-AIR single blocks, recursive blocks (res 2..16, partial bounds,

@@ -922,7 +922,11 @@ aicb_status aicb_scene_upload_light(aicb_scene *s, const uint8_t (*light)[4], si
         s->device_bytes += s->volume * 4;
         s->ds.light = s->d_light;
     }
-    if (s->volume) CU(cudaMemcpy(s->d_light, light, s->volume * 4, cudaMemcpyHostToDevice));
+    if (s->volume) {   // ordered behind queued cube deltas; renders on other streams wait for ev_delta (launch_trace)
+        CU(cudaMemcpyAsync(s->d_light, light, s->volume * 4, cudaMemcpyHostToDevice, s->ctx->stream));
+        CU(cudaEventRecord(s->ctx->ev_delta, s->ctx->stream));
+        CU(cudaStreamSynchronize(s->ctx->stream));
+    }
     return AICB_OK;
 }
 

@@ -3,6 +3,7 @@
 // replacing LightStorage::update_light_from_queue / apply_light_update / fast_evaluate_light /
 // modified_cube_needs_update (space/light/updater.rs) and Mutation::evaluate_light (space.rs:1496-1527).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -130,10 +131,15 @@ std::vector<LightNodePre> build_chart_preorder(const std::vector<LightChartNode>
     return pre;
 }
 
+const std::vector<LightNodePre> &chart_preorder_host() {
+    static const std::vector<LightNodePre> pre = build_chart_preorder(build_chart());
+    return pre;
+}
+
 aicb_status ensure_chart(aicb_ctx *ctx) {
     if (ctx->d_chart) return AICB_OK;
     std::vector<LightChartNode> chart = build_chart();
-    std::vector<LightNodePre> pre = build_chart_preorder(chart);
+    const std::vector<LightNodePre> &pre = chart_preorder_host();
     CU(cudaMalloc(&ctx->d_chart_pre, pre.size() * sizeof(LightNodePre)));
     CU(cudaMemcpy(ctx->d_chart_pre, pre.data(), pre.size() * sizeof(LightNodePre), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&ctx->d_chart, chart.size() * sizeof(LightChartNode)));
@@ -186,10 +192,22 @@ __global__ void __launch_bounds__(256) k_gather(const LightParams P, uint32_t n_
     if (prio <= P.epsilon_priority) return;
     const uint32_t n_words = (P.volume + 3) / 4;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // Thread -> word of the tile.  With a power-of-two z extent the tile is a few whole z-rows, and the threads are
+    // laid out so that 8 consecutive threads (32 cubes: one warp of the lockstep walk) cover a 4 x 8 patch of (y, z)
+    // instead of 32 cubes in a line: neighbours in two directions share more of their chart walk.
+    uint32_t wl = threadIdx.x;
+    {
+        const uint32_t nz = (uint32_t)P.scene.size[2];
+        if (nz >= 8 && nz <= 256 && (nz & (nz - 1)) == 0) {
+            const uint32_t wpr = nz / 4, q = threadIdx.x >> 3, within = threadIdx.x & 7;
+            const uint32_t row_group = q / (wpr / 2), pz = q % (wpr / 2);
+            wl = (row_group * 4 + (within >> 1)) * wpr + pz * 2 + (within & 1);
+        }
+    }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t tm = P.tile_max[tile];
         if (tm <= P.epsilon_priority || tm + P.priority_band < prio) continue;   // (block-uniform)
-        const uint32_t w = tile * (LIGHT_TILE / 4) + threadIdx.x;
+        const uint32_t w = tile * (LIGHT_TILE / 4) + wl;
         uint32_t v = w < n_words ? ((uint32_t *)P.pending)[w] : 0u;
         uint32_t sel = 0, cnt = 0;
 #pragma unroll
@@ -231,7 +249,7 @@ __global__ void __launch_bounds__(256) k_gather(const LightParams P, uint32_t n_
 
 __global__ void __launch_bounds__(128) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
     __shared__ float s_lut[256];
-    __shared__ uint32_t s_path[4][LIGHT_MAX_DEPTH];
+    __shared__ float4 s_path[4][LIGHT_MAX_DEPTH];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
     __syncthreads();
     if (!explicit_cubes) n = P.scalars[0];   // the round's list
@@ -294,7 +312,7 @@ __global__ void k_apply(const LightParams P) {
 // the dependency re-queue of apply_light_update (updater.rs:355-360): re-walk the chart, raising the
 // queue priority of every cube whose light was read
 __global__ void __launch_bounds__(128) k_mark(const LightParams P) {
-    __shared__ uint32_t s_path[4][LIGHT_MAX_DEPTH];
+    __shared__ float4 s_path[4][LIGHT_MAX_DEPTH];
     const uint32_t n = P.scalars[0];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -372,6 +390,7 @@ LightParams make_params(aicb_scene *s) {
     P.blocks = s->d_light_blocks;
     P.chart = s->ctx->d_chart;
     P.chart_pre = s->ctx->d_chart_pre;
+    P.sky_term = s->d_sky_term;
     P.chart_nodes = s->ctx->chart_nodes;
     P.tile_max = s->d_tile_max;
     P.pending = s->d_pending;
@@ -394,6 +413,35 @@ aicb_status ensure_light_state(aicb_scene *s) {
         CU(cudaMemcpy(s->d_light, init.data(), s->volume * 4, cudaMemcpyHostToDevice));
         s->ds.light = s->d_light;
         s->device_bytes += s->volume * 4;
+    }
+    if (!s->d_sky_term) {
+        // end_of_ray (updater.rs:889-924) without the lane's alpha and bundle weight: per chart node, the sky light
+        // its bundle collects — the same f32 operations, in the same order, as the reference evaluates per ray end
+        const std::vector<LightNodePre> &pre = chart_preorder_host();
+        float lut[256];
+        lut[0] = 0.0f;
+        for (int i = 1; i < 256; i++) lut[i] = (float)std::exp2((double)(((float)i - 144.0f) / 10.0f));
+        auto psc = [](float v) { return v > 0.0f ? v : 0.0f; };
+        auto psm = [](float a, float b) { float v = a * b; return (v != v) ? 0.0f : v; };
+        std::vector<float4> sky(pre.size());
+        for (size_t k = 0; k < pre.size(); k++) {
+            const float *cw = pre[k].w;
+            float t[6][3];
+            for (int f = 0; f < 6; f++) {
+                const uint32_t tx = s->ds.sky_faces[f];
+                const float kk = psc(cw[f]);
+                t[f][0] = psm(lut[tx & 255], kk);
+                t[f][1] = psm(lut[(tx >> 8) & 255], kk);
+                t[f][2] = psm(lut[(tx >> 16) & 255], kk);
+            }
+            const float kr = psc(1.0f / ((cw[0] + cw[3]) + (cw[1] + cw[4]) + (cw[2] + cw[5])));
+            float c[3];
+            for (int i = 0; i < 3; i++) c[i] = psm((t[0][i] + t[3][i]) + (t[1][i] + t[4][i]) + (t[2][i] + t[5][i]), kr);
+            sky[k] = make_float4(c[0], c[1], c[2], 0.0f);
+        }
+        CU(cudaMalloc(&s->d_sky_term, sky.size() * sizeof(float4)));
+        CU(cudaMemcpy(s->d_sky_term, sky.data(), sky.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        s->device_bytes += sky.size() * sizeof(float4);
     }
     if (!s->d_pending) {
         CU(cudaMalloc(&s->d_pending, s->volume + 16));
@@ -424,8 +472,9 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
     const int blocks = ctx->num_sms * 8;
     const int wide = ctx->num_sms * 8;    // 128-thread blocks of the lockstep kernels (one warp per 32 list entries, grid-stride)
     const uint32_t n_tiles = (uint32_t)((s->volume + LIGHT_TILE - 1) / LIGHT_TILE);
-    uint64_t total = 0, visits = 0;
+    uint64_t total = 0, visits = 0, rounds = 0;
     uint32_t maxd = 0;
+    CU(cudaEventRecord(ctx->ev0, st));
     CU(cudaMemsetAsync(s->d_scalars, 0, 8 * 4, st));
     k_tile_rebuild<<<blocks, 256, 0, st>>>(P, n_tiles);   // (fast_evaluate / edits write the priority bytes directly)
     const int ROUNDS_PER_SYNC = 8;
@@ -442,11 +491,22 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
         CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
+        if (getenv("AICB_LIGHT_TRACE"))
+            fprintf(stderr, "[aicb200 light] batch %d: last round %u cubes at priority %u; %u updates so far\n", batch, h[0], h[1], h[3]);
         total = h[3];
         visits = (uint64_t)h[4] | ((uint64_t)h[5] << 32);
         maxd = h[2];
+        rounds += ROUNDS_PER_SYNC;
         if (h[1] <= P.epsilon_priority) break;   // the batch's last round found nothing above epsilon
     }
+    CU(cudaEventRecord(ctx->ev1, st));
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    s->light_stats[0] = total;
+    s->light_stats[1] = visits;
+    s->light_stats[2] = rounds;
+    s->light_stats[3] = (uint64_t)(ms * 1000.0f);   // device time of the propagation in microseconds
     if (updates_done) *updates_done = total;
     if (max_diff) *max_diff = (uint8_t)maxd;
     if (node_visits) *node_visits = visits;
@@ -512,6 +572,7 @@ void aicb_light_scene_free(aicb_scene *s) {
     if (s->d_diff) cudaFree(s->d_diff);
     if (s->d_scalars) cudaFree(s->d_scalars);
     if (s->d_tile_max) cudaFree(s->d_tile_max);
+    if (s->d_sky_term) cudaFree(s->d_sky_term);
 }
 
 void aicb_light_ctx_free(aicb_ctx *c) {
@@ -605,10 +666,15 @@ aicb_status aicb_light_edit_and_propagate(aicb_scene *s, const int32_t (*cubes)[
         }
         return it->second;
     };
+    // validate everything before the host mirror (or anything else) changes
     for (size_t i = 0; i < n_edits; i++) {
         uint32_t idx;
         if (!index_of(cubes[i][0], cubes[i][1], cubes[i][2], &idx)) return aicb_fail(AICB_ERR_INVALID, "cube out of bounds");
         if (new_ids[i] >= s->h_block_light.size()) return aicb_fail(AICB_ERR_INVALID, "block id out of range");
+    }
+    for (size_t i = 0; i < n_edits; i++) {
+        uint32_t idx;
+        index_of(cubes[i][0], cubes[i][1], cubes[i][2], &idx);
         if (s->h_ids[idx] == new_ids[i]) continue;  // Mutation::set of the same block changes nothing
         s->h_ids[idx] = new_ids[i];
         EditOp &o = op_of(idx);
@@ -652,7 +718,15 @@ aicb_status aicb_light_download(aicb_scene *s, uint8_t (*out)[4], size_t n_texel
     if (!s->d_light) return aicb_fail(AICB_ERR_INVALID, "scene has no light volume (LightPhysics::None)");
     std::lock_guard<std::mutex> lock(s->ctx->mu);
     CU(cudaSetDevice(s->ctx->device));
-    CU(cudaMemcpy(out, s->d_light, s->volume * 4, cudaMemcpyDeviceToHost));
+    // ordered behind everything queued on the context's stream (cube deltas, propagation)
+    CU(cudaMemcpyAsync(out, s->d_light, s->volume * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
+    CU(cudaStreamSynchronize(s->ctx->stream));
+    return AICB_OK;
+}
+
+aicb_status aicb_light_stats(const aicb_scene *s, uint64_t out[4]) {
+    if (!s || !out) return aicb_fail(AICB_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 4; i++) out[i] = s->light_stats[i];
     return AICB_OK;
 }
 }

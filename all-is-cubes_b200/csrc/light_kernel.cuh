@@ -58,6 +58,7 @@ struct LightParams {
     const LightBlockDev *blocks;
     const LightChartNode *chart;
     const LightNodePre *chart_pre;
+    const float4 *sky_term;         // per preorder node: the sky light its bundle collects at the end of a ray (end_of_ray)
     uint32_t chart_nodes;
     uint32_t *tile_max;             // per LIGHT_TILE cubes: an upper bound of the tile's highest queued priority
     uint8_t *pending;
@@ -157,251 +158,33 @@ __device__ __forceinline__ void mark_dependency(const LightParams &P, int x, int
     if (cube_index(P.scene, x, y, z, &idx)) raise_pending(P.pending, P.tile_max, idx, prio);
 }
 
-struct Frame {
-    uint32_t node;
-    int x, y, z;          // cube entered
-    float alpha;          // ray_state.alpha after traverse()
-    float bundle;         // ray_bundle_weight
-    float child_sum;
-    uint32_t ahead;       // light_ahead_cache
-    uint8_t have_ahead;
-    uint8_t next_child;
-};
-
 struct Accum {
     float in0, in1, in2, total;
 };
 
-// end_of_ray (updater.rs:889-924) + add_weighted_light (:926-929)
-__device__ __forceinline__ void end_of_ray(const LightParams &P, const float *lut, Accum &a, float alpha, float bundle,
-                                           const float cw[6]) {
+// end_of_ray (updater.rs:889-924) + add_weighted_light (:926-929).  The sky light a chart node's bundle collects —
+// sum over the six faces of sky_face * max(weight, 0), times 1 / sum(weights) — depends on the node and the sky
+// only; it is tabulated per scene (`sky`, see light.cu) and a lane only applies its own alpha and bundle weight.
+__device__ __forceinline__ void end_of_ray(Accum &a, float alpha, float bundle, const float4 sky) {
     if (bundle > 0.0f) {
-        float t[6][3];
-#pragma unroll
-        for (int f = 0; f < 6; f++) {
-            uint32_t tx = P.scene.sky_faces[f];
-            float k = ps_clamped(cw[f]);
-            t[f][0] = ps_mul(lut[tx & 255], k);
-            t[f][1] = ps_mul(lut[(tx >> 8) & 255], k);
-            t[f][2] = ps_mul(lut[(tx >> 16) & 255], k);
-        }
-        const float kr = ps_clamped(1.0f / fm_sum(cw));
         const float ka = ps_clamped(alpha), kb = ps_clamped(bundle);
-        float c[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            float s = (t[0][i] + t[3][i]) + (t[1][i] + t[4][i]) + (t[2][i] + t[5][i]);
-            c[i] = ps_mul(ps_mul(s, kr), ka);
-        }
-        a.in0 = a.in0 + ps_mul(c[0], kb);
-        a.in1 = a.in1 + ps_mul(c[1], kb);
-        a.in2 = a.in2 + ps_mul(c[2], kb);
+        a.in0 = a.in0 + ps_mul(ps_mul(sky.x, ka), kb);
+        a.in1 = a.in1 + ps_mul(ps_mul(sky.y, ka), kb);
+        a.in2 = a.in2 + ps_mul(ps_mul(sky.z, ka), kb);
         a.total += bundle;
     }
-}
-
-// compute_light (updater.rs:368-418) with walk_ray_tree (:427-529) and LightBuffer::traverse (:760-884).
-// MARK = false: returns the new texel.  MARK = true: instead of accumulating light, raises the queue
-// priority of every dependency cube to `mark_priority` (apply_light_update's re-queue, updater.rs:355-360).
-template <bool MARK>
-__device__ uint32_t compute_light(const LightParams &P, const float *lut, int ox, int oy, int oz, uint32_t mark_priority,
-                                  uint32_t *visits_out) {
-    const DeviceScene &S = P.scene;
-    Accum acc = {0.f, 0.f, 0.f, 0.f};
-    uint32_t oidx;
-    uint32_t oflags = 0;
-    const LightBlockDev *ob = nullptr;
-    if (cube_index(S, ox, oy, oz, &oidx)) {
-        ob = &P.blocks[block_id_at(S, oidx)];
-        oflags = __ldg(&ob->flags);
-    }
-    const bool origin_opaque = (oflags & LB_ALL_OPAQUE) != 0;
-    uint32_t visits = 0;
-    if (origin_opaque) {
-        if (oflags & LB_EMISSIVE) {  // !opaque_for_light_computation: add_weighted_light(emission, 1.0)
-            acc.in0 = acc.in0 + ps_mul(__ldg(&ob->emission[0]), 1.0f);
-            acc.in1 = acc.in1 + ps_mul(__ldg(&ob->emission[1]), 1.0f);
-            acc.in2 = acc.in2 + ps_mul(__ldg(&ob->emission[2]), 1.0f);
-            acc.total += 1.0f;
-        }
-    } else {
-        float dw[6];
-        if (oflags & LB_VISIBLE) {
-#pragma unroll
-            for (int f = 0; f < 6; f++) dw[f] = 1.0f;
-        } else {  // directions_to_seek_light (updater.rs:669-690)
-#pragma unroll
-            for (int f = 0; f < 6; f++) {
-                const int s = (f < 3) ? -1 : 1, a = f % 3;
-                const uint32_t toward = flags_at(P, ox + (a == 0 ? s : 0), oy + (a == 1 ? s : 0), oz + (a == 2 ? s : 0));
-                const uint32_t away = flags_at(P, ox - (a == 0 ? s : 0), oy - (a == 1 ? s : 0), oz - (a == 2 ? s : 0));
-                dw[f] = ((away & LB_VISIBLE) || (toward & LB_EMISSIVE)) ? 1.0f : 0.0f;
-            }
-        }
-        const double max_d2 = (double)P.max_distance * (double)P.max_distance;
-
-        Frame stack[LIGHT_MAX_DEPTH];
-        int sp = 0;
-        // "call" the root
-        bool entering = true;
-        uint32_t e_node = 0;
-        int e_x = ox, e_y = oy, e_z = oz, e_face = 0;
-        float e_alpha = 1.0f;
-        bool e_have_prev = false;
-        uint32_t e_prev = 0;
-        float ret = 0.0f;
-        for (;;) {
-            if (entering) {
-                entering = false;
-                visits++;
-                const LightChartNode *node = P.chart + e_node;
-                float cw[6];
-#pragma unroll
-                for (int f = 0; f < 6; f++) cw[f] = __ldg(&node->w[f]);
-                float prod[6];
-#pragma unroll
-                for (int f = 0; f < 6; f++) prod[f] = cw[f] * dw[f];
-                const float bundle = fm_sum(prod);
-                bool done = false;
-                if (bundle <= 0.0f) {
-                    done = true;
-                } else {
-                    const double ddx = ((double)e_x + 0.5) - ((double)ox + 0.5), ddy = ((double)e_y + 0.5) - ((double)oy + 0.5),
-                                 ddz = ((double)e_z + 0.5) - ((double)oz + 0.5);
-                    uint32_t cidx;
-                    if ((ddx * ddx + ddy * ddy + ddz * ddz) > max_d2 || !cube_index(S, e_x, e_y, e_z, &cidx)) {
-                        if (!MARK) end_of_ray(P, lut, acc, e_alpha, bundle, cw);
-                        done = true;
-                    } else {
-                        // ---- LightBuffer::traverse ----
-                        const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
-                        const uint32_t fl = __ldg(&ev->flags);
-                        float alpha = e_alpha;
-                        bool have_ahead = false;
-                        uint32_t ahead = 0;
-                        if (fl & LB_VISIBLE) {
-                            const bool hit_opaque_face = (e_face == 0) ? ((fl & LB_ALL_OPAQUE) != 0) : (((fl >> (e_face - 1)) & 1u) != 0);
-                            if (hit_opaque_face && e_face == 0) {
-                                alpha = 0.0f;  // (direction weights are zeroed too; nothing reads them afterwards)
-                            } else {
-                                float col[4];
-#pragma unroll
-                                for (int i = 0; i < 4; i++) col[i] = __ldg(&ev->face_color[e_face][i]);
-#pragma unroll
-                                for (int i = 0; i < 3; i++) col[i] = col[i] > 1.0f ? 1.0f : col[i];  // Rgba::clamp
-                                const float hit_alpha = col[3];
-                                const float kw = ps_clamped(fm_sum(prod));
-                                if (hit_alpha > 0.0f && e_face != 0) {
-                                    int lx = e_x, ly = e_y, lz = e_z;  // hit.adjacent(): the cube the ray came from
-                                    const int ax = (e_face - 1) % 3, sgn = (e_face >= 4) ? 1 : -1;
-                                    if (ax == 0) lx += sgn; else if (ax == 1) ly += sgn; else lz += sgn;
-                                    if (MARK) mark_dependency(P, lx, ly, lz, mark_priority);
-                                    if (!MARK) {
-                                        const uint32_t stored = e_have_prev ? e_prev : light_get(P, lx, ly, lz);
-                                        const float ka = ps_clamped(alpha);
-                                        float lf[3];
-                                        lf[0] = __ldg(&ev->emission[0]) + ps_mul(ps_mul(col[0], lut[stored & 255]), hit_alpha);
-                                        lf[1] = __ldg(&ev->emission[1]) + ps_mul(ps_mul(col[1], lut[(stored >> 8) & 255]), hit_alpha);
-                                        lf[2] = __ldg(&ev->emission[2]) + ps_mul(ps_mul(col[2], lut[(stored >> 16) & 255]), hit_alpha);
-                                        acc.in0 = acc.in0 + ps_mul(ps_mul(lf[0], ka), kw);
-                                        acc.in1 = acc.in1 + ps_mul(ps_mul(lf[1], ka), kw);
-                                        acc.in2 = acc.in2 + ps_mul(ps_mul(lf[2], ka), kw);
-                                    }
-                                    if (hit_opaque_face) alpha = 0.0f; else alpha *= 1.0f - hit_alpha;
-                                }
-                                if (hit_alpha < 1.0f) {
-                                    if (MARK) mark_dependency(P, e_x, e_y, e_z, mark_priority);
-                                    if (!MARK) {
-                                        float sv0 = 0.f, sv1 = 0.f, sv2 = 0.f;
-                                        if (e_face != 0) {
-                                            ahead = S.light[cidx];
-                                            have_ahead = true;
-                                            sv0 = lut[ahead & 255]; sv1 = lut[(ahead >> 8) & 255]; sv2 = lut[(ahead >> 16) & 255];
-                                        }
-                                        const float kh = ps_clamped(hit_alpha), ka = ps_clamped(alpha);
-                                        const float l0 = __ldg(&ev->emission[0]) + ps_mul(sv0, kh);
-                                        const float l1 = __ldg(&ev->emission[1]) + ps_mul(sv1, kh);
-                                        const float l2 = __ldg(&ev->emission[2]) + ps_mul(sv2, kh);
-                                        acc.in0 = acc.in0 + ps_mul(ps_mul(l0, ka), kw);
-                                        acc.in1 = acc.in1 + ps_mul(ps_mul(l1, ka), kw);
-                                        acc.in2 = acc.in2 + ps_mul(ps_mul(l2, ka), kw);
-                                    }
-                                    alpha *= 1.0f - hit_alpha;
-                                }
-                            }
-                        }
-                        if (!(alpha > 0.0f)) {
-                            if (!MARK) end_of_ray(P, lut, acc, alpha, bundle, cw);
-                            done = true;
-                        } else {
-                            Frame &fr = stack[sp++];
-                            fr.node = e_node; fr.x = e_x; fr.y = e_y; fr.z = e_z;
-                            fr.alpha = alpha; fr.bundle = bundle; fr.child_sum = 0.0f;
-                            fr.ahead = ahead; fr.have_ahead = have_ahead ? 1 : 0; fr.next_child = 0;
-                        }
-                    }
-                }
-                if (done) {
-                    ret = bundle;
-                    if (sp == 0) break;
-                    stack[sp - 1].child_sum += ret;
-                }
-                continue;
-            }
-            // resume the frame on top of the stack: next child, or finish
-            Frame &fr = stack[sp - 1];
-            const LightChartNode *node = P.chart + fr.node;
-            int f = fr.next_child;
-            uint32_t child = 0;
-            while (f < 6) {
-                child = __ldg(&node->child[f]);
-                if (child) break;
-                f++;
-            }
-            if (f < 6) {
-                fr.next_child = (uint8_t)(f + 1);
-                const int s = (f < 3) ? -1 : 1, a = f % 3;
-                e_node = child;
-                e_x = fr.x + (a == 0 ? s : 0); e_y = fr.y + (a == 1 ? s : 0); e_z = fr.z + (a == 2 ? s : 0);
-                e_face = ((f < 3) ? f + 3 : f - 3) + 1;
-                e_alpha = fr.alpha;
-                e_have_prev = fr.have_ahead != 0;
-                e_prev = fr.ahead;
-                entering = true;
-                continue;
-            }
-            // all children done
-            if (!MARK) {
-                float cw[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) cw[k] = __ldg(&node->w[k]);
-                end_of_ray(P, lut, acc, fr.alpha, fmaxf(fr.bundle - fr.child_sum, 0.0f), cw);
-            }
-            ret = fr.bundle;
-            sp--;
-            if (sp == 0) break;
-            stack[sp - 1].child_sum += ret;
-        }
-    }
-    if (visits_out) *visits_out = visits;
-    // LightBuffer::finish (updater.rs:932-944)
-    const float scale = ps_clamped(1.0f / fmaxf(acc.total, 1.0f));
-    if (acc.total > 0.0f)
-        return scalar_in_t(S.tables, ps_mul(acc.in0, scale)) | (scalar_in_t(S.tables, ps_mul(acc.in1, scale)) << 8) |
-               (scalar_in_t(S.tables, ps_mul(acc.in2, scale)) << 16) | (255u << 24);
-    return origin_opaque ? TX_OPAQUE : TX_NO_RAYS;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // compute_light (updater.rs:368-418) with walk_ray_tree (:427-529) and LightBuffer::traverse (:760-884) for the 32
 // cubes of a warp in lockstep (see the header).  Warp-collective: every lane calls it; `active` = this lane has a
-// cube.  `path` = LIGHT_MAX_DEPTH words of shared memory per warp (the node index at each depth of the current
-// path).  MARK as in compute_light.  Per-lane state of the walk: `ld`, the depth of the lane's deepest live frame
+// cube.  `path_sky` = LIGHT_MAX_DEPTH float4 of shared memory per warp (the sky term of the node at each depth of
+// the current path).  MARK as in compute_light.  Per-lane state of the walk: `ld`, the depth of the lane's deepest live frame
 // (-1: only the call of the root is pending; -2: the lane does not walk), and its frames (alpha after traverse(),
 // ray_bundle_weight, the children's weight so far, light_ahead_cache) indexed by depth — the depth is warp-uniform,
 // so these local-memory accesses are coalesced.
 template <bool MARK>
-__device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lut, uint32_t *path, bool active, int ox,
+__device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lut, float4 *path_sky, bool active, int ox,
                                            int oy, int oz, uint32_t mark_priority, uint32_t *visits_out) {
     const DeviceScene &S = P.scene;
     Accum acc = {0.f, 0.f, 0.f, 0.f};
@@ -445,23 +228,50 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
         const int lane = threadIdx.x & 31;
         // all children of the frame at depth k are done (updater.rs:518-528): the rest of its bundle ends here
         auto pop_level = [&](int k) {
-            const uint4 *np = reinterpret_cast<const uint4 *>(P.chart_pre + path[k]);
-            const uint4 a = __ldg(np);
-            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(np + 1));
             if (ld == k) {
-                if (!MARK) {
-                    const float cw[6] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
-                                         __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y)};
-                    end_of_ray(P, lut, acc, f_alpha[k], fmaxf(f_bundle[k] - f_csum[k], 0.0f), cw);
-                }
+                if (!MARK) end_of_ray(acc, f_alpha[k], fmaxf(f_bundle[k] - f_csum[k], 0.0f), path_sky[k]);
                 ld = k - 1;
             }
         };
+        // The walk is a chain of dependent loads per node (node record -> cube -> cell -> block flags).  Records are
+        // read two nodes ahead and the lane's cell one node ahead of the node being processed — node n + 1 is the next
+        // node whenever some lane descends, which is the common case in open air; a skip reloads.
+        const bool walker = ld == -1;
+        const uint32_t n_nodes = P.chart_nodes;
+        auto load_rec = [&](uint32_t k, uint4 &a, uint4 &b, float4 &sk) {
+            if (k < n_nodes) {
+                const uint4 *np = reinterpret_cast<const uint4 *>(P.chart_pre + k);
+                a = __ldg(np);
+                b = __ldg(np + 1);
+                sk = __ldg(P.sky_term + k);
+            } else {
+                a = make_uint4(0, 0, 0, 0);
+                b = make_uint4(0, 0, 0, 0);
+                sk = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // the lane's cube at that node — only for lanes whose walk can still enter it: a lane enters a node of depth
+        // e iff its deepest live frame is at e - 1 then, so now it is at e - 2 (and descends) or deeper (and pops)
+        auto load_cell = [&](const uint4 &b, uint32_t &cidx, uint32_t &id) -> bool {
+            id = 0;
+            if (!walker || ld < (int)(b.z >> 24) - 2) return false;
+            const int x = ox + (int)(int8_t)(b.z & 255u), y = oy + (int)(int8_t)((b.z >> 8) & 255u), z = oz + (int)(int8_t)((b.z >> 16) & 255u);
+            if (!cube_index(S, x, y, z, &cidx)) return false;
+            id = block_id_at(S, cidx);
+            return true;
+        };
         uint32_t n = 0;
+        uint4 na, nb, pa, pb, qa, qb;
+        float4 nsky, psky, qsky;
+        load_rec(0, na, nb, nsky);
+        load_rec(1, pa, pb, psky);
+        uint32_t cidx = 0, cell_id = 0, cidx1 = 0, cell_id1 = 0;
+        bool inb = load_cell(nb, cidx, cell_id), inb1 = false;
         int top = -1;   // deepest depth of the current path that holds a frame of some lane
         for (;;) {
-            const uint4 *np = reinterpret_cast<const uint4 *>(P.chart_pre + n);
-            const uint4 na = __ldg(np), nb = __ldg(np + 1);
+            // requests for the next iteration
+            inb1 = (n + 1 < n_nodes) ? load_cell(pb, cidx1, cell_id1) : false;
+            load_rec(n + 2, qa, qb, qsky);
             const int d = (int)(nb.z >> 24);
             for (int k = top; k >= d; k--) pop_level(k);
             top = d - 1;
@@ -480,14 +290,13 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
                 const float e_alpha = d == 0 ? 1.0f : f_alpha[d - 1];
                 if (bundle > 0.0f) {
                     const int e_x = ox + relx, e_y = oy + rely, e_z = oz + relz;
-                    uint32_t cidx;
-                    if (too_far || !cube_index(S, e_x, e_y, e_z, &cidx)) {
-                        if (!MARK) end_of_ray(P, lut, acc, e_alpha, bundle, cw);
+                    if (too_far || !inb) {
+                        if (!MARK) end_of_ray(acc, e_alpha, bundle, nsky);
                     } else {
                         // ---- LightBuffer::traverse ----
                         const int dir = (int)(end_dir >> 29);
                         const int e_face = d == 0 ? 0 : ((dir < 3) ? dir + 3 : dir - 3) + 1;
-                        const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
+                        const LightBlockDev *ev = &P.blocks[cell_id];
                         const uint32_t fl = __ldg(&ev->flags);
                         float alpha = e_alpha;
                         bool have_ahead = false;
@@ -545,7 +354,7 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
                             }
                         }
                         if (!(alpha > 0.0f)) {
-                            if (!MARK) end_of_ray(P, lut, acc, alpha, bundle, cw);
+                            if (!MARK) end_of_ray(acc, alpha, bundle, nsky);
                         } else {
                             f_alpha[d] = alpha; f_bundle[d] = bundle; f_csum[d] = 0.0f;
                             f_ahead[d] = ahead; f_have[d] = have_ahead ? 1 : 0;
@@ -556,15 +365,25 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
                 }
                 if (d > 0) f_csum[d - 1] += bundle;   // the call returns its bundle weight (updater.rs:514, 528)
             }
+            uint32_t next;
             if (__any_sync(0xffffffffu, pushed)) {
-                if (lane == 0) path[d] = n;
+                if (lane == 0) path_sky[d] = nsky;
                 __syncwarp();
                 top = d;
-                n = n + 1;                       // a child if there is one, else the pops above end the frame
+                next = n + 1;                    // a child if there is one, else the pops above end the frame
             } else {
-                n = end_dir & 0x1fffffffu;       // nobody is inside: skip the subtree
+                next = end_dir & 0x1fffffffu;    // nobody is inside: skip the subtree
             }
-            if (n >= P.chart_nodes) break;
+            if (next >= n_nodes) break;
+            if (next == n + 1) {
+                na = pa; nb = pb; nsky = psky; pa = qa; pb = qb; psky = qsky;
+                cidx = cidx1; cell_id = cell_id1; inb = inb1;
+            } else {
+                load_rec(next, na, nb, nsky);
+                load_rec(next + 1, pa, pb, psky);
+                inb = load_cell(nb, cidx, cell_id);
+            }
+            n = next;
         }
         for (int k = top; k >= 0; k--) pop_level(k);
     }

@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py — Mrays/s of the B200-native voxel raytracer on BASELINE.json's workload.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c0|c1|c3|c4]
 
-A "step" is one full frame (1920x1080 primary rays) of the 256^3 mixed-transparent Space
-(BASELINE.json configs[2]) traced through the C ABI of libaicb200.so.
-N > 1: one process per GPU (torchrun), the frame is sharded by interleaved 16-row strips
-(strong scaling, total work fixed) and gathered on rank 0 with NCCL.
+Default workload (the one BASELINE.json's metric is quoted on): a "step" is one full frame (1920x1080 primary
+rays) of the 256^3 mixed-transparent Space (BASELINE.json configs[2]) traced through the C ABI
+of libaicb200.so.  N > 1: one process per GPU (torchrun), the frame is sharded by interleaved 16-row strips (strong
+scaling, total work fixed) and delivered to rank 0 (P2P stores over NVLink, or an NCCL gather).
+The other BASELINE configs are bench lines too: c0 (32^3, 256x256, the reference's CPU case), c1 (128^3 res-16,
+1080p), c3 (256^3 res-16, 3840x2160 — the 8-GPU config), and c4 (256^3 light propagation: converge, then per step
+10 000 random block edits + propagation to epsilon 1 + a re-render; metric cube-updates/s).
 
 Prints ONE JSON line (rank 0).  `value` = rays / device time with inputs resident in HBM;
 `e2e` = the same through the host-buffer call (cube-delta H2D + frame D2H inside the timed
@@ -38,7 +41,9 @@ def parse_args():
     p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="c2", choices=["c0", "c1", "c2", "c3"])
+    p.add_argument("--workload", default="c2", choices=["c0", "c1", "c2", "c3", "c4"])
+    p.add_argument("--light-n", type=int, default=256, help="c4: edge of the Space")
+    p.add_argument("--pageable", action="store_true", help="e2e: the caller's output buffer is pageable host memory")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                    help="N>1: 'p2p' = trace kernel stores its strips straight into rank 0's frame over NVLink "
@@ -125,10 +130,15 @@ def run_reference(args):
         return
     import __graft_entry__ as g
     g.build_oracle()
-    g.build_library()  # host-only camera code lives in the product library
+    import aicb200
+    import orc
+    # This arm never loads libaicb200.so: the scene is numpy, and the camera matrices come from the oracle library
+    # (the same host source compiled under orc_* names, oracle/Makefile).
+    aicb200.use_camera_library(orc.lib(), "orc_")
+    if args.workload == "c4":
+        return run_reference_light(args)
     space, opts, w, h, desc = make_workload(args.workload)
     from aicb200 import scenes
-    import orc
     cam = scenes.standard_camera(space, opts, w, h)
     threads = effective_cpus()
     # each step = one bounded sample of the frame, sized so the whole run stays within minutes
@@ -154,11 +164,168 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour",
         "data": "synthetic",
-        "config": {"workload": desc, "sample": sample, "note": "CPU port of the Rust reference (no rustc in this image)"},
+        "config": {"workload": desc, "sample": sample, "threads": threads,
+                   "note": "CPU port of the Rust reference (no rustc in this image); libaicb200.so is not loaded by this arm"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line))
+
+# ------------------------------------------------------------------------------------------------
+# C4: light propagation (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+C4_EDITS = 10000
+
+
+def c4_description(n):
+    return (f"C4: {n}^3 res-1 Space, LightPhysics::Rays{{30}}, octant sky; converged (fast_evaluate_light + "
+            f"evaluate_light(1)) before timing; step = {C4_EDITS} random block edits + propagation to epsilon 1 + "
+            f"re-render 1920x1080 (Linear lighting)")
+
+
+def light_bytes(updates, node_visits):
+    """nodes_visited x (48 + 2) + 4 per update (chart node record + sky term = 48 B, cell 2 B, the stored
+    texel 4 B).  The per-hit term (4 + 140 B per visible block met) is not counted by the kernel and left out: a
+    lower bound of the algorithmic bytes."""
+    return 50 * node_visits + 4 * updates
+
+
+def run_reference_light(args):
+    """--impl reference --workload c4: the oracle's sequential update_light_from_queue on a bounded Space."""
+    import orc
+    from aicb200 import scenes
+    n = 40   # bounded sample: the queue is sequential in the reference's non-threaded path; 256^3 would take hours
+    space = scenes.config_c4(n)
+    ol = orc.OracleLight(space)
+    ol.fast_evaluate()
+    ol.evaluate(1)
+    n_edits = max(1, C4_EDITS * n ** 3 // args.light_n ** 3)
+    tot_u, tot_t, tot_v = 0, 0.0, 0
+    for step in range(args.warmup + args.steps):
+        cubes, ids = scenes.c4_edits(space, n_edits, step)
+        v0 = int(orc.lib().orc_light_node_visits(ol.handle))
+        t0 = time.perf_counter()
+        ol.set_cubes(cubes, ids)
+        u, _ = ol.evaluate(1)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            tot_u += u
+            tot_t += dt
+            tot_v += int(orc.lib().orc_light_node_visits(ol.handle)) - v0
+    value = tot_u / max(tot_t, 1e-9)
+    sample = (f"{n}^3 Space of the same recipe, {n_edits} edits per step (the same edit density), {args.steps} steps, "
+              f"{tot_u} cube updates in {tot_t:.1f} s, 1 thread (the reference's non-threaded update_light_from_queue)")
+    line = {
+        "impl": "reference", "metric": "cube-updates/s", "value": value, "unit": "cube-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "replicas", "vs_baseline": None, "dtype": "f32 light / u8 packed",
+        "data": "synthetic",
+        "config": {"workload": c4_description(args.light_n), "sample": sample, "threads": 1,
+                   "chart_node_visits_per_s": tot_v / max(tot_t, 1e-9),
+                   "note": "CPU port of the Rust reference (no rustc in this image); libaicb200.so is not loaded by this arm"},
+        "cpu_baseline": {"value": value, "unit": "cube-updates/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cube-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_light(args):
+    """--workload c4: light propagation is not sharded (replicas only) — rank 0 runs it, the line says so."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libaicb200 has no CPU fallback (use --impl reference for the CPU path)")
+    import __graft_entry__ as g
+    g.build_library()
+    g.build_oracle()
+    import aicb200
+    from aicb200 import scenes
+    n = args.light_n
+    space = scenes.config_c4(n)
+    opts = aicb200.GraphicsOptions(view_distance=4.0 * n)   # default options: Linear lighting, fog Abrupt, Volumetric
+    cam = scenes.standard_camera(space, opts, 1920, 1080)
+    rt = aicb200.SpaceRaytracer(space, opts)
+    # ---- setup (untimed, reported): the flood that converges the whole volume ---------------------------
+    t0 = time.perf_counter()
+    rt.light_fast_evaluate()
+    upd0, md0, nv0 = rt.light_evaluate(1)
+    conv_s = time.perf_counter() - t0
+    conv = rt.light_stats()
+    r = aicb200.RtRenderer(cam)
+    r.rt = rt
+    sampler = ClockSampler(0)
+    host_frame = np.zeros((1080, 1920, 4), dtype=np.uint8)
+
+    def step(k, render):
+        cubes, ids = scenes.c4_edits(space, C4_EDITS, k)
+        t0 = time.perf_counter()
+        u, md = rt.light_edit_and_propagate(cubes, ids, 1)   # H2D: the edit list; blocks until the propagation is done
+        st = rt.light_stats()
+        img = r.draw() if render else None                   # D2H: the frame
+        return u, st, time.perf_counter() - t0, img
+
+    for k in range(max(3, args.warmup)):
+        step(k, True)
+    sampler.start()
+    tot_u = tot_v = 0
+    dev_s = e2e_s = 0.0
+    render_ms = []
+    launches = 0
+    for k in range(args.steps):
+        u, st, wall, img = step(max(3, args.warmup) + k, True)
+        tot_u += u
+        tot_v += st["chart_node_visits"]
+        dev_s += st["device_seconds"]
+        e2e_s += wall
+        render_ms.append(img.info.kernel_ms)
+        launches += 2 + 5 * st["rounds"] + 4
+    clocks = sampler.stop()
+    value = tot_u / dev_s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = light_bytes(tot_u, tot_v) / dev_s / 1e9
+    line = {
+        "metric": "cube-updates/s", "value": value, "unit": "cube-updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+        "scaling": "replicas", "vs_baseline": None, "dtype": "f32 light / u8 packed", "data": "synthetic",
+        "config": {"workload": c4_description(n), "edits_per_step": C4_EDITS, "cube_updates_per_step": tot_u / args.steps,
+                   "chart_node_visits_per_s": tot_v / dev_s, "rerender_frame_ms": float(np.mean(render_ms)),
+                   "initial_convergence": {"cube_updates": upd0, "wall_seconds": conv_s, "device_seconds": conv["device_seconds"],
+                                           "cube_updates_per_s": upd0 / max(conv["device_seconds"], 1e-9),
+                                           "chart_node_visits": nv0, "rounds": conv["rounds"]},
+                   "l2": "every step edits and relaxes different cubes of a 256^3 volume (scene + light + queue: 0.2 GB > L2)",
+                   "sharding": "none (light propagation runs on one GPU; SURVEY 8(e) replicas only)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "kernel": "k_compute + k_mark (lockstep chart walk)", "kernel_ms": 1e3 * dev_s / args.steps,
+                     "algorithmic_bytes_per_step": int(light_bytes(tot_u, tot_v) / args.steps),
+                     "formula": "50 B per chart node visited + 4 B per cube update (SURVEY 8(d), per-hit term not counted)"},
+        "e2e": {"value": tot_u / e2e_s, "unit": "cube-updates/s", "h2d_bytes_per_step": C4_EDITS * 14,
+                "d2h_bytes_per_step": 1920 * 1080 * 4, "includes": "edit list H2D, propagation, re-render, frame D2H"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    # CPU baseline: the oracle on a bounded Space of the same recipe
+    import orc
+    nb = 32
+    sp2 = scenes.config_c4(nb)
+    ol = orc.OracleLight(sp2)
+    t0 = time.perf_counter()
+    ol.fast_evaluate()
+    nup, _ = ol.evaluate(1)
+    dt = time.perf_counter() - t0
+    line["cpu_baseline"] = {"value": nup / dt, "unit": "cube-updates/s", "cores": 1, "kind": "port",
+                            "sample": f"initial convergence of a {nb}^3 Space of the same recipe: {nup} cube updates in {dt:.1f} s, "
+                                      f"1 thread (sequential update_light_from_queue)"}
     print(json.dumps(line))
 
 
@@ -475,6 +642,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_light(args)
     else:
         run_ours(args)
 

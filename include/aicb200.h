@@ -298,6 +298,10 @@ aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*cubes)[3
                                           size_t n_edits, uint8_t epsilon, uint64_t *updates_done,
                                           uint8_t *max_diff);
 aicb_status aicb_light_download(aicb_scene *, uint8_t (*out)[4], size_t n_texels);
+/* Counters of the last propagation (aicb_light_evaluate / aicb_light_edit_and_propagate) on this scene:
+ * out[0] cube updates (compute_light calls, updater.rs:368), out[1] chart nodes visited by them, out[2] relaxation
+ * rounds queued, out[3] device time of the propagation in microseconds (CUDA events on the context's stream). */
+aicb_status aicb_light_stats(const aicb_scene *, uint64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -17,15 +17,7 @@ from aicb200 import Block, GraphicsOptions, Space, SpaceRaytracer, scenes  # noq
 
 
 def make_space(n, seed=4):
-    h = scenes.grid_hash(seed, (n, n, n))
-    pal = scenes.make_palette(seed, 14)
-    blocks = [Block.air()] + [Block(color=tuple(pal[i, :4])) for i in range(14)] + \
-             [Block(color=(0.1, 0.1, 0.1, 1.0), emission=(4.0, 3.5, 2.0))]
-    ids = np.where((h & np.uint64(15)) == 0, 1 + ((h >> np.uint64(8)) % np.uint64(15)).astype(np.int64), 0).astype(np.uint16)
-    ids[:, : n // 4, :] = 1 + ((h[:, : n // 4, :] >> np.uint64(8)) % np.uint64(14)).astype(np.uint16)
-    light = np.zeros((n, n, n, 4), dtype=np.uint8)
-    light[..., 3] = 1
-    return Space((0, 0, 0), ids, blocks, light=light, sky_colors=scenes.OCTANT_SKY, light_max_distance=30)
+    return scenes.config_c4(n, seed)
 
 
 def main():
