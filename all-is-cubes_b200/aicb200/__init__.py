@@ -94,6 +94,16 @@ def load_library() -> C.CDLL:
                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
     lib.aicb_light_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.aicb_light_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.aicb_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    lib.aicb_group_destroy.argtypes = [C.c_void_p]
+    lib.aicb_group_destroy.restype = None
+    lib.aicb_group_size.argtypes = [C.c_void_p]
+    lib.aicb_group_scene_create.argtypes = [C.c_void_p, C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
+    lib.aicb_group_scene_destroy.argtypes = [C.c_void_p]
+    lib.aicb_group_scene_destroy.restype = None
+    lib.aicb_group_scene_update_cubes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.aicb_group_render_srgb8.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p,
+                                            C.c_size_t, C.POINTER(abi.RenderInfo)]
     lib.aicb_light_chart.argtypes = [C.c_void_p, C.c_void_p]
     lib.aicb_light_chart.restype = C.c_uint32
     lib.aicb_light_fast_evaluate.argtypes = [C.c_void_p]
@@ -578,6 +588,51 @@ class SpaceRaytracer:
     def upload_light(self, light: np.ndarray):
         lt = np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
         _check(load_library().aicb_scene_upload_light(self.handle, lt.ctypes.data, lt.shape[0]))
+
+
+class DeviceGroup:
+    """Several GPUs driven from this one process through the C ABI (csrc/group.cu): scene replicated, frame cut into
+    interleaved row strips, pixels stored straight into device 0's frame over NVLink."""
+
+    def __init__(self, device_ids):
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        _check(load_library().aicb_group_create(ids, len(device_ids), C.byref(h)))
+        self.handle = h
+        self.scene = None
+
+    def update(self, space: "Space"):
+        if self.scene:
+            load_library().aicb_group_scene_destroy(self.scene)
+            self.scene = None
+        desc, keep = space.to_desc()
+        h = C.c_void_p()
+        _check(load_library().aicb_group_scene_create(self.handle, C.byref(desc), C.byref(h)))
+        del keep
+        self.scene = h
+
+    def draw(self, camera: "Camera", options: "GraphicsOptions") -> "Rendering":
+        w, h = camera.data.fb_width, camera.data.fb_height
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        info = abi.RenderInfo()
+        o = options.to_abi(True)
+        _check(load_library().aicb_group_render_srgb8(self.scene, C.byref(camera.data), C.byref(o), out.ctypes.data, w * h,
+                                                     C.byref(info)))
+        return Rendering((w, h), out, int(info.flaws), RenderInfo.from_abi(info))
+
+    def close(self):
+        if self.scene:
+            load_library().aicb_group_scene_destroy(self.scene)
+            self.scene = None
+        if self.handle:
+            load_library().aicb_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _shard_abi(shard):

@@ -138,4 +138,11 @@ EXPORTED_SYMBOLS = [
     "aicb_light_edit_and_propagate",
     "aicb_light_download",
     "aicb_light_stats",
+    "aicb_group_create",
+    "aicb_group_destroy",
+    "aicb_group_size",
+    "aicb_group_scene_create",
+    "aicb_group_scene_destroy",
+    "aicb_group_scene_update_cubes",
+    "aicb_group_render_srgb8",
 ]

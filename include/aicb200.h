@@ -253,6 +253,28 @@ aicb_status aicb_frame_open(aicb_ctx *, const uint8_t handle[64], void **d_frame
 aicb_status aicb_frame_close(aicb_ctx *, void *d_frame, int opened);
 aicb_status aicb_frame_read(aicb_ctx *, const void *d_frame, uint8_t (*out)[4], size_t n_pixels, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs from ONE process (csrc/group.cu): replaces the Rayon rows x pixels dispatch of
+ * trace_scene_to_image_impl (renderer.rs:516-556) across devices for hosts that own their process (the Rust
+ * `impl HeadlessRenderer`).  The scene is replicated on every device of the group; a frame is cut into
+ * interleaved 16-row strips (strip s -> device s mod n); every device's encode kernel stores its pixels straight into
+ * device 0's frame over NVLink (peer access) and device 0 copies the frame to the caller once the other devices'
+ * completion events have fired: no collective, no host thread per GPU.  The same device may be named more than once
+ * (tests).  aicb_render_info: counters summed over the devices, times = the slowest device's.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct aicb_group aicb_group;
+typedef struct aicb_group_scene aicb_group_scene;
+aicb_status aicb_group_create(const int *device_ids, int n_devices, aicb_group **out);
+void aicb_group_destroy(aicb_group *);
+int aicb_group_size(const aicb_group *);
+aicb_status aicb_group_scene_create(aicb_group *, const aicb_scene_desc *, aicb_group_scene **out);
+void aicb_group_scene_destroy(aicb_group_scene *);
+aicb_status aicb_group_scene_update_cubes(aicb_group_scene *, const int32_t (*cubes)[3], const uint16_t *block_ids,
+                                          const uint8_t (*light)[4], size_t n);
+/* == draw_rgba on the whole group: out_len must be fb_width * fb_height. */
+aicb_status aicb_group_render_srgb8(aicb_group_scene *, const aicb_camera *, const aicb_options *,
+                                    uint8_t (*out)[4], size_t out_len, aicb_render_info *info_or_null);
+
 /* == SpaceRaytracer::trace_ray (sr.rs:113-120) for a batch of explicit rays:
  * origin_dir[i] = {ox,oy,oz,dx,dy,dz}. Output as aicb_render_colorbuf. */
 aicb_status aicb_trace_rays(aicb_scene *, const double (*origin_dir)[6], size_t n, const aicb_options *,

@@ -461,3 +461,23 @@ def test_full_size_bench_frame_c2():
     ulp = orc.ulp_diff(cb, ref["colorbuf"])
     assert ulp.max() == 0, f"max ulp {ulp.max()}, {(ulp > 0).sum()} channels differ"
     assert int(aux["steps"].reshape(h, w)[rows].astype(np.int64).sum()) == ref["cubes_traced"]
+
+
+def test_device_group_frame_equals_single_device_frame(mixed):
+    """csrc/group.cu (aicb_group_*): several GPUs from one process — interleaved 16-row strips stored straight into
+    device 0's frame.  Here the same device is named two and three times: the delivered frame and the summed
+    RaytraceInfo must equal the one-device render's (renderer.rs:555: the info is a sum over the pixels)."""
+    opts = GraphicsOptions(view_distance=40.0)
+    cam = scenes.standard_camera(mixed, opts, 96, 70)
+    r = RtRenderer(cam)
+    r.update(mixed)
+    alone = r.draw()
+    for devices in ([0, 0], [0, 0, 0]):
+        g = aicb200.DeviceGroup(devices)
+        g.update(mixed)
+        img = g.draw(cam, opts)
+        assert np.array_equal(img.data, alone.data)
+        assert img.info.cubes_traced == alone.info.cubes_traced
+        again = g.draw(cam, opts)
+        assert np.array_equal(again.data, alone.data)
+        g.close()
