@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(256) k_gather(const LightParams P, uint32_t n_
 
 __global__ void __launch_bounds__(128) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
     __shared__ float s_lut[256];
-    __shared__ float4 s_path[4][LIGHT_MAX_DEPTH];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
     __syncthreads();
     if (!explicit_cubes) n = P.scalars[0];   // the round's list
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(128) k_compute(const LightParams P, uint32_t n
             }
         }
         uint32_t visits = 0;
-        const uint32_t nv = compute_light_lockstep<false>(P, s_lut, s_path[threadIdx.x >> 5], active, x, y, z, 0, &visits);
+        const uint32_t nv = compute_light_lockstep<false>(P, s_lut, active, x, y, z, 0, &visits);
         if (active) P.new_light[i] = nv;
         total_visits += visits;
     }
@@ -312,7 +311,6 @@ __global__ void k_apply(const LightParams P) {
 // the dependency re-queue of apply_light_update (updater.rs:355-360): re-walk the chart, raising the
 // queue priority of every cube whose light was read
 __global__ void __launch_bounds__(128) k_mark(const LightParams P) {
-    __shared__ float4 s_path[4][LIGHT_MAX_DEPTH];
     const uint32_t n = P.scalars[0];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -323,7 +321,7 @@ __global__ void __launch_bounds__(128) k_mark(const LightParams P) {
         if (!__any_sync(0xffffffffu, active)) continue;
         int x = 0, y = 0, z = 0;
         if (active) cube_of(P.scene, P.list[i], x, y, z);
-        compute_light_lockstep<true>(P, P.scene.tables, s_path[threadIdx.x >> 5], active, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
+        compute_light_lockstep<true>(P, P.scene.tables, active, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
     }
 }
 

@@ -51,6 +51,10 @@ constexpr int LIGHT_MAX_DEPTH = 224;  // longest chart path is 219 (rays end at 
 
 constexpr uint32_t TX_OPAQUE = 128u << 24, TX_NO_RAYS = 1u << 24, TX_UNINIT = 0u;
 constexpr int PRIO_NEWLY_VISIBLE = 250, PRIO_ESTIMATED = 200;
+#ifndef AICB_LIGHT_GROUP
+#define AICB_LIGHT_GROUP 32
+#endif
+constexpr int LIGHT_GROUP = AICB_LIGHT_GROUP;   // lanes (= neighbouring cubes) that walk the chart together: 4, 8, 16 or 32
 constexpr uint32_t LIGHT_TILE = 1024;   // cubes per queue tile (256 words of pending bytes: one 256-thread block)
 
 struct LightParams {
@@ -175,16 +179,24 @@ __device__ __forceinline__ void end_of_ray(Accum &a, float alpha, float bundle, 
     }
 }
 
+__device__ __forceinline__ unsigned gmask_of_lane() {
+    const unsigned lane = threadIdx.x & 31u;
+    return (LIGHT_GROUP >= 32) ? 0xffffffffu : (((1u << (LIGHT_GROUP & 31)) - 1u) << (lane & ~(unsigned)(LIGHT_GROUP - 1)));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // compute_light (updater.rs:368-418) with walk_ray_tree (:427-529) and LightBuffer::traverse (:760-884) for the 32
 // cubes of a warp in lockstep (see the header).  Warp-collective: every lane calls it; `active` = this lane has a
-// cube.  `path_sky` = LIGHT_MAX_DEPTH float4 of shared memory per warp (the sky term of the node at each depth of
-// the current path).  MARK as in compute_light.  Per-lane state of the walk: `ld`, the depth of the lane's deepest live frame
+// cube.  The lockstep unit is a group of LIGHT_GROUP lanes (default: the whole warp).  A group visits the union of
+// its cubes' node sets; with the whole warp 5 of 32 lanes take part in an average node.  Smaller groups have smaller
+// unions, but the groups of a warp then read different node records and cells in the same instruction, and measured
+// on the 128^3 bench scene that costs more than it saves (groups of 4 / 8 / 16 / 32 lanes: 1.31 / 1.44 / 1.61 / 1.87 M
+// cube updates per second): the walk is bound by its memory transactions, not by issue slots.  MARK as in compute_light.  Per-lane state of the walk: `ld`, the depth of the lane's deepest live frame
 // (-1: only the call of the root is pending; -2: the lane does not walk), and its frames (alpha after traverse(),
 // ray_bundle_weight, the children's weight so far, light_ahead_cache) indexed by depth — the depth is warp-uniform,
 // so these local-memory accesses are coalesced.
 template <bool MARK>
-__device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lut, float4 *path_sky, bool active, int ox,
+__device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lut, bool active, int ox,
                                            int oy, int oz, uint32_t mark_priority, uint32_t *visits_out) {
     const DeviceScene &S = P.scene;
     Accum acc = {0.f, 0.f, 0.f, 0.f};
@@ -220,16 +232,18 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
         }
     }
     int ld = (active && !origin_opaque) ? -1 : -2;
-    if (__any_sync(0xffffffffu, ld == -1)) {
+    if (__any_sync(gmask_of_lane(), ld == -1)) {
         float f_alpha[LIGHT_MAX_DEPTH], f_bundle[LIGHT_MAX_DEPTH], f_csum[LIGHT_MAX_DEPTH];
+        float f_sky0[LIGHT_MAX_DEPTH], f_sky1[LIGHT_MAX_DEPTH], f_sky2[LIGHT_MAX_DEPTH];
         uint32_t f_ahead[LIGHT_MAX_DEPTH];
         uint8_t f_have[LIGHT_MAX_DEPTH];
         const int max_d2 = (int)(P.max_distance * P.max_distance);
         const int lane = threadIdx.x & 31;
+        const unsigned gmask = (LIGHT_GROUP >= 32) ? 0xffffffffu : (((1u << (LIGHT_GROUP & 31)) - 1u) << (lane & ~(LIGHT_GROUP - 1)));
         // all children of the frame at depth k are done (updater.rs:518-528): the rest of its bundle ends here
         auto pop_level = [&](int k) {
             if (ld == k) {
-                if (!MARK) end_of_ray(acc, f_alpha[k], fmaxf(f_bundle[k] - f_csum[k], 0.0f), path_sky[k]);
+                if (!MARK) end_of_ray(acc, f_alpha[k], fmaxf(f_bundle[k] - f_csum[k], 0.0f), make_float4(f_sky0[k], f_sky1[k], f_sky2[k], 0.f));
                 ld = k - 1;
             }
         };
@@ -358,6 +372,7 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
                         } else {
                             f_alpha[d] = alpha; f_bundle[d] = bundle; f_csum[d] = 0.0f;
                             f_ahead[d] = ahead; f_have[d] = have_ahead ? 1 : 0;
+                            f_sky0[d] = nsky.x; f_sky1[d] = nsky.y; f_sky2[d] = nsky.z;
                             ld = d;
                             pushed = true;
                         }
@@ -366,9 +381,7 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
                 if (d > 0) f_csum[d - 1] += bundle;   // the call returns its bundle weight (updater.rs:514, 528)
             }
             uint32_t next;
-            if (__any_sync(0xffffffffu, pushed)) {
-                if (lane == 0) path_sky[d] = nsky;
-                __syncwarp();
+            if (__any_sync(gmask, pushed)) {
                 top = d;
                 next = n + 1;                    // a child if there is one, else the pops above end the frame
             } else {
