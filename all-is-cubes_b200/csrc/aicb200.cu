@@ -429,6 +429,12 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.bin_stride = (uint32_t)chunk_cap;
     P.overflow_flag = (unsigned int *)(ctx->d_counters + 7);
     if (stream != ctx->stream) CU(cudaStreamWaitEvent(stream, ctx->ev_delta, 0));  // pending cube edits
+    // The per-frame streams, counters and events belong to the context: a frame issued on another stream than the
+    // previous one must not start before that one is through with them.
+    if (ctx->frame_in_flight && ctx->last_stream != stream) CU(cudaStreamWaitEvent(stream, ctx->ev1, 0));
+    ctx->frame_in_flight = true;
+    ctx->last_stream = stream;
+    ctx->last_scene = sc;
     CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     if (total_tasks > 0) {
@@ -481,7 +487,10 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
 
 static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
     aicb_ctx *ctx = sc->ctx;
+    if (ctx->last_scene != sc)
+        return fail(AICB_ERR_BUSY, "the context's last frame belongs to another scene (one frame per context is tracked)");
     CU(cudaEventSynchronize(ctx->ev1));
+    ctx->frame_in_flight = false;
     unsigned long long c[8];
     CU(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     sc->pending = false;
@@ -504,8 +513,23 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
                 t[3], c[3]);
     }
     if (c[7]) {  // the hit stream of some chunk overflowed: the frame is incomplete
-        if (ctx->hits_per_task < 1024) ctx->hits_per_task *= 4;
+        if (ctx->hits_per_task >= 2048)
+            return fail(AICB_ERR_OOM, "hit stream overflowed at its largest capacity (2048 hit records per ray)");
+        ctx->hits_per_task *= 4;
+        ctx->shallow_frames = 0;
         return fail(AICB_ERR_RETRY, "hit stream overflowed; its capacity has been raised - re-issue the render");
+    }
+    // a deep frame must not inflate the scratch buffers for the life of the context: after 16 frames in a row that
+    // would have fitted a quarter of the capacity, give the large buffers back
+    if (ctx->hits_per_task > 8 && c[3] * 16 < (unsigned long long)sc->pending_rays * ctx->hits_per_task) {
+        if (++ctx->shallow_frames >= 16) {
+            ctx->hits_per_task /= 4;
+            ctx->shallow_frames = 0;
+            if (ctx->d_hits) { cudaFree(ctx->d_hits); ctx->d_hits = nullptr; ctx->d_hits_bytes = 0; }
+            if (ctx->d_contrib) { cudaFree(ctx->d_contrib); ctx->d_contrib = nullptr; ctx->d_contrib_bytes = 0; }
+        }
+    } else {
+        ctx->shallow_frames = 0;
     }
     if (info) {
         std::memset(info, 0, sizeof *info);
@@ -587,6 +611,7 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_bin_list) cudaFree(c->d_bin_list);
     if (c->d_debug) cudaFree(c->d_debug);
     if (c->h_delta) cudaFreeHost(c->h_delta);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_delta) cudaFree(c->d_delta);
     if (c->ev_delta) cudaEventDestroy(c->ev_delta);
     if (c->d_task_aux) cudaFree(c->d_task_aux);
@@ -723,6 +748,11 @@ aicb_status aicb_scene_create(aicb_ctx *ctx, const aicb_scene_desc *d, aicb_scen
 void aicb_scene_destroy(aicb_scene *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    if (s->ctx->last_scene == s) {   // its frame (if any) must be through with the scene's arrays
+        if (s->ctx->frame_in_flight) cudaEventSynchronize(s->ctx->ev1);
+        s->ctx->last_scene = nullptr;
+        s->ctx->frame_in_flight = false;
+    }
     if (s->d_cells) cudaFree(s->d_cells);
     if (s->d_light) cudaFree(s->d_light);
     if (s->d_blocks) cudaFree(s->d_blocks);
@@ -958,15 +988,33 @@ aicb_status aicb_render_srgb8(aicb_scene *s, const aicb_camera *cam, const aicb_
     if (st != AICB_OK) return st;
     Outputs o;
     o.srgb8 = (uchar4 *)ctx->d_out;
+    // A pageable destination (a Rust Vec<[u8; 4]>, a numpy array) cannot take an asynchronous DMA: the frame goes to a
+    // pinned staging buffer of the library's and is copied out by the host.  Pinned / registered memory is written directly.
+    bool staged = false;
+    if (out_len) {
+        cudaPointerAttributes attr;
+        const cudaError_t pe = cudaPointerGetAttributes(&attr, out);
+        if (pe != cudaSuccess) cudaGetLastError();
+        staged = pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        if (staged && ctx->h_stage_bytes < out_len * 4) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr;
+            ctx->h_stage_bytes = 0;
+            CU(cudaMallocHost(&ctx->h_stage, out_len * 4));
+            ctx->h_stage_bytes = out_len * 4;
+        }
+    }
+    void *dst = staged ? ctx->h_stage : (void *)out;
     for (int attempt = 0;; attempt++) {
         st = launch_trace(s, cam, opt, shard, nullptr, 0, o, false, ctx->stream);
         if (st != AICB_OK) return st;
         // the copy is queued behind the frame: one host synchronisation per call
-        if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_len) CU(cudaMemcpyAsync(dst, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         st = finish(s, info);
-        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+        if (st != AICB_ERR_RETRY) break;   // (the capacity grows x4 per retry and ends in AICB_ERR_OOM at its cap)
     }
+    if (st == AICB_OK && staged && out_len) std::memcpy(out, ctx->h_stage, out_len * 4);
     return st;
 }
 
@@ -988,7 +1036,7 @@ aicb_status aicb_render_rgba16f(aicb_scene *s, const aicb_camera *cam, const aic
         if (out_len) CU(cudaMemcpyAsync(out, ctx->d_out, out_len * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         st = finish(s, info);
-        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+        if (st != AICB_ERR_RETRY) break;
     }
     return st;
 }
@@ -1013,7 +1061,7 @@ static aicb_status render_aux(aicb_scene *s, const aicb_camera *cam, const aicb_
         if (st != AICB_OK) return st;
         CU(cudaStreamSynchronize(ctx->stream));
         st = finish(s, info);
-        if (st != AICB_ERR_RETRY || attempt >= 5) break;
+        if (st != AICB_ERR_RETRY) break;
     }
     if (st != AICB_OK) return st;
     if (n) {

@@ -51,7 +51,14 @@ struct aicb_ctx {
     size_t d_contrib_bytes = 0;
     void *d_bin_list = nullptr;  // task ids of the rays that enter the space, per chord-length bin
     size_t d_bin_list_bytes = 0;
-    uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it
+    uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it,
+    uint32_t shallow_frames = 0; //   lowered again after 16 frames in a row that needed a small fraction of it
+    void *h_stage = nullptr;     // pinned staging of frames whose destination is pageable host memory
+    size_t h_stage_bytes = 0;
+    // the frame whose per-frame scratch (streams, counters, events) is in use
+    bool frame_in_flight = false;
+    cudaStream_t last_stream = nullptr;
+    struct aicb_scene *last_scene = nullptr;
     void *d_task_aux = nullptr;
     size_t d_task_aux_bytes = 0;
     // light propagation: the static ray chart (space/light/chart), built and uploaded on first use

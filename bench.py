@@ -483,6 +483,11 @@ def run_ours(args):
         return float(t.item())
 
     # ---- warm-up, then the timed region ------------------------------------------------------------
+    # one blocking render first: it sizes the hit stream for this workload (the blocking call re-issues the frame when
+    # the stream overflows; the asynchronous calls below would report AICB_ERR_RETRY instead)
+    sizing = torch.empty((n_local, 4), dtype=torch.uint8).pin_memory()
+    check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard), sizing.data_ptr(), n_local, None))
+    del sizing
     for _ in range(max(3, args.warmup)):
         device_step()
     torch.cuda.synchronize()
@@ -492,7 +497,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     total_ms = timed(device_step, args.steps)
-    # kernel-only duration of the last frame from the library's own events (same stream)
+    # kernel-only duration of the last frame from the library's own events (same stream); a frame that overflowed its
+    # hit stream inside the timed region would make this call fail (AICB_ERR_RETRY) and with it the run
     check(lib.aicb_render_finish(rt.handle, C.byref(info)))
     kernel_ms_last = float(info.kernel_ms)
     rays_per_frame = w * h
@@ -602,6 +608,24 @@ def run_ours(args):
     e2e_value = rays_per_frame * k_e2e / float(t.item()) / 1e6
     h2d_step = 64 * (12 + 2 + (4 if delta_light is not None else 0))
     d2h_step = w * h * 4
+    # the same call with a PAGEABLE destination (what a Rust Vec<[u8; 4]> or a numpy array is): the library stages the
+    # frame in its own pinned buffer and copies it out on the host
+    e2e_pageable = None
+    if world == 1:
+        page_out = np.zeros((n_local, 4), dtype=np.uint8)
+
+        def pageable_step():
+            rt.update_cubes(cubes[:64], delta_ids[:64], None if delta_light is None else delta_light[:64])
+            check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                        page_out.ctypes.data, n_local, None))
+
+        for _ in range(2):
+            pageable_step()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            pageable_step()
+        e2e_pageable = rays_per_frame * k_e2e / (time.perf_counter() - t0) / 1e6
+        assert np.array_equal(page_out, host_out.numpy()), "pageable and pinned destinations differ"
 
     if rank == 0:
         cpu = None
@@ -627,7 +651,8 @@ def run_ours(args):
                                    "frac": frame_achieved / peak},
                          "counters": {"outer_steps": ai.counters[0], "inner_steps": ai.counters[1], "surface_hits": ai.counters[2],
                                       "light_texels": ai.counters[3], "blocks_entered": ai.counters[4], "pixels": ai.counters[5]}},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "destination": "pinned host buffer", "pageable_destination_value": e2e_pageable},
             "gpu_launches": 4 * args.steps,
             "clocks": clocks,
         }

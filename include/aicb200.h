@@ -30,7 +30,7 @@ typedef enum aicb_status {
     AICB_ERR_OOM = 2,         /* cudaMalloc failed  -> Flaws::OUT_OF_MEMORY (flaws.rs) */
     AICB_ERR_CUDA = 3,        /* no device, launch failure, lost GPU (lib.rs:53 "TODO: lost GPU") */
     AICB_ERR_UNSUPPORTED = 4, /* LightingOption::Bounce etc. */
-    AICB_ERR_BUSY = 5,
+    AICB_ERR_BUSY = 5,        /* aicb_render_finish for a scene whose frame is not the context's last one */
     AICB_ERR_RETRY = 6        /* asynchronous render only: the frame's hit stream overflowed its device buffer; the
                                  buffer has been enlarged, issue the same render again (the synchronous entry points
                                  retry internally) */
