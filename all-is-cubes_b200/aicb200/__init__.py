@@ -94,6 +94,12 @@ def load_library() -> C.CDLL:
                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
     lib.aicb_light_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.aicb_light_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.aicb_render_text.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p, C.c_size_t,
+                                     C.POINTER(abi.RenderInfo)]
+    lib.aicb_render_layers_srgb8.argtypes = [C.POINTER(abi.Layer), C.POINTER(abi.Layer), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.POINTER(abi.RenderInfo)]
+    lib.aicb_ortho_image_size.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.aicb_render_orthographic.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(abi.RenderInfo)]
     lib.aicb_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     lib.aicb_group_destroy.argtypes = [C.c_void_p]
     lib.aicb_group_destroy.restype = None
@@ -588,6 +594,61 @@ class SpaceRaytracer:
     def upload_light(self, light: np.ndarray):
         lt = np.ascontiguousarray(light, dtype=np.uint8).reshape(-1, 4)
         _check(load_library().aicb_scene_upload_light(self.handle, lt.ctypes.data, lt.shape[0]))
+
+
+NO_WORLD_TO_SHOW_SRGB8 = (0xBC, 0xBC, 0xBC, 0xFF)   # content/palette.rs:76
+
+
+def render_layers(world=None, ui=None, backdrop=None, no_world=None) -> "Rendering":
+    """RtRenderer::draw_rgba through every layer (renderer.rs:282-308, 454-478).
+    world / ui = (SpaceRaytracer, Camera, GraphicsOptions) or None; backdrop / no_world = linear RGBA or None."""
+    lead = world if world else ui
+    cam = lead[1]
+    w, h = cam.data.fb_width, cam.data.fb_height
+    keep = []
+
+    def layer(l):
+        if not l:
+            return None
+        o = l[2].to_abi(True)
+        keep.append(o)
+        s = abi.Layer(l[0].handle, C.pointer(l[1].data), C.pointer(o))
+        keep.append(s)
+        return C.byref(s)
+
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    info = abi.RenderInfo()
+    b = np.array(backdrop, dtype=np.float32) if backdrop is not None else None
+    nw = np.array(no_world, dtype=np.float32) if no_world is not None else None
+    _check(load_library().aicb_render_layers_srgb8(layer(world), layer(ui), b.ctypes.data if b is not None else None,
+                                                   nw.ctypes.data if nw is not None else None, out.ctypes.data, w * h,
+                                                   C.byref(info)))
+    return Rendering((w, h), out, int(info.flaws), RenderInfo.from_abi(info))
+
+
+def render_orthographic(rt: "SpaceRaytracer", resolution: int = 32) -> "Rendering":
+    """raytracer::ortho::render_orthographic (ortho.rs:30-84): the five-view pixel-perfect image of the whole Space."""
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    _check(load_library().aicb_ortho_image_size(rt.handle, resolution, C.byref(w), C.byref(h)))
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    info = abi.RenderInfo()
+    _check(load_library().aicb_render_orthographic(rt.handle, resolution, out.ctypes.data, w.value * h.value, C.byref(info)))
+    return Rendering((w.value, h.value), out, int(info.flaws), RenderInfo.from_abi(info))
+
+
+def print_space(space: "Space", direction, block_chars: dict, rt: "SpaceRaytracer" = None) -> list:
+    """raytracer::print_space (text.rs:139-180): the 80 x 40 character image of a Space seen from `direction`, one
+    string per row.  `block_chars` maps a block index to its character (what D::from_block gives each block)."""
+    opts = GraphicsOptions()
+    cam = Camera(opts, Viewport((40.0, 40.0), (80, 40)))
+    center = [space.lower[a] + space.size[a] / 2.0 for a in range(3)]
+    cam.look_at_y_up(eye_for_look_at(space.lower, space.size, direction), center)
+    rt = rt or SpaceRaytracer(space, opts)
+    o = opts.to_abi(True)
+    out = np.zeros(80 * 40, dtype=np.int32)
+    _check(load_library().aicb_render_text(rt.handle, C.byref(cam.data), C.byref(o), out.ctypes.data, out.size, None))
+    special = {abi.TEXT_ENTERED_SPACE: " ", abi.TEXT_EMPTY: ".", abi.TEXT_INCOMPLETE: "X"}
+    return ["".join(special[v] if v < 0 else block_chars[int(v)] for v in out[r * 80:(r + 1) * 80]) for r in range(40)]
 
 
 class DeviceGroup:

@@ -104,6 +104,12 @@ class Hit(C.Structure):
 
 
 # Every symbol include/aicb200.h declares (tests check the built library exports all of them).
+class Layer(C.Structure):
+    _fields_ = [("scene", C.c_void_p), ("camera", C.POINTER(CameraData)), ("options", C.POINTER(Options))]
+
+
+TEXT_ENTERED_SPACE, TEXT_EMPTY, TEXT_INCOMPLETE = -1, -2, -3
+
 EXPORTED_SYMBOLS = [
     "aicb_abi_version",
     "aicb_ctx_create",
@@ -119,6 +125,10 @@ EXPORTED_SYMBOLS = [
     "aicb_render_srgb8",
     "aicb_render_rgba16f",
     "aicb_render_colorbuf",
+    "aicb_render_text",
+    "aicb_render_layers_srgb8",
+    "aicb_ortho_image_size",
+    "aicb_render_orthographic",
     "aicb_render_srgb8_device",
     "aicb_render_srgb8_device_frame",
     "aicb_render_finish",

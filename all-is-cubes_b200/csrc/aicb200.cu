@@ -312,6 +312,13 @@ struct Outputs {
     double *depth = nullptr;
     aicb_hit *hit = nullptr;
     uint32_t *steps = nullptr;
+    int32_t *text = nullptr;
+    // layers (renderer.rs:454-478)
+    const float4 *in_accum = nullptr;
+    float4 *out_accum = nullptr;
+    const float *backdrop = nullptr;    // premultiplied light rgb + transmittance
+    const float *no_world = nullptr;    // ColorBuf (light rgb, transmittance)
+    int force_antialias = -1;           // the world layer's antialiasing option governs every layer's sample points
 };
 
 // Launches the trace kernel on `stream`. Camera rays when cam != NULL, explicit rays otherwise.
@@ -360,6 +367,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.transparency = opt->transparency;
     P.threshold = opt->transparency_threshold;
     P.antialias = (cam && opt->antialiasing_always) ? 1 : 0;
+    if (cam && out.force_antialias >= 0) P.antialias = (uint32_t)out.force_antialias;
     P.tone_mapping = opt->tone_mapping;
     P.maximum_intensity = opt->maximum_intensity;
     P.view_distance = opt->view_distance;
@@ -372,6 +380,11 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.out_depth = out.depth;
     P.out_hit = out.hit;
     P.out_steps = out.steps;
+    P.out_text = out.text;
+    P.in_accum = out.in_accum;
+    P.out_accum = out.out_accum;
+    if (out.backdrop) { std::memcpy(P.backdrop, out.backdrop, 16); P.has_backdrop = 1; }
+    if (out.no_world) { std::memcpy(P.no_world, out.no_world, 16); P.has_no_world = 1; }
     P.counters = ctx->d_counters;
     P.task_counter = ctx->d_tile_counter;
     {
@@ -1156,6 +1169,261 @@ aicb_status aicb_frame_read(aicb_ctx *ctx, const void *d_frame, uint8_t (*out)[4
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     CU(cudaMemcpyAsync(out, d_frame, n_pixels * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return AICB_OK;
+}
+
+// == print_space's per-pixel CharacterBuf (raytracer/text.rs:52-123, 139-180): which block each pixel shows.
+aicb_status aicb_render_text(aicb_scene *s, const aicb_camera *cam, const aicb_options *opt, int32_t *out, size_t out_len,
+                             aicb_render_info *info) {
+    aicb_status st = check_render_args(s, cam, opt, nullptr, out_len);
+    if (st != AICB_OK) return st;
+    if (out_len && !out) return fail(AICB_ERR_INVALID, "out is NULL");
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    st = ensure(&ctx->d_aux, &ctx->d_aux_bytes, out_len * 4 + 16);
+    if (st != AICB_OK) return st;
+    Outputs o;
+    o.text = (int32_t *)ctx->d_aux;
+    for (;;) {
+        st = launch_trace(s, cam, opt, nullptr, nullptr, 0, o, false, ctx->stream);
+        if (st != AICB_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream));
+        st = finish(s, info);
+        if (st != AICB_ERR_RETRY) break;
+    }
+    if (st != AICB_OK) return st;
+    if (out_len) CU(cudaMemcpy(out, ctx->d_aux, out_len * 4, cudaMemcpyDeviceToHost));
+    return AICB_OK;
+}
+
+// == RtScene::trace_ray_through_layers for every pixel + the encoder of draw_rgba (renderer.rs:454-478, 287-291):
+// the UI layer's Space is traced first (its own camera, no sky), the backdrop colour is added, the world layer
+// continues in the same accumulator (its rays start opaque where the UI covered the pixel), and a pixel that is not
+// opaque in the end — there is no world — is painted NO_WORLD_TO_SHOW.  The world layer's options choose the sample
+// points (antialiasing) and the post-processing.
+aicb_status aicb_render_layers_srgb8(const aicb_layer *world, const aicb_layer *ui, const float backdrop_rgba[4],
+                                     const float no_world_rgba[4], uint8_t (*out)[4], size_t out_len,
+                                     aicb_render_info *info) {
+    const bool have_world = world && world->scene, have_ui = ui && ui->scene;
+    if (!have_world && !have_ui && !no_world_rgba) return fail(AICB_ERR_INVALID, "no layer to draw");
+    const aicb_layer *lead = have_world ? world : ui;
+    if (!lead || !lead->camera || !lead->options) return fail(AICB_ERR_INVALID, "a layer needs its camera and options");
+    if (have_ui && (!ui->camera || !ui->options)) return fail(AICB_ERR_INVALID, "a layer needs its camera and options");
+    if (have_world && have_ui) {
+        if (world->scene->ctx != ui->scene->ctx) return fail(AICB_ERR_INVALID, "the layers must live on one context");
+        if (world->camera->fb_width != ui->camera->fb_width || world->camera->fb_height != ui->camera->fb_height)
+            return fail(AICB_ERR_INVALID, "the layers' cameras must share the framebuffer size");
+    }
+    aicb_status st = check_render_args(lead->scene, lead->camera, lead->options, nullptr, out_len);
+    if (st != AICB_OK) return st;
+    if (have_ui && have_world) {
+        st = validate_options(ui->options);
+        if (st != AICB_OK) return st;
+    }
+    if (out_len && !out) return fail(AICB_ERR_INVALID, "out is NULL");
+    aicb_ctx *ctx = lead->scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    st = ensure(&ctx->d_out, &ctx->d_out_bytes, out_len * 4 + 16);
+    if (st != AICB_OK) return st;
+    const int aa = lead->options->antialiasing_always ? 1 : 0;
+    // Rgba -> ColorBuf (raytracer_components.rs:111-120): premultiplied light, transmittance = 1 - alpha
+    float backdrop[4] = {0, 0, 0, 1}, no_world[4] = {0, 0, 0, 0};
+    const bool have_backdrop = backdrop_rgba && !(backdrop_rgba[0] == 0.0f && backdrop_rgba[1] == 0.0f &&
+                                                   backdrop_rgba[2] == 0.0f && backdrop_rgba[3] == 0.0f);
+    if (have_backdrop) {
+        for (int i = 0; i < 3; i++) backdrop[i] = backdrop_rgba[i] * backdrop_rgba[3];
+        backdrop[3] = 1.0f - backdrop_rgba[3];
+    }
+    if (no_world_rgba) {
+        for (int i = 0; i < 3; i++) no_world[i] = no_world_rgba[i] * no_world_rgba[3];
+        no_world[3] = 1.0f - no_world_rgba[3];
+    }
+    aicb_render_info total;
+    std::memset(&total, 0, sizeof total);
+    auto add_info = [&](const aicb_render_info &one) {
+        total.cubes_traced += one.cubes_traced;
+        total.rays += one.rays;
+        total.algorithmic_bytes += one.algorithmic_bytes;
+        for (int k = 0; k < 6; k++) total.counters[k] += one.counters[k];
+        total.kernel_ms += one.kernel_ms;
+        for (int k = 0; k < 4; k++) total.stage_ms[k] += one.stage_ms[k];
+        total.flaws |= one.flaws;
+    };
+    auto run = [&](aicb_scene *sc, const aicb_camera *cam, const aicb_options *opt, const Outputs &o) -> aicb_status {
+        for (;;) {
+            aicb_status r = launch_trace(sc, cam, opt, nullptr, nullptr, 0, o, false, ctx->stream);
+            if (r != AICB_OK) return r;
+            CU(cudaStreamSynchronize(ctx->stream));
+            aicb_render_info one;
+            r = finish(sc, &one);
+            if (r == AICB_ERR_RETRY) continue;
+            if (r == AICB_OK) add_info(one);
+            return r;
+        }
+    };
+    if (have_ui && have_world) {
+        const size_t n_tasks = (((size_t)ui->camera->fb_width + TILE_W - 1) / TILE_W) * (((size_t)ui->camera->fb_height + TILE_H - 1) / TILE_H) * 32 * (aa ? 4 : 1);
+        st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, n_tasks * sizeof(float4) + 16);
+        if (st != AICB_OK) return st;
+        aicb_options ui_opt = *ui->options;
+        ui_opt.include_sky = 0;   // ui.trace_ray(.., false)
+        Outputs o1;
+        o1.out_accum = (float4 *)ctx->d_task_aux;
+        o1.backdrop = have_backdrop ? backdrop : nullptr;
+        o1.force_antialias = aa;
+        st = run(ui->scene, ui->camera, &ui_opt, o1);
+        if (st != AICB_OK) return st;
+        aicb_options w_opt = *world->options;
+        w_opt.include_sky = 1;    // world.trace_ray(.., true)
+        Outputs o2;
+        o2.srgb8 = (uchar4 *)ctx->d_out;
+        o2.in_accum = (const float4 *)ctx->d_task_aux;
+        o2.no_world = no_world_rgba ? no_world : nullptr;
+        st = run(world->scene, world->camera, &w_opt, o2);
+    } else if (have_world) {
+        aicb_options w_opt = *world->options;
+        w_opt.include_sky = 1;
+        Outputs o;
+        o.srgb8 = (uchar4 *)ctx->d_out;
+        // without a UI Space the backdrop is still added in front of the world: as the accumulator's starting value
+        if (have_backdrop) {
+            const size_t n_tasks = (((size_t)world->camera->fb_width + TILE_W - 1) / TILE_W) * (((size_t)world->camera->fb_height + TILE_H - 1) / TILE_H) * 32 * (aa ? 4 : 1);
+            st = ensure(&ctx->d_task_aux, &ctx->d_task_aux_bytes, n_tasks * sizeof(float4) + 16);
+            if (st != AICB_OK) return st;
+            std::vector<float4> init(n_tasks, make_float4(backdrop[0] * 1.0f, backdrop[1] * 1.0f, backdrop[2] * 1.0f, 1.0f * backdrop[3]));
+            CU(cudaMemcpy(ctx->d_task_aux, init.data(), n_tasks * sizeof(float4), cudaMemcpyHostToDevice));
+            o.in_accum = (const float4 *)ctx->d_task_aux;
+        }
+        o.no_world = no_world_rgba ? no_world : nullptr;
+        st = run(world->scene, world->camera, &w_opt, o);
+    } else {
+        aicb_options ui_opt = *ui->options;
+        ui_opt.include_sky = 0;
+        Outputs o;
+        o.srgb8 = (uchar4 *)ctx->d_out;
+        o.backdrop = have_backdrop ? backdrop : nullptr;
+        o.no_world = no_world_rgba ? no_world : nullptr;
+        st = run(ui->scene, ui->camera, &ui_opt, o);
+    }
+    if (st != AICB_OK) return st;
+    if (out_len) CU(cudaMemcpy(out, ctx->d_out, out_len * 4, cudaMemcpyDeviceToHost));
+    if (info) *info = total;
+    return AICB_OK;
+}
+
+// == render_orthographic (raytracer/ortho.rs:30-84) with MultiOrthoCamera (:143-199) / OrthoCamera (:209-297): five
+// pixel-perfect axis-aligned views (top, left, front, right, bottom) of the whole Space in one image, `resolution`
+// pixels per cube, GraphicsOptions::UNALTERED_COLORS, one ray per pixel, Rgba::from(ColorBuf).to_srgb8() (no
+// post-processing); pixels between the views are transparent.  The reference traces AaRays; its AxisAlignedRaycaster
+// "produces exactly the same RaycastSteps" as the Raycaster on Ray::from(aa_ray) (raycast/axis_aligned.rs:8-9 and its
+// tests), so the rays go through the general marching kernel.
+static void ortho_views(const DeviceScene &ds, uint32_t res, uint32_t vw[5], uint32_t vh[5], uint32_t ox[5], uint32_t oy[5],
+                        uint32_t *W, uint32_t *H) {
+    const uint32_t sx = (uint32_t)ds.size[0] * res, sy = (uint32_t)ds.size[1] * res, sz = (uint32_t)ds.size[2] * res;
+    // order: top (PY), left (NX), front (PZ), right (PX), bottom (NY)
+    vw[0] = sx; vh[0] = sz;
+    vw[1] = sz; vh[1] = sy;
+    vw[2] = sx; vh[2] = sy;
+    vw[3] = sz; vh[3] = sy;
+    vw[4] = sx; vh[4] = sz;
+    ox[0] = vw[1] + 1; oy[0] = 0;
+    ox[1] = 0; oy[1] = vh[0] + 1;
+    ox[2] = vw[1] + 1; oy[2] = vh[0] + 1;
+    ox[3] = vw[1] + vw[2] + 2; oy[3] = vh[0] + 1;
+    ox[4] = vw[1] + 1; oy[4] = vh[0] + vh[2] + 2;
+    uint32_t w = 0, h = 0;
+    for (int i = 0; i < 5; i++) {
+        w = std::max(w, ox[i] + vw[i]);
+        h = std::max(h, oy[i] + vh[i]);
+    }
+    *W = w;
+    *H = h;
+}
+
+aicb_status aicb_ortho_image_size(const aicb_scene *s, uint32_t resolution, uint32_t *width, uint32_t *height) {
+    if (!s || !width || !height) return fail(AICB_ERR_INVALID, "NULL argument");
+    if (resolution == 0 || (resolution & (resolution - 1)) || resolution > 128)
+        return fail(AICB_ERR_INVALID, "resolution must be a power of two up to 128");
+    uint32_t vw[5], vh[5], ox[5], oy[5];
+    ortho_views(s->ds, resolution, vw, vh, ox, oy, width, height);
+    return AICB_OK;
+}
+
+aicb_status aicb_render_orthographic(aicb_scene *s, uint32_t resolution, uint8_t (*out)[4], size_t out_len,
+                                     aicb_render_info *info) {
+    uint32_t W = 0, H = 0;
+    aicb_status st = aicb_ortho_image_size(s, resolution, &W, &H);
+    if (st != AICB_OK) return st;
+    if (out_len != (size_t)W * H) return fail(AICB_ERR_INVALID, "Viewport size does not match output buffer length");
+    if (out_len && !out) return fail(AICB_ERR_INVALID, "out is NULL");
+    aicb_ctx *ctx = s->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    const DeviceScene &ds = s->ds;
+    uint32_t vw[5], vh[5], ox[5], oy[5];
+    ortho_views(ds, resolution, vw, vh, ox, oy, &W, &H);
+    const double inv = 1.0 / (double)resolution;   // (a power of two: exact)
+    const double lb[3] = {(double)ds.lo[0], (double)ds.lo[1], (double)ds.lo[2]};
+    const double ub[3] = {(double)ds.lo[0] + ds.size[0], (double)ds.lo[1] + ds.size[1], (double)ds.lo[2] + ds.size[2]};
+    std::vector<double> rays;
+    std::vector<uint32_t> where;
+    for (int v = 0; v < 5; v++) {
+        for (uint32_t py = 0; py < vh[v]; py++)
+            for (uint32_t px = 0; px < vw[v]; px++) {
+                // pixel centre, y flipped, scaled to cubes (ortho.rs:278-283); then the view's rotation and corner
+                const double u = ((double)px + 0.5) * inv, w = -(((double)py + 0.5) * inv);
+                double o[3], d[3] = {0, 0, 0};
+                switch (v) {
+                    case 0: o[0] = lb[0] + u; o[1] = ub[1]; o[2] = lb[2] - w; d[1] = -1.0; break;   // top: Face::PY
+                    case 1: o[0] = lb[0]; o[1] = ub[1] + w; o[2] = lb[2] + u; d[0] = 1.0; break;    // left: Face::NX
+                    case 2: o[0] = lb[0] + u; o[1] = ub[1] + w; o[2] = ub[2]; d[2] = -1.0; break;   // front: Face::PZ
+                    case 3: o[0] = ub[0]; o[1] = ub[1] + w; o[2] = ub[2] - u; d[0] = -1.0; break;   // right: Face::PX
+                    default: o[0] = lb[0] + u; o[1] = lb[1]; o[2] = ub[2] + w; d[1] = 1.0; break;   // bottom: Face::NY
+                }
+                for (int a = 0; a < 3; a++) rays.push_back(o[a]);
+                for (int a = 0; a < 3; a++) rays.push_back(d[a]);
+                where.push_back((oy[v] + py) * W + (ox[v] + px));
+            }
+    }
+    const size_t n = where.size();
+    std::vector<uchar4> px(n);
+    if (n) {
+        double *d_rays = nullptr;
+        CU(cudaMalloc(&d_rays, n * 48 + 16));
+        cudaError_t e = cudaMemcpy(d_rays, rays.data(), n * 48, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            st = ensure(&ctx->d_out, &ctx->d_out_bytes, n * 4 + 16);
+            if (st == AICB_OK) {
+                aicb_options opt;   // GraphicsOptions::UNALTERED_COLORS (graphics_options.rs:168)
+                std::memset(&opt, 0, sizeof opt);
+                opt.fog = AICB_FOG_NONE;
+                opt.lighting_display = AICB_LIGHT_NONE;
+                opt.transparency = AICB_TRANSPARENCY_VOLUMETRIC;
+                opt.tone_mapping = AICB_TONE_CLAMP;
+                opt.maximum_intensity = INFINITY;
+                opt.view_distance = 200.0;
+                opt.include_sky = 1;
+                Outputs o;
+                o.srgb8 = (uchar4 *)ctx->d_out;
+                for (;;) {
+                    st = launch_trace(s, nullptr, &opt, nullptr, d_rays, n, o, false, ctx->stream);
+                    if (st != AICB_OK) break;
+                    e = cudaStreamSynchronize(ctx->stream);
+                    if (e != cudaSuccess) break;
+                    st = finish(s, info);
+                    if (st != AICB_ERR_RETRY) break;
+                }
+                if (st == AICB_OK && e == cudaSuccess) e = cudaMemcpy(px.data(), ctx->d_out, n * 4, cudaMemcpyDeviceToHost);
+            }
+        }
+        cudaFree(d_rays);
+        if (e != cudaSuccess) return cuda_fail(e, "orthographic render");
+        if (st != AICB_OK) return st;
+    }
+    std::memset(out, 0, out_len * 4);   // Rgba::TRANSPARENT between the views
+    for (size_t i = 0; i < n; i++) std::memcpy(out[where[i]], &px[i], 4);
     return AICB_OK;
 }
 

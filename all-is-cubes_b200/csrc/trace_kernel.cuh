@@ -179,6 +179,15 @@ struct TraceParams {
     double *out_depth;
     aicb_hit *out_hit;
     uint32_t *out_steps;
+    int32_t *out_text;          // CharacterBuf (text.rs:52-123) per pixel: block index of the first hit, or AICB_TEXT_*
+    // layers (RtScene::trace_ray_through_layers, renderer.rs:454-478): a ray's accumulator can start from what the
+    // layer in front left in it, and can be handed on instead of becoming a pixel
+    const float4 *in_accum;     // per task (global index): ColorBuf (light, transmittance) to start from, or nullptr
+    float4 *out_accum;          // per task: the ray's ColorBuf goes here and no pixel is produced, or nullptr
+    float backdrop[4];          // Exception::Backdrop hit added after the ray (premultiplied light rgb, transmittance)
+    uint32_t has_backdrop;
+    float no_world[4];          // ColorBuf the accumulator is replaced by if it is not opaque in the end
+    uint32_t has_no_world;
     unsigned long long *counters;  // [0] cubes_traced, [1] outer steps, [2] inner steps, [3] hits, [4] light texels, [5] blocks entered
     unsigned int *task_counter;
     unsigned long long *debug_warp_times;  // AICB_PROFILE_KERNELS: per marching warp {start ns, end ns, passes, rays}
@@ -1097,8 +1106,13 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
                         face = (int)(rec.flags & 7u);
                         valid = (rec.flags & 16u) != 0;
                         L = 0.0f;
-                        steps = 0;
                         step_limit = 1000u;
+                        if (P.in_accum) {   // the layers in front may have made the ray opaque already
+                            const float t0 = __ldg(&P.in_accum[P.task_base + task].w);
+                            L = (t0 > 0.0f) ? __log2f(t0) + 1e-3f : F_NEG_INF;
+                            step_limit = (L < -8.0f) ? 0u : 1000u;
+                        }
+                        steps = 0;
                         n_hits = 0;
                         have_pending = false;
                         inner = false;
@@ -1466,10 +1480,15 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
         uint32_t steps_total = 0;
         double depth = D_INF;          // DepthBuf::mean = min over the sub-samples (accum.rs:284-297)
         uint32_t first_valid = 0xffffffffu;   // Position of the first surface hit: first sub-sample that has one
+        int32_t text = AICB_TEXT_EMPTY;       // CharacterBuf of the pixel (text.rs:100-113 reduces the sub-samples)
         for (uint32_t k = 0; k < P.n_samples; k++) {
             TaskOut o;
             *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + t0 + k);
             float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
+            if (P.in_accum) {   // what the layer in front left in the accumulator (renderer.rs:454-471)
+                const float4 a = P.in_accum[P.task_base + t0 + k];
+                lr = a.x; lg = a.y; lb = a.z; T = a.w;
+            }
             uint32_t steps = o.steps;
             uint32_t sample_first = 0xffffffffu;
             uint32_t hi = o.first_hit;
@@ -1499,6 +1518,25 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
                 depth = fmin(depth, hr->last_t * recip_pow2(1 << ((hr->flags >> 4) & 15u)));
                 if (first_valid == 0xffffffffu) first_valid = sample_first;
             }
+            if (P.out_text) {
+                // CharacterBuf::add (text.rs:84-98): the first hit of a block names it; Exception::Incomplete without one
+                // is "X"; a ray that counted a step entered the space (sr.rs:628-637)
+                int32_t tk = o.steps > 0 ? AICB_TEXT_ENTERED_SPACE : AICB_TEXT_EMPTY;
+                if (sample_first != 0xffffffffu) {
+                    const uint32_t cell = P.hits[sample_first].cell;
+                    tk = S.wide_cells ? (int32_t)(__ldg((const uint32_t *)S.cells + cell) & 0xffffu)
+                                      : (int32_t)((uint32_t)__ldg((const uint16_t *)S.cells + cell) & 0x3fffu);
+                } else if (o.steps > 1000u) {
+                    tk = AICB_TEXT_INCOMPLETE;
+                }
+                // CharacterBuf::mean (text.rs:100-113): the first sample that hit wins; entered only if all entered
+                const bool ah = text >= 0 || text <= AICB_TEXT_INCOMPLETE, bh = tk >= 0 || tk <= AICB_TEXT_INCOMPLETE;
+                if (k == 0) text = tk;
+                else if (ah) {}
+                else if (bh) text = tk;
+                else if (text == AICB_TEXT_ENTERED_SPACE && tk == AICB_TEXT_ENTERED_SPACE) text = AICB_TEXT_ENTERED_SPACE;
+                else text = AICB_TEXT_EMPTY;
+            }
             if (P.include_sky) {  // the sky is an opaque hit at t = inf
                 const int so = S.sky_kind ? (int)(o.flags & 7u) : 0;
                 lr = lr + (S.sky_colors[so][0] * 1.0f) * T;
@@ -1516,10 +1554,19 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
                 lr = red; lg = green; lb = ps_clamped(lum * 0.2f);
                 T = 0.0f;
             }
+            if (P.has_backdrop) {   // Exception::Backdrop between the UI and the world (renderer.rs:458-466)
+                lr = lr + P.backdrop[0] * T; lg = lg + P.backdrop[1] * T; lb = lb + P.backdrop[2] * T;
+                T = T * P.backdrop[3];
+            }
+            if (P.has_no_world && !(T < (1.0f / 256.0f))) {   // P::paint(NO_WORLD_TO_SHOW) replaces it (renderer.rs:474-477)
+                lr = P.no_world[0]; lg = P.no_world[1]; lb = P.no_world[2]; T = P.no_world[3];
+            }
+            if (P.out_accum) P.out_accum[P.task_base + t0 + k] = make_float4(lr, lg, lb, T);
             steps_total += steps;
             a0 = a0 + lr; a1 = a1 + lg; a2 = a2 + lb; aT = aT + T;
         }
         cubes_traced = steps_total;
+        if (P.out_text) P.out_text[out_index] = text;
         float l0 = a0, l1 = a1, l2 = a2, tT = aT;
         if (P.n_samples == 4) { l0 = a0 / 4.0f; l1 = a1 / 4.0f; l2 = a2 / 4.0f; tT = aT / 4.0f; }
         if (P.out_srgb8) P.out_srgb8[out_index] = encode_srgb8(P, s_thr, l0, l1, l2, tT);

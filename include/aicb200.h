@@ -157,6 +157,12 @@ typedef struct aicb_render_info {
     float stage_ms[4];             /* the frame's kernels (first chunk): ray generation, marching, shading, encode */
 } aicb_render_info;
 
+/* CharacterBuf states (raytracer/text.rs:52-123) of aicb_render_text: a value >= 0 is the block index (Space palette
+ * index) of the first block hit; the caller maps it to that block's string like TracingBlock's D::from_block does. */
+#define AICB_TEXT_ENTERED_SPACE (-1) /* the ray entered the Space's bounds but hit nothing: " " */
+#define AICB_TEXT_EMPTY (-2)         /* the ray never entered the Space: "." */
+#define AICB_TEXT_INCOMPLETE (-3)    /* Exception::Incomplete (step cap) before any hit: "X" */
+
 /* Per-pixel hit record: Position of the first non-exception Hit (hit.rs:92-101):
  * cube xyz, voxel xyz, resolution, face; all -1 when the ray hit nothing. */
 typedef struct aicb_hit {
@@ -227,6 +233,35 @@ aicb_status aicb_render_colorbuf(aicb_scene *, const aicb_camera *, const aicb_o
                                  const aicb_shard *shard_or_null,
                                  float (*out_colorbuf)[4], double *depth_or_null, aicb_hit *hit_or_null,
                                  uint32_t *steps_or_null, size_t out_len, aicb_render_info *info_or_null);
+
+/* == print_space's image (raytracer/text.rs:139-180): per pixel the CharacterBuf state (text.rs:52-123) — the block
+ * index of the first block the ray hit, or one of AICB_TEXT_*.  The caller prints each value with the string its block
+ * data gives that block (D::from_block). */
+aicb_status aicb_render_text(aicb_scene *, const aicb_camera *, const aicb_options *, int32_t *out, size_t out_len,
+                             aicb_render_info *info_or_null);
+
+/* == RtScene::trace_ray_through_layers + draw_rgba (renderer.rs:454-478, 282-308): the UI layer (its own Space and
+ * camera, traced without sky), the backdrop colour (StandardCameras' UiViewState::backdrop; NULL or transparent = none),
+ * then the world layer continuing in the same accumulator; a pixel that is still not opaque (no world layer) is
+ * painted `no_world_rgba` (palette::NO_WORLD_TO_SHOW, linear RGBA; NULL = leave).  Either layer may be NULL.  Both
+ * scenes must belong to one context and both cameras to one framebuffer size; the world layer's options choose the
+ * antialiasing sample points and the post-processing.  The info text of draw(info_text) is drawn by the caller over
+ * the returned image (renderer.rs:659-683 needs the font of the universe). */
+typedef struct aicb_layer {
+    aicb_scene *scene;
+    const aicb_camera *camera;
+    const aicb_options *options;
+} aicb_layer;
+aicb_status aicb_render_layers_srgb8(const aicb_layer *world_or_null, const aicb_layer *ui_or_null,
+                                     const float backdrop_rgba[4], const float no_world_rgba[4],
+                                     uint8_t (*out)[4], size_t out_len, aicb_render_info *info_or_null);
+
+/* == render_orthographic (raytracer/ortho.rs:30-84): the five axis-aligned views of MultiOrthoCamera (:143-199) in one
+ * image at `resolution` pixels per cube (the reference uses 32), UNALTERED_COLORS, sRGB8 without post-processing,
+ * transparent between the views.  aicb_ortho_image_size gives the image size for a scene. */
+aicb_status aicb_ortho_image_size(const aicb_scene *, uint32_t resolution, uint32_t *width, uint32_t *height);
+aicb_status aicb_render_orthographic(aicb_scene *, uint32_t resolution, uint8_t (*out)[4], size_t out_len,
+                                     aicb_render_info *info_or_null);
 
 /* Device-resident output (for multi-GPU gather and kernel-only timing): `d_out` is a device
  * pointer on the ctx's device with room for out_len pixels; `stream` is a cudaStream_t (0 =

@@ -1354,6 +1354,74 @@ static size_t trace_pixel(const orc_scene *sc, const aicb_camera &cam, const aic
     return total;
 }
 
+// RtScene::trace_patch + trace_ray_through_layers (renderer.rs:424-478): UI layer (no sky), backdrop, world layer
+// (sky), NO_WORLD_TO_SHOW if the accumulator is not opaque in the end.  ColorBuf accumulators only.
+static size_t trace_pixel_layers(const orc_scene *world, const aicb_camera *wcam, const aicb_options *wopt,
+                                 const orc_scene *ui, const aicb_camera *ucam, const aicb_options *uopt,
+                                 const float *backdrop_rgba, const float *no_world_rgba, uint32_t x, uint32_t y, ColorBuf *out) {
+    size_t total = 0;
+    const aicb_options *lead = world ? wopt : uopt;
+    const int n = lead->antialiasing_always ? 4 : 1;
+    ColorBuf acc_color[4];
+    for (int i = 0; i < n; i++) {
+        Accum acc;
+        acc.init(0);
+        if (ui) {
+            aicb_options o = *uopt;
+            o.include_sky = 0;
+            Tracer tr;
+            tr.sc = ui;
+            tr.opt = &o;
+            tr.acc = &acc;
+            double ro[3], rd[3];
+            pixel_ray(*ucam, x, y, n == 4 ? i : -1, ro, rd);
+            total += tr.trace(ro, rd);
+        }
+        if (backdrop_rgba && !(backdrop_rgba[0] == 0.0f && backdrop_rgba[1] == 0.0f && backdrop_rgba[2] == 0.0f && backdrop_rgba[3] == 0.0f)) {
+            Hit h{};
+            h.exception = EX_BACKDROP;
+            // ColorBuf::from(Rgba) (raytracer_components.rs:111-120)
+            h.surface = ColorBuf{{backdrop_rgba[0] * backdrop_rgba[3], backdrop_rgba[1] * backdrop_rgba[3], backdrop_rgba[2] * backdrop_rgba[3]},
+                                 1.0f - backdrop_rgba[3]};
+            h.block_index = -1;
+            acc.add(h);
+        }
+        if (world) {
+            aicb_options o = *wopt;
+            o.include_sky = 1;
+            Tracer tr;
+            tr.sc = world;
+            tr.opt = &o;
+            tr.acc = &acc;
+            double ro[3], rd[3];
+            pixel_ray(*wcam, x, y, n == 4 ? i : -1, ro, rd);
+            total += tr.trace(ro, rd);
+        }
+        if (!acc.opaque() && no_world_rgba) {   // *accum = P::paint(NO_WORLD_TO_SHOW): a fresh accumulator with that one hit
+            acc.init(0);
+            Hit h{};
+            h.exception = EX_PAINT;
+            h.surface = ColorBuf{{no_world_rgba[0] * no_world_rgba[3], no_world_rgba[1] * no_world_rgba[3], no_world_rgba[2] * no_world_rgba[3]},
+                                 1.0f - no_world_rgba[3]};
+            h.block_index = -1;
+            acc.add(h);
+        }
+        acc_color[i] = acc.color;
+    }
+    if (n == 4) {
+        float l[3] = {0, 0, 0}, t = 0.0f;
+        for (int i = 0; i < 4; i++) {
+            for (int c = 0; c < 3; c++) l[c] = l[c] + acc_color[i].light[c];
+            t = t + acc_color[i].transmittance;
+        }
+        for (int c = 0; c < 3; c++) out->light[c] = l[c] / 4.0f;
+        out->transmittance = t / 4.0f;
+    } else {
+        *out = acc_color[0];
+    }
+    return total;
+}
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------------------------
@@ -1614,6 +1682,32 @@ uint64_t orc_render_rowlist(const orc_scene *sc, const aicb_camera *cam, const a
                             size_t n_rows, int n_threads, uint8_t (*out_srgb8)[4], float (*out_cb)[4]) {
     std::vector<uint32_t> rows(row_list, row_list + n_rows);
     return render_rows_impl(sc, cam, opt, rows, 0, n_threads, out_srgb8, out_cb, nullptr, nullptr, nullptr, nullptr);
+}
+
+// draw_rgba through every layer (renderer.rs:282-308, 454-478); single-threaded (tests).
+uint64_t orc_render_layers(const orc_scene *world, const aicb_camera *wcam, const aicb_options *wopt, const orc_scene *ui,
+                           const aicb_camera *ucam, const aicb_options *uopt, const float *backdrop_rgba,
+                           const float *no_world_rgba, uint8_t (*out_srgb8)[4], float (*out_cb)[4]) {
+    const aicb_camera *lead_cam = world ? wcam : ucam;
+    const aicb_options *lead_opt = world ? wopt : uopt;
+    uint64_t total = 0;
+    for (uint32_t y = 0; y < lead_cam->fb_height; y++)
+        for (uint32_t x = 0; x < lead_cam->fb_width; x++) {
+            ColorBuf c;
+            total += trace_pixel_layers(world, wcam, wopt, ui, ucam, uopt, backdrop_rgba, no_world_rgba, x, y, &c);
+            const size_t o = (size_t)y * lead_cam->fb_width + x;
+            if (out_srgb8) encode_srgb8(c, lead_cam->exposure, lead_opt->tone_mapping, lead_opt->maximum_intensity, out_srgb8[o]);
+            if (out_cb) { out_cb[o][0] = c.light[0]; out_cb[o][1] = c.light[1]; out_cb[o][2] = c.light[2]; out_cb[o][3] = c.transmittance; }
+        }
+    return total;
+}
+
+// Rgba::from(ColorBuf).to_srgb8() (ortho.rs:130) for a batch of accumulators: no exposure, no tone mapping.
+void orc_colorbuf_to_srgb8(const float (*cb)[4], size_t n, uint8_t (*out)[4]) {
+    for (size_t i = 0; i < n; i++) {
+        ColorBuf c{{cb[i][0], cb[i][1], cb[i][2]}, cb[i][3]};
+        encode_srgb8(c, 1.0f, AICB_TONE_CLAMP, std::numeric_limits<float>::infinity(), out[i]);
+    }
 }
 
 void orc_pixel_ray(const aicb_camera *cam, uint32_t x, uint32_t y, int sample, double out[6]) {

@@ -55,6 +55,12 @@ def lib():
     L.orc_render_rowlist.restype = C.c_uint64
     L.orc_render_rowlist.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p,
                                      C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_render_layers.restype = C.c_uint64
+    L.orc_render_layers.argtypes = [C.c_void_p, C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p,
+                                    C.POINTER(abi.CameraData), C.POINTER(abi.Options), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    L.orc_colorbuf_to_srgb8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.orc_colorbuf_to_srgb8.restype = None
     L.orc_pixel_ray.argtypes = [C.POINTER(abi.CameraData), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.orc_pixel_ray.restype = None
     L.orc_hardware_threads.restype = C.c_int
@@ -241,6 +247,35 @@ def pixel_ray(camera, x, y, sample=-1):
 
 def hardware_threads():
     return lib().orc_hardware_threads()
+
+
+def render_layers(world, ui, backdrop=None, no_world=None):
+    """draw_rgba through the layers (renderer.rs:454-478).  world / ui = (OracleScene, Camera, GraphicsOptions) or None."""
+    lead = world if world else ui
+    cam = lead[1].data
+    n = cam.fb_width * cam.fb_height
+    srgb = np.empty((n, 4), dtype=np.uint8)
+    cb = np.empty((n, 4), dtype=np.float32)
+
+    def parts(layer):
+        if not layer:
+            return None, None, None
+        return layer[0].handle, C.byref(layer[1].data), C.byref(layer[2].to_abi(True))
+
+    wh, wc, wo = parts(world)
+    uh, uc, uo = parts(ui)
+    b = np.array(backdrop, dtype=np.float32) if backdrop is not None else None
+    nw = np.array(no_world, dtype=np.float32) if no_world is not None else None
+    total = lib().orc_render_layers(wh, wc, wo, uh, uc, uo, b.ctypes.data if b is not None else None,
+                                    nw.ctypes.data if nw is not None else None, srgb.ctypes.data, cb.ctypes.data)
+    return {"srgb8": srgb, "colorbuf": cb, "cubes_traced": int(total)}
+
+
+def colorbuf_to_srgb8(cb):
+    c = np.ascontiguousarray(cb, dtype=np.float32).reshape(-1, 4)
+    out = np.empty((c.shape[0], 4), dtype=np.uint8)
+    lib().orc_colorbuf_to_srgb8(c.ctypes.data, c.shape[0], out.ctypes.data)
+    return out
 
 
 def ulp_diff(a, b):

@@ -481,3 +481,100 @@ def test_device_group_frame_equals_single_device_frame(mixed):
         again = g.draw(cam, opts)
         assert np.array_equal(again.data, alone.data)
         g.close()
+
+
+def test_print_space_through_the_text_entry():
+    """raytracer/text.rs:196-258, 265-341 through aicb_render_text (CharacterBuf per pixel) — the reference's two
+    80x40 golden images, character for character; and the same states as the oracle's CharacterBuf accumulator."""
+    golden = json.load(open(os.path.join(GOLDEN, "text_images.json")))
+    ids = np.array([1, 2, 3], dtype=np.uint16).reshape(3, 1, 1)
+    grey = lambda i, n: (i / (n - 1),) * 3 + (1.0,) if n > 1 else (0.5, 0.5, 0.5, 1.0)
+    space = Space((0, 0, 0), ids, [Block.air()] + [Block(color=grey(i, 3)) for i in range(3)])
+    assert aicb200.print_space(space, (1.0, 1.0, 1.0), {1: "0", 2: "1", 3: "2"}) == golden["print_space_test"]
+    idx = np.zeros((4, 2, 4), dtype=np.uint16)
+    pal = np.zeros((1, 8), dtype=np.float32)
+    pal[0, :4] = (1, 1, 1, 1)
+    partial = Block(resolution=4, indices=idx, palette=pal)
+    space = Space((0, 0, 0), np.array([1, 2], dtype=np.uint16).reshape(2, 1, 1),
+                  [Block.air(), Block(color=grey(0, 1)), partial])
+    assert aicb200.print_space(space, (1.0, 1.0, 1.0), {1: "0", 2: "P"}) == golden["partial_voxels"]
+
+
+def test_text_output_equals_oracle_character_buf(mixed):
+    import ctypes as C
+    for kw in (dict(), dict(antialiasing_always=True), dict(transparency=TRANSPARENCY_SURFACE)):
+        opts = GraphicsOptions(view_distance=40.0, **kw)
+        cam = scenes.standard_camera(mixed, opts, 72, 40)
+        rt = SpaceRaytracer(mixed, opts)
+        out = np.zeros(72 * 40, dtype=np.int32)
+        o = opts.to_abi(True)
+        st = aicb200.load_library().aicb_render_text(rt.handle, C.byref(cam.data), C.byref(o), out.ctypes.data, out.size, None)
+        assert st == 0
+        ref = orc.OracleScene(mixed).render(cam, opts, accum_mode=1)["text"]
+        ref = np.where(ref == -4, -3, ref)   # (no other exception hit reaches a CharacterBuf in these scenes)
+        assert np.array_equal(out, ref), f"{kw}: {np.argwhere(out != ref)[:5]}"
+
+
+def test_orthographic_render_equals_oracle_on_the_same_rays(mixed):
+    """raytracer/ortho.rs:30-84: five axis-aligned pixel-perfect views.  The image must equal the oracle tracing the
+    reference's rays (OrthoCamera::project_pixel_into_world, ortho.rs:209-297) one by one, and the layout must be
+    MultiOrthoCamera's (:143-199)."""
+    res = 4
+    rt = SpaceRaytracer(mixed, GraphicsOptions.unaltered_colors())
+    img = aicb200.render_orthographic(rt, res)
+    sx, sy, sz = (mixed.size[a] * res for a in range(3))
+    assert img.size == (sz + sx + sz + 2, sz + sy + sz + 2)
+    lb = np.array(mixed.lower, dtype=np.float64)
+    ub = lb + np.array(mixed.size, dtype=np.float64)
+    views = [  # (image origin, size, corner, image right axis, image down axis, ray direction)
+        ((sz + 1, 0), (sx, sz), (lb[0], ub[1], lb[2]), (1, 0, 0), (0, 0, 1), (0, -1, 0)),             # top
+        ((0, sz + 1), (sz, sy), (lb[0], ub[1], lb[2]), (0, 0, 1), (0, -1, 0), (1, 0, 0)),             # left
+        ((sz + 1, sz + 1), (sx, sy), (lb[0], ub[1], ub[2]), (1, 0, 0), (0, -1, 0), (0, 0, -1)),       # front
+        ((sz + sx + 2, sz + 1), (sz, sy), (ub[0], ub[1], ub[2]), (0, 0, -1), (0, -1, 0), (-1, 0, 0)),  # right
+        ((sz + 1, sz + sy + 2), (sx, sz), (lb[0], lb[1], ub[2]), (1, 0, 0), (0, 0, -1), (0, 1, 0)),   # bottom
+    ]
+    expect = np.zeros((img.size[1], img.size[0], 4), dtype=np.uint8)
+    osc = orc.OracleScene(mixed)
+    for (ox, oy), (w, h), corner, right, down, d in views:
+        px, py = np.meshgrid(np.arange(w), np.arange(h))
+        u = (px.ravel() + 0.5) / res
+        v = (py.ravel() + 0.5) / res
+        o = np.array(corner)[None, :] + u[:, None] * np.array(right, dtype=np.float64)[None, :] + v[:, None] * np.array(down, dtype=np.float64)[None, :]
+        rays = np.concatenate([o, np.broadcast_to(np.array(d, dtype=np.float64), o.shape)], axis=1)
+        ref = osc.trace_rays(rays, GraphicsOptions.unaltered_colors(), include_sky=True)
+        expect[oy:oy + h, ox:ox + w] = orc.colorbuf_to_srgb8(ref["colorbuf"]).reshape(h, w, 4)
+    assert np.array_equal(img.data, expect), f"{(img.data != expect).any(axis=2).sum()} pixels differ"
+    assert (img.data[sz, :, 3] == 0).all() and (img.data[:, sz, 3] == 0).all()   # the gaps are transparent
+
+
+def test_layers_ui_backdrop_world_and_no_world(mixed):
+    """RtScene::trace_ray_through_layers (renderer.rs:454-478) against the oracle: a UI Space in front (own camera,
+    no sky), a backdrop colour, the world continuing in the same accumulator; without a world, NO_WORLD_TO_SHOW."""
+    ui_space = scenes.small_mixed_scene(n=6, seed=11, lower=(0, 0, 0))
+    nw = aicb200.srgb8_to_linear((0xBC, 0xBC, 0xBC)) + (1.0,)
+    for aa in (False, True):
+        wopts = GraphicsOptions(view_distance=40.0, antialiasing_always=aa)
+        uopts = GraphicsOptions(view_distance=30.0, fog=FOG_NONE, lighting_display=LIGHT_FLAT)
+        wcam = scenes.standard_camera(mixed, wopts, 64, 48)
+        ucam = scenes.standard_camera(ui_space, uopts, 64, 48, direction=(0.2, 0.1, 1.0), distance_scale=1.6)
+        wrt = SpaceRaytracer(mixed, wopts)
+        urt = SpaceRaytracer(ui_space, uopts, wrt.ctx)
+        wo, uo = orc.OracleScene(mixed), orc.OracleScene(ui_space)
+        cases = [
+            dict(world=True, ui=True, backdrop=(0.1, 0.3, 0.6, 0.5)),
+            dict(world=True, ui=True, backdrop=None),
+            dict(world=True, ui=False, backdrop=(0.9, 0.2, 0.1, 0.25)),
+            dict(world=False, ui=True, backdrop=(0.0, 0.5, 0.0, 0.3)),
+            dict(world=False, ui=True, backdrop=None),
+        ]
+        for c in cases:
+            gw = (wrt, wcam, wopts) if c["world"] else None
+            gu = (urt, ucam, uopts) if c["ui"] else None
+            if not c["world"]:   # the lead layer's options choose the sample points
+                uopts.antialiasing_always = aa
+            got = aicb200.render_layers(gw, gu, c["backdrop"], nw)
+            ref = orc.render_layers((wo, wcam, wopts) if c["world"] else None, (uo, ucam, uopts) if c["ui"] else None,
+                                    c["backdrop"], nw)
+            uopts.antialiasing_always = False
+            assert np.array_equal(got.data.reshape(-1, 4), ref["srgb8"]), f"aa={aa} {c}: {(got.data.reshape(-1, 4) != ref['srgb8']).any(axis=1).sum()} pixels differ"
+            assert got.info.cubes_traced == ref["cubes_traced"], f"aa={aa} {c}"
