@@ -389,7 +389,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     P.task_counter = ctx->d_tile_counter;
     {
         const char *e = getenv("AICB_REFILL_THRESHOLD");
-        int v = e ? atoi(e) : 1;
+        int v = e ? atoi(e) : 4;
         P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         const char *e2 = getenv("AICB_EVENT_THRESHOLD");
         int v2 = e2 ? atoi(e2) : 24;

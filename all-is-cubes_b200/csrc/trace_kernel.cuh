@@ -28,6 +28,7 @@
 // Every function cites the reference lines it reproduces.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "../../include/aicb200.h"
@@ -171,7 +172,8 @@ struct TraceParams {
     unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
     uint32_t hit_capacity;
     uint32_t event_threshold;   // leave the marching loop once this many lanes wait (parked at a level switch, finished, idle)
-    uint32_t refill_threshold;  // refill idle lanes once at least this many are idle (or nobody is running)
+    uint32_t refill_threshold;  // tail mode: once the ray list is exhausted and at most this many lanes of a warp still march,
+                                // they run the lean per-lane loop
     // outputs
     uchar4 *out_srgb8;
     float4 *out_colorbuf;
@@ -936,6 +938,22 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         return (cx | cy | cz) < 0;
     };
 
+    // The same step with one branch per axis instead of selects: a third of the instructions on the path taken.  For
+    // the tail of a frame, when a warp is down to a few long rays and the length of the dependent instruction chain
+    // of one step — not the number of issue slots — is what the frame waits for.
+    auto advance_branchy = [&]() -> bool {
+        if ((tmx < tmy) & (tmx < tmz)) {
+            last_t = tmx; tmx = tmx + tdx; idx += (uint32_t)stx; face = fcx; cx -= 1;
+            return cx < 0;
+        } else if (tmy < tmz) {
+            last_t = tmy; tmy = tmy + tdy; idx += (uint32_t)sty; face = fcy; cy -= 1;
+            return cy < 0;
+        } else {
+            last_t = tmz; tmz = tmz + tdz; idx += (uint32_t)stz; face = fcz; cz -= 1;
+            return cz < 0;
+        }
+    };
+
     // A visible surface (surface.rs:322-331, 399-409): its hit record goes to the lane's chunk of the hit stream.
     auto emit_surface = [&](uint32_t word) {
         uint32_t entry;   // palette entry of the surface, and what the transmittance bound needs of it
@@ -988,14 +1006,14 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     };
 
     // One step of the ray: advance, look at the cube / voxel, count, close the open span, classify.
-    auto step = [&]() {
+    auto step = [&](auto lean) {
         bool left = false;
         if (need_advance) {
             if (!valid) {   // the iterator ends without an exit step (raycast.rs:245-249)
                 st = inner ? ST_POP : ST_DONE;
                 return;
             }
-            left = advance();
+            if constexpr (decltype(lean)::value) left = advance_branchy(); else left = advance();
         }
         need_advance = true;
         uint32_t w = 0;
@@ -1189,11 +1207,19 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         {
             const int n_off = __popc(__ballot_sync(0xffffffffu, st == ST_EXHAUSTED || (list_exhausted && st == ST_IDLE)));
             const int thr = list_exhausted ? 1 : (int)P.event_threshold;
-            for (;;) {
-                const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
-                if (!marching) break;
-                if (32 - __popc(marching) - n_off >= thr) break;   // enough lanes wait for the warp
-                if (st == ST_MARCH) step();
+            const unsigned live = __ballot_sync(0xffffffffu, st == ST_MARCH);
+            if (list_exhausted && __popc(live) <= (int)P.refill_threshold) {
+                // the tail: each of the few remaining rays runs to its next level switch on its own
+                if (st == ST_MARCH) {
+                    do { step(std::true_type{}); } while (st == ST_MARCH);
+                }
+            } else {
+                for (;;) {
+                    const unsigned marching = __ballot_sync(0xffffffffu, st == ST_MARCH);
+                    if (!marching) break;
+                    if (32 - __popc(marching) - n_off >= thr) break;   // enough lanes wait for the warp
+                    if (st == ST_MARCH) step(std::false_type{});
+                }
             }
         }
         __syncwarp();
