@@ -76,6 +76,11 @@ def load_library() -> C.CDLL:
     lib.aicb_frame_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.aicb_frame_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.aicb_frame_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_frame_signal.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.aicb_frame_wait_arrived.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.aicb_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.aicb_frame_wait_consumed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.aicb_frame_timed_out.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
     lib.aicb_render_finish.argtypes = [C.c_void_p, C.POINTER(abi.RenderInfo)]
     lib.aicb_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(abi.Options), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.RenderInfo)]

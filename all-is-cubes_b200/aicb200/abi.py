@@ -136,6 +136,11 @@ EXPORTED_SYMBOLS = [
     "aicb_frame_open",
     "aicb_frame_close",
     "aicb_frame_read",
+    "aicb_frame_signal",
+    "aicb_frame_wait_arrived",
+    "aicb_frame_release",
+    "aicb_frame_wait_consumed",
+    "aicb_frame_timed_out",
     "aicb_trace_rays",
     "aicb_camera_look_at",
     "aicb_camera_from_view",

@@ -77,6 +77,38 @@ class PeerFrame:
             buf = (C.c_uint8 * 64)(*handle.tolist())
             _check(self.lib.aicb_frame_open(ctx.handle, buf, C.byref(self.ptr)))
         self.opened = rank != 0
+        self.frames = 0   # frames delivered through the arrival counter so far
+
+    # ---- delivery without a collective: the counters behind the frame's pixels (aicb_frame_signal & co.) ----------
+    def begin_frame(self, stream_ptr: int = 0):
+        """Before this rank stores into the frame again: the owner must be through with the previous frame."""
+        from . import _check
+        if self.frames:
+            _check(self.lib.aicb_frame_wait_consumed(self.ctx.handle, self.ptr, self.height * self.width, self.frames, stream_ptr))
+
+    def end_frame(self, stream_ptr: int = 0, release: bool = True):
+        """After aicb_render_srgb8_device_frame on the same stream: signal; the owner waits for every rank's signal and
+        (release=True: the frame stays on the device) marks it consumed."""
+        from . import _check
+        n = self.height * self.width
+        self.frames += 1
+        _check(self.lib.aicb_frame_signal(self.ctx.handle, self.ptr, n, stream_ptr))
+        if self.rank == 0:
+            _check(self.lib.aicb_frame_wait_arrived(self.ctx.handle, self.ptr, n, self.frames * self.world, stream_ptr))
+            if release:
+                _check(self.lib.aicb_frame_release(self.ctx.handle, self.ptr, n, self.frames, stream_ptr))
+
+    def release(self, stream_ptr: int = 0):
+        from . import _check
+        if self.rank == 0:
+            _check(self.lib.aicb_frame_release(self.ctx.handle, self.ptr, self.height * self.width, self.frames, stream_ptr))
+
+    def timed_out(self) -> bool:
+        import ctypes as C
+        from . import _check
+        v = C.c_uint32(0)
+        _check(self.lib.aicb_frame_timed_out(self.ctx.handle, self.ptr, self.height * self.width, C.byref(v)))
+        return bool(v.value)
 
     def read(self, out: torch.Tensor, stream_ptr: int = 0):
         """Rank 0: device -> host copy of the frame into a (pinned) uint8 tensor of height*width*4 bytes."""

@@ -1126,21 +1126,113 @@ aicb_status aicb_render_srgb8_device_frame(aicb_scene *s, const aicb_camera *cam
 }
 
 // ---- full-frame buffers shared between ranks (CUDA IPC) ------------------------------------------
+// Behind the pixels of a shared frame sits a small control block in the same allocation (so it travels with the IPC
+// handle): two monotonic counters that replace the collective of the delivery step.
+//   arrived   += 1 by every rank once its strips of a frame are stored (aicb_frame_signal, after the rank's encode_kernel
+//                in stream order; system-scope fence + atomic, so the pixels are visible before the count);
+//   consumed  := k by the owner once it is through with frame k (aicb_frame_release);
+// aicb_frame_wait_arrived / aicb_frame_wait_consumed are one-thread kernels that spin on them in stream order.  A wait
+// gives up after ~2 s (it must never wedge a GPU) and leaves AICB_FRAME_TIMEOUT in the block's third word.
+struct FrameControl {
+    unsigned int arrived;
+    unsigned int consumed;
+    unsigned int timed_out;
+    unsigned int _pad;
+};
+static size_t frame_control_offset(size_t n_pixels) { return (n_pixels * 4 + 255) & ~(size_t)255; }
+
+static __global__ void frame_signal_kernel(FrameControl *c) {
+    __threadfence_system();
+    atomicAdd_system(&c->arrived, 1u);
+}
+static __global__ void frame_release_kernel(FrameControl *c, unsigned int frame_id) {
+    __threadfence_system();
+    *(volatile unsigned int *)&c->consumed = frame_id;
+    __threadfence_system();
+}
+static __global__ void frame_wait_kernel(FrameControl *c, int which, unsigned int target) {
+    volatile unsigned int *p = which ? &c->consumed : &c->arrived;
+    const long long t0 = clock64();
+    while ((int)(*p - target) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz
+            c->timed_out = 1u;
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 aicb_status aicb_frame_create(aicb_ctx *ctx, size_t n_pixels, void **d_frame, uint8_t handle_out[64]) {
     if (!ctx || !d_frame || !handle_out) return fail(AICB_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     void *p = nullptr;
-    CU(cudaMalloc(&p, n_pixels * 4 + 16));
+    const size_t off = frame_control_offset(n_pixels);
+    CU(cudaMalloc(&p, off + 256));
+    cudaError_t e = cudaMemset((char *)p + off, 0, 256);
     cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
         cudaFree(p);
         return cuda_fail(e, "cudaIpcGetMemHandle");
     }
     std::memcpy(handle_out, &h, 64);
     *d_frame = p;
+    return AICB_OK;
+}
+
+static aicb_status frame_ctl(aicb_ctx *ctx, void *d_frame, size_t n_pixels, void *stream, cudaStream_t *st, FrameControl **c) {
+    if (!ctx || !d_frame) return fail(AICB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    *st = stream ? (cudaStream_t)stream : ctx->stream;
+    *c = (FrameControl *)((char *)d_frame + frame_control_offset(n_pixels));
+    return AICB_OK;
+}
+aicb_status aicb_frame_signal(aicb_ctx *ctx, void *d_frame, size_t n_pixels, void *stream) {
+    cudaStream_t st;
+    FrameControl *c;
+    aicb_status r = frame_ctl(ctx, d_frame, n_pixels, stream, &st, &c);
+    if (r != AICB_OK) return r;
+    frame_signal_kernel<<<1, 1, 0, st>>>(c);
+    CU(cudaGetLastError());
+    return AICB_OK;
+}
+aicb_status aicb_frame_release(aicb_ctx *ctx, void *d_frame, size_t n_pixels, uint32_t frame_id, void *stream) {
+    cudaStream_t st;
+    FrameControl *c;
+    aicb_status r = frame_ctl(ctx, d_frame, n_pixels, stream, &st, &c);
+    if (r != AICB_OK) return r;
+    frame_release_kernel<<<1, 1, 0, st>>>(c, frame_id);
+    CU(cudaGetLastError());
+    return AICB_OK;
+}
+aicb_status aicb_frame_wait_arrived(aicb_ctx *ctx, void *d_frame, size_t n_pixels, uint32_t count, void *stream) {
+    cudaStream_t st;
+    FrameControl *c;
+    aicb_status r = frame_ctl(ctx, d_frame, n_pixels, stream, &st, &c);
+    if (r != AICB_OK) return r;
+    frame_wait_kernel<<<1, 1, 0, st>>>(c, 0, count);
+    CU(cudaGetLastError());
+    return AICB_OK;
+}
+aicb_status aicb_frame_wait_consumed(aicb_ctx *ctx, void *d_frame, size_t n_pixels, uint32_t frame_id, void *stream) {
+    cudaStream_t st;
+    FrameControl *c;
+    aicb_status r = frame_ctl(ctx, d_frame, n_pixels, stream, &st, &c);
+    if (r != AICB_OK) return r;
+    frame_wait_kernel<<<1, 1, 0, st>>>(c, 1, frame_id);
+    CU(cudaGetLastError());
+    return AICB_OK;
+}
+// 1 if a wait on this frame ever gave up (a rank died or never rendered its strips).
+aicb_status aicb_frame_timed_out(aicb_ctx *ctx, void *d_frame, size_t n_pixels, uint32_t *out) {
+    if (!ctx || !d_frame || !out) return fail(AICB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    FrameControl h;
+    CU(cudaMemcpy(&h, (char *)d_frame + frame_control_offset(n_pixels), sizeof h, cudaMemcpyDeviceToHost));
+    *out = h.timed_out;
     return AICB_OK;
 }
 

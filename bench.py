@@ -45,9 +45,10 @@ def parse_args():
     p.add_argument("--light-n", type=int, default=256, help="c4: edge of the Space")
     p.add_argument("--pageable", action="store_true", help="e2e: the caller's output buffer is pageable host memory")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
-    p.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                   help="N>1: 'p2p' = trace kernel stores its strips straight into rank 0's frame over NVLink "
-                        "(CUDA IPC mapped peer memory); 'nccl' = packed strips + NCCL gather + reassembly")
+    p.add_argument("--gather", default="p2p", choices=["p2p", "p2p-barrier", "nccl"],
+                   help="N>1: 'p2p' = the encode kernel stores its strips straight into rank 0's frame over NVLink "
+                        "(CUDA IPC mapped peer memory) and an arrival counter in that memory replaces the collective; "
+                        "'p2p-barrier' = the same stores + an NCCL barrier; 'nccl' = packed strips + NCCL gather + reassembly")
     return p.parse_args()
 
 
@@ -431,6 +432,9 @@ def run_ours(args):
             raise RuntimeError(lib.aicb_last_error().decode())
 
     gather_mode = args.gather if world > 1 else "none"
+    use_counter = gather_mode == "p2p"
+    if gather_mode == "p2p-barrier":
+        gather_mode = "p2p"
     peer = None
     if gather_mode == "p2p":
         try:
@@ -447,12 +451,19 @@ def run_ours(args):
         if int(ok.item()) == 0:
             gather_mode, peer = "nccl", None
 
+    release_on_device = True   # e2e: rank 0 releases the frame after its device -> host copy instead
+
     def device_step():
         """One frame with everything resident in HBM: trace kernel + delivery of the strips to rank 0."""
         if gather_mode == "p2p":
+            if use_counter:   # no collective: counters behind the frame's pixels, all in stream order
+                peer.begin_frame(stream.cuda_stream)
             check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
                                                      peer.ptr, w * h, C.c_void_p(stream.cuda_stream)))
-            dist.barrier()  # NCCL barrier on the current stream: rank 0's frame is complete after it
+            if use_counter:
+                peer.end_frame(stream.cuda_stream, release=release_on_device)
+            else:
+                dist.barrier()  # NCCL barrier on the current stream: rank 0's frame is complete after it
         else:
             check(lib.aicb_render_srgb8_device(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
                                                d_out.data_ptr(), n_local, C.c_void_p(stream.cuda_stream)))
@@ -582,10 +593,15 @@ def run_ours(args):
             check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
                                         host_out.data_ptr(), n_local, None))
         else:
+            nonlocal release_on_device
+            release_on_device = False     # the frame is released after rank 0 has copied it out
             device_step()
+            release_on_device = True
             if rank == 0:
                 if gather_mode == "p2p":
                     peer.read(host_frame, stream.cuda_stream)
+                    if use_counter:
+                        peer.release(stream.cuda_stream)
                 else:
                     host_frame.copy_(frame, non_blocking=False)
 
@@ -637,7 +653,9 @@ def run_ours(args):
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
-            "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips", "gather": gather_mode,
+            "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips",
+                       "gather": ("p2p stores + arrival counter (no collective)" if (gather_mode == "p2p" and use_counter) else
+                                  "p2p stores + NCCL barrier" if gather_mode == "p2p" else gather_mode),
                        "n_rank_frame_equals_1_rank_frame": frame_check,
                        "l2": "256 MiB buffer rewritten between timed steps", "scene_device_bytes": rt.device_bytes,
                        "cubes_traced_per_frame_this_rank": int(ai.cubes_traced)},

@@ -287,6 +287,19 @@ aicb_status aicb_frame_create(aicb_ctx *, size_t n_pixels, void **d_frame, uint8
 aicb_status aicb_frame_open(aicb_ctx *, const uint8_t handle[64], void **d_frame);
 aicb_status aicb_frame_close(aicb_ctx *, void *d_frame, int opened);
 aicb_status aicb_frame_read(aicb_ctx *, const void *d_frame, uint8_t (*out)[4], size_t n_pixels, void *stream);
+/* Delivery without a collective.  A shared frame carries two monotonic counters behind its pixels:
+ *   aicb_frame_signal          (every rank, after aicb_render_srgb8_device_frame on the same stream): "my strips of this
+ *                              frame are stored" — arrived += 1, system-scope fence first so the pixels are visible;
+ *   aicb_frame_wait_arrived    (owner): stream-ordered wait until arrived >= count (= ranks x frames so far);
+ *   aicb_frame_release         (owner): consumed := frame_id once it is through with the frame (copied, displayed);
+ *   aicb_frame_wait_consumed   (every rank, before storing into the frame again): wait until consumed >= frame_id.
+ * All four are stream operations (one-thread kernels), none touches the host.  A wait gives up after ~2 s;
+ * aicb_frame_timed_out reports it.  `n_pixels` is the frame's pixel count as given to aicb_frame_create. */
+aicb_status aicb_frame_signal(aicb_ctx *, void *d_frame, size_t n_pixels, void *stream);
+aicb_status aicb_frame_wait_arrived(aicb_ctx *, void *d_frame, size_t n_pixels, uint32_t count, void *stream);
+aicb_status aicb_frame_release(aicb_ctx *, void *d_frame, size_t n_pixels, uint32_t frame_id, void *stream);
+aicb_status aicb_frame_wait_consumed(aicb_ctx *, void *d_frame, size_t n_pixels, uint32_t frame_id, void *stream);
+aicb_status aicb_frame_timed_out(aicb_ctx *, void *d_frame, size_t n_pixels, uint32_t *out);
 
 /* ---------------------------------------------------------------------------------------------
  * Several GPUs from ONE process (csrc/group.cu): replaces the Rayon rows x pixels dispatch of
