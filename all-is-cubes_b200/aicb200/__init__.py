@@ -52,6 +52,7 @@ def load_library() -> C.CDLL:
     lib.aicb_last_error.restype = C.c_char_p
     lib.aicb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.aicb_ctx_destroy.argtypes = [C.c_void_p]
+    lib.aicb_ctx_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.aicb_scene_create.argtypes = [C.c_void_p, C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
     lib.aicb_scene_destroy.argtypes = [C.c_void_p]
     lib.aicb_scene_device_bytes.argtypes = [C.c_void_p]

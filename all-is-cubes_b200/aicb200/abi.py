@@ -114,6 +114,7 @@ EXPORTED_SYMBOLS = [
     "aicb_abi_version",
     "aicb_ctx_create",
     "aicb_ctx_destroy",
+    "aicb_ctx_stage_timing",
     "aicb_last_error",
     "aicb_scene_create",
     "aicb_scene_update_cubes",

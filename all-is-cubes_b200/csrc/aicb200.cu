@@ -448,7 +448,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     ctx->frame_in_flight = true;
     ctx->last_stream = stream;
     ctx->last_scene = sc;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long) + (4 + N_BINS) * sizeof(unsigned int), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     if (total_tasks > 0) {
         const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
@@ -465,12 +465,13 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         for (uint64_t base = 0; base < total_tasks; base += CHUNK) {
             const uint32_t n = (uint32_t)(total_tasks - base < CHUNK ? total_tasks - base : CHUNK);
             P.task_base = (uint32_t)base;
-            CU(cudaMemsetAsync(ctx->d_tile_counter, 0, (4 + N_BINS) * sizeof(unsigned int), stream));
             const bool first = base == 0;  // stage times are reported for the first chunk
+            if (!first) CU(cudaMemsetAsync(ctx->d_tile_counter, 0, (4 + N_BINS) * sizeof(unsigned int), stream));
             const bool prof = ctx->profile_kernels && first;
-            if (first) cudaEventRecord(ctx->ev_k[0], stream);
+            const bool stage = first && ctx->stage_timing;
+            if (stage) cudaEventRecord(ctx->ev_k[0], stream);
             gen_kernel<<<(n + 127) / 128, 128, 0, stream>>>(P, n);
-            if (first) cudaEventRecord(ctx->ev_k[1], stream);
+            if (stage) cudaEventRecord(ctx->ev_k[1], stream);
             uint64_t want = ((uint64_t)n + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
             uint64_t grid = (uint64_t)ctx->num_sms * blocks_per_sm;  // persistent: a multiple of the SM count
             if (grid > want) grid = want;
@@ -481,16 +482,16 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
             }
             k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
             P.debug_warp_times = nullptr;
-            if (first) cudaEventRecord(ctx->ev_k[2], stream);
+            if (stage) cudaEventRecord(ctx->ev_k[2], stream);
             switch (lc) {
                 case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
             }
-            if (first) cudaEventRecord(ctx->ev_k[3], stream);
+            if (stage) cudaEventRecord(ctx->ev_k[3], stream);
             const uint32_t n_pixels = n / P.n_samples;
             encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
-            if (first) cudaEventRecord(ctx->ev_k[4], stream);
+            if (stage) cudaEventRecord(ctx->ev_k[4], stream);
         }
         CU(cudaGetLastError());
     }
@@ -549,7 +550,7 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         info->kernel_ms = ms;
-        if (sc->pending_rays)
+        if (sc->pending_rays && ctx->stage_timing)
             for (int i = 0; i < 4; i++) cudaEventElapsedTime(&info->stage_ms[i], ctx->ev_k[i], ctx->ev_k[i + 1]);
         info->cubes_traced = c[0];
         info->rays = sc->pending_rays;
@@ -598,8 +599,9 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     c->profile_kernels = getenv("AICB_PROFILE_KERNELS") != nullptr;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
     CU(cudaEventCreateWithFlags(&c->ev_delta, cudaEventDisableTiming));
-    CU(cudaMalloc(&c->d_tile_counter, (4 + N_BINS) * sizeof(unsigned int)));
-    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    // the frame counters (8 x u64) and the per-chunk counters (4 + N_BINS x u32) share one allocation: one memset per frame
+    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + (4 + N_BINS) * sizeof(unsigned int)));
+    c->d_tile_counter = (unsigned int *)(c->d_counters + 8);
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
     float lut[768];
     lut[0] = 0.0f;
@@ -609,6 +611,15 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaMalloc(&c->d_lut, sizeof lut));
     CU(cudaMemcpy(c->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
     *out = c;
+    return AICB_OK;
+}
+
+// Per-kernel event records of a frame (aicb_render_info::stage_ms) are on by default; a caller that only wants frames
+// turns them off (five stream operations per frame less).
+aicb_status aicb_ctx_stage_timing(aicb_ctx *c, int enable) {
+    if (!c) return fail(AICB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->stage_timing = enable != 0;
     return AICB_OK;
 }
 
@@ -631,7 +642,6 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     aicb_light_ctx_free(c);
     if (c->d_lut) cudaFree(c->d_lut);
     if (c->d_counters) cudaFree(c->d_counters);
-    if (c->d_tile_counter) cudaFree(c->d_tile_counter);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 5; i++) if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);

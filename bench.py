@@ -507,11 +507,13 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    check(lib.aicb_ctx_stage_timing(ctx.handle, 0))   # the timed frames carry no per-kernel event records
     total_ms = timed(device_step, args.steps)
     # kernel-only duration of the last frame from the library's own events (same stream); a frame that overflowed its
     # hit stream inside the timed region would make this call fail (AICB_ERR_RETRY) and with it the run
     check(lib.aicb_render_finish(rt.handle, C.byref(info)))
     kernel_ms_last = float(info.kernel_ms)
+    check(lib.aicb_ctx_stage_timing(ctx.handle, 1))   # ... the launches below do (stage_ms)
     rays_per_frame = w * h
     value = rays_per_frame * args.steps / (total_ms * 1e-3) / 1e6
 

@@ -182,6 +182,8 @@ uint32_t aicb_abi_version(void);
 /* device_id < 0 selects the current device. Fails with AICB_ERR_CUDA if there is no GPU. */
 aicb_status aicb_ctx_create(int device_id, aicb_ctx **out);
 void aicb_ctx_destroy(aicb_ctx *);
+/* aicb_render_info::stage_ms needs five event records per frame; on by default, off for callers that only want frames. */
+aicb_status aicb_ctx_stage_timing(aicb_ctx *, int enable);
 /* Thread-local message for the last failing call on this thread. Never NULL. */
 const char *aicb_last_error(void);
 

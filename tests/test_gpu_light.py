@@ -170,3 +170,26 @@ def test_light_bench_shape_flood():
     ol.evaluate(0)
     rt.light_edit_and_propagate(cubes, new_ids, 0)
     compare_fields(rt.light_download(), ol.field())
+
+
+def test_c4_full_size_compute_light_is_bit_exact_on_a_sample():
+    """BASELINE configs[4] at full size (256^3, Rays{30}): after fast_evaluate_light and a few relaxation rounds on
+    the GPU, compute_light of cubes sampled over the whole volume — evaluated by the lockstep walk against the GPU's own
+    field — is bit-identical to the oracle's compute_lighting on that same field; statuses of the whole field are
+    consistent with the blocks (opaque cubes OPAQUE)."""
+    space = scenes.config_c4(256)
+    rt = SpaceRaytracer(space, GraphicsOptions())
+    rt.light_fast_evaluate()
+    n, md, nv = rt.light_evaluate(120)          # stops early: a partially converged field is as good a test input
+    assert n > 1_000_000
+    field = rt.light_download()
+    opaque_block = np.array([(not b.is_air) and b.palette[0, 3] == 1.0 and not b.palette[0, 4:7].any() for b in space.blocks])
+    assert (field[..., 3][opaque_block[space.block_ids]] == OPAQUE).all()
+    rng = np.random.default_rng(3)
+    cubes = np.stack([rng.integers(0, 256, 640), rng.integers(60, 256, 640), rng.integers(0, 256, 640)], axis=1).astype(np.int32)
+    cubes[:64, 1] = rng.integers(62, 68, 64)    # near the ground surface
+    gpu = rt.light_compute(cubes)
+    ol = orc.OracleLight(space)
+    ol.set_field(field)
+    ref = ol.compute(cubes)
+    assert np.array_equal(gpu, ref), f"{(gpu != ref).any(axis=1).sum()} of {len(cubes)} cubes differ"

@@ -578,3 +578,32 @@ def test_layers_ui_backdrop_world_and_no_world(mixed):
             uopts.antialiasing_always = False
             assert np.array_equal(got.data.reshape(-1, 4), ref["srgb8"]), f"aa={aa} {c}: {(got.data.reshape(-1, 4) != ref['srgb8']).any(axis=1).sum()} pixels differ"
             assert got.info.cubes_traced == ref["cubes_traced"], f"aa={aa} {c}"
+
+
+def test_full_size_c3_4k_properties():
+    """BASELINE configs[3] at full size (256^3 res-16 blocks, 3840x2160): determinism, cubes_traced == sum of the
+    per-pixel steps, the union of 8 interleaved 16-row shards == the frame (what 8 GPUs deliver), and bit-level parity
+    with the oracle on rows spread over the frame."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench
+    space, opts, w, h, _ = bench.make_workload("c3")
+    cam = scenes.standard_camera(space, opts, w, h)
+    r = RtRenderer(cam)
+    r.update(space)
+    a = r.draw()
+    b = r.draw()
+    assert np.array_equal(a.data, b.data), "render is not deterministic"
+    aux = r.draw_colorbuf(want_depth=False, want_hit=False)
+    assert aux["info"].cubes_traced == int(aux["steps"].astype(np.int64).sum()) == a.info.cubes_traced
+    out = np.zeros_like(a.data)
+    for index in range(8):
+        rows = [y for y in range(h) if (y // 16) % 8 == index]
+        out[rows] = r.draw(shard=(16, index, 8)).data
+    assert np.array_equal(out, a.data)
+    rows = [int((i + 0.5) * h / 12) for i in range(12)]
+    ref = orc.render_rowlist(orc.OracleScene(space), cam, opts, rows, want_colorbuf=True)
+    assert np.array_equal(a.data[rows].reshape(-1, 4), ref["srgb8"])
+    cb = aux["colorbuf"].reshape(h, w, 4)[rows].reshape(-1, 4)
+    assert orc.max_ulp_diff(cb, ref["colorbuf"]) == 0
+    assert int(aux["steps"].reshape(h, w)[rows].astype(np.int64).sum()) == ref["cubes_traced"]
