@@ -570,7 +570,7 @@ def run_ours(args):
     achieved = march_bytes / (march_ms * 1e-3) / 1e9
     traffic = None   # DRAM bytes of the marching kernel per launch from the committed ncu --set full capture
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if tr.get("workload") == args.workload and world == 1:
             traffic = int(tr["traffic_bytes_per_launch"])
     except (OSError, ValueError, KeyError):
