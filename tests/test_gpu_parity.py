@@ -607,3 +607,57 @@ def test_full_size_c3_4k_properties():
     cb = aux["colorbuf"].reshape(h, w, 4)[rows].reshape(-1, 4)
     assert orc.max_ulp_diff(cb, ref["colorbuf"]) == 0
     assert int(aux["steps"].reshape(h, w)[rows].astype(np.int64).sum()) == ref["cubes_traced"]
+
+
+def test_wide_cells_more_than_16384_blocks():
+    """A Space whose palette has more than 16384 block indices (BlockIndex is u16, space.rs): the cells are stored as
+    u32 (id | kind << 16) and the marching kernel runs its WIDE instantiation.  Parity on every output, incl. the
+    CharacterBuf block indices and a cube delta."""
+    import ctypes as C
+    n = 20
+    n_blocks = 17000
+    rng = np.random.default_rng(17)
+    cols = rng.uniform(0.05, 1.0, (n_blocks, 3))
+    blocks = [Block.air()]
+    for i in range(1, n_blocks):
+        if i in (16500, 16600, 16700):
+            blocks.append(scenes.make_voxel_block(i, resolution=8, alpha=(1.0, 0.5, 0.25)[(i // 100) % 3]))
+        elif i % 7 == 0:
+            blocks.append(Block(color=(cols[i, 0], cols[i, 1], cols[i, 2], 0.5)))
+        else:
+            blocks.append(Block(color=(cols[i, 0], cols[i, 1], cols[i, 2], 1.0)))
+    h = scenes.grid_hash(23, (n, n, n))
+    pick = (h >> np.uint64(8)) % np.uint64(n_blocks)
+    special = np.array([16500, 16600, 16700], dtype=np.uint64)
+    pick = np.where((h >> np.uint64(40)) % np.uint64(5) == 0, special[(h >> np.uint64(48)) % np.uint64(3)], pick)
+    ids = np.where((h & np.uint64(7)) < 2, pick, 0).astype(np.uint16)
+    assert ids.max() > 16384
+    space = Space((-4, 0, 3), ids, blocks, light=scenes.noise_light(5, ids, blocks), sky_colors=scenes.OCTANT_SKY)
+    for opts in (GraphicsOptions(view_distance=80.0),
+                 GraphicsOptions(view_distance=80.0, transparency=TRANSPARENCY_SURFACE, lighting_display=LIGHT_FLAT)):
+        cam = scenes.standard_camera(space, opts, 96, 64)
+        gpu, img, ref = render_both(space, cam, opts)
+        compare(gpu, ref, "wide cells")
+        same_srgb8(img, ref)
+        assert gpu["info"].cubes_traced == ref["cubes_traced"]
+    opts = GraphicsOptions(view_distance=80.0)
+    cam = scenes.standard_camera(space, opts, 72, 40)
+    rt = SpaceRaytracer(space, opts)
+    out = np.zeros(72 * 40, dtype=np.int32)
+    o = opts.to_abi(True)
+    assert aicb200.load_library().aicb_render_text(rt.handle, C.byref(cam.data), C.byref(o), out.ctypes.data, out.size, None) == 0
+    ref = orc.OracleScene(space).render(cam, opts, accum_mode=1)["text"]
+    assert np.array_equal(out, np.where(ref == -4, -3, ref))
+    assert out.max() > 16384
+    # SpaceChange::CubeBlock deltas on a wide scene == a fresh snapshot
+    cubes = np.stack([rng.integers(0, n, 40) + space.lower[a] for a in range(3)], axis=1)
+    new_ids = rng.integers(16380, 16990, 40).astype(np.uint16)
+    r = RtRenderer(cam)
+    r.update(space)
+    r.rt.update_cubes(cubes, new_ids, None)
+    ids2 = ids.copy()
+    for c, i in zip(cubes, new_ids):
+        ids2[tuple(c - np.array(space.lower))] = i
+    r2 = RtRenderer(cam)
+    r2.update(Space(space.lower, ids2, blocks, light=space.light, sky_colors=space.sky_colors))
+    assert np.array_equal(r.draw().data, r2.draw().data)
