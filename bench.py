@@ -531,6 +531,8 @@ def run_ours(args):
     stage_avg_ms = [float(v) for v in np.mean(np.array(stage_ms), axis=0)]   # gen, march, shade, encode
     clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the kernel-time launches
 
+    if peer is not None and use_counter and rank == 0 and peer.timed_out():
+        raise SystemExit("bench.py: a wait on the frame's arrival counter gave up (a rank did not deliver its strips)")
     # ---- N > 1: the delivered frame must equal the frame one GPU renders alone -----------------------
     frame_check = None
     if world > 1:
