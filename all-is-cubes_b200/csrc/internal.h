@@ -98,6 +98,7 @@ struct aicb_scene {
     uint8_t *d_diff = nullptr;              // difference_priority of one round
     uint32_t *d_scalars = nullptr;          // [0] list length, [1] max priority, [2] max diff, [3] updates
     float4 *d_sky_term = nullptr;           // per chart node: the sky light its bundle collects (end_of_ray), for this scene's sky
+    uint32_t *d_changed = nullptr;          // list positions whose cube changed by more than one unit this round
     uint32_t *d_tile_max = nullptr;         // per LIGHT_TILE cubes: upper bound of the queued priorities
     uint32_t light_max_distance = 0;
     uint64_t light_stats[4] = {0, 0, 0, 0};  // last propagation: cube updates, chart node visits, rounds queued, device microseconds

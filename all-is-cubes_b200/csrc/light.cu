@@ -313,17 +313,44 @@ __global__ void k_apply(const LightParams P) {
     }
 }
 
+// apply_light_update re-queues a cube's dependencies only when its packed difference exceeds 1 (updater.rs:355-360).
+// The entries of the round's list that did are compacted (in list order within a block of 256) so that the warps of
+// k_mark walk the chart for 32 cubes that all need it.
+__global__ void __launch_bounds__(256) k_compact_changed(const LightParams P) {
+    __shared__ uint32_t s_part[8], s_base;
+    const uint32_t n = P.scalars[0];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t keep = (i < n && P.diff[i] > 1) ? 1u : 0u;
+        uint32_t inc = keep;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)lane >= off) inc += t;
+        }
+        if (lane == 31) s_part[wid] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+            for (int k = 0; k < 8; k++) { const uint32_t c = s_part[k]; s_part[k] = total; total += c; }
+            s_base = total ? atomicAdd(P.scalars + 6, total) : 0u;
+        }
+        __syncthreads();
+        if (keep) P.changed[s_base + s_part[wid] + inc - 1] = i;
+        __syncthreads();
+    }
+}
+
 // the dependency re-queue of apply_light_update (updater.rs:355-360): re-walk the chart, raising the
 // queue priority of every cube whose light was read
 __global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_mark(const LightParams P) {
-    const uint32_t n = P.scalars[0];
+    const uint32_t n = P.scalars[6];   // entries of the round's list that changed by more than one unit
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
-        const uint32_t i = base + lane;
-        const int d = i < n ? (int)P.diff[i] : 0;
-        const bool active = d > 1;   // apply_light_update re-queues only when the packed difference exceeds 1
-        if (!__any_sync(0xffffffffu, active)) continue;
+        const bool active = base + lane < n;
+        const uint32_t i = active ? P.changed[base + lane] : 0u;
+        const int d = active ? (int)P.diff[i] : 0;
         int x = 0, y = 0, z = 0;
         if (active) cube_of(P.scene, P.list[i], x, y, z);
         compute_light_lockstep<true>(P, P.scene.tables, active, x, y, z, (uint32_t)(d / 2 + 1), nullptr);
@@ -396,6 +423,7 @@ LightParams make_params(aicb_scene *s) {
     P.sky_term = s->d_sky_term;
     P.chart_nodes = s->ctx->chart_nodes;
     P.tile_max = s->d_tile_max;
+    P.changed = s->d_changed;
     P.pending = s->d_pending;
     P.list = s->d_list;
     P.new_light = s->d_new_light;
@@ -454,6 +482,8 @@ aicb_status ensure_light_state(aicb_scene *s) {
         CU(cudaMalloc(&s->d_diff, s->volume + 16));
         CU(cudaMalloc(&s->d_scalars, 8 * 4));
         CU(cudaMalloc(&s->d_tile_max, ((s->volume + LIGHT_TILE - 1) / LIGHT_TILE + 1) * 4));
+        CU(cudaMalloc(&s->d_changed, s->volume * 4 + 16));
+        s->device_bytes += s->volume * 4;
         s->device_bytes += s->volume * 10;
     }
     return AICB_OK;
@@ -484,10 +514,12 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
     for (int batch = 0; batch < 100000; batch++) {
         for (int round = 0; round < ROUNDS_PER_SYNC; round++) {
             CU(cudaMemsetAsync(s->d_scalars, 0, 2 * 4, st));   // this round's count and priority
+            CU(cudaMemsetAsync(s->d_scalars + 6, 0, 4, st));   // ... and its count of changed cubes
             k_find_max<<<16, 256, 0, st>>>(P, n_tiles);
             k_gather<<<blocks, 256, 0, st>>>(P, n_tiles);
             k_compute<<<wide, 128, 0, st>>>(P, 0, nullptr);
             k_apply<<<wide, 128, 0, st>>>(P);
+            k_compact_changed<<<blocks, 256, 0, st>>>(P);
             k_mark<<<wide, 128, 0, st>>>(P);
         }
         uint32_t h[8];
@@ -575,6 +607,7 @@ void aicb_light_scene_free(aicb_scene *s) {
     if (s->d_diff) cudaFree(s->d_diff);
     if (s->d_scalars) cudaFree(s->d_scalars);
     if (s->d_tile_max) cudaFree(s->d_tile_max);
+    if (s->d_changed) cudaFree(s->d_changed);
     if (s->d_sky_term) cudaFree(s->d_sky_term);
 }
 

@@ -69,7 +69,8 @@ struct LightParams {
     uint32_t *list;
     uint32_t *new_light;
     uint8_t *diff;
-    uint32_t *scalars;              // [0] list length, [1] max priority, [2] max diff, [3] updates, [4] node visits (lo)
+    uint32_t *changed;              // positions in the round's list whose cube changed by more than one unit (k_mark's work)
+    uint32_t *scalars;              // [0] list length, [1] max priority, [2] max diff, [3] updates, [4..5] node visits, [6] changed
     uint32_t volume;
     uint32_t max_distance;
     uint32_t priority;              // the round's priority level
