@@ -391,6 +391,9 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
         const char *e = getenv("AICB_REFILL_THRESHOLD");
         int v = e ? atoi(e) : 4;
         P.refill_threshold = (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
+        const char *e3 = getenv("AICB_TAIL_DIVISOR");
+        int v3 = e3 ? atoi(e3) : 2;
+        P.tail_divisor = (uint32_t)(v3 < 1 ? 1 : (v3 > 32 ? 32 : v3));
         const char *e2 = getenv("AICB_EVENT_THRESHOLD");
         int v2 = e2 ? atoi(e2) : 24;
         P.event_threshold = (uint32_t)(v2 < 1 ? 1 : (v2 > 32 ? 32 : v2));

@@ -172,6 +172,7 @@ struct TraceParams {
     unsigned int *overflow_flag; // set when a chunk produced more hits than hit_capacity (frame must be re-run)
     uint32_t hit_capacity;
     uint32_t event_threshold;   // leave the marching loop once this many lanes wait (parked at a level switch, finished, idle)
+    uint32_t tail_divisor;      // once the ray list is exhausted: leave the loop when (lanes that still have a ray) / this wait
     uint32_t refill_threshold;  // tail mode: once the ray list is exhausted and at most this many lanes of a warp still march,
                                 // they run the lean per-lane loop
     // outputs
@@ -1242,7 +1243,17 @@ trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
         // =========================== MARCH ================================================================
         {
             const int n_off = __popc(__ballot_sync(0xffffffffu, st == ST_EXHAUSTED || (list_exhausted && st == ST_IDLE)));
-            const int thr = list_exhausted ? 1 : (int)P.event_threshold;
+            // How many waiting lanes end the marching loop.  While the list still has rays: `event_threshold`.  Once it is
+            // exhausted the warp only drains: waiting for as many parked lanes as before would stall the rays the frame
+            // is waiting for, serving every single park (a threshold of 1) makes a warp that still has all its rays —
+            // every warp of a small shard, whose rays are all handed out in the first refill — run a full pass of the
+            // level-switch code per step.  Half of the lanes that still have a ray is the compromise.
+            int thr = (int)P.event_threshold;
+            if (list_exhausted) {
+                const int tail_div = (int)P.tail_divisor;
+                thr = (32 - n_off) / (tail_div > 0 ? tail_div : 2);
+                thr = thr < 1 ? 1 : (thr > (int)P.event_threshold ? (int)P.event_threshold : thr);
+            }
             const unsigned live = __ballot_sync(0xffffffffu, st == ST_MARCH);
             if (list_exhausted && __popc(live) <= (int)P.refill_threshold) {
                 // the tail: each of the few remaining rays runs to its next level switch on its own
