@@ -436,12 +436,19 @@ def run_ours(args):
     if gather_mode == "p2p-barrier":
         gather_mode = "p2p"
     peer = None
+    peers = []
     if gather_mode == "p2p":
         try:
-            peer = multi.PeerFrame(ctx, h, w, rank, world)
-            # touch the mapping once from every rank
-            check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
-                                                     peer.ptr, w * h, C.c_void_p(stream.cuda_stream)))
+            # Two shared frames when the counters are used: frame k + 1 is stored into the other buffer while rank 0 is
+            # still through with frame k, so a step does not contain a round trip of the consumed counter (every frame
+            # is still rendered by all ranks and delivered to rank 0; two frames are in flight).
+            for _ in range(2 if use_counter else 1):
+                pf = multi.PeerFrame(ctx, h, w, rank, world)
+                peers.append(pf)
+                # touch the mapping once from every rank
+                check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
+                                                         pf.ptr, w * h, C.c_void_p(stream.cuda_stream)))
+            peer = peers[0]
             torch.cuda.synchronize()
             ok = torch.tensor([1], device="cuda")
         except Exception as e:  # noqa: BLE001 — any failure falls back to the NCCL gather
@@ -449,13 +456,17 @@ def run_ours(args):
             ok = torch.tensor([0], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            gather_mode, peer = "nccl", None
+            gather_mode, peer, peers = "nccl", None, []
 
     release_on_device = True   # e2e: rank 0 releases the frame after its device -> host copy instead
+    frame_no = [0]
 
     def device_step():
         """One frame with everything resident in HBM: trace kernel + delivery of the strips to rank 0."""
+        nonlocal peer
         if gather_mode == "p2p":
+            peer = peers[frame_no[0] % len(peers)]
+            frame_no[0] += 1
             if use_counter:   # no collective: counters behind the frame's pixels, all in stream order
                 peer.begin_frame(stream.cuda_stream)
             check(lib.aicb_render_srgb8_device_frame(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard),
@@ -531,7 +542,7 @@ def run_ours(args):
     stage_avg_ms = [float(v) for v in np.mean(np.array(stage_ms), axis=0)]   # gen, march, shade, encode
     clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the kernel-time launches
 
-    if peer is not None and use_counter and rank == 0 and peer.timed_out():
+    if peers and use_counter and rank == 0 and any(pf.timed_out() for pf in peers):
         raise SystemExit("bench.py: a wait on the frame's arrival counter gave up (a rank did not deliver its strips)")
     # ---- N > 1: the delivered frame must equal the frame one GPU renders alone -----------------------
     frame_check = None
@@ -658,7 +669,7 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic",
             "config": {"workload": desc, "rays_per_step": rays_per_frame, "sharding": f"{world} x interleaved {STRIP_ROWS}-row strips",
-                       "gather": ("p2p stores + arrival counter (no collective)" if (gather_mode == "p2p" and use_counter) else
+                       "gather": ("p2p stores + arrival counter (no collective), two frames in flight" if (gather_mode == "p2p" and use_counter) else
                                   "p2p stores + NCCL barrier" if gather_mode == "p2p" else gather_mode),
                        "n_rank_frame_equals_1_rank_frame": frame_check,
                        "l2": "256 MiB buffer rewritten between timed steps", "scene_device_bytes": rt.device_bytes,
