@@ -21,7 +21,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import abi
-from .abi import (FOG_ABRUPT, FOG_COMPROMISE, FOG_NONE, FOG_PHYSICAL, LIGHT_COARSE, LIGHT_FLAT, LIGHT_LINEAR,
+from .abi import (FOG_ABRUPT, FOG_COMPROMISE, FOG_NONE, FOG_PHYSICAL, LIGHT_BOUNCE, LIGHT_COARSE, LIGHT_FLAT, LIGHT_LINEAR,
                   LIGHT_NONE, LIGHT_SMOOTHSTEP, TONE_CLAMP, TONE_REINHARD, TRANSPARENCY_SURFACE,
                   TRANSPARENCY_THRESHOLD, TRANSPARENCY_VOLUMETRIC)
 
@@ -188,6 +188,7 @@ class GraphicsOptions:
     transparency_threshold: float = 0.5
     antialiasing_always: bool = False
     debug_pixel_cost: bool = False
+    bounce_samples: int = 1  # LightingOption::Bounce { samples } (graphics_options.rs:464-467)
 
     @staticmethod
     def unaltered_colors() -> "GraphicsOptions":
@@ -208,6 +209,7 @@ class GraphicsOptions:
         o.tone_mapping = self.tone_mapping
         o.debug_pixel_cost = 1 if self.debug_pixel_cost else 0
         o.include_sky = 1 if include_sky else 0
+        o.bounce_samples = self.bounce_samples if self.lighting_display == LIGHT_BOUNCE else 0
         o.transparency_threshold = self.transparency_threshold
         o.maximum_intensity = self.maximum_intensity
         o.view_distance = min(max(self.view_distance, 1.0), 10000.0)

@@ -75,7 +75,7 @@ class Options(C.Structure):
         ("tone_mapping", C.c_uint8),
         ("debug_pixel_cost", C.c_uint8),
         ("include_sky", C.c_uint8),
-        ("_pad0", C.c_uint8),
+        ("bounce_samples", C.c_uint8),
         ("transparency_threshold", C.c_float),
         ("maximum_intensity", C.c_float),
         ("view_distance", C.c_double),

@@ -271,9 +271,9 @@ static __global__ void scatter_cubes_kernel(const CubeDelta *ops, uint32_t n, ui
 static aicb_status validate_options(const aicb_options *o) {
     if (!o) return fail(AICB_ERR_INVALID, "options is NULL");
     if (o->fog > AICB_FOG_PHYSICAL) return fail(AICB_ERR_INVALID, "bad fog option");
-    if (o->lighting_display == AICB_LIGHT_BOUNCE)
-        return fail(AICB_ERR_UNSUPPORTED, "LightingOption::Bounce is not implemented (SURVEY 8(f) N4)");
     if (o->lighting_display > AICB_LIGHT_BOUNCE) return fail(AICB_ERR_INVALID, "bad lighting option");
+    if (o->lighting_display == AICB_LIGHT_BOUNCE && o->bounce_samples < 1)
+        return fail(AICB_ERR_INVALID, "LightingOption::Bounce needs bounce_samples >= 1");
     if (o->transparency > AICB_TRANSPARENCY_THRESHOLD) return fail(AICB_ERR_INVALID, "bad transparency option");
     if (o->tone_mapping > AICB_TONE_REINHARD) return fail(AICB_ERR_INVALID, "bad tone mapping option");
     if (!(o->view_distance >= 1.0 && o->view_distance <= 10000.0))
@@ -451,12 +451,57 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
     ctx->frame_in_flight = true;
     ctx->last_stream = stream;
     ctx->last_scene = sc;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long) + (4 + N_BINS) * sizeof(unsigned int), stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long) + 2 * (4 + N_BINS) * sizeof(unsigned int), stream));
     CU(cudaEventRecord(ctx->ev0, stream));
     if (total_tasks > 0) {
         const bool volumetric = opt->transparency == AICB_TRANSPARENCY_VOLUMETRIC;
         const int lc = opt->lighting_display == AICB_LIGHT_NONE ? LC_NONE
-                       : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT : LC_INTERP);
+                       : (opt->lighting_display == AICB_LIGHT_FLAT ? LC_FLAT
+                          : (opt->lighting_display == AICB_LIGHT_BOUNCE ? LC_BOUNCE : LC_INTERP));
+        // LightingOption::Bounce: the secondary rays of a chunk run through the same kernels on a second set of streams
+        TraceParams Q;
+        const bool bounce = lc == LC_BOUNCE;
+        if (bounce) {
+            aicb_status st = ensure(&ctx->d_rays2, &ctx->d_rays2_bytes, chunk_cap * sizeof(RayRecord) + 16);
+            if (st == AICB_OK) st = ensure(&ctx->d_task_cb2, &ctx->d_task_cb2_bytes, chunk_cap * sizeof(TaskOut) + 16);
+            if (st == AICB_OK) st = ensure(&ctx->d_hits2, &ctx->d_hits2_bytes, (size_t)P.hit_capacity * sizeof(HitRecord) + 64);
+            if (st == AICB_OK) st = ensure(&ctx->d_contrib2, &ctx->d_contrib2_bytes, (size_t)P.hit_capacity * sizeof(ShadedHit) + 64);
+            if (st == AICB_OK) st = ensure(&ctx->d_bin_list2, &ctx->d_bin_list2_bytes, (size_t)N_BINS * chunk_cap * 4 + 64);
+            // per task: request (4) + RNG state (32) + Rgb sum and steps (16) + the secondary ray (48)
+            if (st == AICB_OK) st = ensure(&ctx->d_bounce, &ctx->d_bounce_bytes, chunk_cap * 100 + 256);
+            if (st != AICB_OK) return st;
+            char *b = (char *)ctx->d_bounce;
+            P.bounce_mode = BOUNCE_PRIMARY;
+            P.bounce_samples = opt->bounce_samples;
+            P.bounce_rays = (double *)b;                                   // 48 B per task, 16-aligned
+            P.bounce_rng = (unsigned long long *)(b + chunk_cap * 48);     // 32 B
+            P.bounce_sum = (float4 *)(b + chunk_cap * 80);                 // 16 B
+            P.bounce_req = (uint32_t *)(b + chunk_cap * 96);               // 4 B
+            Q = P;
+            Q.bounce_mode = BOUNCE_SECONDARY;
+            Q.rays = P.bounce_rays;
+            Q.tiles_y = 1;
+            Q.shard_count = 1; Q.shard_index = 0; Q.strip_rows = 1;
+            Q.antialias = 0;
+            Q.n_samples = 1;
+            Q.task_base = 0;
+            Q.lighting = AICB_LIGHT_FLAT;      // no bounce budget left (surface.rs:171-176)
+            Q.include_sky = 1;                 // surface.rs:159
+            Q.exposure = 1.0f;
+            Q.out_full_frame = 0;
+            Q.out_srgb8 = nullptr; Q.out_colorbuf = nullptr; Q.out_rgba16f = nullptr; Q.out_depth = nullptr;
+            Q.out_hit = nullptr; Q.out_steps = nullptr; Q.out_text = nullptr;
+            Q.in_accum = nullptr; Q.out_accum = nullptr; Q.has_backdrop = 0; Q.has_no_world = 0;
+            Q.ray_records = (RayRecord *)ctx->d_rays2;
+            Q.task_out = (TaskOut *)ctx->d_task_cb2;
+            Q.hits = (HitRecord *)ctx->d_hits2;
+            Q.shaded = (ShadedHit *)ctx->d_contrib2;
+            Q.bin_list = (uint32_t *)ctx->d_bin_list2;
+            Q.task_counter = ctx->d_tile_counter + (4 + N_BINS);
+            Q.hit_counter = Q.task_counter + 1;
+            Q.bin_count = Q.task_counter + 4;
+            Q.debug_warp_times = nullptr;
+        }
         kernel_fn k = select_kernel(volumetric, sc->ds.wide_cells != 0, aux);
         int blocks_per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, WARPS_PER_BLOCK * 32, 0));
@@ -489,7 +534,25 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
             switch (lc) {
                 case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+                case LC_BOUNCE: shade_kernel<LC_BOUNCE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
                 default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+            }
+            if (bounce) {
+                const unsigned tb = (n + 127) / 128;
+                bounce_select_kernel<<<tb, 128, 0, stream>>>(P, n);
+                Q.n_rays = n;
+                Q.n_tasks = n;
+                Q.tiles_x = (n + 31) / 32;
+                for (uint32_t pass = 0; pass < P.bounce_samples; pass++) {
+                    Q.bounce_pass = pass;
+                    CU(cudaMemsetAsync(Q.task_counter, 0, (4 + N_BINS) * sizeof(unsigned int), stream));
+                    bounce_gen_kernel<<<tb, 128, 0, stream>>>(P, n);
+                    gen_kernel<<<tb, 128, 0, stream>>>(Q, n);
+                    k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(Q, n);
+                    shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(Q);
+                    encode_kernel<<<tb, 128, 0, stream>>>(Q, n);
+                }
+                bounce_resolve_kernel<<<tb, 128, 0, stream>>>(P, n);
             }
             if (stage) cudaEventRecord(ctx->ev_k[3], stream);
             const uint32_t n_pixels = n / P.n_samples;
@@ -544,6 +607,8 @@ static aicb_status finish(aicb_scene *sc, aicb_render_info *info) {
             ctx->shallow_frames = 0;
             if (ctx->d_hits) { cudaFree(ctx->d_hits); ctx->d_hits = nullptr; ctx->d_hits_bytes = 0; }
             if (ctx->d_contrib) { cudaFree(ctx->d_contrib); ctx->d_contrib = nullptr; ctx->d_contrib_bytes = 0; }
+            if (ctx->d_hits2) { cudaFree(ctx->d_hits2); ctx->d_hits2 = nullptr; ctx->d_hits2_bytes = 0; }
+            if (ctx->d_contrib2) { cudaFree(ctx->d_contrib2); ctx->d_contrib2 = nullptr; ctx->d_contrib2_bytes = 0; }
         }
     } else {
         ctx->shallow_frames = 0;
@@ -603,7 +668,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
     CU(cudaEventCreateWithFlags(&c->ev_delta, cudaEventDisableTiming));
     // the frame counters (8 x u64) and the per-chunk counters (4 + N_BINS x u32) share one allocation: one memset per frame
-    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + (4 + N_BINS) * sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long) + 2 * (4 + N_BINS) * sizeof(unsigned int)));  // + the secondary (Bounce) pass's block
     c->d_tile_counter = (unsigned int *)(c->d_counters + 8);
     // PackedLight decode table (light/data.rs:232-243 scalar_out_arithmetic; table :301-354)
     float lut[768];
@@ -636,6 +701,8 @@ void aicb_ctx_destroy(aicb_ctx *c) {
     if (c->d_hits) cudaFree(c->d_hits);
     if (c->d_contrib) cudaFree(c->d_contrib);
     if (c->d_bin_list) cudaFree(c->d_bin_list);
+    for (void *q : {c->d_rays2, c->d_task_cb2, c->d_hits2, c->d_contrib2, c->d_bin_list2, c->d_bounce})
+        if (q) cudaFree(q);
     if (c->d_debug) cudaFree(c->d_debug);
     if (c->h_delta) cudaFreeHost(c->h_delta);
     if (c->h_stage) cudaFreeHost(c->h_stage);

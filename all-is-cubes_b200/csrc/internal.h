@@ -52,6 +52,11 @@ struct aicb_ctx {
     size_t d_contrib_bytes = 0;
     void *d_bin_list = nullptr;  // task ids of the rays that enter the space, per chord-length bin
     size_t d_bin_list_bytes = 0;
+    // LightingOption::Bounce: the same streams for the secondary rays of a chunk, and the per-task bounce state
+    void *d_rays2 = nullptr, *d_task_cb2 = nullptr, *d_hits2 = nullptr, *d_contrib2 = nullptr, *d_bin_list2 = nullptr;
+    size_t d_rays2_bytes = 0, d_task_cb2_bytes = 0, d_hits2_bytes = 0, d_contrib2_bytes = 0, d_bin_list2_bytes = 0;
+    void *d_bounce = nullptr;    // per task: secondary ray (48 B), RNG state (32 B), Rgb sum + steps (16 B), request (4 B)
+    size_t d_bounce_bytes = 0;
     uint32_t hits_per_task = 8;  // capacity of the hit stream per ray; raised x4 when a frame overflows it,
     uint32_t shallow_frames = 0; //   lowered again after 16 frames in a row that needed a small fraction of it
     void *h_stage = nullptr;     // pinned staging of frames whose destination is pageable host memory

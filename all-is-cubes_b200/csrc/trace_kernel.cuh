@@ -191,6 +191,14 @@ struct TraceParams {
     uint32_t has_backdrop;
     float no_world[4];          // ColorBuf the accumulator is replaced by if it is not opaque in the end
     uint32_t has_no_world;
+    // LightingOption::Bounce (surface.rs:113-166): the frame's primary pass and its secondary passes share these
+    uint32_t bounce_mode;       // BOUNCE_OFF / BOUNCE_PRIMARY / BOUNCE_SECONDARY
+    uint32_t bounce_samples;    // LightingOption::Bounce { samples }
+    uint32_t bounce_pass;       // index of the secondary pass (sample) being traced
+    uint32_t *bounce_req;       // per task of the chunk: slot of the fully opaque hit the ray ends on, or HIT_NONE
+    unsigned long long *bounce_rng;  // per task: xoshiro256++ state (4 words)
+    float4 *bounce_sum;         // per task: sum of the secondary rays' Rgb so far; .w = their cubes_traced (as bits)
+    double *bounce_rays;        // per task: the secondary ray of this pass (origin, direction)
     unsigned long long *counters;  // [0] cubes_traced, [1] outer steps, [2] inner steps, [3] hits, [4] light texels, [5] blocks entered
     unsigned int *task_counter;
     unsigned long long *debug_warp_times;  // AICB_PROFILE_KERNELS: per marching warp {start ns, end ns, passes, rays}
@@ -201,7 +209,8 @@ struct TraceParams {
 #define AICB_DEV __device__ __forceinline__
 #define AICB_NOINLINE static __device__ __noinline__
 
-constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2;  // lighting class (template)
+constexpr int LC_NONE = 0, LC_FLAT = 1, LC_INTERP = 2, LC_BOUNCE = 3;  // lighting class (template)
+constexpr uint32_t BOUNCE_OFF = 0, BOUNCE_PRIMARY = 1, BOUNCE_SECONDARY = 2;  // TraceParams::bounce_mode
 constexpr int TILE_W = 8, TILE_H = 4;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int N_BINS = 8;            // chord-length classes of the ray list (longest first)
@@ -773,7 +782,8 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
     RayRecord rec;
     uint32_t px, py;
     size_t out_index;
-    const bool active = in_range && task_pixel(P, pixel_task, &px, &py, &out_index);
+    bool active = in_range && task_pixel(P, pixel_task, &px, &py, &out_index);
+    if (P.bounce_mode == BOUNCE_SECONDARY && active) active = P.bounce_req[i] != HIT_NONE;   // no surface to light
     rec.flags = 0;
     bool running = false;
     uint32_t octant = 0;
@@ -1337,6 +1347,147 @@ AICB_DEV void decode_hit(const DeviceScene &S, const HitRecord &h, HitGeom &g) {
     g.pal = h.pal;
 }
 
+// One hit record -> one ShadedHit.  `illum_override` (LC_BOUNCE only): the illumination gathered by the hit's secondary
+// rays; without it a Bounce frame lights the surface like Flat (surface.rs:171-176) and marks fully opaque surfaces
+// (the only ones the bounce RNG is handed to, surface.rs:85-88) for bounce_select_kernel.
+template <int LC>
+AICB_DEV void shade_hit(const TraceParams &P, const float *s_lut, const uint32_t i, const float *illum_override,
+                        unsigned long long &texels) {
+    const DeviceScene &S = P.scene;
+    const bool volumetric = P.transparency == AICB_TRANSPARENCY_VOLUMETRIC;
+    const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
+    const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
+    HitRecord h;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + i);
+        uint4 *dst = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = ld_stream(src + k);
+    }
+    // everything the shading reads through the record is requested now, before any of it is needed
+    const RayRecord *rp = P.ray_records + h.task;
+    const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
+    const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
+    const uint2 rmeta = __ldg(reinterpret_cast<const uint2 *>(&rp->t_to_view));   // t_to_view, flags
+    const uint32_t rflags = rmeta.y;
+    Ray rr;
+    rr.ox = rr.oy = rr.oz = rr.dx = rr.dy = rr.dz = 0.0;
+    if constexpr (LC == LC_INTERP) {
+        const double2 *q = reinterpret_cast<const double2 *>(rp);
+        const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        rr.ox = q0.x; rr.oy = q0.y; rr.oz = q1.x; rr.dx = q1.y; rr.dy = q2.x; rr.dz = q2.y;
+    }
+    ShadedHit out;
+    out.r = out.g = out.b = 0.0f;
+    out.factor = -1.0f;
+    out.next = h.next;
+    out.steps = h.steps;
+    out._pad[0] = out._pad[1] = 0;
+    uint4 *outp = reinterpret_cast<uint4 *>(P.shaded + i);
+    HitGeom g;
+    decode_hit(S, h, g);
+    float ca = col.w;
+    float coeff = 1.0f;
+    bool zeroed = false;
+    if (volumetric) {
+        const float thickness = h.thickness;
+        if (thickness == 0.0f) {
+            if (col.w == 1.0f) { coeff = 1.0f; }
+            else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
+        } else if (col.w == 1.0f) {
+            ca = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
+        } else if (col.w == 0.0f) {
+            ca = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
+        } else {
+            const float unit_t = 1.0f - col.w;
+            const float depth_t = powf_exact(unit_t, thickness);
+            ca = zo_clamped(1.0f - depth_t);
+            const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
+            coeff = fmaxf(k, 0.0f);
+        }
+    }
+    const float kc = ps_clamped(coeff);
+    const float er = volumetric ? ps_mul(emi.x, kc) : emi.x, eg = volumetric ? ps_mul(emi.y, kc) : emi.y,
+                eb = volumetric ? ps_mul(emi.z, kc) : emi.z;
+    if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
+        if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
+    }
+    if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) {   // nothing to see: the ray is not touched
+        outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+        outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
+        return;
+    }
+    const double t_scale = recip_pow2(g.res);
+    float tr = 1.0f - ca;
+    float fa = -1.0f;
+    if (have_fog) {  // distance_fog (sr.rs:745-768)
+        float rel = (float)(h.last_t * t_scale) * __uint_as_float(rmeta.x);
+        rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
+        const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
+        const float fudged = fog_exponential / 0.79810348f;
+        const float p4 = (rel * rel) * (rel * rel);
+        fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
+        tr = tr * (1.0f - fa);
+    }
+    const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
+    float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
+    const int face = g.face;
+    if constexpr (LC == LC_BOUNCE) {
+        // marked for bounce_select_kernel: the ray's RNG is only handed to fully opaque surfaces (surface.rs:85-88)
+        if (ca == 1.0f) out._pad[0] = 1u;
+    }
+    if (LC == LC_BOUNCE && illum_override) {
+        i0 = illum_override[0]; i1 = illum_override[1]; i2 = illum_override[2];
+    } else if constexpr (LC == LC_FLAT || LC == LC_BOUNCE) {
+        int x = g.cube[0], y = g.cube[1], z = g.cube[2];
+        if (face != AICB_FACE_WITHIN) {
+            const int dd = face >= AICB_FACE_PX ? 1 : -1;
+            const int ax = (face - 1) % 3;
+            if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
+        }
+        uint32_t tx = 0;
+        const uint32_t t = get_packed_light(S, x, y, z, tx);
+        texels += tx;
+        i0 = s_lut[t & 255]; i1 = s_lut[(t >> 8) & 255]; i2 = s_lut[(t >> 16) & 255];
+    } else if constexpr (LC == LC_INTERP) {
+        // RaycastStep::intersection_point (raycast.rs:409-439) of the level the surface is on, brought to
+        // Space coordinates (surface.rs:406-407)
+        rr.sx = (int)((rflags >> 6) & 3u) - 1; rr.sy = (int)((rflags >> 8) & 3u) - 1; rr.sz = (int)((rflags >> 10) & 3u) - 1;
+        Caster c;
+        c.tmx = h.tmx; c.tmy = h.tmy; c.tmz = h.tmz; c.last_t = h.last_t;
+        c.face = face;
+        double ip[3];
+        if (!(h.flags & 8u)) {
+            intersection_point(c, rr, g.cube[0], g.cube[1], g.cube[2], rr.ox, rr.oy, rr.oz, ip);
+        } else {
+            const double fres = (double)g.res;
+            intersection_point(c, rr, g.voxel[0], g.voxel[1], g.voxel[2], (rr.ox - (double)g.cube[0]) * fres,
+                               (rr.oy - (double)g.cube[1]) * fres, (rr.oz - (double)g.cube[2]) * fres, ip);
+            ip[0] = ip[0] * t_scale + (double)g.cube[0];
+            ip[1] = ip[1] * t_scale + (double)g.cube[1];
+            ip[2] = ip[2] * t_scale + (double)g.cube[2];
+        }
+        uint32_t tx = 0;
+        float il[3];
+        interpolated_light(S, s_lut, P.lighting, g.cube[0], g.cube[1], g.cube[2], face, ip[0], ip[1], ip[2], il, &tx);
+        i0 = il[0]; i1 = il[1]; i2 = il[2];
+        texels += tx;
+    }
+    float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
+    float og = ps_mul(ps_mul(cg, i1), ca) + eg;
+    float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
+    if (fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
+        const int k = S.sky_kind ? (int)((rflags >> 12) & 7u) : 0;
+        const float comp = 1.0f - fa;
+        orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], fa);
+        og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], fa);
+        ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], fa);
+    }
+    out.r = orr; out.g = og; out.b = ob; out.factor = tr;
+    outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
+    outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
+}
+
 // ======================================================================================================
 // Kernel 3 — shading: one thread per HitRecord, fully convergent.  Everything about a surface that does not depend
 // on the surfaces in front of it: its position (cube, voxel, face) and intersection point (raycast.rs:409-439,
@@ -1356,134 +1507,7 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
     uint32_t n = *P.hit_counter;
     if (n > P.hit_capacity) n = P.hit_capacity;
     unsigned long long texels = 0;
-    const bool volumetric = P.transparency == AICB_TRANSPARENCY_VOLUMETRIC;
-    const bool have_fog = (P.fog != AICB_FOG_NONE) && P.include_sky;
-    const float fog_blend = (P.fog == AICB_FOG_ABRUPT) ? 1.0f : (P.fog == AICB_FOG_COMPROMISE ? 0.5f : 0.0f);
-    auto shade_one = [&](const uint32_t i) {
-        HitRecord h;
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + i);
-            uint4 *dst = reinterpret_cast<uint4 *>(&h);
-#pragma unroll
-            for (int k = 0; k < 4; k++) dst[k] = ld_stream(src + k);
-        }
-        // everything the shading reads through the record is requested now, before any of it is needed
-        const RayRecord *rp = P.ray_records + h.task;
-        const float4 col = __ldg(S.palette + 2 * (size_t)h.pal);
-        const float4 emi = __ldg(S.palette + 2 * (size_t)h.pal + 1);
-        const uint2 rmeta = __ldg(reinterpret_cast<const uint2 *>(&rp->t_to_view));   // t_to_view, flags
-        const uint32_t rflags = rmeta.y;
-        Ray rr;
-        rr.ox = rr.oy = rr.oz = rr.dx = rr.dy = rr.dz = 0.0;
-        if constexpr (LC == LC_INTERP) {
-            const double2 *q = reinterpret_cast<const double2 *>(rp);
-            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            rr.ox = q0.x; rr.oy = q0.y; rr.oz = q1.x; rr.dx = q1.y; rr.dy = q2.x; rr.dz = q2.y;
-        }
-        ShadedHit out;
-        out.r = out.g = out.b = 0.0f;
-        out.factor = -1.0f;
-        out.next = h.next;
-        out.steps = h.steps;
-        out._pad[0] = out._pad[1] = 0;
-        uint4 *outp = reinterpret_cast<uint4 *>(P.shaded + i);
-        HitGeom g;
-        decode_hit(S, h, g);
-        float ca = col.w;
-        float coeff = 1.0f;
-        bool zeroed = false;
-        if (volumetric) {
-            const float thickness = h.thickness;
-            if (thickness == 0.0f) {
-                if (col.w == 1.0f) { coeff = 1.0f; }
-                else { zeroed = true; ca = 0.0f; coeff = 0.0f; }
-            } else if (col.w == 1.0f) {
-                ca = 1.0f; coeff = 1.0f;        // 0^thickness == 0 exactly: alpha 1, (0-1)/(0-1) == 1
-            } else if (col.w == 0.0f) {
-                ca = 0.0f; coeff = thickness;   // 1^thickness == 1 exactly
-            } else {
-                const float unit_t = 1.0f - col.w;
-                const float depth_t = powf_exact(unit_t, thickness);
-                ca = zo_clamped(1.0f - depth_t);
-                const float k = (unit_t == 1.0f) ? thickness : (depth_t - 1.0f) / (unit_t - 1.0f);
-                coeff = fmaxf(k, 0.0f);
-            }
-        }
-        const float kc = ps_clamped(coeff);
-        const float er = volumetric ? ps_mul(emi.x, kc) : emi.x, eg = volumetric ? ps_mul(emi.y, kc) : emi.y,
-                    eb = volumetric ? ps_mul(emi.z, kc) : emi.z;
-        if (P.transparency == AICB_TRANSPARENCY_THRESHOLD) {  // limit_alpha (graphics_options.rs:496-507)
-            if (ca > P.threshold) { ca = 1.0f; } else { zeroed = true; ca = 0.0f; }
-        }
-        if (ca == 0.0f && er == 0.0f && eg == 0.0f && eb == 0.0f) {   // nothing to see: the ray is not touched
-            outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
-            outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
-            return;
-        }
-        const double t_scale = recip_pow2(g.res);
-        float tr = 1.0f - ca;
-        float fa = -1.0f;
-        if (have_fog) {  // distance_fog (sr.rs:745-768)
-            float rel = (float)(h.last_t * t_scale) * __uint_as_float(rmeta.x);
-            rel = rel < 0.0f ? 0.0f : (rel > 1.0f ? 1.0f : rel);
-            const float fog_exponential = 1.0f - expf_exact(-1.6f * rel);
-            const float fudged = fog_exponential / 0.79810348f;
-            const float p4 = (rel * rel) * (rel * rel);
-            fa = zo_clamped(fudged * (1.0f - fog_blend) + p4 * fog_blend);
-            tr = tr * (1.0f - fa);
-        }
-        const float cr = zeroed ? 0.0f : col.x, cg = zeroed ? 0.0f : col.y, cb = zeroed ? 0.0f : col.z;
-        float i0 = 1.0f, i1 = 1.0f, i2 = 1.0f;
-        const int face = g.face;
-        if constexpr (LC == LC_FLAT) {
-            int x = g.cube[0], y = g.cube[1], z = g.cube[2];
-            if (face != AICB_FACE_WITHIN) {
-                const int dd = face >= AICB_FACE_PX ? 1 : -1;
-                const int ax = (face - 1) % 3;
-                if (ax == 0) x += dd; else if (ax == 1) y += dd; else z += dd;
-            }
-            uint32_t tx = 0;
-            const uint32_t t = get_packed_light(S, x, y, z, tx);
-            texels += tx;
-            i0 = s_lut[t & 255]; i1 = s_lut[(t >> 8) & 255]; i2 = s_lut[(t >> 16) & 255];
-        } else if constexpr (LC == LC_INTERP) {
-            // RaycastStep::intersection_point (raycast.rs:409-439) of the level the surface is on, brought to
-            // Space coordinates (surface.rs:406-407)
-            rr.sx = (int)((rflags >> 6) & 3u) - 1; rr.sy = (int)((rflags >> 8) & 3u) - 1; rr.sz = (int)((rflags >> 10) & 3u) - 1;
-            Caster c;
-            c.tmx = h.tmx; c.tmy = h.tmy; c.tmz = h.tmz; c.last_t = h.last_t;
-            c.face = face;
-            double ip[3];
-            if (!(h.flags & 8u)) {
-                intersection_point(c, rr, g.cube[0], g.cube[1], g.cube[2], rr.ox, rr.oy, rr.oz, ip);
-            } else {
-                const double fres = (double)g.res;
-                intersection_point(c, rr, g.voxel[0], g.voxel[1], g.voxel[2], (rr.ox - (double)g.cube[0]) * fres,
-                                   (rr.oy - (double)g.cube[1]) * fres, (rr.oz - (double)g.cube[2]) * fres, ip);
-                ip[0] = ip[0] * t_scale + (double)g.cube[0];
-                ip[1] = ip[1] * t_scale + (double)g.cube[1];
-                ip[2] = ip[2] * t_scale + (double)g.cube[2];
-            }
-            uint32_t tx = 0;
-            float il[3];
-            interpolated_light(S, s_lut, P.lighting, g.cube[0], g.cube[1], g.cube[2], face, ip[0], ip[1], ip[2], il, &tx);
-            i0 = il[0]; i1 = il[1]; i2 = il[2];
-            texels += tx;
-        }
-        float orr = ps_mul(ps_mul(cr, i0), ca) + er;   // reflect + emission (color.rs:708-710)
-        float og = ps_mul(ps_mul(cg, i1), ca) + eg;
-        float ob = ps_mul(ps_mul(cb, i2), ca) + eb;
-        if (fa >= 0.0f) {  // blend towards the sky sample of this ray (surface.rs:97-100)
-            const int k = S.sky_kind ? (int)((rflags >> 12) & 7u) : 0;
-            const float comp = 1.0f - fa;
-            orr = ps_mul(orr, comp) + ps_mul(S.sky_colors[k][0], fa);
-            og = ps_mul(og, comp) + ps_mul(S.sky_colors[k][1], fa);
-            ob = ps_mul(ob, comp) + ps_mul(S.sky_colors[k][2], fa);
-        }
-        out.r = orr; out.g = og; out.b = ob; out.factor = tr;
-        outp[0] = reinterpret_cast<const uint4 *>(&out)[0];
-        outp[1] = reinterpret_cast<const uint4 *>(&out)[1];
-    };
+    auto shade_one = [&](const uint32_t i) { shade_hit<LC>(P, s_lut, i, nullptr, texels); };
 
     // The hit stream holds slots that were never shaded (the unused tail of each lane's last chunk, surfaces whose ray
     // stopped before their span closed: a quarter of the slots of the bench frame).  Each warp scans its slots 32 at
@@ -1528,6 +1552,168 @@ __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ Trac
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) texels += __shfl_down_sync(0xffffffffu, texels, off);
     if ((threadIdx.x & 31) == 0 && texels) atomicAdd(P.counters + 4, texels);
+}
+
+// ======================================================================================================
+// LightingOption::Bounce (surface.rs:113-166, sr.rs:165-178).  A ray's RNG is only consulted at a fully opaque
+// surface, and such a surface ends the ray (transmittance 0), so every ray bounces at most once: at its last
+// accumulated hit.  A Bounce frame is therefore
+//     gen -> march -> shade<LC_BOUNCE> (Flat light, marks fully opaque hits) -> bounce_select
+//     -> `samples` x { bounce_gen -> gen -> march -> shade<LC_FLAT> -> encode (secondary mode: sums Rgb) }
+//     -> bounce_resolve (re-shades the selected hits with the gathered illumination) -> encode.
+// The secondary rays are ordinary rays of the same pipeline (trace_ray_impl(ray, .., include_sky = true,
+// allow_ray_bounce = false): Flat lighting at their own hits) on a second set of per-frame streams.
+// rand 0.10 SmallRng (xoshiro256++, SplitMix64 seeding) and rand_distr 0.6 UnitSphere are restated from their
+// published algorithms (not under /root/reference): parity with the reference is unpinned, with the oracle exact.
+// ======================================================================================================
+AICB_DEV unsigned long long rotl64(unsigned long long x, int k) { return (x << k) | (x >> (64 - k)); }
+AICB_DEV unsigned long long xoshiro_next(unsigned long long s[4]) {
+    const unsigned long long result = rotl64(s[0] + s[3], 23) + s[0];
+    const unsigned long long t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl64(s[3], 45);
+    return result;
+}
+AICB_DEV void xoshiro_seed(unsigned long long s[4], unsigned long long state) {
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            state += 0x9e3779b97f4a7c15ull;
+            unsigned long long z = state;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            s[i] = z ^ (z >> 31);
+        }
+        if ((s[0] | s[1] | s[2] | s[3]) != 0ull) break;
+        state = 0ull;   // an all-zero state is replaced by seed_from_u64(0)
+    }
+}
+// Uniform::<f64>::new(-1.0, 1.0).sample(): 52 random mantissa bits in [1, 2), minus 1, times the scale 2, plus -1
+AICB_DEV double uniform_m1_1(unsigned long long s[4]) {
+    const unsigned long long bits = (xoshiro_next(s) >> 12) | 0x3ff0000000000000ull;
+    return (__longlong_as_double((long long)bits) - 1.0) * 2.0 + (-1.0);
+}
+
+// Which hit, if any, a ray bounces at: the chain walk of encode_kernel (same stop rule) — the hit that ends the ray,
+// if shade<LC_BOUNCE> marked it fully opaque.  Seeds the ray's RNG from its direction (sr.rs:165-178).
+static __global__ void __launch_bounds__(128) bounce_select_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunk_tasks) return;
+    TaskOut o;
+    *reinterpret_cast<uint4 *>(&o) = *reinterpret_cast<const uint4 *>(P.task_out + i);
+    float T = 1.0f;
+    if (P.in_accum) T = P.in_accum[P.task_base + i].w;
+    uint32_t hi = o.first_hit, req = HIT_NONE;
+    for (uint32_t hk = 0; hk < o.n_hits; hk++) {
+        ShadedHit c;
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.shaded + hi);
+            reinterpret_cast<uint4 *>(&c)[0] = src[0];
+            reinterpret_cast<uint4 *>(&c)[1] = src[1];
+        }
+        if (c.factor >= 0.0f) {
+            T = T * c.factor;
+            if (c._pad[0]) req = hi;
+            if (T < (1.0f / 256.0f)) break;
+        }
+        hi = ((hi + 1u) & (HIT_CHUNK - 1u)) ? hi + 1u : c.next;
+    }
+    P.bounce_req[i] = req;
+    P.bounce_sum[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+    if (req != HIT_NONE) {
+        const RayRecord *rp = P.ray_records + i;
+        const unsigned long long seed = (unsigned long long)__double_as_longlong(rp->dx) +
+                                        (unsigned long long)__double_as_longlong(rp->dy) +
+                                        (unsigned long long)__double_as_longlong(rp->dz);
+        unsigned long long st[4];
+        xoshiro_seed(st, seed);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(P.bounce_rng + 4 * (size_t)i);
+        dst[0] = make_ulonglong2(st[0], st[1]);
+        dst[1] = make_ulonglong2(st[2], st[3]);
+    }
+}
+
+// The secondary ray of pass `bounce_pass` for every ray that bounces (surface.rs:131-153): from the intersection
+// point, 1e-4 off the surface, towards normal + UnitSphere sample.
+static __global__ void __launch_bounds__(128) bounce_gen_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunk_tasks) return;
+    const uint32_t req = P.bounce_req[i];
+    if (req == HIT_NONE) return;
+    const DeviceScene &S = P.scene;
+    HitRecord h;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.hits + req);
+        uint4 *dst = reinterpret_cast<uint4 *>(&h);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = src[k];
+    }
+    const RayRecord *rp = P.ray_records + i;
+    Ray rr;
+    rr.ox = rp->ox; rr.oy = rp->oy; rr.oz = rp->oz; rr.dx = rp->dx; rr.dy = rp->dy; rr.dz = rp->dz;
+    const uint32_t rflags = rp->flags;
+    rr.sx = (int)((rflags >> 6) & 3u) - 1; rr.sy = (int)((rflags >> 8) & 3u) - 1; rr.sz = (int)((rflags >> 10) & 3u) - 1;
+    HitGeom g;
+    decode_hit(S, h, g);
+    Caster c;
+    c.tmx = h.tmx; c.tmy = h.tmy; c.tmz = h.tmz; c.last_t = h.last_t;
+    c.face = g.face;
+    double ip[3];
+    if (!(h.flags & 8u)) {
+        intersection_point(c, rr, g.cube[0], g.cube[1], g.cube[2], rr.ox, rr.oy, rr.oz, ip);
+    } else {
+        const double fres = (double)g.res, t_scale = recip_pow2(g.res);
+        intersection_point(c, rr, g.voxel[0], g.voxel[1], g.voxel[2], (rr.ox - (double)g.cube[0]) * fres,
+                           (rr.oy - (double)g.cube[1]) * fres, (rr.oz - (double)g.cube[2]) * fres, ip);
+        ip[0] = ip[0] * t_scale + (double)g.cube[0];
+        ip[1] = ip[1] * t_scale + (double)g.cube[1];
+        ip[2] = ip[2] * t_scale + (double)g.cube[2];
+    }
+    double nrm[3] = {0.0, 0.0, 0.0};
+    if (g.face != AICB_FACE_WITHIN) nrm[(g.face - 1) % 3] = g.face >= AICB_FACE_PX ? 1.0 : -1.0;
+    unsigned long long st[4];
+    {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(P.bounce_rng + 4 * (size_t)i);
+        const ulonglong2 a = src[0], b = src[1];
+        st[0] = a.x; st[1] = a.y; st[2] = b.x; st[3] = b.y;
+    }
+    // rand_distr::UnitSphere (Marsaglia): reject until x1^2 + x2^2 < 1
+    double x1, x2, sum;
+    do {
+        x1 = uniform_m1_1(st);
+        x2 = uniform_m1_1(st);
+        sum = x1 * x1 + x2 * x2;
+    } while (sum >= 1.0);
+    const double factor = 2.0 * sqrt(1.0 - sum);
+    const double sph[3] = {x1 * factor, x2 * factor, 1.0 - 2.0 * sum};
+    {
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(P.bounce_rng + 4 * (size_t)i);
+        dst[0] = make_ulonglong2(st[0], st[1]);
+        dst[1] = make_ulonglong2(st[2], st[3]);
+    }
+    double *out = P.bounce_rays + 6 * (size_t)i;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        out[a] = ip[a] + nrm[a] * 0.0001;
+        out[3 + a] = nrm[a] + sph[a];
+    }
+}
+
+// Re-shades the hit each bouncing ray ends on with the mean of its secondary rays' light (surface.rs:161-165).
+static __global__ void __launch_bounds__(128) bounce_resolve_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    __shared__ float s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunk_tasks) return;
+    const uint32_t req = P.bounce_req[i];
+    if (req == HIT_NONE) return;
+    const float4 sum = P.bounce_sum[i];
+    const float recip = ps_clamped(1.0f / (float)P.bounce_samples);   // Rgb * f32 clamps the scalar (color.rs:912-927)
+    const float illum[3] = {ps_mul(sum.x, recip), ps_mul(sum.y, recip), ps_mul(sum.z, recip)};
+    unsigned long long texels = 0;
+    shade_hit<LC_BOUNCE>(P, s_lut, req, illum, texels);
 }
 
 // ======================================================================================================
@@ -1635,6 +1821,20 @@ static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constan
                 lr = P.no_world[0]; lg = P.no_world[1]; lb = P.no_world[2]; T = P.no_world[3];
             }
             if (P.out_accum) P.out_accum[P.task_base + t0 + k] = make_float4(lr, lg, lb, T);
+            if (P.bounce_mode == BOUNCE_SECONDARY) {
+                // Rgba::from(light_accum_buf.inner).to_rgb() added to the surface's multi_ray_accum (surface.rs:158-160)
+                if (P.bounce_req[t0 + k] != HIT_NONE) {
+                    float rgba[4];
+                    colorbuf_to_rgba(lr, lg, lb, T, rgba);
+                    float4 acc = P.bounce_sum[t0 + k];
+                    acc.x = acc.x + rgba[0]; acc.y = acc.y + rgba[1]; acc.z = acc.z + rgba[2];
+                    acc.w = __uint_as_float(__float_as_uint(acc.w) + steps);
+                    P.bounce_sum[t0 + k] = acc;
+                }
+                steps = 0;   // counted by the primary ray (RaytraceInfo + secondary_info, sr.rs:689-692)
+            } else if (P.bounce_mode == BOUNCE_PRIMARY) {
+                if (P.bounce_req[t0 + k] != HIT_NONE) steps += __float_as_uint(P.bounce_sum[t0 + k].w);
+            }
             steps_total += steps;
             a0 = a0 + lr; a1 = a1 + lg; a2 = a2 + lb; aT = aT + T;
         }

@@ -99,7 +99,7 @@ pub struct aicb_options {
     pub tone_mapping: u8,
     pub debug_pixel_cost: u8,
     pub include_sky: u8,
-    pub _pad0: u8,
+    pub bounce_samples: u8,
     pub transparency_threshold: f32,
     pub maximum_intensity: f32,
     pub view_distance: f64,

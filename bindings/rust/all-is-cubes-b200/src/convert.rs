@@ -141,7 +141,7 @@ pub fn options_of(options: &GraphicsOptions) -> sys::aicb_options {
             LightingOption::Coarse => 2,
             LightingOption::Linear => 3,
             LightingOption::Smoothstep => 4,
-            LightingOption::Bounce => 5, // AICB_ERR_UNSUPPORTED
+            LightingOption::Bounce { .. } => 5,
             _ => 3,
         },
         transparency: match options.transparency {
@@ -158,7 +158,10 @@ pub fn options_of(options: &GraphicsOptions) -> sys::aicb_options {
         },
         debug_pixel_cost: u8::from(options.debug_pixel_cost),
         include_sky: 1,
-        _pad0: 0,
+        bounce_samples: match options.lighting_display {
+            LightingOption::Bounce { samples } => samples.max(1),
+            _ => 0,
+        },
         transparency_threshold: match options.transparency {
             TransparencyOption::Threshold(t) => t.into_inner(),
             _ => 0.0,

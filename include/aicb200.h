@@ -29,7 +29,7 @@ typedef enum aicb_status {
     AICB_ERR_INVALID = 1,     /* bad argument / length mismatch (the reference panics: renderer.rs:193-197) */
     AICB_ERR_OOM = 2,         /* cudaMalloc failed  -> Flaws::OUT_OF_MEMORY (flaws.rs) */
     AICB_ERR_CUDA = 3,        /* no device, launch failure, lost GPU (lib.rs:53 "TODO: lost GPU") */
-    AICB_ERR_UNSUPPORTED = 4, /* LightingOption::Bounce etc. */
+    AICB_ERR_UNSUPPORTED = 4, /* an option value this build does not implement */
     AICB_ERR_BUSY = 5,        /* aicb_render_finish for a scene whose frame is not the context's last one */
     AICB_ERR_RETRY = 6        /* asynchronous render only: the frame's hit stream overflowed its device buffer; the
                                  buffer has been enlarged, issue the same render again (the synchronous entry points
@@ -118,7 +118,7 @@ typedef struct aicb_camera {
 
 enum { AICB_FOG_NONE = 0, AICB_FOG_ABRUPT = 1, AICB_FOG_COMPROMISE = 2, AICB_FOG_PHYSICAL = 3 };
 enum { AICB_LIGHT_NONE = 0, AICB_LIGHT_FLAT = 1, AICB_LIGHT_COARSE = 2, AICB_LIGHT_LINEAR = 3,
-       AICB_LIGHT_SMOOTHSTEP = 4, AICB_LIGHT_BOUNCE = 5 /* unsupported */ };
+       AICB_LIGHT_SMOOTHSTEP = 4, AICB_LIGHT_BOUNCE = 5 /* secondary Lambertian rays (surface.rs:113-166); needs aicb_options::bounce_samples */ };
 enum { AICB_TRANSPARENCY_SURFACE = 0, AICB_TRANSPARENCY_VOLUMETRIC = 1, AICB_TRANSPARENCY_THRESHOLD = 2 };
 enum { AICB_TONE_CLAMP = 0, AICB_TONE_REINHARD = 1 };
 
@@ -131,7 +131,7 @@ typedef struct aicb_options {
     uint8_t tone_mapping;
     uint8_t debug_pixel_cost;
     uint8_t include_sky;           /* trace_ray's include_sky argument (sr.rs:113-120); renders use 1 */
-    uint8_t _pad0;
+    uint8_t bounce_samples;        /* LightingOption::Bounce { samples } (graphics_options.rs:464-467); >= 1 with Bounce */
     float transparency_threshold;  /* TransparencyOption::Threshold(t) */
     float maximum_intensity;       /* +inf disables tone mapping (graphics_options.rs:352-357) */
     double view_distance;          /* repaired to [1, 10000] by the caller (graphics_options.rs:194-198) */

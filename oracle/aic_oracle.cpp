@@ -939,6 +939,64 @@ struct Accum {
 };
 
 // ---------------------------------------------------------------------------------------------
+// The bounce RNG (raytracer/mod.rs:56: `type BounceRng = rand::rngs::SmallRng`) and the direction distribution
+// (surface.rs:135-136: rand_distr::UnitSphere).  Both crates are dependencies that are NOT under /root/reference
+// (Cargo.lock: rand 0.10.1, rand_distr 0.6.0): restated from their published algorithms, parity UNPINNED — the
+// reference itself excludes LightingOption::Bounce from its image tests (test-renderers/cases/src/lib.rs:45-50).
+//   SmallRng on 64-bit targets = xoshiro256++ (Blackman & Vigna); seed_from_u64 fills the 256-bit state with
+//   SplitMix64 outputs; an all-zero state is replaced by seed_from_u64(0).
+//   Uniform<f64>::new(-1, 1): value1_2 = f64 from (next_u64 >> 12) with exponent 0; (value1_2 - 1) * 2 + (-1).
+//   UnitSphere (Marsaglia 1972): draw (x1, x2) until x1^2 + x2^2 < 1; (2 x1 sqrt(1-s), 2 x2 sqrt(1-s), 1 - 2 s).
+// The known-answer vectors of the xoshiro256++ reference implementation pin the generator itself
+// (tests/test_oracle_bounce.py).
+// ---------------------------------------------------------------------------------------------
+struct BounceRng {
+    uint64_t s[4];
+};
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static void bounce_rng_seed(BounceRng *r, uint64_t state) {
+    for (int i = 0; i < 4; i++) {
+        state += 0x9e3779b97f4a7c15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        r->s[i] = z ^ (z >> 31);
+    }
+    if ((r->s[0] | r->s[1] | r->s[2] | r->s[3]) == 0) bounce_rng_seed(r, 0);
+}
+static uint64_t bounce_rng_next(BounceRng *r) {
+    uint64_t *s = r->s;
+    const uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+    const uint64_t t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl64(s[3], 45);
+    return result;
+}
+static inline double bounce_uniform_m1_1(BounceRng *r) {
+    const uint64_t bits = (bounce_rng_next(r) >> 12) | 0x3ff0000000000000ull;
+    double value1_2;
+    std::memcpy(&value1_2, &bits, 8);
+    const double value0_1 = value1_2 - 1.0;
+    return value0_1 * 2.0 + (-1.0);
+}
+static void bounce_unit_sphere(BounceRng *r, double out[3]) {
+    for (;;) {
+        const double x1 = bounce_uniform_m1_1(r), x2 = bounce_uniform_m1_1(r);
+        const double sum = x1 * x1 + x2 * x2;
+        if (sum >= 1.0) continue;
+        const double factor = 2.0 * std::sqrt(1.0 - sum);
+        out[0] = x1 * factor;
+        out[1] = x2 * factor;
+        out[2] = 1.0 - 2.0 * sum;
+        return;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TracingState + trace_ray_impl (sr.rs:135-238, 595-769)
 // ---------------------------------------------------------------------------------------------
 struct Tracer {
@@ -951,6 +1009,10 @@ struct Tracer {
     float fog_light[3];
     float fog_blend;
     size_t cubes_traced;
+    size_t secondary_cubes = 0;   // TracingState::secondary_info (sr.rs:615-616)
+    bool allow_bounce = true;     // trace_ray_impl's allow_ray_bounce (sr.rs:139)
+    bool force_sky = false;       // secondary rays are traced with include_sky = true (surface.rs:159)
+    BounceRng rng{};
 
     // count_step_should_stop (sr.rs:625-656)
     bool count_step_should_stop() {
@@ -1101,14 +1163,43 @@ struct Tracer {
         }
     }
 
-    // compute_illumination (surface.rs:113-206), non-bounce arms
-    void illumination(const Surface &s, float out[3]) const {
+    // compute_illumination (surface.rs:113-206)
+    void illumination(const Surface &s, bool bounce, float out[3]) {
+        if (opt->lighting_display == AICB_LIGHT_BOUNCE && bounce) {   // surface.rs:119-166
+            const int samples = opt->bounce_samples;
+            float accum[3] = {0.0f, 0.0f, 0.0f};
+            double normal[3] = {0, 0, 0};
+            if (s.normal != AICB_FACE_WITHIN) normal[(s.normal - 1) % 3] = (s.normal >= AICB_FACE_PX) ? 1.0 : -1.0;
+            for (int k = 0; k < samples; k++) {
+                double sphere[3], dir[3], origin[3];
+                bounce_unit_sphere(&rng, sphere);
+                for (int a = 0; a < 3; a++) {
+                    dir[a] = normal[a] + sphere[a];
+                    origin[a] = s.ip[a] + normal[a] * 0.0001;
+                }
+                Accum light_accum;
+                light_accum.init(0);
+                Tracer child;
+                child.sc = sc;
+                child.opt = opt;
+                child.acc = &light_accum;
+                child.allow_bounce = false;
+                child.force_sky = true;
+                secondary_cubes += child.trace(origin, dir);
+                float rgba[4];
+                colorbuf_to_rgba(light_accum.color, rgba);
+                for (int a = 0; a < 3; a++) accum[a] = accum[a] + rgba[a];
+            }
+            const float recip = ps_clamped(1.0f / (float)samples);   // Rgb * f32 (color.rs:912-927)
+            for (int a = 0; a < 3; a++) out[a] = ps_mul(accum[a], recip);
+            return;
+        }
         switch (opt->lighting_display) {
             case AICB_LIGHT_NONE:
                 out[0] = out[1] = out[2] = 1.0f;
                 return;
             case AICB_LIGHT_FLAT:
-            case AICB_LIGHT_BOUNCE: {  // bounce budget exhausted / unsupported -> Flat (surface.rs:171-176)
+            case AICB_LIGHT_BOUNCE: {  // no bounce at this surface (budget spent, or not fully opaque) -> Flat (surface.rs:171-176)
                 int32_t c[3] = {s.cube[0], s.cube[1], s.cube[2]};
                 if (s.normal != AICB_FACE_WITHIN) {
                     int ax = (s.normal - 1) % 3;
@@ -1140,7 +1231,7 @@ struct Tracer {
         if (diffuse[3] == 0.0f && s.emission[0] == 0.0f && s.emission[1] == 0.0f && s.emission[2] == 0.0f) return;
 
         float illum[3];
-        illumination(s, illum);
+        illumination(s, allow_bounce && diffuse[3] == 1.0f, illum);   // surface.rs:85-88: the RNG only where fully opaque
 
         // diffuse.reflect(illum) + emission (color.rs:708-710)
         float outgoing[3];
@@ -1187,7 +1278,13 @@ struct Tracer {
 
     // trace_ray_impl (sr.rs:135-238) + finish (sr.rs:658-693)
     size_t trace(const double origin[3], const double dir[3]) {
-        bool include_sky = opt->include_sky != 0;
+        bool include_sky = force_sky || opt->include_sky != 0;
+        if (allow_bounce) {   // sr.rs:165-178: seeded from the direction's bits
+            uint64_t b[3];
+            std::memcpy(b, dir, 24);
+            bounce_rng_seed(&rng, b[0] + b[1] + b[2]);
+        }
+        secondary_cubes = 0;
         float sky_light[3] = {0, 0, 0};
         if (include_sky) sky_sample(sc->sky, dir, sky_light);
         t_to_absolute_distance = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
@@ -1235,7 +1332,7 @@ struct Tracer {
             d.block_index = -1;
             acc->add(d);
         }
-        return cubes_traced;
+        return cubes_traced + secondary_cubes;   // RaytraceInfo + secondary_info (sr.rs:689-692)
     }
 };
 
@@ -1484,6 +1581,16 @@ int orc_recursive_raycast(const double origin[3], const double dir[3], int nth, 
         n++;
     }
     return n;
+}
+
+// The bounce RNG for tests/test_oracle_bounce.py: state from seed_from_u64(seed) or, if state_or_null is given, from
+// those four words; writes n next_u64() outputs, then n_dirs UnitSphere samples drawn after them.
+void orc_bounce_rng(uint64_t seed, const uint64_t *state_or_null, size_t n, uint64_t *out, size_t n_dirs, double (*dirs)[3]) {
+    BounceRng r;
+    if (state_or_null) std::memcpy(r.s, state_or_null, 32);
+    else bounce_rng_seed(&r, seed);
+    for (size_t i = 0; i < n; i++) out[i] = bounce_rng_next(&r);
+    for (size_t i = 0; i < n_dirs; i++) bounce_unit_sphere(&r, dirs[i]);
 }
 
 void orc_apply_transmittance(const float rgba[4], float thickness, float out[5]) {

@@ -661,3 +661,74 @@ def test_wide_cells_more_than_16384_blocks():
     r2 = RtRenderer(cam)
     r2.update(Space(space.lower, ids2, blocks, light=space.light, sky_colors=space.sky_colors))
     assert np.array_equal(r.draw().data, r2.draw().data)
+
+
+# ---- LightingOption::Bounce (surface.rs:113-166) ------------------------------------------------------------------
+@pytest.mark.parametrize("transparency", [TRANSPARENCY_SURFACE, TRANSPARENCY_VOLUMETRIC, TRANSPARENCY_THRESHOLD])
+@pytest.mark.parametrize("samples,fog", [(1, FOG_NONE), (3, FOG_ABRUPT), (2, FOG_PHYSICAL)])
+def test_bounce_lighting(mixed, transparency, samples, fog):
+    """Secondary Lambertian rays from every fully opaque surface a ray ends on: ColorBuf, hits, per-pixel step counts
+    (primary + secondary, sr.rs:689-692) and sRGB8 bit-identical to the oracle — same RNG stream per ray (xoshiro256++
+    seeded from the direction's bits), same rejection sampling, same summation order."""
+    opts = GraphicsOptions(fog=fog, lighting_display=aicb200.LIGHT_BOUNCE, bounce_samples=samples,
+                           transparency=transparency, view_distance=40.0, transparency_threshold=0.3)
+    cam = scenes.standard_camera(mixed, opts, 96, 64)
+    gpu, img, ref = render_both(mixed, cam, opts)
+    compare(gpu, ref, f"bounce t{transparency} s{samples} f{fog}")
+    assert gpu["info"].cubes_traced == ref["cubes_traced"] == int(ref["steps"].sum())
+    same_srgb8(img, ref)
+    # it is not Flat lighting in disguise
+    flat = orc.OracleScene(mixed).render(cam, GraphicsOptions(fog=fog, lighting_display=LIGHT_FLAT, transparency=transparency,
+                                                              view_distance=40.0, transparency_threshold=0.3))
+    assert not np.array_equal(flat["colorbuf"], ref["colorbuf"])
+    assert ref["cubes_traced"] > flat["cubes_traced"]
+
+
+def test_bounce_lighting_variants(mixed):
+    """Antialiasing (4 rays per pixel, each with its own RNG), debug_pixel_cost (secondary rays carry the override too),
+    a camera inside the Space, a sharded frame, and explicit rays through aicb_trace_rays."""
+    base = dict(lighting_display=aicb200.LIGHT_BOUNCE, bounce_samples=2, view_distance=40.0)
+    for kw in (dict(antialiasing_always=True), dict(debug_pixel_cost=True), dict(fog=FOG_COMPROMISE)):
+        opts = GraphicsOptions(**base, **kw)
+        cam = scenes.standard_camera(mixed, opts, 48, 32)
+        gpu, img, ref = render_both(mixed, cam, opts)
+        compare(gpu, ref, str(kw))
+        same_srgb8(img, ref)
+    opts = GraphicsOptions(**base)
+    cam = scenes.standard_camera(mixed, opts, 64, 48, direction=(0.3, -1, -0.7), distance_scale=0.2)
+    gpu, img, ref = render_both(mixed, cam, opts)
+    compare(gpu, ref, "inside")
+    cam = scenes.standard_camera(mixed, opts, 64, 48)
+    gpu, img, ref = render_both(mixed, cam, opts, shard=(4, 1, 3))
+    compare(gpu, ref, "shard")
+    rng = np.random.default_rng(5)
+    lo = np.array(mixed.lower, dtype=np.float64)
+    size = np.array(mixed.size, dtype=np.float64)
+    origin = lo + size * rng.uniform(-0.5, 1.5, (500, 3))
+    target = lo + size * rng.uniform(0.1, 0.9, (500, 3))
+    od = np.concatenate([origin, target - origin], axis=1)
+    rt = SpaceRaytracer(mixed, opts)
+    got = rt.trace_rays(od, want_steps=True)
+    want = orc.OracleScene(mixed).trace_rays(od, opts)
+    assert orc.ulp_diff(got["colorbuf"], want["colorbuf"]).max() == 0
+    assert np.array_equal(got["steps"], want["steps"])
+
+
+def test_bounce_needs_a_sample_count(mixed):
+    opts = GraphicsOptions(lighting_display=aicb200.LIGHT_BOUNCE, bounce_samples=0, view_distance=40.0)
+    cam = scenes.standard_camera(mixed, opts, 16, 16)
+    r = RtRenderer(cam)
+    r.update(mixed)
+    with pytest.raises(aicb200.AicbError):
+        r.draw()
+
+
+def test_bounce_voxel_blocks():
+    """Recursive blocks: the bounce starts from the intersection point on a voxel face (surface.rs:406-407)."""
+    space = scenes.config_c1(n=12, seed=5, n_voxel_blocks=8, with_light=True, resolution=8)
+    opts = GraphicsOptions(lighting_display=aicb200.LIGHT_BOUNCE, bounce_samples=2, view_distance=60.0)
+    cam = scenes.standard_camera(space, opts, 80, 60)
+    gpu, img, ref = render_both(space, cam, opts)
+    compare(gpu, ref, "voxel blocks")
+    same_srgb8(img, ref)
+    assert gpu["info"].cubes_traced == ref["cubes_traced"]
