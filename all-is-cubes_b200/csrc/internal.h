@@ -18,6 +18,7 @@ aicb_status aicb_cuda_fail(cudaError_t e, const char *what);
 
 struct LightChartNode;  // light_kernel.cuh
 struct LightNodePre;    // light_kernel.cuh
+struct LightChain;      // light_kernel.cuh
 struct LightBlockDev;   // light_kernel.cuh
 
 struct aicb_ctx {
@@ -71,6 +72,12 @@ struct aicb_ctx {
     LightChartNode *d_chart = nullptr;
     LightNodePre *d_chart_pre = nullptr;   // the same chart in depth-first preorder (the lockstep walk)
     uint32_t chart_nodes = 0;
+    LightChain *d_chains = nullptr;         // the chart as chains, the per-node cube offsets, the Euler tour of the chain tree
+    uchar4 *d_node_rel = nullptr;
+    uint16_t *d_euler = nullptr;
+    uint32_t n_chains = 0, n_euler = 0;
+    float4 *d_term_scratch = nullptr;       // term slots of the chain walk, one set per resident warp
+    uint32_t chain_walk_blocks = 0;
     std::mutex mu;
 };
 

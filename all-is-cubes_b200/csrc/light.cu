@@ -19,6 +19,8 @@ using namespace aicb_light;
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int CHAIN_WALK_BLOCKS_PER_SM = 5;   // 4 warps and 40 KB of shared memory each
+
 struct TreeNode {
     int8_t cube[3];
     int children[6];
@@ -136,8 +138,91 @@ const std::vector<LightNodePre> &chart_preorder_host() {
     return pre;
 }
 
+// The chart as chains (light_kernel.cuh: LightChain): maximal single-child paths of the preorder chart, numbered
+// breadth first; the Euler tour of the chain tree is the depth-first order the terms of a walk are added in.
+struct ChainTables {
+    std::vector<LightChain> chains;
+    std::vector<uchar4> node_rel;
+    std::vector<uint16_t> euler;
+};
+const ChainTables &chain_tables_host() {
+    static const ChainTables tables = [] {
+        const std::vector<LightNodePre> &pre = chart_preorder_host();
+        const uint32_t n = (uint32_t)pre.size();
+        auto end_of = [&](uint32_t i) { return pre[i].end_dir & 0x1fffffffu; };
+        auto children_of = [&](uint32_t i) {
+            std::vector<uint32_t> c;
+            for (uint32_t k = i + 1; k < end_of(i); k = end_of(k)) c.push_back(k);
+            return c;
+        };
+        ChainTables t;
+        t.node_rel.resize(n);
+        for (uint32_t i = 0; i < n; i++)
+            t.node_rel[i] = make_uchar4((uint8_t)pre[i].rel[0], (uint8_t)pre[i].rel[1], (uint8_t)pre[i].rel[2], (uint8_t)(pre[i].end_dir >> 29));
+        std::vector<uint32_t> start;           // chain -> first node
+        std::vector<uint16_t> parent_branch;
+        start.push_back(0);
+        parent_branch.push_back(0xffff);
+        uint16_t n_branches = 0;
+        for (size_t c = 0; c < start.size(); c++) {
+            LightChain ch;
+            std::memset(&ch, 0, sizeof ch);
+            std::memcpy(ch.w, pre[start[c]].w, sizeof ch.w);
+            ch.first_node = start[c];
+            uint32_t e = start[c];
+            std::vector<uint32_t> kids = children_of(e);
+            while (kids.size() == 1) { e = kids[0]; kids = children_of(e); }
+            ch.length = (uint16_t)(e - start[c] + 1);
+            ch.n_children = (uint8_t)kids.size();
+            ch.parent_branch = parent_branch[c];
+            ch.branch = kids.empty() ? (uint16_t)0xffff : n_branches++;
+            ch.first_child = (uint32_t)start.size();
+            for (uint32_t k : kids) { start.push_back(k); parent_branch.push_back(ch.branch); }
+            t.chains.push_back(ch);
+        }
+        // Euler tour (iterative): enter(c), children in order, exit(c)
+        struct It { uint32_t c; uint32_t next; };
+        std::vector<It> stack;
+        stack.push_back(It{0, 0});
+        t.euler.push_back(0);
+        while (!stack.empty()) {
+            It &it = stack.back();
+            const LightChain &ch = t.chains[it.c];
+            if (it.next < ch.n_children) {
+                const uint32_t k = ch.first_child + it.next++;
+                t.euler.push_back((uint16_t)k);
+                stack.push_back(It{k, 0});
+            } else {
+                t.euler.push_back((uint16_t)(it.c | 0x8000u));
+                stack.pop_back();
+            }
+        }
+        return t;
+    }();
+    return tables;
+}
+
 aicb_status ensure_chart(aicb_ctx *ctx) {
     if (ctx->d_chart) return AICB_OK;
+    {
+        const ChainTables &t = chain_tables_host();
+        if (t.chains.size() > (size_t)LIGHT_MAX_CHAINS || t.chains.size() >= 0x8000u)
+            return aicb_fail(AICB_ERR_INVALID, "light chart has more chains than the walk's shared arrays hold");
+        size_t branches = 0;
+        for (const LightChain &c : t.chains) branches += c.n_children ? 1 : 0;
+        if (branches > (size_t)LIGHT_MAX_BRANCHES) return aicb_fail(AICB_ERR_INVALID, "light chart has more branching chains than expected");
+        CU(cudaMalloc(&ctx->d_chains, t.chains.size() * sizeof(LightChain)));
+        CU(cudaMemcpy(ctx->d_chains, t.chains.data(), t.chains.size() * sizeof(LightChain), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_node_rel, t.node_rel.size() * sizeof(uchar4)));
+        CU(cudaMemcpy(ctx->d_node_rel, t.node_rel.data(), t.node_rel.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ctx->d_euler, t.euler.size() * sizeof(uint16_t)));
+        CU(cudaMemcpy(ctx->d_euler, t.euler.data(), t.euler.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        ctx->n_chains = (uint32_t)t.chains.size();
+        ctx->n_euler = (uint32_t)t.euler.size();
+        // one set of term slots per resident warp of the chain walk
+        ctx->chain_walk_blocks = (uint32_t)ctx->num_sms * CHAIN_WALK_BLOCKS_PER_SM;
+        CU(cudaMalloc(&ctx->d_term_scratch, (size_t)ctx->chain_walk_blocks * 4 * LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS * sizeof(float4)));
+    }
     std::vector<LightChartNode> chart = build_chart();
     const std::vector<LightNodePre> &pre = chart_preorder_host();
     CU(cudaMalloc(&ctx->d_chart_pre, pre.size() * sizeof(LightNodePre)));
@@ -252,6 +337,18 @@ __global__ void __launch_bounds__(256) k_gather(const LightParams P, uint32_t n_
 #ifndef AICB_LIGHT_MIN_BLOCKS
 #define AICB_LIGHT_MIN_BLOCKS 8
 #endif
+// How many consecutive list entries (neighbouring cubes) one warp walks for together.  The walk is a chain of dependent
+// loads per node; a lone warp takes ~1250 cycles per node whatever the number of its lanes that take part.  32 cubes
+// share the most node records, but a round of a few ten thousand cubes then occupies a fraction of the resident
+// warps and lasts as long as its slowest warp (a 32-cube union of ~20 K nodes = 14 ms).  Narrower batches make more,
+// shorter walks: the width is the largest power of two that still yields `P.batches_per_warp` batches per resident warp.
+__device__ __forceinline__ uint32_t batch_width(const LightParams &P, uint32_t n, uint32_t n_warps) {
+    if (P.batch_width) return P.batch_width;
+    uint32_t w = 32;
+    while (w > P.min_batch_width && (uint64_t)n < (uint64_t)n_warps * P.batches_per_warp * w) w >>= 1;
+    return w;
+}
+
 __global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_compute(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
     __shared__ float s_lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
@@ -259,10 +356,22 @@ __global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_compute(const Li
     if (!explicit_cubes) n = P.scalars[0];   // the round's list
     unsigned long long total_visits = 0;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {   // one warp per 32 consecutive list entries
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t width = batch_width(P, n, n_warps);
+    // batches of `width` consecutive list entries, handed out by a counter: a warp whose cubes see open air walks
+    // ten times the nodes of one whose cubes are enclosed
+    for (;;) {
+        uint32_t batch = 0;
+        if (explicit_cubes) {
+            batch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (one batch per warp: the grid covers n)
+        } else {
+            if (lane == 0) batch = atomicAdd(P.scalars + 7, 1u);
+            batch = __shfl_sync(0xffffffffu, batch, 0);
+        }
+        const uint32_t base = batch * (explicit_cubes ? 32u : width);
+        if (base >= n) break;
         const uint32_t i = base + lane;
-        const bool active = i < n;
+        const bool active = i < n && (explicit_cubes || lane < width);
         int x = 0, y = 0, z = 0;
         if (active) {
             if (explicit_cubes) {
@@ -270,6 +379,70 @@ __global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_compute(const Li
             } else {
                 cube_of(P.scene, P.list[i], x, y, z);
             }
+        }
+        uint32_t visits = 0;
+        const uint32_t nv = compute_light_lockstep<false>(P, s_lut, active, x, y, z, 0, &visits);
+        if (active) P.new_light[i] = nv;
+        total_visits += visits;
+        if (explicit_cubes) break;
+    }
+    for (int off = 16; off > 0; off >>= 1) total_visits += __shfl_down_sync(0xffffffffu, total_visits, off);
+    if (lane == 0 && total_visits) atomicAdd(reinterpret_cast<unsigned long long *>(P.scalars + 4), total_visits);
+}
+
+// compute_light / the dependency re-queue with the chain walk (light_kernel.cuh: compute_light_chains): one warp per
+// cube, cubes handed out by a counter.  k_walk_chains<false> writes new_light for the round's list (or explicit
+// cubes); a cube one of whose chains needs more than LIGHT_CHAIN_K terms goes to the overflow list and is computed by
+// the lockstep walk (k_compute_overflow).  k_walk_chains<true> is k_mark for the entries of `changed`.
+template <bool MARK>
+__global__ void __launch_bounds__(128, CHAIN_WALK_BLOCKS_PER_SM) k_walk_chains(const LightParams P, uint32_t n, const int32_t *explicit_cubes) {
+    __shared__ float s_lut[256];
+    __shared__ ChainShared s_sh[4];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    ChainShared &sh = s_sh[wib];
+    float4 *terms = MARK ? nullptr : P.term_scratch + (size_t)(blockIdx.x * 4 + wib) * (LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS);
+    if (!explicit_cubes) n = MARK ? P.scalars[6] : P.scalars[0];
+    unsigned long long total_visits = 0;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(P.scalars + (MARK ? 8 : 7), 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n) break;
+        const uint32_t i = MARK ? P.changed[item] : item;   // position in the round's list
+        int x, y, z;
+        if (explicit_cubes) { x = explicit_cubes[3 * i]; y = explicit_cubes[3 * i + 1]; z = explicit_cubes[3 * i + 2]; }
+        else cube_of(P.scene, P.list[i], x, y, z);
+        const uint32_t prio = MARK ? (uint32_t)P.diff[i] / 2u + 1u : 0u;
+        uint32_t visits = 0;
+        bool overflowed = false;
+        const uint32_t nv = compute_light_chains<MARK>(P, s_lut, sh, terms, x, y, z, prio, &visits, &overflowed);
+        if (!MARK && lane == 0) {
+            if (overflowed) P.overflow[atomicAdd(P.scalars + 9, 1u)] = i;
+            else P.new_light[i] = nv;
+        }
+        total_visits += visits;
+    }
+    if (!MARK && lane == 0 && total_visits) atomicAdd(reinterpret_cast<unsigned long long *>(P.scalars + 4), total_visits);
+}
+
+// the cubes the chain walk could not hold (scalars[9] entries of `overflow`), by the lockstep walk
+__global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_compute_overflow(const LightParams P, const int32_t *explicit_cubes) {
+    __shared__ float s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    __syncthreads();
+    const uint32_t n = P.scalars[9];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long total_visits = 0;
+    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
+        const bool active = base + lane < n;
+        const uint32_t i = active ? P.overflow[base + lane] : 0u;
+        int x = 0, y = 0, z = 0;
+        if (active) {
+            if (explicit_cubes) { x = explicit_cubes[3 * i]; y = explicit_cubes[3 * i + 1]; z = explicit_cubes[3 * i + 2]; }
+            else cube_of(P.scene, P.list[i], x, y, z);
         }
         uint32_t visits = 0;
         const uint32_t nv = compute_light_lockstep<false>(P, s_lut, active, x, y, z, 0, &visits);
@@ -346,9 +519,15 @@ __global__ void __launch_bounds__(256) k_compact_changed(const LightParams P) {
 __global__ void __launch_bounds__(128, AICB_LIGHT_MIN_BLOCKS) k_mark(const LightParams P) {
     const uint32_t n = P.scalars[6];   // entries of the round's list that changed by more than one unit
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
-        const bool active = base + lane < n;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t width = batch_width(P, n, n_warps);
+    for (;;) {
+        uint32_t batch = 0;
+        if (lane == 0) batch = atomicAdd(P.scalars + 8, 1u);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        const uint32_t base = batch * width;
+        if (base >= n) break;
+        const bool active = base + lane < n && lane < width;
         const uint32_t i = active ? P.changed[base + lane] : 0u;
         const int d = active ? (int)P.diff[i] : 0;
         int x = 0, y = 0, z = 0;
@@ -421,6 +600,13 @@ LightParams make_params(aicb_scene *s) {
     P.chart = s->ctx->d_chart;
     P.chart_pre = s->ctx->d_chart_pre;
     P.sky_term = s->d_sky_term;
+    P.chains = s->ctx->d_chains;
+    P.node_rel = s->ctx->d_node_rel;
+    P.euler = s->ctx->d_euler;
+    P.n_chains = s->ctx->n_chains;
+    P.n_euler = s->ctx->n_euler;
+    P.term_scratch = s->ctx->d_term_scratch;
+    P.overflow = s->d_changed;   // (k_compute's overflow list and k_mark's work list are never live together)
     P.chart_nodes = s->ctx->chart_nodes;
     P.tile_max = s->d_tile_max;
     P.changed = s->d_changed;
@@ -480,13 +666,19 @@ aicb_status ensure_light_state(aicb_scene *s) {
         CU(cudaMalloc(&s->d_list, s->volume * 4 + 16));
         CU(cudaMalloc(&s->d_new_light, s->volume * 4 + 16));
         CU(cudaMalloc(&s->d_diff, s->volume + 16));
-        CU(cudaMalloc(&s->d_scalars, 8 * 4));
+        CU(cudaMalloc(&s->d_scalars, 16 * 4));
         CU(cudaMalloc(&s->d_tile_max, ((s->volume + LIGHT_TILE - 1) / LIGHT_TILE + 1) * 4));
         CU(cudaMalloc(&s->d_changed, s->volume * 4 + 16));
         s->device_bytes += s->volume * 4;
         s->device_bytes += s->volume * 10;
     }
     return AICB_OK;
+}
+
+// AICB_LIGHT_WALK=lockstep selects the previous walk (32 cubes per warp in lockstep) for comparisons
+bool use_chain_walk() {
+    const char *e = getenv("AICB_LIGHT_WALK");
+    return !(e && std::strcmp(e, "lockstep") == 0);
 }
 
 // evaluate_light (space.rs:1496-1527): rounds until the highest queued priority is <= from_difference(epsilon)
@@ -501,6 +693,15 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
         // contract (tests/test_gpu_light.py) holds for every band, 0 = one level per round, 255 = all pending cubes.
         const char *e = getenv("AICB_LIGHT_BAND");
         P.priority_band = e ? (uint32_t)atoi(e) : 16u;
+        const char *w = getenv("AICB_LIGHT_WIDTH");        // experiments: a fixed batch width (1..32)
+        P.batch_width = w ? (uint32_t)atoi(w) : 0u;
+        const char *b = getenv("AICB_LIGHT_BATCHES_PER_WARP");
+        P.batches_per_warp = b ? (uint32_t)atoi(b) : 2u;
+        const char *m = getenv("AICB_LIGHT_MIN_WIDTH");
+        P.min_batch_width = m ? (uint32_t)atoi(m) : 4u;
+        if (P.batch_width > 32) P.batch_width = 32;
+        if (P.batches_per_warp < 1) P.batches_per_warp = 1;
+        if (P.min_batch_width < 1) P.min_batch_width = 1;
     }
     const int blocks = ctx->num_sms * 8;
     const int wide = ctx->num_sms * 8;    // 128-thread blocks of the lockstep kernels (one warp per 32 list entries, grid-stride)
@@ -508,19 +709,26 @@ aicb_status propagate(aicb_scene *s, uint8_t epsilon, uint64_t *updates_done, ui
     uint64_t total = 0, visits = 0, rounds = 0;
     uint32_t maxd = 0;
     CU(cudaEventRecord(ctx->ev0, st));
-    CU(cudaMemsetAsync(s->d_scalars, 0, 8 * 4, st));
+    CU(cudaMemsetAsync(s->d_scalars, 0, 16 * 4, st));
     k_tile_rebuild<<<blocks, 256, 0, st>>>(P, n_tiles);   // (fast_evaluate / edits write the priority bytes directly)
     const int ROUNDS_PER_SYNC = 8;
+    const bool chains = use_chain_walk();
     for (int batch = 0; batch < 100000; batch++) {
         for (int round = 0; round < ROUNDS_PER_SYNC; round++) {
             CU(cudaMemsetAsync(s->d_scalars, 0, 2 * 4, st));   // this round's count and priority
-            CU(cudaMemsetAsync(s->d_scalars + 6, 0, 4, st));   // ... and its count of changed cubes
+            CU(cudaMemsetAsync(s->d_scalars + 6, 0, 4 * 4, st));   // ... its count of changed cubes, the two work counters, the overflow count
             k_find_max<<<16, 256, 0, st>>>(P, n_tiles);
             k_gather<<<blocks, 256, 0, st>>>(P, n_tiles);
-            k_compute<<<wide, 128, 0, st>>>(P, 0, nullptr);
+            if (chains) {
+                k_walk_chains<false><<<ctx->chain_walk_blocks, 128, 0, st>>>(P, 0, nullptr);
+                k_compute_overflow<<<wide, 128, 0, st>>>(P, nullptr);
+            } else {
+                k_compute<<<wide, 128, 0, st>>>(P, 0, nullptr);
+            }
             k_apply<<<wide, 128, 0, st>>>(P);
             k_compact_changed<<<blocks, 256, 0, st>>>(P);
-            k_mark<<<wide, 128, 0, st>>>(P);
+            if (chains) k_walk_chains<true><<<ctx->chain_walk_blocks, 128, 0, st>>>(P, 0, nullptr);
+            else k_mark<<<wide, 128, 0, st>>>(P);
         }
         uint32_t h[8];
         CU(cudaMemcpyAsync(h, s->d_scalars, 8 * 4, cudaMemcpyDeviceToHost, st));
@@ -614,6 +822,10 @@ void aicb_light_scene_free(aicb_scene *s) {
 void aicb_light_ctx_free(aicb_ctx *c) {
     if (c->d_chart) cudaFree(c->d_chart);
     if (c->d_chart_pre) cudaFree(c->d_chart_pre);
+    if (c->d_chains) cudaFree(c->d_chains);
+    if (c->d_node_rel) cudaFree(c->d_node_rel);
+    if (c->d_euler) cudaFree(c->d_euler);
+    if (c->d_term_scratch) cudaFree(c->d_term_scratch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -656,7 +868,13 @@ aicb_status aicb_light_compute(aicb_scene *s, const int32_t (*cubes)[3], size_t 
     int32_t *d_cubes = nullptr;
     CU(cudaMalloc(&d_cubes, n * 12));
     CU(cudaMemcpy(d_cubes, cubes, n * 12, cudaMemcpyHostToDevice));
-    k_compute<<<(unsigned)((n + 127) / 128), 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
+    if (use_chain_walk()) {
+        cudaMemsetAsync(s->d_scalars + 7, 0, 3 * 4, s->ctx->stream);
+        k_walk_chains<false><<<s->ctx->chain_walk_blocks, 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
+        k_compute_overflow<<<s->ctx->num_sms * 8, 128, 0, s->ctx->stream>>>(P, d_cubes);
+    } else {
+        k_compute<<<(unsigned)((n + 127) / 128), 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
+    }
     cudaError_t e = cudaMemcpyAsync(out, s->d_new_light, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
     cudaFree(d_cubes);

@@ -46,6 +46,27 @@ struct LightBlockDev {
 };
 static_assert(sizeof(LightBlockDev) == 128, "LightBlockDev must be 128 bytes");
 
+// The chart as chains.  99 % of the chart's nodes have exactly one child, with bit-identical weights (they carry the
+// same rays): the tree is 1043 chains (maximal single-child paths; 602 of them end in leaves) joined at 441 branching
+// nodes, 8 chain levels deep.  A chain's nodes are consecutive in preorder.  One record per chain, numbered breadth
+// first so that the children of a chain are consecutive; 48 bytes.
+struct LightChain {
+    float w[6];             // the weights of every node of the chain
+    uint32_t first_node;    // preorder index of the chain's first node
+    uint32_t first_child;   // first of its child chains
+    uint16_t length;        // nodes
+    uint8_t n_children;
+    uint8_t _pad;
+    uint16_t parent_branch; // branch slot of the chain it hangs off (0xffff: the root chain)
+    uint16_t branch;        // its own branch slot if it has children, else 0xffff
+    uint32_t _pad2[2];
+};
+static_assert(sizeof(LightChain) == 48, "LightChain must be 48 bytes");
+constexpr int LIGHT_MAX_CHAINS = 1056;      // 1043, padded
+constexpr int LIGHT_MAX_BRANCHES = 448;     // 441 chains have children
+constexpr int LIGHT_CHAIN_K = 8;            // entry terms a chain can hold (more: the cube takes the lockstep walk)
+constexpr int LIGHT_CHAIN_SLOTS = LIGHT_CHAIN_K + 1;   // + the term of the pop at the chain's end
+
 constexpr uint32_t LB_ALL_OPAQUE = 1u << 6, LB_VISIBLE = 1u << 7, LB_EMISSIVE = 1u << 8;
 constexpr int LIGHT_MAX_DEPTH = 224;  // longest chart path is 219 (rays end at t = 127, generator.rs:101)
 
@@ -62,6 +83,12 @@ struct LightParams {
     const LightBlockDev *blocks;
     const LightChartNode *chart;
     const LightNodePre *chart_pre;
+    const LightChain *chains;       // the chart as chains (breadth-first numbering)
+    const uchar4 *node_rel;         // per preorder node: cube relative to the origin (int8 x 3), direction of the step from its parent
+    const uint16_t *euler;          // the Euler tour of the chain tree: chain | (0: its entry terms, 1: its pop term) << 15
+    uint32_t n_chains, n_euler;
+    float4 *term_scratch;           // per resident warp: LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS terms
+    uint32_t *overflow;             // list entries whose walk needs more than LIGHT_CHAIN_K terms in one chain ([9] counts them)
     const float4 *sky_term;         // per preorder node: the sky light its bundle collects at the end of a ray (end_of_ray)
     uint32_t chart_nodes;
     uint32_t *tile_max;             // per LIGHT_TILE cubes: an upper bound of the tile's highest queued priority
@@ -70,11 +97,14 @@ struct LightParams {
     uint32_t *new_light;
     uint8_t *diff;
     uint32_t *changed;              // positions in the round's list whose cube changed by more than one unit (k_mark's work)
-    uint32_t *scalars;              // [0] list length, [1] max priority, [2] max diff, [3] updates, [4..5] node visits, [6] changed
+    uint32_t *scalars;              // [0] list length, [1] max priority, [2] max diff, [3] updates, [4..5] node visits, [6] changed,
+                                    // [7] / [8] batches handed out by k_compute / k_mark this round, [9] overflow list length
     uint32_t volume;
     uint32_t max_distance;
     uint32_t priority;              // the round's priority level
     uint32_t epsilon_priority;
+    uint32_t batch_width;       // cubes per warp of the lockstep walk (0: chosen per round from the list length)
+    uint32_t batches_per_warp, min_batch_width;
     uint32_t priority_band;     // cubes whose queued priority is within this many levels of the round's maximum are updated together
 };
 
@@ -409,6 +439,333 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
         return scalar_in_t(S.tables, ps_mul(acc.in0, scale)) | (scalar_in_t(S.tables, ps_mul(acc.in1, scale)) << 8) |
                (scalar_in_t(S.tables, ps_mul(acc.in2, scale)) << 16) | (255u << 24);
     return origin_opaque ? TX_OPAQUE : TX_NO_RAYS;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// compute_light for ONE cube by the whole warp, chain by chain.
+//
+// Phase 1 — the walk.  Ready chains wait in a per-warp queue (shared memory); an idle lane takes one and walks its
+// nodes in order (LightBuffer::traverse, updater.rs:760-884, per node exactly as the lockstep walk does), 32 chains of
+// the cube at a time.  A chain that is still alive at its end leaves (alpha, light_ahead_cache) in its branch slot and
+// queues its children.  The walk of a cube visits ~3 K nodes on average; the lockstep walk stepped a warp through the
+// union of 32 cubes' node sets with 5 lanes taking part per node, here every lane steps a node of its own.
+//
+// What the reference accumulates in depth-first order (incoming_light, total_rays: f32 additions, not associative) is
+// not added during the walk: a lane writes each term (the three colour contributions and the weight) to its chain's
+// slots.  Depth-first order over the tree = the Euler tour of the chain tree: a chain's entry terms in node order, its
+// child chains, then the term of its pop (walk_ray_tree's `remaining bundle` end_of_ray, updater.rs:518-528 — non-zero
+// only at branching nodes: inside a chain parent and child carry identical weights, so bundle - children is exactly 0).
+// Phase 2 — the sum.  The warp goes through the static Euler tour 32 positions at a time, gathers the terms that
+// exist, and adds them up in order (one lane per channel), bit-identical to the sequential walk.
+// MARK: walk only, raising the queue priority of every cube whose light the walk reads (apply_light_update's
+// dependency re-queue, updater.rs:355-360); no terms.
+// ---------------------------------------------------------------------------------------------------------------
+struct ChainShared {
+    uint16_t queue[LIGHT_MAX_CHAINS];
+    float br_alpha[LIGHT_MAX_BRANCHES];
+    uint32_t br_ahead[LIGHT_MAX_BRANCHES];
+    uint8_t br_have[LIGHT_MAX_BRANCHES];
+    uint8_t cnt_entry[LIGHT_MAX_CHAINS];
+    uint8_t cnt_pop[LIGHT_MAX_CHAINS];
+    float4 stage[32];
+    uint32_t list[32 * LIGHT_CHAIN_K];
+};
+
+// returns the new PackedLight texel (every lane); *overflowed: some chain had more terms than its slots hold
+template <bool MARK>
+__device__ uint32_t compute_light_chains(const LightParams &P, const float *lut, ChainShared &sh, float4 *terms,
+                                         int ox, int oy, int oz, uint32_t mark_priority, uint32_t *visits_out,
+                                         bool *overflowed) {
+    const DeviceScene &S = P.scene;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // ---- compute_light's prologue (updater.rs:368-418), warp-uniform: every lane evaluates the same cube
+    uint32_t oidx;
+    uint32_t oflags = 0;
+    const LightBlockDev *ob = nullptr;
+    if (cube_index(S, ox, oy, oz, &oidx)) {
+        ob = &P.blocks[block_id_at(S, oidx)];
+        oflags = __ldg(&ob->flags);
+    }
+    const bool origin_opaque = (oflags & LB_ALL_OPAQUE) != 0;
+    __syncwarp();   // (the previous cube's phase 2 is through with the shared arrays)
+    *overflowed = false;
+    if (visits_out) *visits_out = 0;
+    if (origin_opaque) {
+        if (MARK) return 0u;
+        Accum acc = {0.f, 0.f, 0.f, 0.f};
+        if (oflags & LB_EMISSIVE) {
+            acc.in0 = acc.in0 + ps_mul(__ldg(&ob->emission[0]), 1.0f);
+            acc.in1 = acc.in1 + ps_mul(__ldg(&ob->emission[1]), 1.0f);
+            acc.in2 = acc.in2 + ps_mul(__ldg(&ob->emission[2]), 1.0f);
+            acc.total += 1.0f;
+        }
+        const float scale = ps_clamped(1.0f / fmaxf(acc.total, 1.0f));
+        if (acc.total > 0.0f)
+            return scalar_in_t(S.tables, ps_mul(acc.in0, scale)) | (scalar_in_t(S.tables, ps_mul(acc.in1, scale)) << 8) |
+                   (scalar_in_t(S.tables, ps_mul(acc.in2, scale)) << 16) | (255u << 24);
+        return TX_OPAQUE;
+    }
+    float dw[6];
+    if (oflags & LB_VISIBLE) {
+#pragma unroll
+        for (int f = 0; f < 6; f++) dw[f] = 1.0f;
+    } else {  // directions_to_seek_light (updater.rs:669-690)
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            const int s = (f < 3) ? -1 : 1, a = f % 3;
+            const uint32_t toward = flags_at(P, ox + (a == 0 ? s : 0), oy + (a == 1 ? s : 0), oz + (a == 2 ? s : 0));
+            const uint32_t away = flags_at(P, ox - (a == 0 ? s : 0), oy - (a == 1 ? s : 0), oz - (a == 2 ? s : 0));
+            dw[f] = ((away & LB_VISIBLE) || (toward & LB_EMISSIVE)) ? 1.0f : 0.0f;
+        }
+    }
+    const int max_d2 = (int)(P.max_distance * P.max_distance);
+    if (!MARK) {   // no chain has a term yet
+        uint32_t *z0 = reinterpret_cast<uint32_t *>(sh.cnt_entry), *z1 = reinterpret_cast<uint32_t *>(sh.cnt_pop);
+        for (unsigned k = lane; k < LIGHT_MAX_CHAINS / 4; k += 32) { z0[k] = 0u; z1[k] = 0u; }
+    }
+    if (lane == 0) sh.queue[0] = 0;
+    __syncwarp();
+
+    // ---- phase 1 ----
+    constexpr uint32_t NONE = 0xffffffffu;
+    uint32_t head = 0, tail = 1;          // (warp-uniform)
+    uint32_t cur = NONE;                  // the lane's chain
+    uint32_t node = 0, remaining = 0, tcount = 0, visits = 0;
+    uint32_t push_n = 0, push_first = 0;
+    float alpha = 0.f, bundle = 0.f;
+    bool have = false, over = false;
+    uint32_t ahead = 0;
+    uint32_t c_first_child = 0, c_meta = 0;   // n_children | branch << 16
+    for (;;) {
+        // children of the chains that ended alive in the last iteration
+        {
+            uint32_t inc = push_n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)lane >= off) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total) {
+                const uint32_t at = tail + inc - push_n;
+                for (uint32_t j = 0; j < push_n; j++) sh.queue[at + j] = (uint16_t)(push_first + j);
+                tail += total;
+                push_n = 0;
+                __syncwarp();
+            }
+        }
+        // idle lanes take chains
+        {
+            const bool idle = cur == NONE;
+            const unsigned m = __ballot_sync(0xffffffffu, idle);
+            const uint32_t avail = tail - head;
+            const uint32_t rank = __popc(m & lt_mask);
+            if (idle && rank < avail) {
+                cur = sh.queue[head + rank];
+                const uint4 *cp = reinterpret_cast<const uint4 *>(P.chains + cur);
+                const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+                const float cw[6] = {__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z),
+                                     __uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y)};
+                float prod[6];
+#pragma unroll
+                for (int f = 0; f < 6; f++) prod[f] = cw[f] * dw[f];
+                bundle = fm_sum(prod);
+                node = c1.z;
+                c_first_child = c1.w;
+                remaining = c2.x & 0xffffu;
+                const uint32_t n_children = (c2.x >> 16) & 0xffu;
+                const uint32_t pb = c2.y & 0xffffu, br = c2.y >> 16;
+                c_meta = n_children | (br << 16);
+                tcount = 0;
+                if (pb == 0xffffu) { alpha = 1.0f; have = false; ahead = 0; }
+                else { alpha = sh.br_alpha[pb]; have = sh.br_have[pb] != 0; ahead = sh.br_ahead[pb]; }
+                if (!(bundle > 0.0f)) {   // the walk enters the chain's first node and leaves at once (updater.rs:447-450)
+                    visits++;
+                    cur = NONE;
+                }
+            }
+            const uint32_t takers = __popc(m);
+            head += takers < avail ? takers : avail;
+        }
+        if (__ballot_sync(0xffffffffu, cur != NONE) == 0u) break;
+        if (cur != NONE) {
+            visits++;
+            const uchar4 r4 = __ldg(P.node_rel + node);
+            const int relx = (int)(int8_t)r4.x, rely = (int)(int8_t)r4.y, relz = (int)(int8_t)r4.z;
+            const bool too_far = relx * relx + rely * rely + relz * relz > max_d2;   // updater.rs:452-455
+            const int e_x = ox + relx, e_y = oy + rely, e_z = oz + relz;
+            uint32_t cidx = 0;
+            const bool inb = cube_index(S, e_x, e_y, e_z, &cidx);
+            bool ended = false;      // the ray bundle ends here: end_of_ray with the whole bundle
+            if (too_far || !inb) {
+                ended = true;
+            } else {
+                // ---- LightBuffer::traverse ----
+                const int dir = (int)r4.w;
+                const int e_face = node == 0u ? 0 : ((dir < 3) ? dir + 3 : dir - 3) + 1;
+                const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
+                const uint32_t fl = __ldg(&ev->flags);
+                const float e_alpha = alpha;
+                const bool e_have_prev = have;
+                const uint32_t e_ahead_prev = ahead;
+                have = false;
+                ahead = 0;
+                if (fl & LB_VISIBLE) {
+                    const bool hit_opaque_face = (e_face == 0) ? ((fl & LB_ALL_OPAQUE) != 0) : (((fl >> (e_face - 1)) & 1u) != 0);
+                    if (hit_opaque_face && e_face == 0) {
+                        alpha = 0.0f;
+                    } else {
+                        float col[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) col[i] = __ldg(&ev->face_color[e_face][i]);
+#pragma unroll
+                        for (int i = 0; i < 3; i++) col[i] = col[i] > 1.0f ? 1.0f : col[i];  // Rgba::clamp
+                        const float hit_alpha = col[3];
+                        const float kw = ps_clamped(bundle);
+                        if (hit_alpha > 0.0f && e_face != 0) {
+                            int lx = e_x, ly = e_y, lz = e_z;  // hit.adjacent(): the cube the ray came from
+                            const int ax = (e_face - 1) % 3, sgn = (e_face >= 4) ? 1 : -1;
+                            if (ax == 0) lx += sgn; else if (ax == 1) ly += sgn; else lz += sgn;
+                            if (MARK) mark_dependency(P, lx, ly, lz, mark_priority);
+                            if (!MARK) {
+                                const uint32_t stored = e_have_prev ? e_ahead_prev : light_get(P, lx, ly, lz);
+                                const float ka = ps_clamped(e_alpha);
+                                float lf[3];
+                                lf[0] = __ldg(&ev->emission[0]) + ps_mul(ps_mul(col[0], lut[stored & 255]), hit_alpha);
+                                lf[1] = __ldg(&ev->emission[1]) + ps_mul(ps_mul(col[1], lut[(stored >> 8) & 255]), hit_alpha);
+                                lf[2] = __ldg(&ev->emission[2]) + ps_mul(ps_mul(col[2], lut[(stored >> 16) & 255]), hit_alpha);
+                                if (tcount < (uint32_t)LIGHT_CHAIN_K)
+                                    terms[cur * LIGHT_CHAIN_SLOTS + tcount] = make_float4(ps_mul(ps_mul(lf[0], ka), kw), ps_mul(ps_mul(lf[1], ka), kw), ps_mul(ps_mul(lf[2], ka), kw), 0.0f);
+                                else over = true;
+                                tcount++;
+                            }
+                            if (hit_opaque_face) alpha = 0.0f; else alpha *= 1.0f - hit_alpha;
+                        }
+                        if (hit_alpha < 1.0f) {
+                            if (MARK) mark_dependency(P, e_x, e_y, e_z, mark_priority);
+                            if (!MARK) {
+                                float sv0 = 0.f, sv1 = 0.f, sv2 = 0.f;
+                                if (e_face != 0) {
+                                    ahead = S.light[cidx];
+                                    have = true;
+                                    sv0 = lut[ahead & 255]; sv1 = lut[(ahead >> 8) & 255]; sv2 = lut[(ahead >> 16) & 255];
+                                }
+                                const float kh = ps_clamped(hit_alpha), ka = ps_clamped(alpha);
+                                const float l0 = __ldg(&ev->emission[0]) + ps_mul(sv0, kh);
+                                const float l1 = __ldg(&ev->emission[1]) + ps_mul(sv1, kh);
+                                const float l2 = __ldg(&ev->emission[2]) + ps_mul(sv2, kh);
+                                if (tcount < (uint32_t)LIGHT_CHAIN_K)
+                                    terms[cur * LIGHT_CHAIN_SLOTS + tcount] = make_float4(ps_mul(ps_mul(l0, ka), kw), ps_mul(ps_mul(l1, ka), kw), ps_mul(ps_mul(l2, ka), kw), 0.0f);
+                                else over = true;
+                                tcount++;
+                            }
+                            alpha *= 1.0f - hit_alpha;
+                        }
+                    }
+                }
+                if (!(alpha > 0.0f)) ended = true;
+            }
+            if (ended) {
+                if (!MARK) {   // end_of_ray (bundle > 0 here)
+                    const float4 sky = __ldg(P.sky_term + node);
+                    const float ka = ps_clamped(alpha), kb = ps_clamped(bundle);
+                    if (tcount < (uint32_t)LIGHT_CHAIN_K)
+                        terms[cur * LIGHT_CHAIN_SLOTS + tcount] = make_float4(ps_mul(ps_mul(sky.x, ka), kb), ps_mul(ps_mul(sky.y, ka), kb), ps_mul(ps_mul(sky.z, ka), kb), bundle);
+                    else over = true;
+                    tcount++;
+                    sh.cnt_entry[cur] = (uint8_t)(tcount < (uint32_t)LIGHT_CHAIN_K ? tcount : (uint32_t)LIGHT_CHAIN_K);
+                }
+                cur = NONE;
+            } else if (--remaining == 0u) {
+                // alive at the chain's last node: its children are walked, then the rest of its bundle ends here
+                const uint32_t n_children = c_meta & 0xffffu, br = c_meta >> 16;
+                if (!MARK) {
+                    float csum = 0.0f;
+                    for (uint32_t j = 0; j < n_children; j++) {
+                        const uint4 *cp = reinterpret_cast<const uint4 *>(P.chains + c_first_child + j);
+                        const uint4 c0 = __ldg(cp);
+                        const uint2 c1 = __ldg(reinterpret_cast<const uint2 *>(cp + 1));
+                        const float cw[6] = {__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z),
+                                             __uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y)};
+                        float prod[6];
+#pragma unroll
+                        for (int f = 0; f < 6; f++) prod[f] = cw[f] * dw[f];
+                        csum += fm_sum(prod);
+                    }
+                    const float rem = fmaxf(bundle - csum, 0.0f);
+                    if (rem > 0.0f) {
+                        const float4 sky = __ldg(P.sky_term + node);
+                        const float ka = ps_clamped(alpha), kb = ps_clamped(rem);
+                        terms[cur * LIGHT_CHAIN_SLOTS + LIGHT_CHAIN_K] = make_float4(ps_mul(ps_mul(sky.x, ka), kb), ps_mul(ps_mul(sky.y, ka), kb), ps_mul(ps_mul(sky.z, ka), kb), rem);
+                        sh.cnt_pop[cur] = 1;
+                    }
+                    sh.cnt_entry[cur] = (uint8_t)(tcount < (uint32_t)LIGHT_CHAIN_K ? tcount : (uint32_t)LIGHT_CHAIN_K);
+                }
+                if (n_children) {
+                    sh.br_alpha[br] = alpha;
+                    sh.br_have[br] = have ? 1 : 0;
+                    sh.br_ahead[br] = ahead;
+                    push_n = n_children;
+                    push_first = c_first_child;
+                }
+                cur = NONE;
+            } else {
+                node++;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, off);
+    if (visits_out) *visits_out = visits;
+    if (MARK) return 0u;
+    if (__any_sync(0xffffffffu, over)) { *overflowed = true; return 0u; }
+    __syncwarp();
+
+    // ---- phase 2: the terms in depth-first order; lane (k & 3) of every quad carries channel k ----
+    float acc = 0.0f;
+    const unsigned ch = lane & 3u;
+    for (uint32_t p0 = 0; p0 < P.n_euler; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        uint32_t c = 0, kind = 0, cnt = 0;
+        if (p < P.n_euler) {
+            const uint32_t e = __ldg(P.euler + p);
+            c = e & 0x7fffu; kind = e >> 15;
+            cnt = kind ? sh.cnt_pop[c] : sh.cnt_entry[c];
+        }
+        if (__ballot_sync(0xffffffffu, cnt != 0u) == 0u) continue;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)lane >= off) inc += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t at = inc - cnt;
+        for (uint32_t k = 0; k < cnt; k++) sh.list[at + k] = c * LIGHT_CHAIN_SLOTS + (kind ? (uint32_t)LIGHT_CHAIN_K : k);
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t m = total - base < 32u ? total - base : 32u;
+            if (lane < m) sh.stage[lane] = terms[sh.list[base + lane]];
+            __syncwarp();
+            const float *st = reinterpret_cast<const float *>(sh.stage);
+            for (uint32_t j = 0; j < m; j++) acc = acc + st[j * 4 + ch];
+            __syncwarp();
+        }
+    }
+    Accum a;
+    a.in0 = __shfl_sync(0xffffffffu, acc, 0);
+    a.in1 = __shfl_sync(0xffffffffu, acc, 1);
+    a.in2 = __shfl_sync(0xffffffffu, acc, 2);
+    a.total = __shfl_sync(0xffffffffu, acc, 3);
+    // LightBuffer::finish (updater.rs:932-944)
+    const float scale = ps_clamped(1.0f / fmaxf(a.total, 1.0f));
+    if (a.total > 0.0f)
+        return scalar_in_t(S.tables, ps_mul(a.in0, scale)) | (scalar_in_t(S.tables, ps_mul(a.in1, scale)) << 8) |
+               (scalar_in_t(S.tables, ps_mul(a.in2, scale)) << 16) | (255u << 24);
+    return TX_NO_RAYS;
 }
 
 }  // namespace aicb_light
