@@ -19,7 +19,7 @@ using namespace aicb_light;
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int CHAIN_WALK_BLOCKS_PER_SM = 5;   // 4 warps and 40 KB of shared memory each
+constexpr int CHAIN_WALK_BLOCKS_PER_SM = 6;   // 4 warps, 80 registers, 26 KB of shared memory each (8 blocks of 64 registers: -15 %)
 
 struct TreeNode {
     int8_t cube[3];
@@ -220,8 +220,13 @@ aicb_status ensure_chart(aicb_ctx *ctx) {
         ctx->n_chains = (uint32_t)t.chains.size();
         ctx->n_euler = (uint32_t)t.euler.size();
         // one set of term slots per resident warp of the chain walk
-        ctx->chain_walk_blocks = (uint32_t)ctx->num_sms * CHAIN_WALK_BLOCKS_PER_SM;
-        CU(cudaMalloc(&ctx->d_term_scratch, (size_t)ctx->chain_walk_blocks * 4 * LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS * sizeof(float4)));
+        int per_sm = CHAIN_WALK_BLOCKS_PER_SM;
+        if (const char *e = getenv("AICB_LIGHT_CTAS")) {   // experiments: fewer resident blocks
+            const int v = atoi(e);
+            if (v >= 1 && v < per_sm) per_sm = v;
+        }
+        ctx->chain_walk_blocks = (uint32_t)ctx->num_sms * (uint32_t)per_sm;
+        CU(cudaMalloc(&ctx->d_term_scratch, (size_t)ctx->num_sms * CHAIN_WALK_BLOCKS_PER_SM * 4 * LIGHT_WARP_SCRATCH_F4 * sizeof(float4)));
     }
     std::vector<LightChartNode> chart = build_chart();
     const std::vector<LightNodePre> &pre = chart_preorder_host();
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(128, CHAIN_WALK_BLOCKS_PER_SM) k_walk_chains(c
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     ChainShared &sh = s_sh[wib];
-    float4 *terms = MARK ? nullptr : P.term_scratch + (size_t)(blockIdx.x * 4 + wib) * (LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS);
+    float4 *terms = P.term_scratch + (size_t)(blockIdx.x * 4 + wib) * LIGHT_WARP_SCRATCH_F4;
     if (!explicit_cubes) n = MARK ? P.scalars[6] : P.scalars[0];
     unsigned long long total_visits = 0;
     for (;;) {

@@ -66,6 +66,8 @@ constexpr int LIGHT_MAX_CHAINS = 1056;      // 1043, padded
 constexpr int LIGHT_MAX_BRANCHES = 448;     // 441 chains have children
 constexpr int LIGHT_CHAIN_K = 8;            // entry terms a chain can hold (more: the cube takes the lockstep walk)
 constexpr int LIGHT_CHAIN_SLOTS = LIGHT_CHAIN_K + 1;   // + the term of the pop at the chain's end
+// per-warp scratch in global memory: the term slots, then one light_ahead_cache word per branch slot (rarely used)
+constexpr int LIGHT_WARP_SCRATCH_F4 = LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS + LIGHT_MAX_BRANCHES / 4;
 
 constexpr uint32_t LB_ALL_OPAQUE = 1u << 6, LB_VISIBLE = 1u << 7, LB_EMISSIVE = 1u << 8;
 constexpr int LIGHT_MAX_DEPTH = 224;  // longest chart path is 219 (rays end at t = 127, generator.rs:101)
@@ -462,14 +464,18 @@ __device__ uint32_t compute_light_lockstep(const LightParams &P, const float *lu
 // dependency re-queue, updater.rs:355-360); no terms.
 // ---------------------------------------------------------------------------------------------------------------
 struct ChainShared {
-    uint16_t queue[LIGHT_MAX_CHAINS];
-    float br_alpha[LIGHT_MAX_BRANCHES];
-    uint32_t br_ahead[LIGHT_MAX_BRANCHES];
-    uint8_t br_have[LIGHT_MAX_BRANCHES];
+    union {
+        struct {   // phase 1
+            uint16_t queue[LIGHT_MAX_CHAINS];
+            float br_alpha[LIGHT_MAX_BRANCHES];   // alpha at the branching node (> 0); negated when it left a light_ahead_cache
+        };
+        struct {   // phase 2
+            float4 stage[128];
+            uint16_t list[128 * LIGHT_CHAIN_K];
+        };
+    };
     uint8_t cnt_entry[LIGHT_MAX_CHAINS];
     uint8_t cnt_pop[LIGHT_MAX_CHAINS];
-    float4 stage[32];
-    uint32_t list[32 * LIGHT_CHAIN_K];
 };
 
 // returns the new PackedLight texel (every lane); *overflowed: some chain had more terms than its slots hold
@@ -521,6 +527,7 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
         }
     }
     const int max_d2 = (int)(P.max_distance * P.max_distance);
+    uint32_t *br_ahead = reinterpret_cast<uint32_t *>(terms + LIGHT_MAX_CHAINS * LIGHT_CHAIN_SLOTS);
     if (!MARK) {   // no chain has a term yet
         uint32_t *z0 = reinterpret_cast<uint32_t *>(sh.cnt_entry), *z1 = reinterpret_cast<uint32_t *>(sh.cnt_pop);
         for (unsigned k = lane; k < LIGHT_MAX_CHAINS / 4; k += 32) { z0[k] = 0u; z1[k] = 0u; }
@@ -538,6 +545,18 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
     bool have = false, over = false;
     uint32_t ahead = 0;
     uint32_t c_first_child = 0, c_meta = 0;   // n_children | branch << 16
+    // the lane's node pipeline: the current node's cube offset, index and block id are in registers when its step
+    // begins (requested one step earlier), the next node's offset too (requested two steps earlier)
+    uchar4 r4c = make_uchar4(0, 0, 0, 0), r4n = make_uchar4(0, 0, 0, 0);
+    bool inb_c = false;
+    uint32_t cidx_c = 0, id_c = 0;
+    auto locate = [&](const uchar4 r4, uint32_t &cidx, uint32_t &id) -> bool {
+        const int x = ox + (int)(int8_t)r4.x, y = oy + (int)(int8_t)r4.y, z = oz + (int)(int8_t)r4.z;
+        id = 0;
+        if (!cube_index(S, x, y, z, &cidx)) return false;
+        id = block_id_at(S, cidx);
+        return true;
+    };
     for (;;) {
         // children of the chains that ended alive in the last iteration
         {
@@ -580,10 +599,19 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
                 c_meta = n_children | (br << 16);
                 tcount = 0;
                 if (pb == 0xffffu) { alpha = 1.0f; have = false; ahead = 0; }
-                else { alpha = sh.br_alpha[pb]; have = sh.br_have[pb] != 0; ahead = sh.br_ahead[pb]; }
+                else {
+                    alpha = sh.br_alpha[pb];
+                    have = alpha < 0.0f;
+                    ahead = 0;
+                    if (have) { alpha = -alpha; ahead = br_ahead[pb]; }
+                }
                 if (!(bundle > 0.0f)) {   // the walk enters the chain's first node and leaves at once (updater.rs:447-450)
                     visits++;
                     cur = NONE;
+                } else {
+                    r4c = __ldg(P.node_rel + node);
+                    r4n = remaining > 1u ? __ldg(P.node_rel + node + 1) : r4c;
+                    inb_c = locate(r4c, cidx_c, id_c);
                 }
             }
             const uint32_t takers = __popc(m);
@@ -592,12 +620,17 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
         if (__ballot_sync(0xffffffffu, cur != NONE) == 0u) break;
         if (cur != NONE) {
             visits++;
-            const uchar4 r4 = __ldg(P.node_rel + node);
+            // requests for the steps to come
+            bool inb_n = false;
+            uint32_t cidx_n = 0, id_n = 0;
+            if (remaining > 1u) inb_n = locate(r4n, cidx_n, id_n);
+            const uchar4 r4nn = remaining > 2u ? __ldg(P.node_rel + node + 2) : r4n;
+            const uchar4 r4 = r4c;
             const int relx = (int)(int8_t)r4.x, rely = (int)(int8_t)r4.y, relz = (int)(int8_t)r4.z;
             const bool too_far = relx * relx + rely * rely + relz * relz > max_d2;   // updater.rs:452-455
             const int e_x = ox + relx, e_y = oy + rely, e_z = oz + relz;
-            uint32_t cidx = 0;
-            const bool inb = cube_index(S, e_x, e_y, e_z, &cidx);
+            const uint32_t cidx = cidx_c;
+            const bool inb = inb_c;
             bool ended = false;      // the ray bundle ends here: end_of_ray with the whole bundle
             if (too_far || !inb) {
                 ended = true;
@@ -605,7 +638,7 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
                 // ---- LightBuffer::traverse ----
                 const int dir = (int)r4.w;
                 const int e_face = node == 0u ? 0 : ((dir < 3) ? dir + 3 : dir - 3) + 1;
-                const LightBlockDev *ev = &P.blocks[block_id_at(S, cidx)];
+                const LightBlockDev *ev = &P.blocks[id_c];
                 const uint32_t fl = __ldg(&ev->flags);
                 const float e_alpha = alpha;
                 const bool e_have_prev = have;
@@ -704,15 +737,16 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
                     sh.cnt_entry[cur] = (uint8_t)(tcount < (uint32_t)LIGHT_CHAIN_K ? tcount : (uint32_t)LIGHT_CHAIN_K);
                 }
                 if (n_children) {
-                    sh.br_alpha[br] = alpha;
-                    sh.br_have[br] = have ? 1 : 0;
-                    sh.br_ahead[br] = ahead;
+                    sh.br_alpha[br] = have ? -alpha : alpha;
+                    if (have) br_ahead[br] = ahead;
                     push_n = n_children;
                     push_first = c_first_child;
                 }
                 cur = NONE;
             } else {
                 node++;
+                r4c = r4n; r4n = r4nn;
+                inb_c = inb_n; cidx_c = cidx_n; id_c = id_n;
             }
         }
         __syncwarp();
@@ -725,30 +759,51 @@ __device__ uint32_t compute_light_chains(const LightParams &P, const float *lut,
     __syncwarp();
 
     // ---- phase 2: the terms in depth-first order; lane (k & 3) of every quad carries channel k ----
+    // 128 positions of the Euler tour at a time: their terms' slots are listed in order, then fetched 128 at a time
+    // (four independent loads per lane) into shared memory and added one after the other.
     float acc = 0.0f;
     const unsigned ch = lane & 3u;
-    for (uint32_t p0 = 0; p0 < P.n_euler; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        uint32_t c = 0, kind = 0, cnt = 0;
-        if (p < P.n_euler) {
-            const uint32_t e = __ldg(P.euler + p);
-            c = e & 0x7fffu; kind = e >> 15;
-            cnt = kind ? sh.cnt_pop[c] : sh.cnt_entry[c];
-        }
-        if (__ballot_sync(0xffffffffu, cnt != 0u) == 0u) continue;
-        uint32_t inc = cnt;
+    for (uint32_t p0 = 0; p0 < P.n_euler; p0 += 128) {
+        uint32_t c[4], kind[4], cnt[4];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-            if ((int)lane >= off) inc += t;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t p = p0 + 32u * q + lane;
+            c[q] = 0; kind[q] = 0; cnt[q] = 0;
+            if (p < P.n_euler) {
+                const uint32_t e = __ldg(P.euler + p);
+                c[q] = e & 0x7fffu; kind[q] = e >> 15;
+                cnt[q] = kind[q] ? sh.cnt_pop[c[q]] : sh.cnt_entry[c[q]];
+            }
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t at = inc - cnt;
-        for (uint32_t k = 0; k < cnt; k++) sh.list[at + k] = c * LIGHT_CHAIN_SLOTS + (kind ? (uint32_t)LIGHT_CHAIN_K : k);
+        if (__ballot_sync(0xffffffffu, (cnt[0] | cnt[1] | cnt[2] | cnt[3]) != 0u) == 0u) continue;
+        uint32_t total = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t inc = cnt[q];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)lane >= off) inc += t;
+            }
+            const uint32_t at = total + inc - cnt[q];
+            for (uint32_t k = 0; k < cnt[q]; k++)
+                sh.list[at + k] = (uint16_t)(c[q] * LIGHT_CHAIN_SLOTS + (kind[q] ? (uint32_t)LIGHT_CHAIN_K : k));
+            total += __shfl_sync(0xffffffffu, inc, 31);
+        }
         __syncwarp();
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t m = total - base < 32u ? total - base : 32u;
-            if (lane < m) sh.stage[lane] = terms[sh.list[base + lane]];
+        for (uint32_t base = 0; base < total; base += 128) {
+            const uint32_t m = total - base < 128u ? total - base : 128u;
+            float4 t[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t j = 32u * r + lane;
+                if (j < m) t[r] = terms[sh.list[base + j]];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t j = 32u * r + lane;
+                if (j < m) sh.stage[j] = t[r];
+            }
             __syncwarp();
             const float *st = reinterpret_cast<const float *>(sh.stage);
             for (uint32_t j = 0; j < m; j++) acc = acc + st[j * 4 + ch];
