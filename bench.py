@@ -307,7 +307,7 @@ def run_light(args):
                    "sharding": "none (light propagation runs on one GPU; SURVEY 8(e) replicas only)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "kernel": "k_compute + k_mark (lockstep chart walk)", "kernel_ms": 1e3 * dev_s / args.steps,
+                     "kernel": "k_walk_chains<compute> + k_walk_chains<mark> (chart walk, one warp per cube)", "kernel_ms": 1e3 * dev_s / args.steps,
                      "algorithmic_bytes_per_step": int(light_bytes(tot_u, tot_v) / args.steps),
                      "formula": "50 B per chart node visited + 4 B per cube update (SURVEY 8(d), per-hit term not counted)"},
         "e2e": {"value": tot_u / e2e_s, "unit": "cube-updates/s", "h2d_bytes_per_step": C4_EDITS * 14,
