@@ -255,6 +255,23 @@ static kernel_fn select_kernel(bool volumetric, bool wide, bool aux) {
     return nullptr;
 }
 
+// Launch with (or without) programmatic stream serialization: see grid_dependency_sync() in trace_kernel.cuh.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_after(bool overlap, void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // One edited cube of aicb_scene_update_cubes: linear index, encoded cell, optional light texel.
 struct CubeDelta {
     uint32_t idx, cell, light, has_light;
@@ -528,14 +545,16 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
                 P.debug_warp_times = (unsigned long long *)ctx->d_debug;
                 ctx->debug_warps = (uint32_t)grid * WARPS_PER_BLOCK;
             }
-            k<<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(P, n);
+            // the frame's kernels follow each other with programmatic dependent launch (no events between them)
+            const bool overlap = ctx->dependent_launch && !stage && !prof && !bounce;
+            CU(launch_after(overlap, k, (unsigned)grid, WARPS_PER_BLOCK * 32, stream, P, n));
             P.debug_warp_times = nullptr;
             if (stage) cudaEventRecord(ctx->ev_k[2], stream);
             switch (lc) {
-                case LC_NONE: shade_kernel<LC_NONE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
-                case LC_FLAT: shade_kernel<LC_FLAT><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
-                case LC_BOUNCE: shade_kernel<LC_BOUNCE><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
-                default: shade_kernel<LC_INTERP><<<ctx->num_sms * 8, 128, 0, stream>>>(P); break;
+                case LC_NONE: CU(launch_after(overlap, shade_kernel<LC_NONE>, ctx->num_sms * 8, 128, stream, P)); break;
+                case LC_FLAT: CU(launch_after(overlap, shade_kernel<LC_FLAT>, ctx->num_sms * 8, 128, stream, P)); break;
+                case LC_BOUNCE: CU(launch_after(overlap, shade_kernel<LC_BOUNCE>, ctx->num_sms * 8, 128, stream, P)); break;
+                default: CU(launch_after(overlap, shade_kernel<LC_INTERP>, ctx->num_sms * 8, 128, stream, P)); break;
             }
             if (bounce) {
                 const unsigned tb = (n + 127) / 128;
@@ -556,7 +575,7 @@ static aicb_status launch_trace(aicb_scene *sc, const aicb_camera *cam, const ai
             }
             if (stage) cudaEventRecord(ctx->ev_k[3], stream);
             const uint32_t n_pixels = n / P.n_samples;
-            encode_kernel<<<(n_pixels + 127) / 128, 128, 0, stream>>>(P, n);
+            CU(launch_after(overlap, encode_kernel, (n_pixels + 127) / 128, 128, stream, P, n));
             if (stage) cudaEventRecord(ctx->ev_k[4], stream);
         }
         CU(cudaGetLastError());
@@ -665,6 +684,7 @@ aicb_status aicb_ctx_create(int device_id, aicb_ctx **out) {
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     c->profile_kernels = getenv("AICB_PROFILE_KERNELS") != nullptr;
+    if (const char *e = getenv("AICB_PDL")) c->dependent_launch = atoi(e) != 0;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&c->ev_k[i]));
     CU(cudaEventCreateWithFlags(&c->ev_delta, cudaEventDisableTiming));
     // the frame counters (8 x u64) and the per-chunk counters (4 + N_BINS x u32) share one allocation: one memset per frame

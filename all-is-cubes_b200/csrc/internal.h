@@ -28,6 +28,7 @@ struct aicb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // AICB_PROFILE_KERNELS
     bool profile_kernels = false;
+    bool dependent_launch = true; // programmatic dependent launch between the kernels of a frame (AICB_PDL=0 disables)
     bool stage_timing = true;    // record the per-kernel events of a frame (aicb_render_info::stage_ms)
     void *h_delta = nullptr, *d_delta = nullptr;  // staging of aicb_scene_update_cubes batches (pinned / device)
     size_t h_delta_bytes = 0;

@@ -873,15 +873,23 @@ aicb_status aicb_light_compute(aicb_scene *s, const int32_t (*cubes)[3], size_t 
     int32_t *d_cubes = nullptr;
     CU(cudaMalloc(&d_cubes, n * 12));
     CU(cudaMemcpy(d_cubes, cubes, n * 12, cudaMemcpyHostToDevice));
+    cudaMemsetAsync(s->d_scalars, 0, 16 * 4, s->ctx->stream);
     if (use_chain_walk()) {
-        cudaMemsetAsync(s->d_scalars + 7, 0, 3 * 4, s->ctx->stream);
         k_walk_chains<false><<<s->ctx->chain_walk_blocks, 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
         k_compute_overflow<<<s->ctx->num_sms * 8, 128, 0, s->ctx->stream>>>(P, d_cubes);
     } else {
         k_compute<<<(unsigned)((n + 127) / 128), 128, 0, s->ctx->stream>>>(P, (uint32_t)n, d_cubes);
     }
+    uint32_t h[16];
     cudaError_t e = cudaMemcpyAsync(out, s->d_new_light, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, s->d_scalars, sizeof h, cudaMemcpyDeviceToHost, s->ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
+    if (e == cudaSuccess) {
+        s->light_stats[0] = n;
+        s->light_stats[1] = (uint64_t)h[4] | ((uint64_t)h[5] << 32);
+        s->light_stats[2] = h[9];   // cubes that took the lockstep walk (a chain with more terms than its slots)
+        s->light_stats[3] = 0;
+    }
     cudaFree(d_cubes);
     if (e != cudaSuccess) return aicb_cuda_fail(e, "light compute");
     return AICB_OK;

@@ -230,6 +230,16 @@ constexpr int MIN_BLOCKS_PER_SM = AICB_MIN_BLOCKS;
 
 constexpr double D_INF = __builtin_huge_val();
 
+// Programmatic dependent launch: the frame's kernels are launched back to back with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's blocks may become resident while the previous
+// kernel is still draining; every kernel lets its successor in at once and waits here — until the previous grid has
+// completed and its writes are visible — before it touches anything that grid produced.  Without the attribute both
+// instructions do nothing.
+__device__ __forceinline__ void grid_dependency_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct Ray {
     double ox, oy, oz, dx, dy, dz;   // original ray
     double tdx, tdy, tdz;            // t_delta = 1/|d| (raycast.rs:769)
@@ -775,6 +785,7 @@ AICB_DEV bool task_pixel(const TraceParams &P, uint32_t pixel_task, uint32_t *px
 // Raycaster::new().within(space bounds) (raycast.rs:196-230, 632-704).  One thread per ray, fully convergent.
 // ======================================================================================================
 static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    grid_dependency_sync();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = i < n_chunk_tasks;
     const uint32_t task = P.task_base + i;
@@ -897,6 +908,7 @@ static __global__ void __launch_bounds__(128) gen_kernel(const __grid_constant__
 template <bool VOLUMETRIC, bool WIDE, bool AUX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, AUX ? 1 : MIN_BLOCKS_PER_SM)
 trace_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    grid_dependency_sync();
     const DeviceScene &S = P.scene;
     const int lane = threadIdx.x & 31;
     constexpr float F_NEG_INF = -__builtin_huge_valf();
@@ -1502,6 +1514,7 @@ template <int LC>
 __global__ void __launch_bounds__(128) shade_kernel(const __grid_constant__ TraceParams P) {
     __shared__ float s_lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.scene.tables[i];
+    grid_dependency_sync();
     __syncthreads();
     const DeviceScene &S = P.scene;
     uint32_t n = *P.hit_counter;
@@ -1598,6 +1611,7 @@ AICB_DEV double uniform_m1_1(unsigned long long s[4]) {
 // Which hit, if any, a ray bounces at: the chain walk of encode_kernel (same stop rule) — the hit that ends the ray,
 // if shade<LC_BOUNCE> marked it fully opaque.  Seeds the ray's RNG from its direction (sr.rs:165-178).
 static __global__ void __launch_bounds__(128) bounce_select_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    grid_dependency_sync();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chunk_tasks) return;
     TaskOut o;
@@ -1637,6 +1651,7 @@ static __global__ void __launch_bounds__(128) bounce_select_kernel(const __grid_
 // The secondary ray of pass `bounce_pass` for every ray that bounces (surface.rs:131-153): from the intersection
 // point, 1e-4 off the surface, towards normal + UnitSphere sample.
 static __global__ void __launch_bounds__(128) bounce_gen_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
+    grid_dependency_sync();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chunk_tasks) return;
     const uint32_t req = P.bounce_req[i];
@@ -1725,6 +1740,7 @@ static __global__ void __launch_bounds__(128) bounce_resolve_kernel(const __grid
 static __global__ void __launch_bounds__(128) encode_kernel(const __grid_constant__ TraceParams P, uint32_t n_chunk_tasks) {
     __shared__ float s_thr[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_thr[i] = P.scene.tables[256 + i];
+    grid_dependency_sync();
     __syncthreads();
     const DeviceScene &S = P.scene;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // pixel task within the chunk

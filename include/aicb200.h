@@ -372,7 +372,9 @@ aicb_status aicb_light_edit_and_propagate(aicb_scene *, const int32_t (*cubes)[3
 aicb_status aicb_light_download(aicb_scene *, uint8_t (*out)[4], size_t n_texels);
 /* Counters of the last propagation (aicb_light_evaluate / aicb_light_edit_and_propagate) on this scene:
  * out[0] cube updates (compute_light calls, updater.rs:368), out[1] chart nodes visited by them, out[2] relaxation
- * rounds queued, out[3] device time of the propagation in microseconds (CUDA events on the context's stream). */
+ * rounds queued, out[3] device time of the propagation in microseconds (CUDA events on the context's stream).
+ * After aicb_light_compute: out[0] cubes computed, out[1] chart nodes visited, out[2] cubes whose walk needed more
+ * term slots than the chain walk holds and took the lockstep walk instead, out[3] 0. */
 aicb_status aicb_light_stats(const aicb_scene *, uint64_t out[4]);
 
 #ifdef __cplusplus

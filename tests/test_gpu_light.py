@@ -193,3 +193,35 @@ def test_c4_full_size_compute_light_is_bit_exact_on_a_sample():
     ol.set_field(field)
     ref = ol.compute(cubes)
     assert np.array_equal(gpu, ref), f"{(gpu != ref).any(axis=1).sum()} of {len(cubes)} cubes differ"
+
+
+def test_compute_light_through_translucent_slabs_takes_the_lockstep_walk_and_stays_exact():
+    """A chain of the chart holds 8 entry terms in the chain walk; a ray that crosses more than four translucent
+    blocks needs more (two terms per block) and its cube is recomputed by the lockstep walk.  Both walks must give the
+    oracle's bits, and the overflow path must actually have run (`rounds` of light_stats after light_compute = cubes
+    that took it)."""
+    n = 14
+    ids = np.zeros((n, n, n), dtype=np.uint16)
+    ids[:, 0, :] = 1
+    ids[3:11, 2:9, 6] = 2          # a wall of glass ...
+    ids[3:11, 2:9, 7] = 3          # ... two more layers behind it
+    ids[3:11, 2:9, 8] = 2
+    ids[5:9, 9:13, 3:12] = 3       # a translucent beam rays travel along
+    ids[6, 4, 2] = 4               # an emitter in front of the wall
+    blocks = [Block.air(), Block(color=(0.7, 0.7, 0.7, 1.0)), Block(color=(0.3, 0.6, 0.9, 0.125)),
+              Block(color=(0.9, 0.5, 0.2, 0.0625), emission=(0.05, 0.02, 0.0)), Block(color=(0.1, 0.1, 0.1, 1.0), emission=(6.0, 5.0, 3.0))]
+    light = np.zeros((n, n, n, 4), dtype=np.uint8)
+    light[..., 3] = NO_RAYS
+    space = Space((0, 0, 0), ids, blocks, light=light, sky_colors=scenes.OCTANT_SKY, light_max_distance=20)
+    ol = orc.OracleLight(space)
+    ol.fast_evaluate()
+    ol.evaluate(0, max_updates=1500)
+    field = ol.field()
+    sp2 = Space(space.lower, space.block_ids, space.blocks, light=field, sky_colors=space.sky_colors, light_max_distance=20)
+    cubes = all_cubes(space)
+    rt = SpaceRaytracer(sp2, GraphicsOptions())
+    gpu = rt.light_compute(cubes)
+    ref = ol.compute(cubes)
+    assert np.array_equal(gpu, ref), np.argwhere((gpu != ref).any(axis=1))[:5]
+    took_lockstep = rt.light_stats()["rounds"]
+    assert 0 < took_lockstep < len(cubes), took_lockstep
