@@ -202,8 +202,16 @@ const ChainTables &chain_tables_host() {
     return tables;
 }
 
-aicb_status ensure_chart(aicb_ctx *ctx) {
-    if (ctx->d_chart) return AICB_OK;
+void free_chart(aicb_ctx *c) {
+    void **ptrs[] = {(void **)&c->d_chart, (void **)&c->d_chart_pre, (void **)&c->d_chains, (void **)&c->d_node_rel,
+                     (void **)&c->d_euler, (void **)&c->d_term_scratch};
+    for (void **p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+}
+
+aicb_status upload_chart(aicb_ctx *ctx) {
     {
         const ChainTables &t = chain_tables_host();
         if (t.chains.size() > (size_t)LIGHT_MAX_CHAINS || t.chains.size() >= 0x8000u)
@@ -236,6 +244,13 @@ aicb_status ensure_chart(aicb_ctx *ctx) {
     CU(cudaMemcpy(ctx->d_chart, chart.data(), chart.size() * sizeof(LightChartNode), cudaMemcpyHostToDevice));
     ctx->chart_nodes = (uint32_t)chart.size();
     return AICB_OK;
+}
+
+aicb_status ensure_chart(aicb_ctx *ctx) {
+    if (ctx->d_chart) return AICB_OK;   // (d_chart is the last allocation of upload_chart)
+    const aicb_status st = upload_chart(ctx);
+    if (st != AICB_OK) free_chart(ctx);   // a later call starts over instead of leaking the tables that did fit
+    return st;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -824,14 +839,7 @@ void aicb_light_scene_free(aicb_scene *s) {
     if (s->d_sky_term) cudaFree(s->d_sky_term);
 }
 
-void aicb_light_ctx_free(aicb_ctx *c) {
-    if (c->d_chart) cudaFree(c->d_chart);
-    if (c->d_chart_pre) cudaFree(c->d_chart_pre);
-    if (c->d_chains) cudaFree(c->d_chains);
-    if (c->d_node_rel) cudaFree(c->d_node_rel);
-    if (c->d_euler) cudaFree(c->d_euler);
-    if (c->d_term_scratch) cudaFree(c->d_term_scratch);
-}
+void aicb_light_ctx_free(aicb_ctx *c) { free_chart(c); }
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
