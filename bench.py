@@ -284,7 +284,7 @@ def run_light(args):
         dev_s += st["device_seconds"]
         e2e_s += wall
         render_ms.append(img.info.kernel_ms)
-        launches += 2 + 5 * st["rounds"] + 4
+        launches += 2 + 7 * st["rounds"] + 4   # edits + tile rebuild; 7 kernels per relaxation round; the 4 kernels of the re-render
     clocks = sampler.stop()
     value = tot_u / dev_s
     peaks = {}
@@ -341,6 +341,12 @@ class ClockSampler:
         self.samples = []
         self.proc = None
         self.device_index = device_index
+        self.first = 0
+
+    def mark(self):
+        """The timed region begins: samples taken before this point (nvidia-smi needs ~0.1 s to start streaming, so it
+        is started before the warm-up) are not reported."""
+        self.first = len(self.samples)
 
     def start(self):
         try:
@@ -366,7 +372,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[self.first:]:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 6:
                 continue
@@ -507,6 +513,9 @@ def run_ours(args):
     # ---- warm-up, then the timed region ------------------------------------------------------------
     # one blocking render first: it sizes the hit stream for this workload (the blocking call re-issues the frame when
     # the stream overflows; the asynchronous calls below would report AICB_ERR_RETRY instead)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # (streams a sample every 20 ms from here on; the ones of the timed region are reported)
     sizing = torch.empty((n_local, 4), dtype=torch.uint8).pin_memory()
     check(lib.aicb_render_srgb8(rt.handle, C.byref(cam.data), C.byref(o_abi), C.byref(shard), sizing.data_ptr(), n_local, None))
     del sizing
@@ -515,9 +524,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     check(lib.aicb_render_finish(rt.handle, C.byref(info)))
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     check(lib.aicb_ctx_stage_timing(ctx.handle, 0))   # the timed frames carry no per-kernel event records
     total_ms = timed(device_step, args.steps)
     # kernel-only duration of the last frame from the library's own events (same stream); a frame that overflowed its
