@@ -440,6 +440,21 @@ def light_chart():
     return w, ch
 
 
+def light_chart_chains():
+    """The chart as the chain walk sees it: (preorder [n] -> node of light_chart(), chains [c,6] u32 = first node in
+    preorder, nodes, child chains, first child chain, parent's branch slot, own branch slot; euler [2c] u16)."""
+    lib = load_library()
+    lib.aicb_light_chart_chains.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.aicb_light_chart_chains.restype = C.c_uint32
+    n_nodes = lib.aicb_light_chart(None, None)
+    n_chains = lib.aicb_light_chart_chains(None, None, None)
+    pre = np.zeros(n_nodes, dtype=np.uint32)
+    chains = np.zeros((n_chains, 6), dtype=np.uint32)
+    euler = np.zeros(2 * n_chains, dtype=np.uint16)
+    lib.aicb_light_chart_chains(pre.ctypes.data, chains.ctypes.data, euler.ctypes.data)
+    return pre, chains, euler
+
+
 def srgb8_to_linear(rgb) -> tuple:
     """component_from_srgb8 (color.rs): f32 sRGB decode, used only for named palette constants."""
     out = []

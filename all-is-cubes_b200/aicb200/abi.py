@@ -148,6 +148,7 @@ EXPORTED_SYMBOLS = [
     "aicb_eye_for_look_at",
     "aicb_camera_project_ndc",
     "aicb_light_chart",
+    "aicb_light_chart_chains",
     "aicb_light_fast_evaluate",
     "aicb_light_compute",
     "aicb_light_evaluate",

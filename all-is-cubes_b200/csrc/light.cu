@@ -95,7 +95,7 @@ std::vector<LightChartNode> build_chart() {
 // The chart in depth-first preorder, as the lockstep walk (light_kernel.cuh) steps through it: children in Face6
 // order (the order walk_ray_tree recurses in, updater.rs:500), each node with its depth, its cube relative to the
 // origin, the direction of the step from its parent and the index one past its last descendant.
-std::vector<LightNodePre> build_chart_preorder(const std::vector<LightChartNode> &flat) {
+std::vector<LightNodePre> build_chart_preorder(const std::vector<LightChartNode> &flat, std::vector<uint32_t> *flat_index = nullptr) {
     std::vector<LightNodePre> pre;
     pre.reserve(flat.size());
     struct Item { uint32_t node; int8_t rel[3]; uint8_t depth; uint8_t dir; uint32_t slot; uint8_t next_child; };
@@ -111,6 +111,7 @@ std::vector<LightNodePre> build_chart_preorder(const std::vector<LightChartNode>
             n.depth = it.depth;
             n.end_dir = (uint32_t)it.dir << 29;
             pre.push_back(n);
+            if (flat_index) flat_index->push_back(it.node);
         }
         int f = it.next_child;
         while (f < 6 && flat[it.node].child[f] == 0) f++;
@@ -845,6 +846,23 @@ void aicb_light_ctx_free(aicb_ctx *c) { free_chart(c); }
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
+
+uint32_t aicb_light_chart_chains(uint32_t *preorder, uint32_t (*chains)[6], uint16_t *euler) {
+    const ChainTables &t = chain_tables_host();
+    if (preorder) {
+        std::vector<uint32_t> order;
+        build_chart_preorder(build_chart(), &order);
+        std::memcpy(preorder, order.data(), order.size() * sizeof(uint32_t));
+    }
+    if (chains)
+        for (size_t c = 0; c < t.chains.size(); c++) {
+            const LightChain &ch = t.chains[c];
+            chains[c][0] = ch.first_node; chains[c][1] = ch.length; chains[c][2] = ch.n_children;
+            chains[c][3] = ch.first_child; chains[c][4] = ch.parent_branch; chains[c][5] = ch.branch;
+        }
+    if (euler) std::memcpy(euler, t.euler.data(), t.euler.size() * sizeof(uint16_t));
+    return (uint32_t)t.chains.size();
+}
 
 uint32_t aicb_light_chart(float *weights, uint32_t *children) {
     static const std::vector<LightChartNode> chart = build_chart();

@@ -227,6 +227,7 @@ unsafe extern "C" {
     pub fn aicb_camera_project_ndc(cam: *const aicb_camera, ndc_x: f64, ndc_y: f64, out_origin_dir: *mut [f64; 6]);
 
     pub fn aicb_light_chart(weights: *mut f32, children: *mut u32) -> u32;
+    pub fn aicb_light_chart_chains(preorder: *mut u32, chains: *mut [u32; 6], euler: *mut u16) -> u32;
     pub fn aicb_light_fast_evaluate(s: *mut aicb_scene) -> aicb_status;
     pub fn aicb_light_compute(s: *mut aicb_scene, cubes: *const [i32; 3], n: usize, out: *mut [u8; 4]) -> aicb_status;
     pub fn aicb_light_evaluate(s: *mut aicb_scene, epsilon: u8, updates_done: *mut u64, max_diff: *mut u8,

@@ -357,6 +357,14 @@ void aicb_camera_project_ndc(const aicb_camera *, double ndc_x, double ndc_y, do
  * walk: 6 f32 weights + 6 child indices (0 = none) per node, root = 0.  Returns the node count
  * (114 779); either pointer may be NULL.  Host only. */
 uint32_t aicb_light_chart(float *weights_or_null, uint32_t *children_or_null);
+/* The same chart the way the kernels walk it: in depth-first preorder (children in Face6 order, the order walk_ray_tree
+ * recurses in, updater.rs:500) and cut into chains — maximal paths of single-child nodes, which carry bit-identical
+ * weights; a chain's nodes are consecutive in preorder and chains are numbered breadth first.  Host only; any pointer
+ * may be NULL.  preorder[i] = index in aicb_light_chart's numbering of the i-th node in preorder (node count entries);
+ * chains[c] = {first node (preorder), nodes, child chains, first child chain, parent's branch slot or 0xffff, own
+ * branch slot or 0xffff}; euler = the Euler tour of the chain tree, chain | 0x8000 for the chain's exit (n_euler
+ * entries = 2 * n_chains): the order in which the terms of a walk are added.  Returns the number of chains (1043). */
+uint32_t aicb_light_chart_chains(uint32_t *preorder_or_null, uint32_t (*chains_or_null)[6], uint16_t *euler_or_null);
 /* LightStorage::fast_evaluate_light (updater.rs:537-582): column-sweep initial guess + queue seeding. */
 aicb_status aicb_light_fast_evaluate(aicb_scene *);
 /* LightStorage::compute_light (updater.rs:368-418) for explicit cubes against the current field; does not
