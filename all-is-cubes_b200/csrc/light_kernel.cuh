@@ -8,15 +8,18 @@
 // gather (tiles in index order, so the list is spatially sorted) -> compute -> apply (store, fill uninitialised
 // neighbours) -> mark (re-queue the dependencies of the cubes that changed).
 //
-// compute: ONE WARP WALKS THE CHART FOR 32 NEIGHBOURING CUBES IN LOCKSTEP.  The chart is a static prefix tree; in
-// depth-first preorder every lane would visit a subsequence of the same node sequence.  So the warp steps through
-// the nodes in preorder — node record, depth and weights are warp-uniform, one broadcast load — and a lane takes
-// part in a node iff its own walk would enter it (its frame of the parent is alive); a subtree that no lane of the
-// warp enters is skipped through the node's `subtree_end`.  Control flow is uniform, the cell / light loads of
-// neighbouring cubes coalesce, and every lane's f32 additions happen in exactly the reference's depth-first order,
-// so compute_light on a given field stays bit-identical to the reference (the old one-thread-per-cube walk diverged
-// on every node).  The relaxation order differs from the reference's (batch = a priority band), which the
-// reference leaves unspecified (queue.rs:226-246) — parity contract SURVEY §8(a) L4.
+// compute / mark, the chain walk (compute_light_chains, below): ONE WARP PER CUBE, 32 CHAINS OF THE CHART AT A TIME.
+// 99 % of the chart's nodes have exactly one child with bit-identical weights, so the tree is 1043 chains joined at 441
+// branching nodes.  Lanes take ready chains from a per-warp queue and walk them node by node; the terms the reference
+// adds up in depth-first order are written to per-chain slots and added afterwards in the Euler tour of the chain
+// tree, which is that order — compute_light on a given field stays bit-identical to the reference.
+//
+// The lockstep walk (compute_light_lockstep) is the previous design, kept for cubes whose walk needs more term slots
+// than a chain holds: one warp steps through the chart in preorder for 32 neighbouring cubes — node record, depth and
+// weights are warp-uniform — and a lane takes part in a node iff its own walk would enter it; a subtree that no lane
+// enters is skipped.  Every lane's f32 additions happen in place, in the reference's order.
+// The relaxation order differs from the reference's (batch = a priority band), which the reference leaves unspecified
+// (queue.rs:226-246) — parity contract SURVEY §8(a) L4.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -18,6 +18,9 @@
 //    compute_illumination;
 //  * encode_kernel (one thread per pixel): the exact transmittance chain in ray order, the opacity cut, sky, tone
 //    mapping, sRGB8.
+//  The kernels of a frame follow each other with programmatic dependent launch (grid_dependency_sync).  A frame with
+//  LightingOption::Bounce runs the same kernels a second time per sample for the secondary rays (see the bounce_*
+//  kernels).
 //  The two-level grid (Space cubes -> block id; block -> N^3 brick of palette indices) is walked by ONE unified DDA;
 //  entering a recursive block pushes the outer state (shared memory) and re-initialises the same DDA on the brick.
 //  Cell words carry their classification in the top bits (bit 15 = nothing to see, on both levels).
