@@ -11,6 +11,7 @@
 // apply.  f32 arithmetic order is kept (FaceMap::sum = (nx+px)+(ny+py)+(nz+pz), face.rs:1053).
 #include <cmath>
 #include <cstring>
+#include <array>
 #include <map>
 #include <set>
 #include <unordered_map>
@@ -246,6 +247,9 @@ struct LightBuffer {
     std::vector<size_t> deps_cubes;  // as linear indices, or SIZE_MAX for out-of-bounds cubes
     std::vector<int32_t> deps_xyz;
     double max_dist_sq;
+    // orc_light_compute_by_chains: when set, what would be added to incoming / total_weight is appended here instead
+    // ({x0, x1, x2, weight}; weight 0 for the terms that leave total_weight alone)
+    std::vector<std::array<float, 4>> *rec = nullptr;
 };
 struct RayState {
     float alpha;
@@ -254,6 +258,10 @@ struct RayState {
 
 static void add_weighted_light(LightBuffer &b, const float color[3], float weight) {  // updater.rs:926-929
     float k = ps_clamped_l(weight);
+    if (b.rec) {
+        b.rec->push_back({ps_mul_l(color[0], k), ps_mul_l(color[1], k), ps_mul_l(color[2], k), weight});
+        return;
+    }
     for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + ps_mul_l(color[i], k);
     b.total_weight += weight;
 }
@@ -317,7 +325,8 @@ static void traverse(const orc_light &L, LightBuffer &b, RayState &rs, const int
         float lf[3];
         for (int i = 0; i < 3; i++) lf[i] = ev.emission[i] + ps_mul_l(ps_mul_l(col[i], sv[i]), hit_alpha);  // emission + reflect
         float ka = ps_clamped_l(rs.alpha), kw = ps_clamped_l(fm_sum(wprod));
-        for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + ps_mul_l(ps_mul_l(lf[i], ka), kw);
+        if (b.rec) b.rec->push_back({ps_mul_l(ps_mul_l(lf[0], ka), kw), ps_mul_l(ps_mul_l(lf[1], ka), kw), ps_mul_l(ps_mul_l(lf[2], ka), kw), 0.0f});
+        else for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + ps_mul_l(ps_mul_l(lf[i], ka), kw);
         push_dep(L, b, lc, true);
         if (hit_opaque_face) rs.alpha = 0.0f;
         else rs.alpha *= 1.0f - hit_alpha;
@@ -335,7 +344,8 @@ static void traverse(const orc_light &L, LightBuffer &b, RayState &rs, const int
         float lt[3];
         for (int i = 0; i < 3; i++) lt[i] = ev.emission[i] + ps_mul_l(sv[i], kh);
         float ka = ps_clamped_l(rs.alpha), kw = ps_clamped_l(fm_sum(wprod));
-        for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + ps_mul_l(ps_mul_l(lt[i], ka), kw);
+        if (b.rec) b.rec->push_back({ps_mul_l(ps_mul_l(lt[0], ka), kw), ps_mul_l(ps_mul_l(lt[1], ka), kw), ps_mul_l(ps_mul_l(lt[2], ka), kw), 0.0f});
+        else for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + ps_mul_l(ps_mul_l(lt[i], ka), kw);
         push_dep(L, b, cube, false);
         rs.alpha *= 1.0f - hit_alpha;
     }
@@ -600,6 +610,155 @@ void orc_light_compute(orc_light *L, const int32_t (*cubes)[3], size_t n, uint8_
     for (size_t i = 0; i < n; i++) {
         PL p = compute_light(*L, cubes[i], nullptr);
         out[i][0] = p.r; out[i][1] = p.g; out[i][2] = p.b; out[i][3] = p.s;
+    }
+}
+
+// compute_light evaluated the way the CUDA chain walk does (all-is-cubes_b200/csrc/light_kernel.cuh:
+// compute_light_chains), with the chain tables of the PRODUCT library handed in (aicb_light_chart_chains): every chain
+// of the chart is walked on its own — traverse / end_of_ray per node exactly as walk() above, but the terms are
+// recorded per chain instead of added —, chains in breadth-first order (a child starts from what its parent left at the
+// branching node), and the terms are then added in the Euler tour of the chain tree.  tests/test_light_chains.py
+// asserts that this gives the bits of the recursive walk: the argument the kernel's bit-exactness rests on (a chain's
+// nodes share their weights, so `bundle - children` is exactly 0 except at chain ends; depth-first order of the
+// terms = the Euler tour), checked on the CPU.
+void orc_light_compute_by_chains(orc_light *Lp, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4], float (*raw_or_null)[4],
+                                 const uint32_t *preorder, const uint32_t (*chains)[6], uint32_t n_chains, const uint16_t *euler,
+                                 uint32_t n_euler) {
+    orc_light &L = *Lp;
+    const std::vector<FlatNode> &ch = chart();
+    // cube offset and entry face of every node of the flat chart
+    static std::vector<std::array<int32_t, 4>> place;
+    if (place.empty()) {
+        place.assign(ch.size(), {0, 0, 0, 0});
+        std::vector<uint32_t> stack{0};
+        while (!stack.empty()) {
+            const uint32_t i = stack.back();
+            stack.pop_back();
+            for (int f = 0; f < 6; f++)
+                if (ch[i].children[f]) {
+                    std::array<int32_t, 4> p = place[i];
+                    p[f % 3] += (f < 3) ? -1 : 1;
+                    p[3] = ((f < 3) ? f + 3 : f - 3) + 1;   // face7 through which the child cube is entered
+                    place[ch[i].children[f]] = p;
+                    stack.push_back(ch[i].children[f]);
+                }
+        }
+    }
+    struct BranchState { float alpha; bool have; PL ahead; };
+    for (size_t q = 0; q < n; q++) {
+        const int32_t *cube = cubes[q];
+        LightBuffer b;
+        b.max_dist_sq = (double)L.max_distance * (double)L.max_distance;
+        const LBlock &ev = get_evaluated(L, cube);
+        const bool origin_opaque = ev.all_opaque;
+        if (origin_opaque) {
+            if (!opaque_for_light(ev)) add_weighted_light(b, ev.emission, 1.0f);
+        } else {
+            float dw[6];
+            if (ev.visible) {
+                for (int f = 0; f < 6; f++) dw[f] = 1.0f;
+            } else {
+                for (int f = 0; f < 6; f++) {
+                    int opp = (f < 3) ? f + 3 : f - 3;
+                    int32_t nf[3] = {cube[0], cube[1], cube[2]}, no[3] = {cube[0], cube[1], cube[2]};
+                    nf[f % 3] += (f < 3) ? -1 : 1;
+                    no[opp % 3] += (opp < 3) ? -1 : 1;
+                    dw[f] = (get_evaluated(L, no).visible || get_evaluated(L, nf).has_emission) ? 1.0f : 0.0f;
+                }
+            }
+            std::vector<std::vector<std::array<float, 4>>> entry(n_chains), pop(n_chains);
+            std::vector<char> ready(n_chains, 0);
+            std::vector<BranchState> branch(n_chains, BranchState{0.0f, false, L_UNINIT});
+            ready[0] = 1;
+            for (uint32_t c = 0; c < n_chains; c++) {
+                if (!ready[c]) continue;
+                const uint32_t first = chains[c][0], length = chains[c][1], kids = chains[c][2], first_child = chains[c][3];
+                const uint32_t pb = chains[c][4], br = chains[c][5];
+                RayState rs;
+                for (int f = 0; f < 6; f++) rs.dw[f] = dw[f];
+                bool have_prev = false;
+                PL prev = L_UNINIT;
+                if (pb == 0xffffu) rs.alpha = 1.0f;
+                else { rs.alpha = branch[pb].alpha; have_prev = branch[pb].have; prev = branch[pb].ahead; }
+                b.rec = &entry[c];
+                bool alive = true;
+                float bundle = 0.0f;
+                uint32_t last_node = 0;
+                for (uint32_t k = 0; k < length && alive; k++) {
+                    const uint32_t node_index = preorder[first + k];
+                    const FlatNode &node = ch[node_index];
+                    last_node = node_index;
+                    L.node_visits++;
+                    float prod[6];
+                    for (int f = 0; f < 6; f++) prod[f] = node.weight[f] * rs.dw[f];
+                    bundle = fm_sum(prod);
+                    if (bundle <= 0.0f) { alive = false; break; }
+                    const std::array<int32_t, 4> &pl = place[node_index];
+                    const int32_t nc[3] = {cube[0] + pl[0], cube[1] + pl[1], cube[2] + pl[2]};
+                    const double dx = (double)pl[0], dy = (double)pl[1], dz = (double)pl[2];
+                    size_t idx;
+                    if (dx * dx + dy * dy + dz * dz > b.max_dist_sq || !l_index(L, nc, &idx)) {
+                        end_of_ray(L, b, rs, bundle, node.weight);
+                        alive = false;
+                        break;
+                    }
+                    bool have_ahead = false;
+                    PL ahead = L_UNINIT;
+                    traverse(L, b, rs, nc, pl[3], L.blocks[L.ids[idx]], &have_ahead, &ahead, have_prev, prev, node.weight);
+                    if (!(rs.alpha > 0.0f)) {
+                        end_of_ray(L, b, rs, bundle, node.weight);
+                        alive = false;
+                        break;
+                    }
+                    have_prev = have_ahead;
+                    prev = ahead;
+                }
+                if (!alive) continue;
+                // alive at the chain's last node: the children start from here; the rest of the bundle ends here
+                float child_sum = 0.0f;
+                for (uint32_t j = 0; j < kids; j++) {
+                    const FlatNode &cn = ch[preorder[chains[first_child + j][0]]];
+                    float prod[6];
+                    for (int f = 0; f < 6; f++) prod[f] = cn.weight[f] * rs.dw[f];
+                    child_sum += fm_sum(prod);
+                    ready[first_child + j] = 1;
+                }
+                if (kids) branch[br] = BranchState{rs.alpha, have_prev, prev};
+                b.rec = &pop[c];
+                end_of_ray(L, b, rs, std::fmax(bundle - child_sum, 0.0f), ch[last_node].weight);
+            }
+            b.rec = nullptr;
+            for (uint32_t p = 0; p < n_euler; p++) {
+                const uint32_t c = euler[p] & 0x7fffu;
+                const std::vector<std::array<float, 4>> &terms = (euler[p] & 0x8000u) ? pop[c] : entry[c];
+                for (const std::array<float, 4> &t : terms) {
+                    for (int i = 0; i < 3; i++) b.incoming[i] = b.incoming[i] + t[i];
+                    b.total_weight += t[3];
+                }
+            }
+        }
+        PL result;
+        float scale = ps_clamped_l(1.0f / std::fmax(b.total_weight, 1.0f));
+        if (b.total_weight > 0.0f)
+            result = PL{scalar_in_l(ps_mul_l(b.incoming[0], scale)), scalar_in_l(ps_mul_l(b.incoming[1], scale)),
+                        scalar_in_l(ps_mul_l(b.incoming[2], scale)), 255};
+        else if (origin_opaque) result = L_OPAQUE;
+        else result = L_NO_RAYS;
+        out[q][0] = result.r; out[q][1] = result.g; out[q][2] = result.b; out[q][3] = result.s;
+        if (raw_or_null) {
+            raw_or_null[q][0] = b.incoming[0]; raw_or_null[q][1] = b.incoming[1]; raw_or_null[q][2] = b.incoming[2];
+            raw_or_null[q][3] = b.total_weight;
+        }
+    }
+}
+
+// compute_light with the unquantised accumulators (incoming_light, total_rays) beside the packed result
+void orc_light_compute_raw(orc_light *L, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4], float (*raw)[4]) {
+    for (size_t i = 0; i < n; i++) {
+        LightBuffer b;
+        PL p = compute_light(*L, cubes[i], &b);
+        out[i][0] = p.r; out[i][1] = p.g; out[i][2] = p.b; out[i][3] = p.s;
+        raw[i][0] = b.incoming[0]; raw[i][1] = b.incoming[1]; raw[i][2] = b.incoming[2]; raw[i][3] = b.total_weight;
     }
 }
 

@@ -82,6 +82,9 @@ def lib():
     L.orc_light_evaluate.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64, C.c_void_p]
     L.orc_light_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.orc_light_get.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_light_compute_by_chains.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_uint32, C.c_void_p, C.c_uint32]
+    L.orc_light_compute_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.orc_light_set_field.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_light_get_outside.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_light_set_pop_order.argtypes = [C.c_void_p, C.c_int]
@@ -342,6 +345,27 @@ class OracleLight:
         out = np.zeros((c.shape[0], 4), dtype=np.uint8)
         lib().orc_light_compute(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data)
         return out
+
+    def compute_by_chains(self, cubes, preorder, chains, euler):
+        """compute_light evaluated chain by chain with the terms added in the Euler tour of the chain tree — the CUDA
+        chain walk's algorithm on the CPU, with the product library's chain tables."""
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros((c.shape[0], 4), dtype=np.uint8)
+        raw = np.zeros((c.shape[0], 4), dtype=np.float32)
+        pre = np.ascontiguousarray(preorder, dtype=np.uint32)
+        chn = np.ascontiguousarray(chains, dtype=np.uint32)
+        eul = np.ascontiguousarray(euler, dtype=np.uint16)
+        lib().orc_light_compute_by_chains(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data, raw.ctypes.data, pre.ctypes.data,
+                                          chn.ctypes.data, chn.shape[0], eul.ctypes.data, eul.shape[0])
+        return out, raw
+
+    def compute_raw(self, cubes):
+        """compute_light: the packed results and the unquantised accumulators (incoming_light rgb, total_rays)."""
+        c = np.ascontiguousarray(cubes, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros((c.shape[0], 4), dtype=np.uint8)
+        raw = np.zeros((c.shape[0], 4), dtype=np.float32)
+        lib().orc_light_compute_raw(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data, raw.ctypes.data)
+        return out, raw
 
     def field(self):
         out = np.zeros(self.shape + (4,), dtype=np.uint8)

@@ -11,6 +11,8 @@ rests on, checked without a GPU against the flat chart (space/light/chart/genera
 import numpy as np
 
 import aicb200
+import orc
+from aicb200 import Block, Space, scenes
 
 
 def tables():
@@ -81,3 +83,55 @@ def test_euler_tour_is_the_depth_first_order_of_the_chain_tree():
     entered = [e for e in euler.tolist() if e < 0x8000]
     firsts = [int(chains[c][0]) for c in entered]
     assert firsts == sorted(firsts)
+
+
+# ---- the algorithm of the chain walk, on the CPU -------------------------------------------------------------------
+NO_RAYS = 1
+
+
+def _scenes():
+    """Random atoms (opaque / translucent / emissive / invisible) over a floor, and translucent slabs that give single
+    chains many terms."""
+    n = 12
+    h = scenes.grid_hash(5, (n, n, n))
+    blocks = [Block.air(), Block(color=(0.8, 0.7, 0.6, 1.0)), Block(color=(0.2, 0.9, 0.3, 1.0)),
+              Block(color=(0.9, 0.2, 0.1, 0.5)), Block(color=(0.3, 0.3, 0.9, 0.125)),
+              Block(color=(0.1, 0.1, 0.1, 1.0), emission=(4.0, 3.0, 1.0)),
+              Block(color=(0.0, 0.0, 0.0, 0.0), emission=(0.2, 0.6, 2.0)), Block(color=(0.5, 0.5, 0.5, 0.0))]
+    sel = (h % np.uint64(40)).astype(np.int64)
+    ids = np.where(sel < 7, sel + 1, 0).astype(np.uint16)
+    ids[:, 0, :] = 1
+    light = np.zeros((n, n, n, 4), dtype=np.uint8)
+    light[..., 3] = NO_RAYS
+    yield Space((-2, 1, 3), ids, blocks, light=light, sky_colors=scenes.OCTANT_SKY, light_max_distance=12)
+    ids = np.zeros((n, n, n), dtype=np.uint16)
+    ids[:, 0, :] = 1
+    ids[2:10, 2:8, 5:8] = 4
+    ids[5, 3, 2] = 5
+    yield Space((0, 0, 0), ids, blocks, light=light, sky_colors=[(0.9, 0.9, 0.9)], light_max_distance=30)
+
+
+def test_chain_order_summation_gives_the_bits_of_the_recursive_walk():
+    """compute_light for every cube of two scenes, at three stages of convergence: the oracle's recursive walk_ray_tree
+    against the same oracle walking the PRODUCT's chains one by one and adding the recorded terms in Euler-tour order
+    (oracle/aic_light.cpp: orc_light_compute_by_chains) — the chain walk kernel's algorithm, without a GPU."""
+    pre, chains, euler = aicb200.light_chart_chains()
+    for space in _scenes():
+        ol = orc.OracleLight(space)
+        ol.fast_evaluate()
+        x, y, z = np.meshgrid(*[np.arange(space.lower[a], space.lower[a] + space.size[a]) for a in range(3)], indexing="ij")
+        cubes = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).astype(np.int32)
+        for stage in range(3):
+            want, want_raw = ol.compute_raw(cubes)
+            got, got_raw = ol.compute_by_chains(cubes, pre, chains, euler)
+            assert np.array_equal(got, want), f"stage {stage}: {np.argwhere((got != want).any(axis=1))[:5]}"
+            # the unquantised f32 accumulators too, bit for bit: the packed light alone would not notice an order of
+            # summation that differs in the last bits
+            assert np.array_equal(got_raw.view(np.uint32), want_raw.view(np.uint32)), f"stage {stage}: accumulators differ"
+            assert (want[:, 3] == 255).sum() > 100
+            ol.evaluate(0, max_updates=300 * (stage + 1))
+        # ... and they do notice: the same terms with every node's children taken in reverse order
+        reverse = euler[::-1].copy()
+        reverse = np.where(reverse >= 0x8000, reverse - 0x8000, reverse + 0x8000).astype(np.uint16)
+        _, other_raw = ol.compute_by_chains(cubes, pre, chains, reverse)
+        assert (other_raw.view(np.uint32) != want_raw.view(np.uint32)).any()
