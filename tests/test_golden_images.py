@@ -325,3 +325,45 @@ def fog_universe():
 @pytest.fixture(scope="module")
 def tone_mapping_universe():
     return build_tone_mapping_universe()
+
+
+# ---- one_cube_space cases (cases/src/lib.rs:1239-1257): viewport_prime, no_update ---------------------------------
+def one_cube_space():
+    """GridAab::ORIGIN_CUBE filled with block::from_color!(0, 1, 0, 1), sky 0.5 grey (cases/src/lib.rs:1239-1248)."""
+    return Space((0, 0, 0), np.ones((1, 1, 1), dtype=np.uint16), [Block.air(), Block(color=(0.0, 1.0, 0.0, 1.0))],
+                 sky_colors=[(0.5, 0.5, 0.5)])
+
+
+def no_world_to_show():
+    """palette::NO_WORLD_TO_SHOW = srgb[0xBC 0xBC 0xBC 0xFF] (all-is-cubes/src/content/palette.rs:76), linear RGBA."""
+    g = float(srgb8_to_linear((0xBC, 0xBC, 0xBC))[0])
+    return (g, g, g, 1.0)
+
+
+def test_viewport_prime():
+    """cases/src/lib.rs:1215-1229: a 101 x 37 viewport ("should not require the viewport to be a multiple of a certain
+    size"), UNALTERED_COLORS, threshold COLOR_ROUNDING_MAX_DIFF."""
+    opts = GraphicsOptions.unaltered_colors()
+    cam = Camera(opts, Viewport((101.0, 37.0), (101, 37)))
+    cam.set_view_transform((0.0, 0.0, 0.0, 1.0), (0.5, 0.5, 2.0))
+    img = orc.OracleScene(one_cube_space()).render(cam, opts)["srgb8"].reshape(37, 101, 4)
+    exp = golden("viewport_prime-all")
+    assert exp.shape == (37, 101, 4)
+    check_threshold(img, exp, [(2, 101 * 37)])
+    assert (img == exp).all(axis=2).mean() > 0.97      # only the cube's silhouette pixels may differ
+
+
+def test_no_update():
+    """cases/src/lib.rs:988-1005: draw() before any update() has no world to show — every pixel is
+    palette::NO_WORLD_TO_SHOW (renderer.rs:474-477); after update() the green cube in front of the grey sky.
+    Reference threshold 5 for both; the first image is reproduced exactly."""
+    opts = GraphicsOptions.unaltered_colors()
+    cam = common_camera(opts)
+    # a renderer without a world layer: trace_ray_through_layers leaves the accumulator transparent (here: an all-AIR
+    # UI layer, traced without sky like every UI layer) and paints NO_WORLD_TO_SHOW
+    nothing = Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [Block.air()], sky_colors=[(0.5, 0.5, 0.5)])
+    first = orc.render_layers(None, (orc.OracleScene(nothing), cam, opts), no_world=no_world_to_show())["srgb8"].reshape(96, 128, 4)
+    assert np.array_equal(first, golden("no_update-all"))
+    second = orc.OracleScene(one_cube_space()).render(cam, opts)["srgb8"].reshape(96, 128, 4)
+    check_threshold(second, golden("no_update-2-all"), [(5, 128 * 96)])
+    assert (second == golden("no_update-2-all")).all(axis=2).mean() > 0.97

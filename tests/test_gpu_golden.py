@@ -111,3 +111,21 @@ def test_white_furnace_with_gpu_light():
     img = r.draw().data
     check_threshold(img, golden("furnace-Clear-Opaque-all"), [(2, 128 * 96)])
     assert int(img[..., :3].min()) >= 223 and int(img[..., :3].max()) <= 228
+
+
+def test_one_cube_cases_on_gpu():
+    """viewport_prime (a 101 x 37 viewport) and no_update (NO_WORLD_TO_SHOW before the first update, the cube after it):
+    cases/src/lib.rs:1215-1229, 988-1005 — through the CUDA path, bit-identical to the oracle and within the
+    reference's thresholds of its expected images."""
+    from test_golden_images import common_camera, no_world_to_show, one_cube_space
+    opts = GraphicsOptions.unaltered_colors()
+    cam = Camera(opts, Viewport((101.0, 37.0), (101, 37)))
+    cam.set_view_transform((0.0, 0.0, 0.0, 1.0), (0.5, 0.5, 2.0))
+    img = gpu_and_oracle(one_cube_space(), cam, opts)
+    check_threshold(img, golden("viewport_prime-all"), [(2, 101 * 37)])
+    cam = common_camera(opts)
+    img = gpu_and_oracle(one_cube_space(), cam, opts)
+    check_threshold(img, golden("no_update-2-all"), [(5, 128 * 96)])
+    nothing = Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [aicb200.Block.air()], sky_colors=[(0.5, 0.5, 0.5)])
+    first = aicb200.render_layers(None, (SpaceRaytracer(nothing, opts), cam, opts), no_world=no_world_to_show())
+    assert np.array_equal(first.data.reshape(96, 128, 4), golden("no_update-all"))
