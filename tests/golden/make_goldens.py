@@ -46,7 +46,8 @@ def pngs():
                  "fog-Abrupt-all", "fog-Compromise-all", "fog-Physical-all", "light_spread-None-all", "light_spread-Flat-all",
                  "light_spread-Coarse-all", "light_spread-Linear-all", "light_spread-Smoothstep-all", "tone_map-Clamp-1.0-0.5-all",
                  "tone_map-Clamp-1.0-2.0-all", "tone_map-Reinhard-0.5-0.5-all", "tone_map-Reinhard-1.0-0.5-all",
-                 "tone_map-Reinhard-1.0-2.0-all", "viewport_prime-all", "no_update-all", "no_update-2-all"]:
+                 "tone_map-Reinhard-1.0-2.0-all", "viewport_prime-all", "no_update-all", "no_update-2-all", "layers_all-all", "layers_hidden_ui-all", "layers_ui_only-all",
+                 "layers_none_but_text-all"]:
         im = np.array(Image.open(f"{REF}/test-renderers/expected/renderers/{name}.png").convert("RGBA"))
         np.save(f"{OUT}/png_{name}.npy", im)
 

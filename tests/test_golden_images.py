@@ -367,3 +367,53 @@ def test_no_update():
     second = orc.OracleScene(one_cube_space()).render(cam, opts)["srgb8"].reshape(96, 128, 4)
     check_threshold(second, golden("no_update-2-all"), [(5, 128 * 96)])
     assert (second == golden("no_update-2-all")).all(axis=2).mean() > 0.97
+
+
+# ---- layers_* (cases/src/lib.rs:889-972): trace_ray_through_layers against the reference's expected images ---------
+INFO_TEXT_BOX = (slice(7, 19), slice(4, 82))   # where draw_info_text puts "hello world" (needs the universe's font: not drawn here)
+
+
+def ui_space():
+    """cases/src/lib.rs:1260-1267: one green cube at (-3, -3, -4), LightPhysics::None, a sky that must never be seen."""
+    return Space((-3, -3, -4), np.ones((1, 1, 1), dtype=np.uint16), [Block.air(), Block(color=(0.0, 1.0, 0.0, 1.0))],
+                 sky_colors=[(1.0, 1.0, 0.5)])
+
+
+def layer_cases():
+    """name -> (world layer?, UI layer?, options): layers_all (Flat lighting), layers_hidden_ui (show_ui off: the host
+    leaves the UI layer out), layers_ui_only and layers_none_but_text (no world: NO_WORLD_TO_SHOW)."""
+    flat = GraphicsOptions.unaltered_colors()
+    flat.lighting_display = aicb200.LIGHT_FLAT
+    plain = GraphicsOptions.unaltered_colors()
+    return {"layers_all-all": (True, True, flat), "layers_hidden_ui-all": (True, False, flat),
+            "layers_ui_only-all": (False, True, plain), "layers_none_but_text-all": (False, False, plain)}
+
+
+def layer_cameras(opts):
+    """The world camera of looking_at_one_cube_spawn and the UI camera of UiViewState { view_transform: identity }."""
+    ucam = Camera(opts, Viewport((128.0, 96.0), (128, 96)))
+    ucam.set_view_transform((0.0, 0.0, 0.0, 1.0), (0.0, 0.0, 0.0))
+    return common_camera(opts), ucam
+
+
+def check_layers_image(img, name):
+    """Outside the info-text box the image must equal the reference's byte for byte (its own thresholds are 0 or
+    COLOR_ROUNDING_MAX_DIFF); inside, the reference has the black-on-white text this repository does not draw."""
+    exp = golden(name)
+    outside = np.ones(exp.shape[:2], dtype=bool)
+    outside[INFO_TEXT_BOX] = False
+    assert np.array_equal(img[outside], exp[outside]), f"{name}: {(img != exp).any(axis=2)[outside].sum()} pixels differ outside the text box"
+    text = {tuple(v) for v in np.unique(exp[INFO_TEXT_BOX].reshape(-1, 4), axis=0).tolist()}
+    assert (0, 0, 0, 255) in text and (255, 255, 255, 255) in text
+
+
+@pytest.mark.parametrize("name", ["layers_all-all", "layers_hidden_ui-all", "layers_ui_only-all", "layers_none_but_text-all"])
+def test_layers(name):
+    has_world, has_ui, opts = layer_cases()[name]
+    wcam, ucam = layer_cameras(opts)
+    world = (orc.OracleScene(one_cube_space()), wcam, opts) if has_world else None
+    ui = (orc.OracleScene(ui_space()), ucam, opts) if has_ui else None
+    if not world and not ui:   # nothing at all: an all-AIR layer stands in for "no layers" (the accumulator stays transparent)
+        ui = (orc.OracleScene(Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [Block.air()])), ucam, opts)
+    img = orc.render_layers(world, ui, no_world=no_world_to_show())["srgb8"].reshape(96, 128, 4)
+    check_layers_image(img, name)

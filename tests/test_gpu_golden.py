@@ -129,3 +129,22 @@ def test_one_cube_cases_on_gpu():
     nothing = Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [aicb200.Block.air()], sky_colors=[(0.5, 0.5, 0.5)])
     first = aicb200.render_layers(None, (SpaceRaytracer(nothing, opts), cam, opts), no_world=no_world_to_show())
     assert np.array_equal(first.data.reshape(96, 128, 4), golden("no_update-all"))
+
+
+@pytest.mark.parametrize("name", ["layers_all-all", "layers_hidden_ui-all", "layers_ui_only-all", "layers_none_but_text-all"])
+def test_layers_on_gpu(name):
+    """RtScene::trace_ray_through_layers (renderer.rs:454-478) through aicb_render_layers_srgb8 against the reference's
+    layers_* expectations: byte-identical outside the box where the reference draws its info text."""
+    from test_golden_images import check_layers_image, layer_cameras, layer_cases, no_world_to_show, one_cube_space, ui_space
+    has_world, has_ui, opts = layer_cases()[name]
+    wcam, ucam = layer_cameras(opts)
+    world = (SpaceRaytracer(one_cube_space(), opts), wcam, opts) if has_world else None
+    ui = (SpaceRaytracer(ui_space(), opts), ucam, opts) if has_ui else None
+    if not world and not ui:
+        ui = (SpaceRaytracer(Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [aicb200.Block.air()]), opts), ucam, opts)
+    img = aicb200.render_layers(world, ui, no_world=no_world_to_show()).data.reshape(96, 128, 4)
+    check_layers_image(img, name)
+    oworld = (orc.OracleScene(one_cube_space()), wcam, opts) if has_world else None
+    oui = (orc.OracleScene(ui_space()), ucam, opts) if has_ui else None
+    if oworld or oui:
+        assert np.array_equal(img.reshape(-1, 4), orc.render_layers(oworld, oui, no_world=no_world_to_show())["srgb8"])
