@@ -202,6 +202,13 @@ unsafe extern "C" {
     pub fn aicb_frame_open(ctx: *mut aicb_ctx, handle: *const [u8; 64], d_frame: *mut *mut c_void) -> aicb_status;
     pub fn aicb_frame_close(ctx: *mut aicb_ctx, d_frame: *mut c_void, opened: c_int) -> aicb_status;
     pub fn aicb_frame_read(ctx: *mut aicb_ctx, d_frame: *const c_void, out: *mut [u8; 4], n_pixels: usize, stream: *mut c_void) -> aicb_status;
+    // delivery without a collective: two monotonic counters behind the frame's pixels (include/aicb200.h)
+    pub fn aicb_frame_signal(ctx: *mut aicb_ctx, d_frame: *mut c_void, n_pixels: usize, stream: *mut c_void) -> aicb_status;
+    pub fn aicb_frame_wait_arrived(ctx: *mut aicb_ctx, d_frame: *mut c_void, n_pixels: usize, count: u32, stream: *mut c_void) -> aicb_status;
+    pub fn aicb_frame_release(ctx: *mut aicb_ctx, d_frame: *mut c_void, n_pixels: usize, frame_id: u32, stream: *mut c_void) -> aicb_status;
+    pub fn aicb_frame_wait_consumed(ctx: *mut aicb_ctx, d_frame: *mut c_void, n_pixels: usize, frame_id: u32, stream: *mut c_void) -> aicb_status;
+    pub fn aicb_frame_timed_out(ctx: *mut aicb_ctx, d_frame: *mut c_void, n_pixels: usize, out: *mut u32) -> aicb_status;
+    pub fn aicb_ctx_stage_timing(ctx: *mut aicb_ctx, enable: c_int) -> aicb_status;
 
     pub fn aicb_group_create(device_ids: *const c_int, n_devices: c_int, out: *mut *mut aicb_group) -> aicb_status;
     pub fn aicb_group_destroy(g: *mut aicb_group);

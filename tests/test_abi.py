@@ -74,3 +74,15 @@ def test_scene_hash_is_deterministic():
     assert np.array_equal(a.block_ids, b.block_ids)
     assert int(scenes.hash3(1, 2, 3, 4)) == int(scenes.hash3(1, 2, 3, 4))
     assert 0.10 < (a.block_ids != 0).mean() < 0.15  # 12.5 % fill
+
+
+def test_rust_sys_crate_declares_every_function_of_the_header():
+    """bindings/rust/all-is-cubes-b200-sys (source only; no Rust toolchain here) must not drift from include/aicb200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "aicb200.h")).read()
+    declared = set(re.findall(r"\b(aicb_[a-z0-9_]+)\s*\(", header))
+    rust = open(os.path.join(root, "bindings", "rust", "all-is-cubes-b200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (aicb_[a-z0-9_]+)", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    assert declared == set(abi.EXPORTED_SYMBOLS)
