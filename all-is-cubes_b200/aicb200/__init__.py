@@ -313,10 +313,9 @@ class Block:
         self._derive_for_light()
 
     def _derive_for_light(self):
-        """EvaluatedBlock derived data read by light propagation (block/eval/derived.rs:80-104 for single
-        voxels).  For recursive blocks only the face-opacity rule (derived.rs:196-209) is exact; the
-        face colours are a plain mean of the surface voxels (block evaluation is out of scope) —
-        both the oracle and the GPU consume whatever is supplied here."""
+        """EvaluatedBlock derived data read by light propagation (block/eval/derived.rs:80-104 for single voxels,
+        :105-235 for recursive blocks: a restatement for the synthetic blocks of the tests and benches — block
+        evaluation itself is out of scope, SURVEY §2 #11; the oracle and the GPU consume whatever is supplied here)."""
         if self.is_air:
             self.light_opaque_faces = 0
             self.light_visible = False
@@ -333,30 +332,81 @@ class Block:
             self.light_opaque_faces = 0x3F if c[3] == 1.0 else 0
             self.light_visible = (c[3] != 0.0) or any(v != 0.0 for v in e)
             return
+        # compute_derived (block/eval/derived.rs:80-235): every face is "rendered" by axis-aligned rays through the voxel
+        # data (trace_for_eval, raytracer_components.rs:174-200), starting at the first layer of the DATA bounds seen
+        # from that face; a face colour is the alpha-weighted mean of its pixels with alpha = coverage of the full
+        # face.  The sums run in numpy's order, not iproduct!'s: last-bit differences only.
+        f32 = np.float32
         r = self.resolution
-        full = np.zeros((r, r, r, 8), dtype=np.float32)
-        lo = self.voxel_lower
-        sz = self.voxel_size
-        full[lo[0]:lo[0] + sz[0], lo[1]:lo[1] + sz[1], lo[2]:lo[2] + sz[2]] = self.palette[self.indices]
-        faces = [full[0], full[:, 0], full[:, :, 0], full[-1], full[:, -1], full[:, :, -1]]  # NX NY NZ PX PY PZ layers
+        lo, sz = self.voxel_lower, self.voxel_size
+        vox = self.palette[self.indices]            # [sx, sy, sz, 8]: rgba, emission
+        thickness = f32(1.0) / f32(r)
+
+        # apply_transmittance (raytracer_components.rs:215-258) of every voxel for thickness 1/resolution
+        alpha_v = vox[..., 3]
+        unit_t = (f32(1.0) - alpha_v).astype(np.float32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            depth_t = np.power(unit_t, thickness, dtype=np.float32)
+            adj = np.clip(f32(1.0) - depth_t, f32(0.0), f32(1.0)).astype(np.float32)
+            coeff = np.where(unit_t == 1.0, thickness, np.maximum((depth_t - f32(1.0)) / (unit_t - f32(1.0)), f32(0.0))).astype(np.float32)
+        adj = np.where(alpha_v >= 1.0, f32(1.0), np.where(alpha_v <= 0.0, f32(0.0), adj)).astype(np.float32)
+        coeff = np.where(alpha_v >= 1.0, f32(1.0), coeff).astype(np.float32)
+
         self.light_opaque_faces = 0
         cols = []
-        for f, layer in enumerate(faces):
-            a = layer[..., 3]
-            if np.all(a == 1.0):
-                self.light_opaque_faces |= 1 << f
-            w = float(a.sum())
-            if w > 0:
-                rgb = (layer[..., :3] * a[..., None]).sum(axis=(0, 1)) / w
-                cols.append((float(rgb[0]), float(rgb[1]), float(rgb[2]), min(1.0, w / (r * r))))
+        all_color = np.zeros(3, dtype=np.float32)
+        all_alpha = f32(0.0)
+        all_em = np.zeros(3, dtype=np.float32)
+        count = 0
+        area = f32(r * r)
+        for f in range(6):                          # NX NY NZ PX PY PZ
+            axis, positive = f % 3, f >= 3
+            # trace_for_eval for all pixels of the face at once: layers of the data from the face inwards
+            order = range(sz[axis] - 1, -1, -1) if positive else range(sz[axis])
+            shape = tuple(sz[a] for a in range(3) if a != axis)
+            light = np.zeros(shape + (3,), dtype=np.float32)
+            T = np.ones(shape, dtype=np.float32)
+            em = np.zeros(shape + (3,), dtype=np.float32)
+            live = np.ones(shape, dtype=bool)
+            for k in order:
+                v = np.take(vox, k, axis=axis)
+                a = np.take(adj, k, axis=axis)
+                c = np.take(coeff, k, axis=axis)
+                em = np.where(live[..., None], em + (v[..., 4:7] * c[..., None]) * T[..., None], em).astype(np.float32)
+                light = np.where(live[..., None], light + (v[..., :3] * a[..., None]) * T[..., None], light).astype(np.float32)
+                T = np.where(live, T * (f32(1.0) - a), T).astype(np.float32)
+                live &= ~(T < f32(1.0 / 256.0))
+                if not live.any():
+                    break
+            pa = np.where(T >= 1.0, f32(0.0), f32(1.0) - T).astype(np.float32)              # Rgba::from(ColorBuf)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                prgb = np.where(pa[..., None] > 0, light / pa[..., None], f32(0.0)).astype(np.float32)
+            csum = (prgb * pa[..., None]).reshape(-1, 3).sum(axis=0, dtype=np.float32)
+            asum = f32(pa.sum(dtype=np.float32))
+            all_em = (all_em + em.reshape(-1, 3).sum(axis=0, dtype=np.float32)).astype(np.float32)
+            count += pa.size
+            all_color = (all_color + csum).astype(np.float32)
+            all_alpha = f32(all_alpha + asum)
+            if asum > 0:
+                cm = csum / asum
+                cols.append((float(cm[0]), float(cm[1]), float(cm[2]), float(min(max(asum / area, f32(0.0)), f32(1.0)))))
             else:
                 cols.append((0.0, 0.0, 0.0, 0.0))
+            # opaque[face] (derived.rs:196-209): the block's own surface layer lies inside the data and is fully opaque
+            others = [a_ for a_ in range(3) if a_ != axis]
+            covers = all((lo[a_] == 0 and sz[a_] == r) for a_ in others) and \
+                ((lo[axis] + sz[axis] == r) if positive else (lo[axis] == 0))
+            if covers and np.all(np.take(alpha_v, sz[axis] - 1 if positive else 0, axis=axis) == 1.0):
+                self.light_opaque_faces |= 1 << f
         self.light_face_colors = cols
-        m = np.mean(np.array(cols), axis=0)
-        self.light_color = tuple(float(v) for v in m)
-        em = full[..., 4:7].sum(axis=(0, 1, 2)) / (6.0 * r * r)
-        self.light_emission = tuple(float(v) for v in em)
-        self.light_visible = bool((full[..., 3] != 0).any() or (full[..., 4:7] != 0).any())
+        surface = f32(6 * r * r)
+        if all_alpha > 0:
+            c = all_color / all_alpha
+            self.light_color = (float(c[0]), float(c[1]), float(c[2]), float(min(max(all_alpha / surface, f32(0.0)), f32(1.0))))
+        else:
+            self.light_color = (0.0, 0.0, 0.0, 0.0)
+        self.light_emission = tuple(float(v) for v in (all_em / surface)) if count else (0.0, 0.0, 0.0)
+        self.light_visible = bool((vox[..., 3] != 0).any() or (vox[..., 4:7] != 0).any())
 
     @staticmethod
     def air() -> "Block":

@@ -47,7 +47,8 @@ def pngs():
                  "light_spread-Coarse-all", "light_spread-Linear-all", "light_spread-Smoothstep-all", "tone_map-Clamp-1.0-0.5-all",
                  "tone_map-Clamp-1.0-2.0-all", "tone_map-Reinhard-0.5-0.5-all", "tone_map-Reinhard-1.0-0.5-all",
                  "tone_map-Reinhard-1.0-2.0-all", "viewport_prime-all", "no_update-all", "no_update-2-all", "layers_all-all", "layers_hidden_ui-all", "layers_ui_only-all",
-                 "layers_none_but_text-all"]:
+                 "layers_none_but_text-all", "light_on_slab-None-all", "light_on_slab-Flat-all", "light_on_slab-Coarse-all",
+                 "light_on_slab-Linear-all", "light_on_slab-Smoothstep-all"]:
         im = np.array(Image.open(f"{REF}/test-renderers/expected/renderers/{name}.png").convert("RGBA"))
         np.save(f"{OUT}/png_{name}.npy", im)
 

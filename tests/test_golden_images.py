@@ -417,3 +417,59 @@ def test_layers(name):
         ui = (orc.OracleScene(Space((0, 0, 0), np.zeros((1, 1, 1), dtype=np.uint16), [Block.air()])), ucam, opts)
     img = orc.render_layers(world, ui, no_world=no_world_to_show())["srgb8"].reshape(96, 128, 4)
     check_layers_image(img, name)
+
+
+# ---- light_on_slab (cases/src/lib.rs:1455-1500): light on surfaces that are not aligned with a cube face -------------
+def slab_block(height):
+    """content::make_slab(universe, height, R16).rotate(GridRotation::RXZy) (all-is-cubes/src/content.rs:165-211): a
+    16 x height x 16 checkerboard of palette::PLANK and PLANK x 1.06, attached to NY; RXZy (basis +X, +Z, -Y) turns it so
+    that it rises from z = 0 towards +z: the rotated cube (X, Y, Z) holds the original voxel (X, Z, 15 - Y)."""
+    plank = np.array(srgb8_to_linear((0xE8, 0xCC, 0x95)), dtype=np.float32)
+    lighter = np.minimum(plank * np.float32(1.06), np.float32(1.0)).astype(np.float32)   # Rgb01::saturating_scale
+    pal = np.zeros((2, 8), dtype=np.float32)
+    pal[0, :3], pal[0, 3] = plank, 1.0
+    pal[1, :3], pal[1, 3] = lighter, 1.0
+    x, y, z = np.meshgrid(np.arange(16), np.arange(16), np.arange(height), indexing="ij")
+    return Block(indices=((x + z + (15 - y)) % 2).astype(np.uint16), palette=pal, resolution=16, voxel_lower=(0, 0, 0))
+
+
+def build_light_on_slab_universe():
+    """A grey back wall at z = -1 and sixteen slabs of height 1/16 .. 16/16 on it, two cubes apart; light converged like
+    the reference does (fast_evaluate_light + evaluate_light(1), default LightPhysics and sky)."""
+    ids = np.zeros((20, 20, 5), dtype=np.uint16)
+    blocks = [Block.air(), Block(color=(0.5, 0.5, 0.5, 1.0))] + [slab_block(h) for h in range(1, 17)]
+    ids[:, :, 0] = 1
+    for p in range(16):
+        ids[-3 + (p % 4) * 2 + 10, -3 + (p // 4) * 2 + 10, 0 + 1] = 2 + p
+    return _converged((-10, -10, -1), ids, blocks, _day_sky())
+
+
+@pytest.fixture(scope="module")
+def light_on_slab_universe():
+    return build_light_on_slab_universe()
+
+
+def light_on_slab_camera(opts):
+    """Spawn: eye (0.5, -6, 6), look direction (0, 1, -1); fov 45 (light_test_options)."""
+    cam = Camera(opts, Viewport((128.0, 96.0), (128, 96)))
+    cam.look_at_y_up((0.5, -6.0, 6.0), (0.5, -5.0, 5.0))
+    return cam
+
+
+@pytest.mark.parametrize("name,lighting", [("None", aicb200.LIGHT_NONE), ("Flat", aicb200.LIGHT_FLAT),
+                                           ("Coarse", aicb200.LIGHT_COARSE), ("Linear", aicb200.LIGHT_LINEAR),
+                                           ("Smoothstep", aicb200.LIGHT_SMOOTHSTEP)])
+def test_light_on_slab(light_on_slab_universe, name, lighting):
+    """cases/src/lib.rs:976-982 `light` over the light_on_slab universe: recursive blocks with partial voxel bounds whose
+    top faces lie INSIDE their cubes — the second interpolation plane of get_interpolated_light (sr.rs:248-359, the
+    height_in_cube mix) and the light propagation around partially opaque blocks (face colours with coverage alpha,
+    block/eval/derived.rs) against the reference's expected images, with the reference's threshold (7 on every pixel).
+    Without lighting the image is reproduced exactly."""
+    opts = GraphicsOptions.unaltered_colors()
+    opts.lighting_display = lighting
+    opts.fov_y = 45.0
+    img = orc.OracleScene(light_on_slab_universe).render(light_on_slab_camera(opts), opts)["srgb8"].reshape(96, 128, 4)
+    exp = golden(f"light_on_slab-{name}-all")
+    check_threshold(img, exp, [(7, 128 * 96)])
+    if lighting == aicb200.LIGHT_NONE:
+        assert np.array_equal(img, exp)

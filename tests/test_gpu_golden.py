@@ -148,3 +148,28 @@ def test_layers_on_gpu(name):
     oui = (orc.OracleScene(ui_space()), ucam, opts) if has_ui else None
     if oworld or oui:
         assert np.array_equal(img.reshape(-1, 4), orc.render_layers(oworld, oui, no_world=no_world_to_show())["srgb8"])
+
+
+@pytest.mark.parametrize("name,lighting", [("None", aicb200.LIGHT_NONE), ("Flat", aicb200.LIGHT_FLAT),
+                                           ("Coarse", aicb200.LIGHT_COARSE), ("Linear", aicb200.LIGHT_LINEAR),
+                                           ("Smoothstep", aicb200.LIGHT_SMOOTHSTEP)])
+def test_light_on_slab_on_gpu(name, lighting):
+    """Light on surfaces inside their cubes (partial voxel bounds): the reference's light_on_slab expectations through
+    the CUDA path, bit-identical to the oracle."""
+    from test_golden_images import build_light_on_slab_universe, light_on_slab_camera
+    space = _slab_universe()
+    opts = GraphicsOptions.unaltered_colors()
+    opts.lighting_display = lighting
+    opts.fov_y = 45.0
+    img = gpu_and_oracle(space, light_on_slab_camera(opts), opts)
+    check_threshold(img, golden(f"light_on_slab-{name}-all"), [(8, 128 * 96)])
+
+
+_SLAB = []
+
+
+def _slab_universe():
+    if not _SLAB:
+        from test_golden_images import build_light_on_slab_universe
+        _SLAB.append(build_light_on_slab_universe())
+    return _SLAB[0]
