@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstring>
 #include <array>
+#include <atomic>
+#include <thread>
 #include <map>
 #include <set>
 #include <unordered_map>
@@ -143,7 +145,7 @@ struct orc_light {
     // queue: by priority -> set of cube linear indices; by cube -> priority
     std::map<int, std::set<size_t>> by_priority;
     std::unordered_map<size_t, int> by_cube;
-    uint64_t node_visits = 0;
+    std::atomic<uint64_t> node_visits{0};
     int pop_order = 0;  // 0: lowest cube index first, 1: highest first (the reference's order is unspecified)
 };
 
@@ -250,6 +252,7 @@ struct LightBuffer {
     // orc_light_compute_by_chains: when set, what would be added to incoming / total_weight is appended here instead
     // ({x0, x1, x2, weight}; weight 0 for the terms that leave total_weight alone)
     std::vector<std::array<float, 4>> *rec = nullptr;
+    uint64_t visits = 0;   // chart nodes entered by this cube's walk
 };
 struct RayState {
     float alpha;
@@ -355,7 +358,7 @@ static void traverse(const orc_light &L, LightBuffer &b, RayState &rs, const int
 static float walk(orc_light &L, LightBuffer &b, const int32_t origin[3], const int32_t cube[3], int face7, uint32_t node_index,
                   bool have_prev, PL prev, RayState rs) {
     const FlatNode &node = chart()[node_index];
-    L.node_visits++;
+    b.visits++;
     float prod[6];
     for (int f = 0; f < 6; f++) prod[f] = node.weight[f] * rs.dw[f];
     float bundle = fm_sum(prod);
@@ -426,6 +429,7 @@ static PL compute_light(orc_light &L, const int32_t cube[3], LightBuffer *out_bu
     } else {
         result = L_NO_RAYS;
     }
+    L.node_visits.fetch_add(b.visits, std::memory_order_relaxed);
     if (out_buf) *out_buf = b;
     return result;
 }
@@ -606,6 +610,72 @@ uint64_t orc_light_evaluate(orc_light *L, uint8_t epsilon, uint64_t max_updates,
     return count;
 }
 
+// update_light_from_queue as the reference runs it with its `auto-threads` feature (updater.rs:211-252): pop up to 32
+// cubes, compute their light in parallel from the same stored light, apply the results one after the other in pop
+// order.  The result does not depend on the number of threads.  (orc_light_evaluate above is the non-threaded
+// variant, :254-270, which pops and applies one cube at a time.)
+uint64_t orc_light_evaluate_threaded(orc_light *L, uint8_t epsilon, uint64_t max_updates, int n_threads, uint8_t *max_diff_out) {
+    uint64_t count = 0;
+    int max_diff = 0;
+    if (L->max_distance == 0) return 0;
+    const int eps = prio_from_difference(epsilon);
+    constexpr int BATCH = 32;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > BATCH) n_threads = BATCH;
+    struct Item { int32_t c[3]; PL nv; LightBuffer b; };
+    std::vector<Item> items(BATCH);
+    // workers spin on a generation counter: a batch is ~32 x 50 us of work, too short for thread creation per batch
+    std::atomic<int> generation{0}, next{0}, done{0}, n_items{0};
+    std::atomic<bool> quit{false};
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_items.load(std::memory_order_acquire)) break;
+            items[i].b = LightBuffer();
+            items[i].nv = compute_light(*L, items[i].c, &items[i].b);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++)
+        pool.emplace_back([&]() {
+            int seen = 0;
+            for (;;) {
+                while (generation.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed)) std::this_thread::yield();
+                if (quit.load(std::memory_order_relaxed)) return;
+                seen = generation.load(std::memory_order_acquire);
+                work();
+            }
+        });
+    while (count < max_updates) {
+        int n = 0;
+        while (n < BATCH && count + n < max_updates) {
+            if (q_peek(*L) <= eps) break;
+            size_t idx;
+            if (!q_pop(*L, &idx)) break;
+            l_cube_of(*L, idx, items[n].c);
+            n++;
+        }
+        if (n == 0) break;
+        done.store(0, std::memory_order_relaxed);
+        next.store(0, std::memory_order_relaxed);
+        n_items.store(n, std::memory_order_release);
+        generation.fetch_add(1, std::memory_order_release);
+        work();
+        while (done.load(std::memory_order_acquire) < n) std::this_thread::yield();
+        for (int i = 0; i < n; i++) {
+            int d = apply_light_update(*L, items[i].c, items[i].nv, items[i].b);
+            if (d > max_diff) max_diff = d;
+            count++;
+        }
+    }
+    quit.store(true);
+    generation.fetch_add(1, std::memory_order_release);
+    for (std::thread &t : pool) t.join();
+    if (max_diff_out) *max_diff_out = (uint8_t)max_diff;
+    return count;
+}
+
 void orc_light_compute(orc_light *L, const int32_t (*cubes)[3], size_t n, uint8_t (*out)[4]) {
     for (size_t i = 0; i < n; i++) {
         PL p = compute_light(*L, cubes[i], nullptr);
@@ -688,7 +758,7 @@ void orc_light_compute_by_chains(orc_light *Lp, const int32_t (*cubes)[3], size_
                     const uint32_t node_index = preorder[first + k];
                     const FlatNode &node = ch[node_index];
                     last_node = node_index;
-                    L.node_visits++;
+                    b.visits++;
                     float prod[6];
                     for (int f = 0; f < 6; f++) prod[f] = node.weight[f] * rs.dw[f];
                     bundle = fm_sum(prod);
@@ -737,6 +807,7 @@ void orc_light_compute_by_chains(orc_light *Lp, const int32_t (*cubes)[3], size_
                 }
             }
         }
+        L.node_visits.fetch_add(b.visits, std::memory_order_relaxed);
         PL result;
         float scale = ps_clamped_l(1.0f / std::fmax(b.total_weight, 1.0f));
         if (b.total_weight > 0.0f)
@@ -777,5 +848,5 @@ void orc_light_get_outside(const orc_light *L, const int32_t c[3], uint8_t out[4
 void orc_light_set_pop_order(orc_light *L, int order) { L->pop_order = order; }
 size_t orc_light_queue_len(const orc_light *L) { return L->by_cube.size(); }
 int orc_light_queue_peek(const orc_light *L) { return q_peek(*L); }
-uint64_t orc_light_node_visits(const orc_light *L) { return L->node_visits; }
+uint64_t orc_light_node_visits(const orc_light *L) { return L->node_visits.load(); }
 }

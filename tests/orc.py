@@ -84,6 +84,8 @@ def lib():
     L.orc_light_get.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_light_compute_by_chains.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_uint32, C.c_void_p, C.c_uint32]
+    L.orc_light_evaluate_threaded.restype = C.c_uint64
+    L.orc_light_evaluate_threaded.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64, C.c_int, C.c_void_p]
     L.orc_light_compute_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.orc_light_set_field.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_light_get_outside.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -358,6 +360,13 @@ class OracleLight:
         lib().orc_light_compute_by_chains(self.handle, c.ctypes.data, c.shape[0], out.ctypes.data, raw.ctypes.data, pre.ctypes.data,
                                           chn.ctypes.data, chn.shape[0], eul.ctypes.data, eul.shape[0])
         return out, raw
+
+    def evaluate_threaded(self, epsilon, n_threads, max_updates=(1 << 62)):
+        """update_light_from_queue with the reference's `auto-threads` batches (32 cubes computed in parallel from the
+        same stored light, applied in pop order); returns (updates, max difference)."""
+        md = C.c_uint8(0)
+        n = lib().orc_light_evaluate_threaded(self.handle, epsilon, max_updates, n_threads, C.byref(md))
+        return int(n), int(md.value)
 
     def compute_raw(self, cubes):
         """compute_light: the packed results and the unquantised accumulators (incoming_light rgb, total_rays)."""

@@ -197,3 +197,24 @@ def test_order_dependence_of_the_reference_algorithm():
     d = np.abs(fields[0][..., :3].astype(int) - fields[1][..., :3].astype(int)).max(axis=-1)
     assert 1 <= d.max() <= 8
     assert (d <= 2).mean() > 0.97
+
+
+def test_threaded_update_is_deterministic_and_within_the_contract_of_the_sequential_one():
+    """update_light_from_queue with `auto-threads` (updater.rs:211-252: 32 cubes popped, computed in parallel from the
+    same stored light, applied in pop order) — the variant the CPU arm of bench.py --workload c4 times.  Its result
+    must not depend on the thread count, and it must land where the one-at-a-time variant lands up to the order
+    dependence the reference itself has (same statuses, values within a few units)."""
+    from aicb200 import scenes
+    space = scenes.config_c4(20)
+    fields, counts = {}, {}
+    for mode in ("sequential", 1, 3, 8):
+        ol = orc.OracleLight(space)
+        ol.fast_evaluate()
+        counts[mode], _ = ol.evaluate(1) if mode == "sequential" else ol.evaluate_threaded(1, mode)
+        fields[mode] = ol.field()
+        assert ol.queue_len() == 0 or ol.queue_peek() <= 1
+    assert np.array_equal(fields[1], fields[3]) and np.array_equal(fields[1], fields[8])
+    assert counts[1] == counts[3] == counts[8]
+    assert np.array_equal(fields["sequential"][..., 3], fields[1][..., 3])
+    d = np.abs(fields["sequential"][..., :3].astype(int) - fields[1][..., :3].astype(int))
+    assert d.max() <= 8 and (d > 2).mean() < 0.03
